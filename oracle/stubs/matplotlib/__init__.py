@@ -1,0 +1,1 @@
+"""Empty stub: imported by the reference, never used on the hot path."""
