@@ -1,0 +1,87 @@
+"""ctypes binding of libbadger_b200.so (include/badger_b200.h).
+
+The shared library is built in-tree by ``__graft_entry__.build()`` / ``make -C badger_b200/csrc``.
+There is no CPU fallback: if the library is missing, or no B200 is visible, every operator raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libbadger_b200.so")
+
+BDG_OK, BDG_ERR_CUDA, BDG_ERR_OOM, BDG_ERR_ARG, BDG_ERR_NODEVICE, BDG_ERR_CAPACITY = 0, -1, -2, -3, -4, -5
+ROW_TILE = 2048  # BDG_ROW_TILE
+
+
+class BadgerB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__("libbadger_b200: %s (code %d)" % (msg, code))
+        self.code = code
+
+
+_lib = None
+_vp, _sz, _i = C.c_void_p, C.c_size_t, C.c_int
+
+
+def lib():
+    """Load the library once; raise loudly when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BadgerB200Error(BDG_ERR_NODEVICE, "%s not found - build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "or `make -C badger_b200/csrc`; there is no CPU fallback" % LIB_PATH)
+    L = C.CDLL(LIB_PATH)
+    L.bdg_last_error.restype = C.c_char_p
+    L.bdg_version.restype = C.c_char_p
+    L.bdg_init.argtypes = [_vp, _i]
+    L.bdg_device_count.restype = _i
+    L.bdg_launch_count.restype = C.c_ulonglong
+    L.bdg_pack16.argtypes = [_vp, _sz, _vp, _vp]
+    L.bdg_edges_build.argtypes = [_vp, _sz, _i, C.POINTER(_vp)]
+    L.bdg_edges_build_part.argtypes = [_vp, _sz, _i, _i, _i, C.POINTER(_vp)]
+    L.bdg_edges_count.argtypes = [_vp]
+    L.bdg_edges_count.restype = _sz
+    L.bdg_edges_copy.argtypes = [_vp, _vp, _vp, _vp]
+    L.bdg_edges_free.argtypes = [_vp]
+    L.bdg_edges_free.restype = None
+    L.bdg_member_sorted.argtypes = [_vp, _sz, _vp, _sz, _vp]
+    L.bdg_nearest_bounded.argtypes = [_vp, _sz, _vp, _sz, _i, _vp, _vp]
+    L.bdg_kmer_score.argtypes = [_vp, _sz, _vp, _sz, _i, _sz, _vp, _vp, _vp, _vp, C.POINTER(_sz)]
+    L.bdg_dev_edges_build.argtypes = [_vp, _sz, _i, _i, _i, _vp, _vp, _vp, _sz, _vp, _vp]
+    L.bdg_dev_pack16.argtypes = [_vp, _sz, _vp, _vp, _vp]
+    L.bdg_dev_member_sorted.argtypes = [_vp, _sz, _vp, _sz, _vp, _vp]
+    L.bdg_dev_nearest_bounded.argtypes = [_vp, _sz, _vp, _sz, _i, _vp, _vp, _vp, _vp]
+    L.bdg_part_pairs.argtypes = [_sz, _i, _i]
+    L.bdg_part_pairs.restype = C.c_ulonglong
+    L.bdg_dev_pipe_probe.argtypes = [_i, _i, _i, _vp, C.POINTER(C.c_ulonglong), _vp]
+    for name in ("bdg_init", "bdg_pack16", "bdg_edges_build", "bdg_edges_build_part", "bdg_edges_copy", "bdg_member_sorted",
+                 "bdg_nearest_bounded", "bdg_kmer_score", "bdg_dev_edges_build", "bdg_dev_pack16", "bdg_dev_member_sorted",
+                 "bdg_dev_nearest_bounded", "bdg_dev_pipe_probe"):
+        getattr(L, name).restype = _i
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != BDG_OK:
+        raise BadgerB200Error(rc, (lib().bdg_last_error() or b"").decode(errors="replace"))
+
+
+def init(device_ids=None) -> int:
+    """bdg_init: claim the listed CUDA devices (default: all visible). Returns the device count."""
+    L = lib()
+    if device_ids is None:
+        check(L.bdg_init(None, 0))
+    else:
+        arr = (C.c_int * len(device_ids))(*device_ids)
+        check(L.bdg_init(arr, len(device_ids)))
+    return L.bdg_device_count()
+
+
+def ptr(a: np.ndarray):
+    return a.ctypes.data if a.size else None

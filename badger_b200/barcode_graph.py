@@ -1,0 +1,361 @@
+"""BarcodeGraph with the reference's interface (algbio/Badger barcode_graph.py:38-410), backed by the
+B200 kernels.  Same method names, arguments, attributes and results; the O(N^2) candidate search and the
+edit-distance verification (barcode_graph.py:224-249, index.py:77-93) run in ``libbadger_b200.so``.
+
+What stays on the host (numpy): first-seen-order dedup/count, centre selection bookkeeping, the two BFS
+rounds of ``cluster`` (vectorised, order-free restatement), dict-shaped views for downstream readers.
+"""
+from __future__ import annotations
+
+import logging
+from collections import defaultdict
+from statistics import StatisticsError
+
+import numpy as np
+
+from . import ops
+from .common import rank, unrank
+from .index import QGramIndex
+
+logger = logging.getLogger("BarcodeGraph")
+
+READ_CHUNK_SIZE = 100000   # kept for interface parity (barcode_graph.py:25-26); unused by the GPU path
+BC_CHUNK_SIZE = 10000
+
+
+def _unrank_many(ranks: np.ndarray, bc_len: int = 16) -> list:
+    ranks = np.asarray(ranks, dtype=np.uint32)
+    codes = np.empty((ranks.size, bc_len), dtype=np.uint8)
+    for i in range(bc_len):
+        codes[:, i] = (ranks >> np.uint32(2 * i)) & np.uint32(3)
+    letters = np.frombuffer(b"ACGT", dtype=np.uint8)[codes]
+    return [s.decode() for s in letters.view("S%d" % bc_len).reshape(-1).tolist()]
+
+
+class _EdgeView:
+    """Read-only stand-in for ``defaultdict(list)`` rank -> neighbour ranks (barcode_graph.py:44) over CSR
+    arrays.  A missing key yields an empty list and, like the defaultdict it replaces, is remembered as a key
+    (badger.py:131 prints ``len(counts) - len(edges.keys())``)."""
+
+    def __init__(self, nodes: np.ndarray, indptr: np.ndarray, nbrs: np.ndarray):
+        self._nodes, self._indptr, self._nbrs = nodes, indptr, nbrs
+        self._touched = set()
+
+    def _slot(self, key):
+        i = int(np.searchsorted(self._nodes, key))
+        return i if i < self._nodes.size and int(self._nodes[i]) == int(key) else -1
+
+    def __getitem__(self, key):
+        i = self._slot(key)
+        if i < 0:
+            self._touched.add(int(key))
+            return []
+        return self._nbrs[self._indptr[i]:self._indptr[i + 1]].tolist()
+
+    def get(self, key, default=None):
+        i = self._slot(key)
+        return default if i < 0 else self._nbrs[self._indptr[i]:self._indptr[i + 1]].tolist()
+
+    def __contains__(self, key):
+        return self._slot(key) >= 0 or int(key) in self._touched
+
+    def keys(self):
+        extra = [k for k in self._touched if self._slot(k) < 0]
+        return self._nodes.tolist() + extra
+
+    def __iter__(self):
+        return iter(self.keys())
+
+    def __len__(self):
+        return len(self.keys())
+
+    def items(self):
+        return ((k, self[k]) for k in self.keys())
+
+
+class _DistView:
+    """Stand-in for ``defaultdict(int)`` (a,b) -> D holding both orientations (barcode_graph.py:45,248-249)."""
+
+    def __init__(self, a: np.ndarray, b: np.ndarray, d: np.ndarray):
+        self._key = (a.astype(np.uint64) << np.uint64(32)) | b.astype(np.uint64)   # sorted by (a,b), a<b
+        self._d = d
+
+    def __getitem__(self, pair):
+        x, y = int(pair[0]), int(pair[1])
+        if x > y:
+            x, y = y, x
+        k = np.uint64((x << 32) | y)
+        i = int(np.searchsorted(self._key, k))
+        return int(self._d[i]) if i < self._key.size and self._key[i] == k else 0
+
+    def __len__(self):
+        return 2 * int(self._key.size)
+
+    def keys(self):
+        a = (self._key >> np.uint64(32)).tolist(); b = (self._key & np.uint64(0xFFFFFFFF)).tolist()
+        return [(x, y) for x, y in zip(a, b)] + [(y, x) for x, y in zip(a, b)]
+
+    def items(self):
+        return ((k, self[k]) for k in self.keys())
+
+
+class BarcodeGraph:
+
+    def __init__(self, threshold):
+        self.threshold = threshold
+        self.counts = defaultdict(int)      # rank -> count, first-seen order (barcode_graph.py:43)
+        self.edges = defaultdict(list)
+        self.dists = defaultdict(int)
+        self.clusters = defaultdict(list)
+        self.clustering = dict()
+        self.clustered = defaultdict(bool)
+        self.index = None
+        self._ranks = np.empty(0, np.uint32)      # distinct ranks, first-seen order
+        self._cnt = np.empty(0, np.int64)
+        self._edge_arrays = (np.empty(0, np.uint32), np.empty(0, np.uint32), np.empty(0, np.uint8))
+
+    @classmethod
+    def from_arrays(cls, threshold, ranks_first_seen, counts, edges=None):
+        """Array entry point: distinct ranks in first-seen order with their counts, optionally an edge list
+        (a, b, d).  Used by bench.py / tests and by callers that already hold packed barcodes."""
+        g = cls(threshold)
+        g._ranks = np.ascontiguousarray(ranks_first_seen, dtype=np.uint32)
+        g._cnt = np.ascontiguousarray(counts, dtype=np.int64)
+        g.counts.update(zip(g._ranks.tolist(), g._cnt.tolist()))
+        if edges is not None:
+            g._set_edges(*edges)
+        return g
+
+    # ------------------------------------------------------------------ a-1/a-2: pack, dedup, count
+    def index_bc_single_thread(self, barcodes, bc_len):
+        """barcode_graph.py:192-204: 17-mers lose their last base, other lengths are skipped, the rest is
+        ranked (GPU, ops.pack16) and counted in first-seen order."""
+        if bc_len != 16:
+            raise NotImplementedError("the B200 path packs 16-bp barcodes into uint32; bc_len=%r is not supported" % bc_len)
+        keep = []
+        for s in barcodes:
+            n = len(s)
+            if n == bc_len + 1:
+                keep.append(s[:-1])
+            elif n == bc_len:
+                keep.append(s)
+        if not keep:
+            return
+        ranks, valid = ops.pack16(keep)
+        if not valid.all():
+            bad = keep[int(np.argmin(valid))]
+            raise KeyError(next(c for c in bad if c not in "ACGT"))      # common.py:24 raises KeyError(letter)
+        uniq, first, cnt = np.unique(ranks, return_index=True, return_counts=True)
+        order = np.argsort(first, kind="stable")
+        new_r, new_c = uniq[order], cnt[order].astype(np.int64)
+        if self._ranks.size:                                               # merge with an earlier call
+            for r, c in zip(new_r.tolist(), new_c.tolist()):
+                self.counts[r] += c
+            self._ranks = np.fromiter(self.counts.keys(), dtype=np.uint32, count=len(self.counts))
+            self._cnt = np.fromiter(self.counts.values(), dtype=np.int64, count=len(self.counts))
+        else:
+            self._ranks, self._cnt = new_r, new_c
+            self.counts.update(zip(new_r.tolist(), new_c.tolist()))
+
+    index_bc_in_parallel = lambda self, barcodes, bc_len, threads: self.index_bc_single_thread(barcodes, bc_len)  # noqa: E731
+
+    # ------------------------------------------------------------------ a-3/a-4: edges
+    def graph_construction(self, barcodes, bc_len, threads):
+        """barcode_graph.py:207-249.  ``threads`` is accepted for compatibility; the GPUs claimed by
+        ``badger_b200.init`` replace the process pool."""
+        self.index = QGramIndex(self.threshold, bc_len, 6)
+        self.index_bc_single_thread(barcodes, bc_len)
+        self.index._adopt(self._ranks)
+        a, b, d = ops.edges_build(np.sort(self._ranks), self.threshold)
+        self._set_edges(a, b, d)
+
+    def compare_in_parallel(self, bc_len, threads):
+        a, b, d = ops.edges_build(np.sort(self._ranks), self.threshold)
+        self._set_edges(a, b, d)
+
+    def _set_edges(self, a, b, d):
+        a, b, d = ops.canonical(np.asarray(a, np.uint32), np.asarray(b, np.uint32), np.asarray(d, np.uint8))
+        self._edge_arrays = (a, b, d)
+        src = np.concatenate([a, b]); dst = np.concatenate([b, a])
+        order = np.lexsort((dst, src))
+        src, dst = src[order], dst[order]
+        nodes, start = np.unique(src, return_index=True)
+        indptr = np.append(start, src.size).astype(np.int64)
+        self._csr = (nodes, indptr, dst)
+        self.edges = _EdgeView(nodes, indptr, dst)
+        self.dists = _DistView(a, b, d)
+
+    def edge_arrays(self):
+        """(a, b, d) with a < b, sorted by (a, b): the array form of ``edges``/``dists``."""
+        return self._edge_arrays
+
+    # ------------------------------------------------------------------ a-6: centres
+    def _whitelist_hits(self, barcode_list, bc_len):
+        """`unrank(r, bc_len) in barcode_list` (barcode_graph.py:264) for every distinct barcode: the set is
+        packed once, sorted, and probed on the GPU (ops.member_sorted)."""
+        cache = getattr(self, "_wl_cache", None)
+        if cache is None or cache[0] is not barcode_list:
+            good = [s for s in barcode_list if len(s) == bc_len and not (set(s) - set("ACGT"))]
+            wl = np.sort(ops.pack16(good)[0]) if good else np.empty(0, np.uint32)
+            self._wl_cache = cache = (barcode_list, wl)
+        return ops.member_sorted(cache[1], self._ranks)
+
+    def get_cluster_centers(self, true_barcodes, bc_len, barcode_list, n_cells, interval):
+        """barcode_graph.py:252-277, vectorised; same list, same order, same IndexError when N is too small."""
+        N = self._ranks.size
+        if N == 0:
+            raise StatisticsError("mean requires at least one data point")      # statistics.mean([]) at :255
+        order = np.argsort(-self._cnt, kind="stable")                           # sorted(..., reverse=True) is stable
+        by_counts = self._ranks[order]
+        cnt_sorted = self._cnt[order]
+        first = self._cnt[:n_cells]
+        if first.size == 0:
+            raise StatisticsError("mean requires at least one data point")
+        cutoff = max((int(first.sum()) / first.size) / 5.0, 5)
+        hi = n_cells + n_cells * interval * 0.01
+        lo = n_cells - n_cells * interval * 0.01
+        tbcs, n, i = [], 0, 0
+        n_above = int(np.searchsorted(-cnt_sorted, -cutoff, side="left"))        # entries with count > cutoff
+        if true_barcodes:
+            tbcs = [rank(bc, bc_len) for bc in true_barcodes]
+        elif barcode_list:
+            hits = self._whitelist_hits(barcode_list, bc_len)[order][:n_above]
+            csum = np.cumsum(hits)
+            want = int(np.floor(hi)) + 1                                         # loop runs while n <= hi
+            if csum.size and csum[-1] >= want:
+                i = int(np.searchsorted(csum, want, side="left")) + 1
+                n = want
+            else:
+                i = n_above
+                n = int(csum[-1]) if csum.size else 0
+            tbcs = by_counts[:i][hits[:i]].tolist()
+        else:
+            if n_above >= N and N <= int(np.floor(hi)) + 1:
+                raise IndexError("list index out of range")                     # :269 runs off the list
+            n = i = min(n_above, int(np.floor(hi)) + 1)
+            tbcs = by_counts[:i].tolist()
+        while n < lo:
+            if i >= N:
+                raise IndexError("list index out of range")                     # :274 in the reference
+            tbcs.append(int(by_counts[i]))
+            i += 1
+            n += 1
+        return tbcs
+
+    # ------------------------------------------------------------------ clustering (host, order-free)
+    def cluster(self, true_barcodes, barcode_list, n_cells, bc_len, interval):
+        """barcode_graph.py:279-301.  The reference's two rounds are level-synchronous and independent of the
+        adjacency order: a node joins centre c at level i iff, among the nodes expanded in
+        round i, its neighbours all belong to c; two different centres in the same round evict it."""
+        tbcs = self.get_cluster_centers(true_barcodes, bc_len, barcode_list, n_cells, interval)
+        nodes, indptr, nbrs = getattr(self, "_csr", (np.empty(0, np.uint32), np.zeros(1, np.int64), np.empty(0, np.uint32)))
+        centres = list(dict.fromkeys(int(t) for t in tbcs))
+        for t in centres:
+            self.clusters[t] = [t]
+            self.clustering[t] = (t, 0)
+            self.clustered[t] = True
+            _ = self.edges[t]                       # the reference touches edges[centre] (:293)
+        # universe: every node with an edge, plus the centres
+        uni = np.unique(np.concatenate([nodes, np.asarray(centres, dtype=np.uint32)]))
+        centre_of = np.full(uni.size, -2, dtype=np.int64)      # -2 unclustered, -1 evicted, else index into uni
+        level = np.full(uni.size, -1, dtype=np.int64)
+        cidx = np.searchsorted(uni, np.asarray(centres, dtype=np.uint32))
+        centre_of[cidx] = cidx
+        level[cidx] = 0
+        node_pos = np.searchsorted(uni, nodes)                  # CSR row -> universe slot
+        row_of = np.full(uni.size, -1, dtype=np.int64)
+        row_of[node_pos] = np.arange(nodes.size)
+        frontier = cidx
+        for i in (1, 2):
+            print(i)                                             # barcode_graph.py:289
+            rows = row_of[frontier]
+            ok = rows >= 0
+            rows, src = rows[ok], frontier[ok]
+            if rows.size == 0:
+                frontier = np.empty(0, dtype=np.int64)
+                continue
+            lens = indptr[rows + 1] - indptr[rows]
+            tot = int(lens.sum())
+            offs = np.repeat(indptr[rows] - np.concatenate([[0], np.cumsum(lens)[:-1]]), lens) + np.arange(tot)
+            nb = np.searchsorted(uni, nbrs[offs])
+            who = np.repeat(centre_of[src], lens)                # centre (universe slot) claiming nb
+            free = centre_of[nb] == -2
+            nb, who = nb[free], who[free]
+            if nb.size == 0:
+                frontier = np.empty(0, dtype=np.int64)
+                continue
+            o = np.lexsort((who, nb))
+            nb, who = nb[o], who[o]
+            first = np.concatenate([[True], nb[1:] != nb[:-1]])
+            start = np.nonzero(first)[0]
+            end = np.append(start[1:], nb.size)
+            single = who[start] == who[end - 1]                 # sorted by who inside a node: one centre iff min == max
+            tgt = nb[start]
+            centre_of[tgt] = np.where(single, who[start], -1)
+            level[tgt] = np.where(single, i, -1)
+            frontier = tgt[single]
+        # materialise the reference's dict attributes
+        got = np.nonzero(centre_of != -2)[0]
+        got = got[level[got] != 0]
+        uni_l = uni.tolist()
+        for slot in got.tolist():
+            node = uni_l[slot]
+            c = int(centre_of[slot])
+            if c >= 0:
+                cen = uni_l[c]
+                self.clusters[cen].append(node)
+                self.clustering[node] = (cen, int(level[slot]))
+            else:
+                self.clustering[node] = (-1, -1)
+            self.clustered[node] = True
+
+    # ------------------------------------------------------------------ assignment / post-processing / output
+    def assign_by_cluster(self, bc_len):
+        """barcode_graph.py:322-329 (dict built in `counts` order, which fixes the iteration order of
+        ``set(assignments.values())`` used by postprocessing)."""
+        observed_assignments = defaultdict(str)
+        nodes = [n for n in self.counts.keys() if n in self.clustering and self.clustering[n][0] != -1]
+        if nodes:
+            bcs = _unrank_many(np.asarray(nodes, dtype=np.uint32), bc_len)
+            cens = _unrank_many(np.asarray([self.clustering[n][0] for n in nodes], dtype=np.uint32), bc_len)
+            for bc, tbc in zip(bcs, cens):
+                observed_assignments[bc] = tbc
+        return observed_assignments
+
+    def postprocessing(self, assignments, bc_len, _centre_order=None):
+        """barcode_graph.py:370-385 (--high_sens): every still-unassigned distinct barcode goes to the first
+        centre, in the iteration order of ``set(assignments.values())``, at minimum plain edit distance when
+        that distance is < 3.  The Q x W scoring runs on the GPU (ops.nearest_bounded)."""
+        cluster_centers = list(set(assignments.values())) if _centre_order is None else list(_centre_order)
+        all_bc = _unrank_many(self._ranks, bc_len)
+        todo_idx = [i for i, bc in enumerate(all_bc) if assignments[bc] == "" or assignments[bc] == "*"]
+        good = [c for c in cluster_centers if len(c) == bc_len and not (set(c) - set("ACGT"))]
+        if not todo_idx or not good:
+            return assignments
+        pos = [j for j, c in enumerate(cluster_centers) if len(c) == bc_len and not (set(c) - set("ACGT"))]
+        targets = ops.pack16(good)[0]
+        am, _ = ops.nearest_bounded(self._ranks[todo_idx], targets, 2)
+        for i, j in zip(todo_idx, am.tolist()):
+            if j >= 0:
+                assignments[all_bc[i]] = cluster_centers[pos[j]]
+        return assignments
+
+    def output_file(self, read_assignment, out, true_barcodes, bc_len, post):
+        """barcode_graph.py:388-410: `<out>_output_file.tsv`, header readID/barcode, '*' when unassigned."""
+        import pandas as pd
+        assignments = self.assign_by_cluster(bc_len)
+        if post:
+            assignments = self.postprocessing(assignments, bc_len)
+        read_ids, results = [], []
+        for read in read_assignment:
+            observed_bc = read[1]
+            assigned_bc = "*"
+            if observed_bc != "*":
+                assigned_bc = assignments[observed_bc]
+                if assigned_bc == "":
+                    assigned_bc = "*"
+            read_ids.append(read[0])
+            results.append(assigned_bc)
+        out_file = out + "_output_file.tsv"
+        res = pd.DataFrame({"readID": read_ids, "barcode": results})
+        res.to_csv(out_file, sep='\t', index=False)

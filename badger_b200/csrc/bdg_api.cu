@@ -1,0 +1,565 @@
+// bdg_api.cu -- C ABI of libbadger_b200.so (see include/badger_b200.h for the contract and the
+// reference call sites each entry point replaces).  Host side only: contexts, buffers, work plans,
+// launches.  All arithmetic lives in bdg_kernels.cuh / bdg_core.cuh.  There is no CPU fallback.
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "../../include/badger_b200.h"
+#include "bdg_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t e_ = (expr);                                                                       \
+        if (e_ != cudaSuccess)                                                                         \
+            return fail(e_ == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "%s failed: %s", \
+                        #expr, cudaGetErrorString(e_));                                                \
+    } while (0)
+
+struct DevCtx {
+    int dev = -1;
+    cudaStream_t stream = nullptr;
+    int sms = 0;
+};
+std::vector<DevCtx> g_ctx;
+
+int owner_of_tile(uint64_t I, int P)
+{
+    const uint64_t m = I % (2ull * P);
+    return (int)(m < (uint64_t)P ? m : 2ull * P - 1 - m);
+}
+
+int grid_for(const void* kernel, int* out)
+{
+    int dev = 0, sms = 0, occ = 0;
+    CU_TRY(cudaGetDevice(&dev));
+    CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, bdg::NT, 0));
+    if (occ < 1) occ = 1;
+    *out = sms * occ;
+    return BDG_OK;
+}
+
+// ---- the work plan of one part: owned row tiles, column chunks per tile --------------------------------
+struct Plan {
+    std::vector<uint32_t> tile_ids;
+    std::vector<uint32_t> item_start;
+    uint32_t chunk_cols = 256;
+    uint64_t pairs = 0;
+};
+
+void build_plan(size_t N, int part, int nparts, int grid, Plan& p)
+{
+    const uint64_t tiles = (N + bdg::ROW_TILE - 1) / bdg::ROW_TILE;
+    p.tile_ids.clear();
+    p.pairs = 0;
+    for (uint64_t I = 0; I < tiles; I++) {
+        if (owner_of_tile(I, nparts) != part) continue;
+        p.tile_ids.push_back((uint32_t)I);
+        const uint64_t r0 = I * bdg::ROW_TILE, r1 = std::min<uint64_t>(N, r0 + bdg::ROW_TILE);
+        const uint64_t n = r1 - r0;                       // rows i in [r0,r1): N-1-i partners each
+        p.pairs += n * (N - 1) - (r0 + r1 - 1) * n / 2;
+    }
+    // aim at >= 16 work items per resident CTA so that the dynamic scheduler can level the load
+    const double want_items = 16.0 * std::max(grid, 1);
+    double cols = ((double)p.pairs / bdg::ROW_TILE) / want_items;
+    uint64_t cc = (uint64_t)cols / 256 * 256;
+    cc = std::min<uint64_t>(std::max<uint64_t>(cc, 256), 16384);
+    p.chunk_cols = (uint32_t)cc;
+    p.item_start.assign(p.tile_ids.size() + 1, 0);
+    uint64_t acc = 0;
+    for (size_t k = 0; k < p.tile_ids.size(); k++) {
+        p.item_start[k] = (uint32_t)acc;
+        const uint64_t ncols = N - (uint64_t)p.tile_ids[k] * bdg::ROW_TILE;
+        acc += (ncols + cc - 1) / cc;
+    }
+    p.item_start[p.tile_ids.size()] = (uint32_t)acc;
+}
+
+// Launch the edge kernel for one part on the current device / stream.  d_count is zeroed on the stream.
+int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts, uint32_t* d_a, uint32_t* d_b,
+                 uint8_t* d_d, size_t cap, unsigned long long* d_count, cudaStream_t st)
+{
+    if (nparts < 1 || part < 0 || part >= nparts) return fail(BDG_ERR_ARG, "part %d of %d is not a valid part", part, nparts);
+    if (N > 0xFFFFFFFFull) return fail(BDG_ERR_ARG, "N = %zu exceeds the 2^32 distinct 16-mers", N);
+    CU_TRY(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
+    if (t <= 0 || N < 2) return BDG_OK;   // D >= 1 for distinct barcodes: no edges (barcode_graph.py:245)
+    const void* kern = t == 1 ? (const void*)bdg::edges_kernel<1> : t == 2 ? (const void*)bdg::edges_kernel<2>
+                                                                           : (const void*)bdg::edges_kernel<3>;
+    int grid = 0;
+    if (int rc = grid_for(kern, &grid)) return rc;
+    Plan plan;
+    build_plan(N, part, nparts, grid, plan);
+    const uint32_t n_items = plan.item_start.back();
+    if (n_items == 0) return BDG_OK;
+    const size_t nb_tiles = plan.tile_ids.size() * sizeof(uint32_t), nb_items = plan.item_start.size() * sizeof(uint32_t);
+    char* d_plan = nullptr;   // [counter | tile_ids | item_start]
+    CU_TRY(cudaMallocAsync((void**)&d_plan, 16 + nb_tiles + nb_items, st));
+    CU_TRY(cudaMemsetAsync(d_plan, 0, 16, st));
+    CU_TRY(cudaMemcpyAsync(d_plan + 16, plan.tile_ids.data(), nb_tiles, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_plan + 16 + nb_tiles, plan.item_start.data(), nb_items, cudaMemcpyHostToDevice, st));
+    bdg::EdgeWork w;
+    w.sorted = d_sorted;
+    w.N = (uint32_t)N;
+    w.t = t;
+    w.T = bdg::qgram_threshold(t);
+    w.tile_ids = (const uint32_t*)(d_plan + 16);
+    w.item_start = (const uint32_t*)(d_plan + 16 + nb_tiles);
+    w.K = (uint32_t)plan.tile_ids.size();
+    w.n_items = n_items;
+    w.chunk_cols = plan.chunk_cols;
+    w.item_counter = (unsigned int*)d_plan;
+    w.one = 1u;
+    bdg::EdgeOut o{d_a, d_b, d_d, d_count, (unsigned long long)cap};
+    const int blocks = (int)std::min<uint64_t>((uint64_t)grid, n_items);
+    if (t == 1) bdg::edges_kernel<1><<<blocks, bdg::NT, 0, st>>>(w, o);
+    else if (t == 2) bdg::edges_kernel<2><<<blocks, bdg::NT, 0, st>>>(w, o);
+    else bdg::edges_kernel<3><<<blocks, bdg::NT, 0, st>>>(w, o);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaFreeAsync(d_plan, st));
+    return BDG_OK;
+}
+
+int need_ctx()
+{
+    if (g_ctx.empty()) {
+        int rc = bdg_init(nullptr, 0);
+        if (rc) return rc;
+    }
+    return BDG_OK;
+}
+
+int check_sorted(const uint32_t* v, size_t N)
+{
+    for (size_t i = 1; i < N; i++)
+        if (v[i] <= v[i - 1]) return fail(BDG_ERR_ARG, "input not strictly increasing at index %zu", i);
+    return BDG_OK;
+}
+
+size_t edge_cap_guess(size_t N, int nparts)
+{
+    size_t per_row = 16;
+    if (const char* e = getenv("BDG_EDGE_CAP_PER_ROW")) per_row = (size_t)std::max(1ll, atoll(e));
+    return std::max<size_t>(1u << 16, per_row * N / (size_t)nparts + 1024);
+}
+
+}  // namespace
+
+struct bdg_edges {
+    std::vector<uint32_t> a, b;
+    std::vector<uint8_t> d;
+};
+
+extern "C" {
+
+const char* bdg_version(void) { return "badger_b200 0.1 (sm_100a)"; }
+const char* bdg_last_error(void) { return g_err; }
+int bdg_device_count(void) { return (int)g_ctx.size(); }
+unsigned long long bdg_launch_count(void) { return g_launches.load(); }
+
+int bdg_init(const int* device_ids, int n_devices)
+{
+    int visible = 0;
+    cudaError_t e = cudaGetDeviceCount(&visible);
+    if (e != cudaSuccess || visible == 0)
+        return fail(BDG_ERR_NODEVICE, "no CUDA device: %s (libbadger_b200 has no CPU fallback)",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    std::vector<int> ids;
+    if (!device_ids || n_devices <= 0) for (int i = 0; i < visible; i++) ids.push_back(i);
+    else ids.assign(device_ids, device_ids + n_devices);
+    bool same = ids.size() == g_ctx.size();
+    for (size_t i = 0; same && i < ids.size(); i++) same = g_ctx[i].dev == ids[i];
+    if (same) return BDG_OK;
+    bdg_shutdown();
+    for (int id : ids) {
+        if (id < 0 || id >= visible) { bdg_shutdown(); return fail(BDG_ERR_ARG, "device id %d out of range (%d visible)", id, visible); }
+        DevCtx c;
+        c.dev = id;
+        CU_TRY(cudaSetDevice(id));
+        cudaDeviceProp prop;
+        CU_TRY(cudaGetDeviceProperties(&prop, id));
+        if (prop.major < 10) { bdg_shutdown(); return fail(BDG_ERR_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", id, prop.major, prop.minor); }
+        c.sms = prop.multiProcessorCount;
+        CU_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        g_ctx.push_back(c);
+    }
+    CU_TRY(cudaSetDevice(g_ctx[0].dev));
+    return BDG_OK;
+}
+
+void bdg_shutdown(void)
+{
+    for (auto& c : g_ctx) {
+        if (c.stream) { cudaSetDevice(c.dev); cudaStreamSynchronize(c.stream); cudaStreamDestroy(c.stream); }
+    }
+    g_ctx.clear();
+}
+
+unsigned long long bdg_part_pairs(size_t N, int part, int nparts)
+{
+    if (nparts < 1 || part < 0 || part >= nparts) return 0;
+    Plan p;
+    build_plan(N, part, nparts, 1, p);
+    return p.pairs;
+}
+
+// ---------------------------------------------------------------- device-resident entry points
+int bdg_dev_edges_build(const uint32_t* d_sorted, size_t N, int t, int part, int nparts, uint32_t* d_a, uint32_t* d_b,
+                        uint8_t* d_d, size_t cap, unsigned long long* d_count, void* stream)
+{
+    if (!d_count || (N && !d_sorted) || (cap && (!d_a || !d_b || !d_d))) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    return launch_edges(d_sorted, N, t, part, nparts, d_a, d_b, d_d, cap, d_count, (cudaStream_t)stream);
+}
+
+int bdg_dev_pack16(const char* d_seqs, size_t R, uint32_t* d_out, uint8_t* d_valid, void* stream)
+{
+    if (R == 0) return BDG_OK;
+    if (!d_seqs || !d_out || !d_valid) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if ((uintptr_t)d_seqs % 16) return fail(BDG_ERR_ARG, "sequence buffer must be 16-byte aligned");
+    int grid = 0;
+    if (int rc = grid_for((const void*)bdg::pack16_kernel, &grid)) return rc;
+    const int blocks = (int)std::min<uint64_t>((uint64_t)grid, (R + bdg::NT - 1) / bdg::NT);
+    bdg::pack16_kernel<<<blocks, bdg::NT, 0, (cudaStream_t)stream>>>((const uint4*)d_seqs, R, d_out, d_valid);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    return BDG_OK;
+}
+
+int bdg_dev_member_sorted(const uint32_t* d_wl, size_t W, const uint32_t* d_q, size_t Q, uint8_t* d_hit, void* stream)
+{
+    if (Q == 0) return BDG_OK;
+    if (!d_q || !d_hit || (W && !d_wl)) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if (W > 0xFFFFFFFFull || Q > 0xFFFFFFFFull) return fail(BDG_ERR_ARG, "size exceeds 2^32");
+    if (W == 0) { CU_TRY(cudaMemsetAsync(d_hit, 0, Q, (cudaStream_t)stream)); return BDG_OK; }
+    int grid = 0;
+    if (int rc = grid_for((const void*)bdg::member_kernel, &grid)) return rc;
+    const int blocks = (int)std::min<uint64_t>((uint64_t)grid, (Q + bdg::NT - 1) / bdg::NT);
+    bdg::member_kernel<<<blocks, bdg::NT, 0, (cudaStream_t)stream>>>(d_wl, (uint32_t)W, d_q, (uint32_t)Q, d_hit);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    return BDG_OK;
+}
+
+int bdg_dev_nearest_bounded(const uint32_t* d_q, size_t Q, const uint32_t* d_t, size_t W, int max_d, uint32_t* d_keys,
+                            int32_t* d_argmin, uint8_t* d_dist, void* stream)
+{
+    if (Q == 0) return BDG_OK;
+    if (!d_q || !d_keys || !d_argmin || !d_dist || (W && !d_t)) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if (W >= (1ull << bdg::NEAR_IDX_BITS) || Q > 0xFFFFFFFFull) return fail(BDG_ERR_ARG, "W must be < 2^28 and Q < 2^32");
+    cudaStream_t st = (cudaStream_t)stream;
+    CU_TRY(cudaMemsetAsync(d_keys, 0xFF, Q * sizeof(uint32_t), st));
+    if (W > 0 && max_d >= 0) {
+        int sms = 0, dev = 0;
+        CU_TRY(cudaGetDevice(&dev));
+        CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        const uint32_t gx = (uint32_t)((Q + bdg::ROW_TILE - 1) / bdg::ROW_TILE);
+        uint32_t gy = std::max<uint32_t>(1, (uint32_t)(4 * sms) / gx);          // split targets when there are few query tiles
+        gy = std::min<uint32_t>(gy, (uint32_t)((W + bdg::NEAR_TB - 1) / bdg::NEAR_TB));
+        gy = std::min<uint32_t>(gy, 65535u);
+        uint32_t wpb = (uint32_t)((W + gy - 1) / gy);
+        wpb = (wpb + bdg::NEAR_TB - 1) / bdg::NEAR_TB * bdg::NEAR_TB;
+        gy = (uint32_t)((W + wpb - 1) / wpb);
+        dim3 grid(gx, gy);
+        if (max_d <= 2) bdg::nearest_kernel<true><<<grid, bdg::NT, 0, st>>>(d_q, (uint32_t)Q, d_t, (uint32_t)W, max_d, wpb, d_keys);
+        else bdg::nearest_kernel<false><<<grid, bdg::NT, 0, st>>>(d_q, (uint32_t)Q, d_t, (uint32_t)W, max_d, wpb, d_keys);
+        g_launches++;
+        CU_TRY(cudaGetLastError());
+    }
+    bdg::nearest_finish_kernel<<<(unsigned)((Q + 255) / 256), 256, 0, st>>>(d_keys, (uint32_t)Q, d_argmin, d_dist);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    return BDG_OK;
+}
+
+int bdg_dev_pipe_probe(int kind, int blocks, int iters, uint32_t* d_sink, unsigned long long* ops_per_thread, void* stream)
+{
+    if (!d_sink || blocks < 1 || iters < 1) return fail(BDG_ERR_ARG, "bad probe arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (kind) {
+    case 0: bdg::pipe_probe_kernel<0><<<blocks, bdg::NT, 0, st>>>(iters, d_sink); break;
+    case 1: bdg::pipe_probe_kernel<1><<<blocks, bdg::NT, 0, st>>>(iters, d_sink); break;
+    case 2: bdg::pipe_probe_kernel<2><<<blocks, bdg::NT, 0, st>>>(iters, d_sink); break;
+    case 3: bdg::pipe_probe_kernel<3><<<blocks, bdg::NT, 0, st>>>(iters, d_sink); break;
+    default: return fail(BDG_ERR_ARG, "unknown probe kind %d", kind);
+    }
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    if (ops_per_thread) *ops_per_thread = 64ull * (unsigned long long)iters;
+    return BDG_OK;
+}
+
+// ---------------------------------------------------------------- host-buffer entry points
+int bdg_pack16(const char* seqs, size_t R, uint32_t* out, uint8_t* valid)
+{
+    if (R == 0) return BDG_OK;
+    if (!seqs || !out || !valid) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if (int rc = need_ctx()) return rc;
+    DevCtx& c = g_ctx[0];
+    CU_TRY(cudaSetDevice(c.dev));
+    char* d_in = nullptr; uint32_t* d_out = nullptr; uint8_t* d_valid = nullptr;
+    CU_TRY(cudaMallocAsync((void**)&d_in, R * 16, c.stream));
+    CU_TRY(cudaMallocAsync((void**)&d_out, R * 4, c.stream));
+    CU_TRY(cudaMallocAsync((void**)&d_valid, R, c.stream));
+    CU_TRY(cudaMemcpyAsync(d_in, seqs, R * 16, cudaMemcpyHostToDevice, c.stream));
+    int rc = bdg_dev_pack16(d_in, R, d_out, d_valid, c.stream);
+    if (rc == BDG_OK) {
+        CU_TRY(cudaMemcpyAsync(out, d_out, R * 4, cudaMemcpyDeviceToHost, c.stream));
+        CU_TRY(cudaMemcpyAsync(valid, d_valid, R, cudaMemcpyDeviceToHost, c.stream));
+    }
+    cudaFreeAsync(d_in, c.stream); cudaFreeAsync(d_out, c.stream); cudaFreeAsync(d_valid, c.stream);
+    CU_TRY(cudaStreamSynchronize(c.stream));
+    return rc;
+}
+
+static int edges_on_devices(const uint32_t* sorted, size_t N, int t, const std::vector<int>& ctx_idx,
+                            const std::vector<int>& parts, int nparts, bdg_edges* res)
+{
+    struct Run { uint32_t* d_sorted = nullptr; uint32_t *d_a = nullptr, *d_b = nullptr; uint8_t* d_d = nullptr;
+                 unsigned long long* d_count = nullptr; size_t cap = 0; unsigned long long count = 0; };
+    std::vector<Run> runs(ctx_idx.size());
+    int rc = BDG_OK;
+    auto cleanup = [&]() {
+        for (size_t g = 0; g < runs.size(); g++) {
+            cudaSetDevice(g_ctx[ctx_idx[g]].dev);
+            cudaFree(runs[g].d_sorted); cudaFree(runs[g].d_a); cudaFree(runs[g].d_b); cudaFree(runs[g].d_d); cudaFree(runs[g].d_count);
+        }
+    };
+    auto alloc_out = [&](Run& r, size_t cap) -> int {
+        cudaFree(r.d_a); cudaFree(r.d_b); cudaFree(r.d_d);
+        r.d_a = r.d_b = nullptr; r.d_d = nullptr;
+        r.cap = cap;
+        CU_TRY(cudaMalloc((void**)&r.d_a, cap * 4));
+        CU_TRY(cudaMalloc((void**)&r.d_b, cap * 4));
+        CU_TRY(cudaMalloc((void**)&r.d_d, cap));
+        return BDG_OK;
+    };
+    // upload + launch on every device first (asynchronous), then collect
+    for (size_t g = 0; g < runs.size() && rc == BDG_OK; g++) {
+        DevCtx& c = g_ctx[ctx_idx[g]];
+        Run& r = runs[g];
+        rc = [&]() -> int {
+            CU_TRY(cudaSetDevice(c.dev));
+            CU_TRY(cudaMalloc((void**)&r.d_sorted, std::max<size_t>(N, 1) * 4));
+            CU_TRY(cudaMalloc((void**)&r.d_count, sizeof(unsigned long long)));
+            CU_TRY(cudaMemcpyAsync(r.d_sorted, sorted, N * 4, cudaMemcpyHostToDevice, c.stream));
+            if (int e = alloc_out(r, edge_cap_guess(N, nparts))) return e;
+            return launch_edges(r.d_sorted, N, t, parts[g], nparts, r.d_a, r.d_b, r.d_d, r.cap, r.d_count, c.stream);
+        }();
+    }
+    for (size_t g = 0; g < runs.size() && rc == BDG_OK; g++) {
+        DevCtx& c = g_ctx[ctx_idx[g]];
+        Run& r = runs[g];
+        rc = [&]() -> int {
+            CU_TRY(cudaSetDevice(c.dev));
+            CU_TRY(cudaMemcpyAsync(&r.count, r.d_count, sizeof(r.count), cudaMemcpyDeviceToHost, c.stream));
+            CU_TRY(cudaStreamSynchronize(c.stream));
+            if (r.count > r.cap) {   // rare: the guess was too small; the edge set is deterministic, so run again
+                if (int e = alloc_out(r, (size_t)r.count)) return e;
+                if (int e = launch_edges(r.d_sorted, N, t, parts[g], nparts, r.d_a, r.d_b, r.d_d, r.cap, r.d_count, c.stream)) return e;
+                CU_TRY(cudaMemcpyAsync(&r.count, r.d_count, sizeof(r.count), cudaMemcpyDeviceToHost, c.stream));
+                CU_TRY(cudaStreamSynchronize(c.stream));
+                if (r.count > r.cap) return fail(BDG_ERR_CUDA, "edge count changed between identical launches");
+            }
+            const size_t off = res->a.size(), n = (size_t)r.count;
+            res->a.resize(off + n); res->b.resize(off + n); res->d.resize(off + n);
+            if (n) {
+                CU_TRY(cudaMemcpyAsync(res->a.data() + off, r.d_a, n * 4, cudaMemcpyDeviceToHost, c.stream));
+                CU_TRY(cudaMemcpyAsync(res->b.data() + off, r.d_b, n * 4, cudaMemcpyDeviceToHost, c.stream));
+                CU_TRY(cudaMemcpyAsync(res->d.data() + off, r.d_d, n, cudaMemcpyDeviceToHost, c.stream));
+                CU_TRY(cudaStreamSynchronize(c.stream));
+            }
+            return BDG_OK;
+        }();
+    }
+    cleanup();
+    if (!g_ctx.empty()) cudaSetDevice(g_ctx[0].dev);
+    return rc;
+}
+
+int bdg_edges_build(const uint32_t* sorted_unique, size_t N, int t, bdg_edges** out)
+{
+    if (!out || (N && !sorted_unique)) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    *out = nullptr;
+    if (int rc = check_sorted(sorted_unique, N)) return rc;
+    if (int rc = need_ctx()) return rc;
+    bdg_edges* res = new (std::nothrow) bdg_edges();
+    if (!res) return fail(BDG_ERR_OOM, "host allocation failed");
+    std::vector<int> idx, parts;
+    const int G = (int)g_ctx.size();
+    for (int g = 0; g < G; g++) { idx.push_back(g); parts.push_back(g); }
+    int rc = BDG_OK;
+    try { rc = edges_on_devices(sorted_unique, N, t, idx, parts, G, res); }
+    catch (const std::bad_alloc&) { rc = fail(BDG_ERR_OOM, "host allocation failed"); }
+    if (rc) { delete res; return rc; }
+    *out = res;
+    return BDG_OK;
+}
+
+int bdg_edges_build_part(const uint32_t* sorted_unique, size_t N, int t, int part, int nparts, bdg_edges** out)
+{
+    if (!out || (N && !sorted_unique)) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    *out = nullptr;
+    if (nparts < 1 || part < 0 || part >= nparts) return fail(BDG_ERR_ARG, "part %d of %d is not a valid part", part, nparts);
+    if (int rc = check_sorted(sorted_unique, N)) return rc;
+    if (int rc = need_ctx()) return rc;
+    bdg_edges* res = new (std::nothrow) bdg_edges();
+    if (!res) return fail(BDG_ERR_OOM, "host allocation failed");
+    int rc = BDG_OK;
+    try { rc = edges_on_devices(sorted_unique, N, t, {0}, {part}, nparts, res); }
+    catch (const std::bad_alloc&) { rc = fail(BDG_ERR_OOM, "host allocation failed"); }
+    if (rc) { delete res; return rc; }
+    *out = res;
+    return BDG_OK;
+}
+
+size_t bdg_edges_count(const bdg_edges* e) { return e ? e->a.size() : 0; }
+
+int bdg_edges_copy(const bdg_edges* e, uint32_t* a, uint32_t* b, uint8_t* d)
+{
+    if (!e) return fail(BDG_ERR_ARG, "NULL edge handle");
+    const size_t n = e->a.size();
+    if (n && (!a || !b || !d)) return fail(BDG_ERR_ARG, "NULL output pointer");
+    if (n) { memcpy(a, e->a.data(), n * 4); memcpy(b, e->b.data(), n * 4); memcpy(d, e->d.data(), n); }
+    return BDG_OK;
+}
+
+void bdg_edges_free(bdg_edges* e) { delete e; }
+
+int bdg_member_sorted(const uint32_t* sorted_wl, size_t W, const uint32_t* q, size_t Q, uint8_t* hit)
+{
+    if (Q == 0) return BDG_OK;
+    if (!q || !hit || (W && !sorted_wl)) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    for (size_t i = 1; i < W; i++)
+        if (sorted_wl[i] < sorted_wl[i - 1]) return fail(BDG_ERR_ARG, "whitelist not sorted at index %zu", i);
+    if (int rc = need_ctx()) return rc;
+    DevCtx& c = g_ctx[0];
+    CU_TRY(cudaSetDevice(c.dev));
+    uint32_t *d_wl = nullptr, *d_q = nullptr; uint8_t* d_hit = nullptr;
+    CU_TRY(cudaMallocAsync((void**)&d_wl, std::max<size_t>(W, 1) * 4, c.stream));
+    CU_TRY(cudaMallocAsync((void**)&d_q, Q * 4, c.stream));
+    CU_TRY(cudaMallocAsync((void**)&d_hit, Q, c.stream));
+    CU_TRY(cudaMemcpyAsync(d_wl, sorted_wl, W * 4, cudaMemcpyHostToDevice, c.stream));
+    CU_TRY(cudaMemcpyAsync(d_q, q, Q * 4, cudaMemcpyHostToDevice, c.stream));
+    int rc = bdg_dev_member_sorted(d_wl, W, d_q, Q, d_hit, c.stream);
+    if (rc == BDG_OK) CU_TRY(cudaMemcpyAsync(hit, d_hit, Q, cudaMemcpyDeviceToHost, c.stream));
+    cudaFreeAsync(d_wl, c.stream); cudaFreeAsync(d_q, c.stream); cudaFreeAsync(d_hit, c.stream);
+    CU_TRY(cudaStreamSynchronize(c.stream));
+    return rc;
+}
+
+int bdg_nearest_bounded(const uint32_t* q, size_t Q, const uint32_t* targets, size_t W, int max_d, int32_t* argmin, uint8_t* dist)
+{
+    if (Q == 0) return BDG_OK;
+    if (!q || !argmin || !dist || (W && !targets)) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if (int rc = need_ctx()) return rc;
+    // queries are independent: deal contiguous slices to the devices, targets replicated
+    const int G = (int)g_ctx.size();
+    struct Run { uint32_t *d_q = nullptr, *d_t = nullptr, *d_keys = nullptr; int32_t* d_arg = nullptr; uint8_t* d_dist = nullptr; size_t lo = 0, n = 0; };
+    std::vector<Run> runs(G);
+    int rc = BDG_OK;
+    const size_t per = (Q + G - 1) / G;
+    for (int g = 0; g < G && rc == BDG_OK; g++) {
+        Run& r = runs[g];
+        r.lo = std::min(Q, per * g);
+        r.n = std::min(Q, per * (g + 1)) - r.lo;
+        if (r.n == 0) continue;
+        DevCtx& c = g_ctx[g];
+        rc = [&]() -> int {
+            CU_TRY(cudaSetDevice(c.dev));
+            CU_TRY(cudaMallocAsync((void**)&r.d_q, r.n * 4, c.stream));
+            CU_TRY(cudaMallocAsync((void**)&r.d_t, std::max<size_t>(W, 1) * 4, c.stream));
+            CU_TRY(cudaMallocAsync((void**)&r.d_keys, r.n * 4, c.stream));
+            CU_TRY(cudaMallocAsync((void**)&r.d_arg, r.n * 4, c.stream));
+            CU_TRY(cudaMallocAsync((void**)&r.d_dist, r.n, c.stream));
+            CU_TRY(cudaMemcpyAsync(r.d_q, q + r.lo, r.n * 4, cudaMemcpyHostToDevice, c.stream));
+            CU_TRY(cudaMemcpyAsync(r.d_t, targets, W * 4, cudaMemcpyHostToDevice, c.stream));
+            if (int e = bdg_dev_nearest_bounded(r.d_q, r.n, r.d_t, W, max_d, r.d_keys, r.d_arg, r.d_dist, c.stream)) return e;
+            CU_TRY(cudaMemcpyAsync(argmin + r.lo, r.d_arg, r.n * 4, cudaMemcpyDeviceToHost, c.stream));
+            CU_TRY(cudaMemcpyAsync(dist + r.lo, r.d_dist, r.n, cudaMemcpyDeviceToHost, c.stream));
+            return BDG_OK;
+        }();
+    }
+    for (int g = 0; g < G; g++) {
+        Run& r = runs[g];
+        if (r.n == 0) continue;
+        DevCtx& c = g_ctx[g];
+        cudaSetDevice(c.dev);
+        cudaFreeAsync(r.d_q, c.stream); cudaFreeAsync(r.d_t, c.stream); cudaFreeAsync(r.d_keys, c.stream);
+        cudaFreeAsync(r.d_arg, c.stream); cudaFreeAsync(r.d_dist, c.stream);
+        cudaError_t e = cudaStreamSynchronize(c.stream);
+        if (e != cudaSuccess && rc == BDG_OK) rc = fail(BDG_ERR_CUDA, "stream sync failed: %s", cudaGetErrorString(e));
+    }
+    cudaSetDevice(g_ctx[0].dev);
+    return rc;
+}
+
+int bdg_kmer_score(const uint32_t* q, size_t Q, const uint32_t* wl, size_t W, int min_kmers, size_t cap, uint32_t* hit_q,
+                   uint32_t* hit_w, uint8_t* cnt, uint64_t* mult, size_t* total)
+{
+    if (!total) return fail(BDG_ERR_ARG, "NULL total pointer");
+    *total = 0;
+    if (Q == 0 || W == 0) return BDG_OK;
+    if (!q || !wl || (cap && (!hit_q || !hit_w || !cnt || !mult))) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if (W > 0xFFFFFFFFull || Q > 0xFFFFFFFFull) return fail(BDG_ERR_ARG, "size exceeds 2^32");
+    if (int rc = need_ctx()) return rc;
+    DevCtx& c = g_ctx[0];
+    CU_TRY(cudaSetDevice(c.dev));
+    uint32_t *d_q = nullptr, *d_wl = nullptr, *d_hq = nullptr, *d_hw = nullptr; uint8_t* d_cnt = nullptr;
+    unsigned long long *d_mult = nullptr, *d_total = nullptr;
+    const size_t capa = std::max<size_t>(cap, 1);
+    CU_TRY(cudaMallocAsync((void**)&d_q, Q * 4, c.stream));
+    CU_TRY(cudaMallocAsync((void**)&d_wl, W * 4, c.stream));
+    CU_TRY(cudaMallocAsync((void**)&d_hq, capa * 4, c.stream));
+    CU_TRY(cudaMallocAsync((void**)&d_hw, capa * 4, c.stream));
+    CU_TRY(cudaMallocAsync((void**)&d_cnt, capa, c.stream));
+    CU_TRY(cudaMallocAsync((void**)&d_mult, capa * 8, c.stream));
+    CU_TRY(cudaMallocAsync((void**)&d_total, 8, c.stream));
+    CU_TRY(cudaMemsetAsync(d_total, 0, 8, c.stream));
+    CU_TRY(cudaMemcpyAsync(d_q, q, Q * 4, cudaMemcpyHostToDevice, c.stream));
+    CU_TRY(cudaMemcpyAsync(d_wl, wl, W * 4, cudaMemcpyHostToDevice, c.stream));
+    const uint32_t gy_total = (uint32_t)((Q + bdg::KS_QB - 1) / bdg::KS_QB);
+    const uint32_t gx = (uint32_t)((W + bdg::NT - 1) / bdg::NT);
+    if (gy_total > 65535u) return fail(BDG_ERR_ARG, "Q too large for one call (> 65535*256 queries)");
+    bdg::kmer_score_kernel<<<dim3(gx, gy_total), bdg::NT, 0, c.stream>>>(d_q, (uint32_t)Q, d_wl, (uint32_t)W, min_kmers,
+                                                                      (unsigned long long)cap, d_hq, d_hw, d_cnt, d_mult, d_total);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    unsigned long long tot = 0;
+    CU_TRY(cudaMemcpyAsync(&tot, d_total, 8, cudaMemcpyDeviceToHost, c.stream));
+    CU_TRY(cudaStreamSynchronize(c.stream));
+    const size_t n = (size_t)std::min<unsigned long long>(tot, cap);
+    if (n) {
+        CU_TRY(cudaMemcpyAsync(hit_q, d_hq, n * 4, cudaMemcpyDeviceToHost, c.stream));
+        CU_TRY(cudaMemcpyAsync(hit_w, d_hw, n * 4, cudaMemcpyDeviceToHost, c.stream));
+        CU_TRY(cudaMemcpyAsync(cnt, d_cnt, n, cudaMemcpyDeviceToHost, c.stream));
+        CU_TRY(cudaMemcpyAsync(mult, d_mult, n * 8, cudaMemcpyDeviceToHost, c.stream));
+    }
+    cudaFreeAsync(d_q, c.stream); cudaFreeAsync(d_wl, c.stream); cudaFreeAsync(d_hq, c.stream); cudaFreeAsync(d_hw, c.stream);
+    cudaFreeAsync(d_cnt, c.stream); cudaFreeAsync(d_mult, c.stream); cudaFreeAsync(d_total, c.stream);
+    CU_TRY(cudaStreamSynchronize(c.stream));
+    *total = (size_t)tot;
+    if (tot > cap) return fail(BDG_ERR_CAPACITY, "%llu hits but room for %zu", tot, cap);
+    return BDG_OK;
+}
+
+}  // extern "C"

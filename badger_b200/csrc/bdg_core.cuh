@@ -1,0 +1,247 @@
+// bdg_core.cuh -- per-pair arithmetic of the barcode hot path on packed 16-mers.
+//
+// A barcode is a uint32 in the reference's own packing (reference common.py:21-25): base i occupies
+// bits 2i..2i+1, A0 C1 G2 T3.  Everything here is integer bit arithmetic on those words.
+//
+// The functions are __host__ __device__ so that tests/test_core_host.py can compile this very header
+// with g++ and check every function against the CPU oracle on millions of pairs without a GPU.  The
+// product only ever calls them from CUDA kernels (bdg_kernels.cu); there is no CPU execution path.
+//
+// Reference semantics restated (file:line in /root/reference):
+//   D(a,b) = min(ed(a,b), ed(a[:-1],b), ed(a,b[:-1]))          barcode_graph.py:96, :243
+//   S(a,b) = #{(p,q) in [0,10]^2 : 6mer_a[p] == 6mer_b[q]}      index.py:29-35, :77-93
+//   T(t)   = 16-6+1-6t, replaced by 4 when <= 0                 index.py:19-24
+//   edge(a,b) <=> a<b, S >= T(t), D <= t ; stored distance = D  barcode_graph.py:233-249
+//   plain ed(q,c) for --high_sens post-processing               barcode_graph.py:379
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define BDG_HD __host__ __device__ __forceinline__
+#else
+#define BDG_HD static inline
+#endif
+
+namespace bdg {
+
+constexpr uint32_t EVEN = 0x55555555u;   // one marker bit per base (bit 2i)
+constexpr uint32_t ODD = 0xAAAAAAAAu;
+
+BDG_HD int popc(uint32_t x)
+{
+#if defined(__CUDA_ARCH__)
+    return __popc(x);
+#else
+    return __builtin_popcount(x);
+#endif
+}
+
+// T(t): index.py:22-24
+BDG_HD int qgram_threshold(int t)
+{
+    int T = 16 - 6 + 1 - 6 * t;
+    return T <= 0 ? 4 : T;
+}
+
+// Mismatch marks of two aligned words: bit 2i set <=> base i differs.
+BDG_HD uint32_t mism(uint32_t a, uint32_t b)
+{
+    uint32_t x = a ^ b;
+    return (x | (x >> 1)) & EVEN;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage-1 prefilters: cheap NECESSARY conditions for D(a,b) <= t.  A reject proves D > t.
+//
+// Why only the diagonals -1, 0, +1 matter for t <= 2: the three alignments behind D have length
+// differences 0, +1, -1, and an edit script of <= 2 operations with that net length change can hold
+// at most one insertion and one deletion, so no aligned column is ever more than one base off the main
+// diagonal.  Every script cuts a[0:15] with at most two "events" (a substituted column, a removed base
+// or a diagonal change), so of any three disjoint blocks of a[0:15] one is untouched and matches b
+// exactly on diagonal -1, 0 or +1 (pigeonhole).
+//
+//   t = 2: blocks a[0:5], a[5:10], a[10:15] = bit fields 0-9, 10-19, 20-29 against b, b>>2, b<<2.
+//   t = 1: one event, two blocks: a[0:8] / a[8:16] on diagonal 0, a[8:15] on +1, a[9:16] on -1.
+//
+// "some field of x is zero" is evaluated for all fields of a word at once with the classic
+// (x - ones) & ~x & highs test, which is exact as a whole-word predicate.
+// ---------------------------------------------------------------------------------------------
+constexpr uint32_t F10_ONES = (1u << 0) | (1u << 10) | (1u << 20);
+constexpr uint32_t F10_HIGH = (1u << 9) | (1u << 19) | (1u << 29);
+constexpr uint32_t F16_ONES = 0x00010001u;
+constexpr uint32_t F16_HIGH = 0x80008000u;
+
+// second word of the t=1 test: low half = a[8:15] (for diagonal +1), high half = a[9:16] (diagonal -1)
+BDG_HD uint32_t t1_word_a(uint32_t a) { return ((a >> 16) & 0x3FFFu) | ((a >> 18) << 16); }
+// matching word of b: low half = b[9:16], high half = b[8:15]
+BDG_HD uint32_t t1_word_b(uint32_t b) { return (b >> 18) | (((b >> 16) & 0x3FFFu) << 16); }
+
+BDG_HD uint32_t zero_field_marks(uint32_t x, uint32_t ones) { return (x - ones) & ~x; }
+
+BDG_HD bool prefilter_t1(uint32_t a, uint32_t b)
+{
+    uint32_t m = zero_field_marks(a ^ b, F16_ONES) | zero_field_marks(t1_word_a(a) ^ t1_word_b(b), F16_ONES);
+    return (m & F16_HIGH) != 0;
+}
+
+BDG_HD bool prefilter_t2(uint32_t a, uint32_t b)
+{
+    uint32_t m = zero_field_marks(a ^ b, F10_ONES) | zero_field_marks(a ^ (b >> 2), F10_ONES) |
+                 zero_field_marks(a ^ (b << 2), F10_ONES);
+    return (m & F10_HIGH) != 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stage-2, exact for small distances: returns min(D(a,b), 3) for a != b, i.e. 1, 2, or 3 (= "3 or more").
+// With plain_only it returns min(ed(a,b), 3) instead (no truncated variants; barcode_graph.py:379).
+//
+// Case analysis of all edit scripts of length <= 2 (see the block comment above):
+//   ed(a,b):        <=2 substitutions                      -> popc(X0) <= 2
+//                   1 deletion + 1 insertion, no mismatch  -> X0 clean outside [L,H], the middle clean on
+//                                                             diagonal -1 (or +1), L/H = first/last mark of X0
+//   ed(a[:15],b):   1 insertion in b + <=1 substitution    -> diagonal 0 before it, +1 after it
+//   ed(a,b[:15]):   1 deletion from a + <=1 substitution   -> diagonal 0 before it, -1 after it
+// X0 / XP / XM are the mismatch marks on diagonals 0 / +1 / -1 with out-of-range columns marked.
+// ---------------------------------------------------------------------------------------------
+BDG_HD int dist_small(uint32_t a, uint32_t b, bool plain_only = false)
+{
+    const uint32_t X0 = mism(a, b);
+    const int h = popc(X0);
+    if (h == 0) return 0;                              // identical words (callers exclude this)
+    const uint32_t XP = mism(a, b >> 2) | (1u << 30);  // a[i] vs b[i+1], i = 0..14; column 15 invalid
+    const uint32_t XM = mism(a, b << 2) | 1u;          // a[i] vs b[i-1], i = 1..15; column 0 invalid
+    const uint32_t low1 = X0 & (0u - X0);              // first mismatch on the main diagonal (position L)
+    const uint32_t ge1 = 0u - low1;                    // columns >= L (all bits from low1 upwards)
+    const uint32_t gt1 = ge1 << 2;                     // columns >  L (marker bits; ge1 has both bits of a column set)
+    int best = h <= 2 ? h : 3;
+    if (h >= 2) {
+        // one deletion + one insertion: the columns strictly between the events run on one side diagonal
+        uint32_t s = X0;                               // smear downwards: all columns <= H
+        s |= s >> 2; s |= s >> 4; s |= s >> 8; s |= s >> 16;
+        const uint32_t leH = s;                        // marker bits of columns <= H (H = last mismatch)
+        const uint32_t ltH = s >> 2;                   // columns < H
+        const bool delins = (XM & gt1 & leH) == 0;     // a[L] removed, b gains a base after column H: XM clean on (L,H]
+        const bool insdel = (XP & ge1 & ltH) == 0;     // b gains a base at L, a[H] removed:           XP clean on [L,H)
+        if (delins || insdel) best = 2;
+    }
+    if (plain_only) return best;
+    // truncated variants: one indel (free last base) + at most one substitution
+    const uint32_t VALID15 = EVEN & 0x3FFFFFFFu;       // columns 0..14
+    {
+        // ed(a[:15], b): diagonal 0 on [0,p), diagonal +1 on [p,15)
+        const uint32_t tailP = XP & ge1 & VALID15;     // p = L
+        const int cP = popc(tailP);
+        // ed(a, b[:15]): diagonal 0 on [0,p), a[p] removed, diagonal -1 on (p,16)
+        const uint32_t tailM = XM & gt1;
+        const int cM = popc(tailM);
+        if (cP == 0 || cM == 0) return 1;
+        if (cP == 1 || cM == 1) best = best < 2 ? best : 2;
+        // or spend the substitution on the main diagonal: run through L up to the second mismatch L2
+        const uint32_t X0b = X0 & (X0 - 1);            // X0 without its first mark
+        const uint32_t low2 = X0b & (0u - X0b);
+        const uint32_t ge2 = X0b ? (0u - low2) : 0u;   // columns >= L2 (none when X0 has a single mark)
+        const uint32_t gt2 = ge2 << 2;
+        if ((XP & ge2 & VALID15) == 0 || (XM & gt2) == 0) best = best < 2 ? best : 2;
+    }
+    return best;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Generic exact distances (any threshold): Myers' bit-vector algorithm for GLOBAL edit distance with the
+// pattern a on the rows, run directly on the 2-bit-stride words (marker bit 2i = row i; the odd bits are
+// fed as ones into the adder so carries ripple from row to row).  One pass yields all three distances of
+// barcode_graph.py:243:  ed(a,b[:15]) = bottom-row score after column 15, ed(a,b) after column 16,
+// ed(a[:15],b) = ed(a,b) minus the vertical delta of the last row in the last column.
+// ---------------------------------------------------------------------------------------------
+struct Dist3 { int full, a15, b15; };   // ed(a,b), ed(a[:15],b), ed(a,b[:15])
+
+BDG_HD Dist3 myers3(uint32_t a, uint32_t b)
+{
+    uint32_t Pv = EVEN, Mv = 0;
+    int score = 16, score15 = 16;
+    const uint32_t TOP = 1u << 30;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 16; j++) {
+        const uint32_t c = (b >> (2 * j)) & 3u;
+        const uint32_t x = a ^ (c * EVEN);
+        const uint32_t Eq = ~(x | (x >> 1)) & EVEN;
+        const uint32_t Xv = Eq | Mv;
+        const uint32_t Xh = ((((Eq & Pv) + (Pv | ODD)) ^ Pv) | Eq) & EVEN;
+        uint32_t Ph = (Mv | ~(Xh | Pv)) & EVEN;
+        uint32_t Mh = Pv & Xh;
+        score += (Ph & TOP) ? 1 : 0;
+        score -= (Mh & TOP) ? 1 : 0;
+        Ph = ((Ph << 2) | 1u) & EVEN;   // the row above the matrix grows by one per column (global alignment)
+        Mh = (Mh << 2) & EVEN;
+        Pv = (Mh | ~(Xv | Ph)) & EVEN;
+        Mv = Ph & Xv;
+        if (j == 14) score15 = score;
+    }
+    Dist3 r;
+    r.full = score;
+    r.b15 = score15;
+    r.a15 = score - ((Pv & TOP) ? 1 : 0) + ((Mv & TOP) ? 1 : 0);
+    return r;
+}
+
+BDG_HD int dist3_min(uint32_t a, uint32_t b)
+{
+    Dist3 r = myers3(a, b);
+    int d = r.full < r.a15 ? r.full : r.a15;
+    return d < r.b15 ? d : r.b15;
+}
+
+// ---------------------------------------------------------------------------------------------
+// S(a,b): number of (p,q) with the 6-mer of a at p equal to the 6-mer of b at q, p,q in 0..10, summed
+// diagonal by diagonal (q - p = s, s = -10..10): a 6-mer match at p on diagonal s is a run of six
+// matching bases starting at p.  multiplicity out: per query position p the number of matching q
+// (kmer_indexer.py:53-55 `positions`), packed 4 bits per position into a uint64.
+// ---------------------------------------------------------------------------------------------
+BDG_HD uint32_t run6(uint32_t m)   // m: match marks; result bit 2p set <=> columns p..p+5 all match
+{
+    const uint32_t m2 = m & (m >> 2);
+    const uint32_t m4 = m2 & (m2 >> 4);
+    return m4 & (m2 >> 8);
+}
+
+BDG_HD int qgram_score(uint32_t a, uint32_t b, uint64_t* mult = nullptr)
+{
+    int s = 0;
+    uint64_t mu = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k <= 10; k++) {
+        // diagonal +k: a[i] vs b[i+k], valid a-columns 0..15-k
+        {
+            const uint32_t valid = EVEN >> (2 * k);
+            const uint32_t r = run6(~mism(a, b >> (2 * k)) & valid);
+            s += popc(r);
+            if (mult) for (int p = 0; p <= 10; p++) mu += (uint64_t)((r >> (2 * p)) & 1u) << (4 * p);
+        }
+        if (k == 0) continue;
+        // diagonal -k: a[i] vs b[i-k], valid a-columns k..15
+        {
+            const uint32_t valid = EVEN << (2 * k);
+            const uint32_t r = run6(~mism(a, b << (2 * k)) & valid);
+            s += popc(r);
+            if (mult) for (int p = 0; p <= 10; p++) mu += (uint64_t)((r >> (2 * p)) & 1u) << (4 * p);
+        }
+    }
+    if (mult) *mult = mu;
+    return s;
+}
+
+// Full predicate of barcode_graph.py:233-249 for a != b: returns D when (a,b) is an edge at threshold t,
+// else 0.  t <= 2 uses the case analysis, larger t the generic bit-vector pass.
+BDG_HD int edge_dist(uint32_t a, uint32_t b, int t)
+{
+    if (t <= 0) return 0;
+    int d = t <= 2 ? dist_small(a, b) : dist3_min(a, b);
+    if (d > t || d == 0) return 0;
+    return qgram_score(a, b) >= qgram_threshold(t) ? d : 0;
+}
+
+}  // namespace bdg

@@ -1,0 +1,109 @@
+"""numpy-level operators over the C ABI (host buffers in, host buffers out).
+
+Each function names the reference code it stands in for (file:line in algbio/Badger).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check, lib, ptr
+
+BC_LEN = 16
+
+
+def pack16(seqs) -> tuple[np.ndarray, np.ndarray]:
+    """common.py:21-25 `rank` for many 16-mers at once.  seqs: list of str/bytes (each exactly 16 long) or one
+    bytes object of R*16 characters.  Returns (ranks uint32[R], valid bool[R])."""
+    if isinstance(seqs, (bytes, bytearray, memoryview)):
+        buf = bytes(seqs)
+    else:
+        buf = "".join(seqs).encode("ascii", "replace") if (len(seqs) and isinstance(seqs[0], str)) else b"".join(seqs)
+    if len(buf) % BC_LEN:
+        raise ValueError("pack16 needs records of exactly 16 characters")
+    R = len(buf) // BC_LEN
+    out = np.empty(R, np.uint32)
+    valid = np.empty(R, np.uint8)
+    if R:
+        check(lib().bdg_pack16(buf, R, ptr(out), ptr(valid)))
+    return out, valid.astype(bool)
+
+
+def _collect_edges(handle):
+    L = lib()
+    try:
+        n = L.bdg_edges_count(handle)
+        a = np.empty(n, np.uint32); b = np.empty(n, np.uint32); d = np.empty(n, np.uint8)
+        check(L.bdg_edges_copy(handle, ptr(a), ptr(b), ptr(d)))
+    finally:
+        L.bdg_edges_free(handle)
+    return a, b, d
+
+
+def edges_build(sorted_unique: np.ndarray, t: int):
+    """index.py:77-93 + barcode_graph.py:224-249 over all initialised GPUs.
+    Returns (a, b, d): every undirected edge once with a < b; order unspecified."""
+    s = np.ascontiguousarray(sorted_unique, dtype=np.uint32)
+    h = C.c_void_p()
+    check(lib().bdg_edges_build(ptr(s), s.size, int(t), C.byref(h)))
+    return _collect_edges(h)
+
+
+def edges_build_part(sorted_unique: np.ndarray, t: int, part: int, nparts: int):
+    """Rows of one part only (one process per GPU; rows dealt in BDG_ROW_TILE tiles)."""
+    s = np.ascontiguousarray(sorted_unique, dtype=np.uint32)
+    h = C.c_void_p()
+    check(lib().bdg_edges_build_part(ptr(s), s.size, int(t), int(part), int(nparts), C.byref(h)))
+    return _collect_edges(h)
+
+
+def canonical(a, b, d):
+    """Sort an edge list by (a, b) - the order-free comparison form."""
+    order = np.lexsort((b, a))
+    return a[order], b[order], d[order]
+
+
+def member_sorted(sorted_wl: np.ndarray, q: np.ndarray) -> np.ndarray:
+    """barcode_graph.py:262-267 `unrank(r) in barcode_list` for many r at once."""
+    wl = np.ascontiguousarray(sorted_wl, dtype=np.uint32)
+    q = np.ascontiguousarray(q, dtype=np.uint32)
+    hit = np.zeros(q.size, np.uint8)
+    if q.size:
+        check(lib().bdg_member_sorted(ptr(wl), wl.size, ptr(q), q.size, ptr(hit)))
+    return hit.astype(bool)
+
+
+def nearest_bounded(q: np.ndarray, targets_in_order: np.ndarray, max_d: int = 2):
+    """barcode_graph.py:370-385: first minimum of the plain edit distance over the targets, kept if <= max_d."""
+    q = np.ascontiguousarray(q, dtype=np.uint32)
+    tg = np.ascontiguousarray(targets_in_order, dtype=np.uint32)
+    am = np.full(q.size, -1, np.int32)
+    dist = np.full(q.size, 255, np.uint8)
+    if q.size:
+        check(lib().bdg_nearest_bounded(ptr(q), q.size, ptr(tg), tg.size, int(max_d), ptr(am), ptr(dist)))
+    return am, dist
+
+
+def kmer_score(q: np.ndarray, wl: np.ndarray, min_kmers: int = 1, cap: int | None = None):
+    """kmer_indexer.py:49-61 counting step for packed 16-mers, k=6.
+    Returns (hit_q, hit_w, cnt, mult[hits,11]) for every pair with cnt >= min_kmers (order unspecified)."""
+    q = np.ascontiguousarray(q, dtype=np.uint32)
+    wl = np.ascontiguousarray(wl, dtype=np.uint32)
+    if cap is None:
+        cap = max(1024, 4 * wl.size)
+    while True:
+        hq = np.empty(cap, np.uint32); hw = np.empty(cap, np.uint32)
+        cnt = np.empty(cap, np.uint8); mult = np.empty(cap, np.uint64)
+        total = C.c_size_t(0)
+        rc = lib().bdg_kmer_score(ptr(q), q.size, ptr(wl), wl.size, int(min_kmers), cap,
+                                  ptr(hq), ptr(hw), ptr(cnt), ptr(mult), C.byref(total))
+        if rc == _lib.BDG_ERR_CAPACITY:
+            cap = int(total.value)
+            continue
+        check(rc)
+        n = int(total.value)
+        m = mult[:n]
+        nib = np.stack([(m >> np.uint64(4 * p)) & np.uint64(15) for p in range(11)], 1).astype(np.uint8) if n else np.zeros((0, 11), np.uint8)
+        return hq[:n].copy(), hw[:n].copy(), cnt[:n].copy(), nib

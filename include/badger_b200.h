@@ -1,0 +1,117 @@
+/*
+ * badger_b200.h -- C ABI of libbadger_b200.so: the B200-native replacement for the barcode
+ * edit-distance hot path of algbio/Badger.
+ *
+ * The reference is pure Python and has no FFI of its own; the seam this library sits behind is the set
+ * of Python methods listed beside each entry point (file:line in the reference checkout).  The Python
+ * package badger_b200/ binds these symbols with ctypes and mirrors those methods; INTEGRATION.md shows
+ * the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; host entry points take HOST buffers (read-only during the call) and
+ *     do their own host<->device copies; bdg_dev_* entry points take DEVICE pointers on the current CUDA
+ *     device plus a cudaStream_t passed as void*, and are asynchronous on that stream.
+ *   - every int-returning function returns BDG_OK (0) or a negative error code; bdg_last_error() gives the
+ *     text.  There is NO CPU fallback: without a usable CUDA device every compute call fails with
+ *     BDG_ERR_NODEVICE.
+ *   - barcodes are uint32 in the reference's packing (common.py:21-25): base i in bits 2i..2i+1, A0 C1 G2 T3.
+ *   - the library is not re-entrant across threads except bdg_last_error (thread-local).
+ */
+#ifndef BADGER_B200_H
+#define BADGER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    BDG_OK = 0,
+    BDG_ERR_CUDA = -1,     /* a CUDA runtime call failed */
+    BDG_ERR_OOM = -2,      /* host or device allocation failed */
+    BDG_ERR_ARG = -3,      /* bad argument (NULL, unsorted input, size limit) */
+    BDG_ERR_NODEVICE = -4, /* no CUDA device / library not initialised on one */
+    BDG_ERR_CAPACITY = -5  /* caller-provided output capacity too small; *total holds the need */
+};
+
+/* Rows of the sorted distinct-barcode array are dealt to parts (GPUs / ranks) in tiles of this many
+ * rows, boustrophedon order: tile I belongs to part  m<P ? m : 2P-1-m,  m = I mod 2P.  A part emits every
+ * edge whose SMALLER barcode lies in one of its tiles.  (Replaces the 10 000-barcode chunks dealt to
+ * worker processes in barcode_graph.py:26,164-189.) */
+#define BDG_ROW_TILE 2048
+
+/* ---- life cycle ------------------------------------------------------------------------------- */
+/* Create per-device contexts (stream, scratch).  device_ids == NULL or n_devices <= 0: every visible
+ * device.  Idempotent for the same list.  Replaces ProcessPoolExecutor(max_workers=threads)
+ * (barcode_graph.py:142,177). */
+int bdg_init(const int* device_ids, int n_devices);
+void bdg_shutdown(void);
+int bdg_device_count(void);         /* devices held by this process after bdg_init, else 0 */
+const char* bdg_last_error(void);   /* thread-local; valid until the next call on this thread */
+const char* bdg_version(void);
+
+/* ---- a-1  rank(): common.py:21-25 (called per read at barcode_graph.py:198) ----------------------- */
+/* seqs: R records of exactly 16 bytes, no terminator.  valid[i] = 1 iff all 16 bytes are in "ACGT"
+ * (the reference raises KeyError otherwise, common.py:24); out[i] is undefined when valid[i] == 0. */
+int bdg_pack16(const char* seqs, size_t R, uint32_t* out, uint8_t* valid);
+
+/* ---- a-3 + a-4  QGramIndex.get_close + verify/emit: index.py:77-93, barcode_graph.py:224-249 ------ */
+/* Edge set {(a,b,D): a<b, S(a,b) >= T(t), D(a,b) <= t} over a STRICTLY INCREASING array of distinct
+ * barcodes (checked).  bdg_edges_build uses every initialised device (rows dealt per BDG_ROW_TILE) and
+ * returns the union; bdg_edges_build_part computes one part on the first initialised device (one process
+ * per GPU).  Edge order is unspecified.  t <= 0 yields the empty set, as in the reference. */
+typedef struct bdg_edges bdg_edges;
+int bdg_edges_build(const uint32_t* sorted_unique, size_t N, int t, bdg_edges** out);
+int bdg_edges_build_part(const uint32_t* sorted_unique, size_t N, int t, int part, int nparts, bdg_edges** out);
+size_t bdg_edges_count(const bdg_edges* e);
+int bdg_edges_copy(const bdg_edges* e, uint32_t* a, uint32_t* b, uint8_t* d); /* caller-allocated, length = count */
+void bdg_edges_free(bdg_edges* e);
+
+/* ---- a-6  whitelist membership: `unrank(r) in barcode_list`, barcode_graph.py:262-267 -------------- */
+int bdg_member_sorted(const uint32_t* sorted_wl, size_t W, const uint32_t* q, size_t Q, uint8_t* hit);
+
+/* ---- a-7  postprocessing(): barcode_graph.py:370-385 ---------------------------------------------- */
+/* For every q: the FIRST index (in the given order) of the minimum plain edit distance to the targets,
+ * kept when that minimum is <= max_d (the reference's `min_dist < 3` is max_d = 2); else argmin = -1,
+ * dist = 255.  W < 2^28. */
+int bdg_nearest_bounded(const uint32_t* q, size_t Q, const uint32_t* targets_in_order, size_t W, int max_d,
+                        int32_t* argmin, uint8_t* dist);
+
+/* ---- a-5  KmerIndexer.get_occurrences counting step: kmer_indexer.py:49-61 (k = 6, 16-mers) -------- */
+/* All (query, entry) pairs with cnt = #{(p,p'): 6mer_q[p] == 6mer_wl[p']} >= min_kmers.  mult packs, 4 bits
+ * per query position p = 0..10, the number of matching positions of the entry (the reference's
+ * `positions` list is p repeated mult[p] times).  Outputs are caller-allocated with room for cap hits;
+ * *total receives the number found; BDG_ERR_CAPACITY when total > cap (first cap hits are valid).
+ * Also serves QGramIndex.get_close (index.py:77-93): min_kmers = T(t), keep entries > query. */
+int bdg_kmer_score(const uint32_t* q, size_t Q, const uint32_t* wl, size_t W, int min_kmers, size_t cap,
+                   uint32_t* hit_q, uint32_t* hit_w, uint8_t* cnt, uint64_t* mult, size_t* total);
+
+/* ---- device-resident variants (bench.py "value" path; torch owns the memory and the stream) -------- */
+/* Edge kernel over rows of part/nparts.  d_count (one uint64, device) is zeroed by the call and receives
+ * the number of edges found, which may exceed cap (only the first cap are stored). */
+int bdg_dev_edges_build(const uint32_t* d_sorted, size_t N, int t, int part, int nparts, uint32_t* d_a,
+                        uint32_t* d_b, uint8_t* d_d, size_t cap, unsigned long long* d_count, void* stream);
+int bdg_dev_pack16(const char* d_seqs, size_t R, uint32_t* d_out, uint8_t* d_valid, void* stream);
+int bdg_dev_member_sorted(const uint32_t* d_sorted_wl, size_t W, const uint32_t* d_q, size_t Q, uint8_t* d_hit,
+                          void* stream);
+int bdg_dev_nearest_bounded(const uint32_t* d_q, size_t Q, const uint32_t* d_targets, size_t W, int max_d,
+                            uint32_t* d_keys /* Q words of scratch */, int32_t* d_argmin, uint8_t* d_dist,
+                            void* stream);
+/* Number of pairs the edge kernel decides for this part: sum over owned rows i of (N-1-i). */
+unsigned long long bdg_part_pairs(size_t N, int part, int nparts);
+/* Kernel launches issued by this process so far (bench.py's gpu_launches). */
+unsigned long long bdg_launch_count(void);
+
+/* Integer-pipe roofline probe (the INT peak is not in MEASURED_PEAKS.json and must be
+ * measured).  kind 0: LOP3 only (ALU pipe), 1: IMAD only (FMA pipe), 2: LOP3+IMAD interleaved 1:1,
+ * 3: POPC.  Runs `iters` loop trips of 64 independent warp instructions per thread on blocks x 256
+ * threads; the caller times it with CUDA events.  *ops_per_thread receives the instruction count. */
+int bdg_dev_pipe_probe(int kind, int blocks, int iters, uint32_t* d_sink, unsigned long long* ops_per_thread,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BADGER_B200_H */

@@ -1,0 +1,21 @@
+// Host build of badger_b200/csrc/bdg_core.cuh for the CPU-side unit tests (tests/test_core_host.py).
+// Test infrastructure: lets the per-pair device arithmetic be checked against the oracle without a GPU.
+#include "../badger_b200/csrc/bdg_core.cuh"
+#include <stddef.h>
+
+extern "C" {
+void shim_pairs(const uint32_t* a, const uint32_t* b, size_t n, uint8_t* pre1, uint8_t* pre2, uint8_t* dsmall,
+                uint8_t* dplain, uint8_t* dfull, uint8_t* da15, uint8_t* db15, uint8_t* S, uint64_t* mult)
+{
+    for (size_t i = 0; i < n; i++) {
+        pre1[i] = bdg::prefilter_t1(a[i], b[i]);
+        pre2[i] = bdg::prefilter_t2(a[i], b[i]);
+        dsmall[i] = (uint8_t)bdg::dist_small(a[i], b[i], false);
+        dplain[i] = (uint8_t)bdg::dist_small(a[i], b[i], true);
+        bdg::Dist3 r = bdg::myers3(a[i], b[i]);
+        dfull[i] = (uint8_t)r.full; da15[i] = (uint8_t)r.a15; db15[i] = (uint8_t)r.b15;
+        S[i] = (uint8_t)bdg::qgram_score(a[i], b[i], &mult[i]);
+    }
+}
+int shim_edge(uint32_t a, uint32_t b, int t) { return bdg::edge_dist(a, b, t); }
+}

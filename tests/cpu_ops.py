@@ -1,0 +1,57 @@
+"""Oracle-backed stand-ins for badger_b200.ops, used ONLY by the CPU (`not gpu`) tests to exercise the
+host-side logic of the Python layer (centre selection, clustering, assignment, output) without a GPU."""
+import numpy as np
+
+from badger_b200 import synth
+from oracle import oracle as orc
+
+
+def pack16(seqs):
+    if isinstance(seqs, (bytes, bytearray)):
+        seqs = [bytes(seqs[i:i + 16]) for i in range(0, len(seqs), 16)]
+    out = np.zeros(len(seqs), np.uint32); valid = np.ones(len(seqs), bool)
+    for i, s in enumerate(seqs):
+        s = s.decode() if isinstance(s, bytes) else s
+        try:
+            out[i] = orc.rank(s)
+        except KeyError:
+            valid[i] = False
+    return out, valid
+
+
+def edges_build(sorted_unique, t):
+    s = np.ascontiguousarray(sorted_unique, dtype=np.uint32)
+    if s.size < 2 or t <= 0:
+        return np.empty(0, np.uint32), np.empty(0, np.uint32), np.empty(0, np.uint8)
+    a, b, d, _ = orc.Index(s).edges(t)
+    return a, b, d
+
+
+def edges_build_part(sorted_unique, t, part, nparts):
+    from badger_b200.parallel import part_rows
+    s = np.ascontiguousarray(sorted_unique, dtype=np.uint32)
+    rows = part_rows(s.size, part, nparts)
+    if s.size < 2 or t <= 0 or rows.size == 0:
+        return np.empty(0, np.uint32), np.empty(0, np.uint32), np.empty(0, np.uint8)
+    a, b, d, _ = orc.Index(s).edges(t, rows=rows)
+    return a, b, d
+
+
+def member_sorted(wl, q):
+    return orc.member(wl, q).astype(bool)
+
+
+def nearest_bounded(q, targets, max_d=2):
+    return orc.nearest(q, targets, max_d)
+
+
+def kmer_score(q, wl, min_kmers=1, cap=None):
+    cnt, mult = orc.kmer_score(q, wl)
+    qi, wi = np.nonzero((cnt >= max(min_kmers, 1)))
+    return qi.astype(np.uint32), wi.astype(np.uint32), cnt[qi, wi], mult[qi, wi]
+
+
+def install(monkeypatch):
+    from badger_b200 import ops
+    for name in ("pack16", "edges_build", "edges_build_part", "member_sorted", "nearest_bounded", "kmer_score"):
+        monkeypatch.setattr(ops, name, globals()[name])

@@ -1,0 +1,169 @@
+"""Per-pair device arithmetic (badger_b200/csrc/bdg_core.cuh), compiled for the host, against the oracle.
+
+The same header is what the CUDA kernels include; this test is the CPU-side proof that the prefilters
+are sound (never reject a pair with D <= t) and that the exact stage equals the reference's distances.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from badger_b200 import synth
+from oracle import oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+u64p = np.ctypeslib.ndpointer(dtype=np.uint64, flags="C_CONTIGUOUS")
+
+
+@pytest.fixture(scope="module")
+def shim(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("shim") / "core_host_shim.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-x", "c++",
+                           os.path.join(HERE, "core_host_shim.cpp"), "-o", so])
+    L = C.CDLL(so)
+    L.shim_pairs.argtypes = [u32p, u32p, C.c_size_t] + [u8p] * 8 + [u64p]
+    L.shim_edge.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
+    L.shim_edge.restype = C.c_int
+    return L
+
+
+def run(shim, a, b):
+    n = a.size
+    outs = [np.zeros(n, np.uint8) for _ in range(8)]
+    mult = np.zeros(n, np.uint64)
+    shim.shim_pairs(a, b, n, *outs, mult)
+    return dict(zip(["pre1", "pre2", "dsmall", "dplain", "dfull", "da15", "db15", "S"], outs)), mult
+
+
+def edit_ops(rng, a, k):
+    """Apply k random edit operations to the 16-mer a, keep 16 bases (pad randomly)."""
+    s = [(a >> (2 * i)) & 3 for i in range(16)]
+    for _ in range(k):
+        op = rng.integers(0, 3); pos = int(rng.integers(0, len(s)))
+        if op == 0:
+            s[pos] = (s[pos] + int(rng.integers(1, 4))) & 3
+        elif op == 1:
+            s.insert(pos, int(rng.integers(0, 4)))
+        else:
+            del s[pos]
+    while len(s) < 16:
+        s.append(int(rng.integers(0, 4)))
+    return sum(c << (2 * i) for i, c in enumerate(s[:16]))
+
+
+def make_pairs(seed, n_near=60000, n_rand=20000, n_low=20000):
+    rng = np.random.default_rng(seed)
+    a, b = [], []
+    for _ in range(n_near):
+        x = int(rng.integers(0, 1 << 32))
+        if rng.random() < 0.3:   # low-complexity seeds exercise the multiplicity side of S
+            unit = int(rng.integers(0, 1 << (2 * int(rng.integers(1, 5)))))
+            ul = max(1, unit.bit_length() + 1) // 2 or 1
+            x = 0
+            for i in range(16):
+                x |= ((unit >> (2 * (i % ul))) & 3) << (2 * i)
+        y = edit_ops(rng, x, int(rng.integers(1, 5)))
+        if x != y:
+            a.append(x); b.append(y)
+    ra = rng.integers(0, 1 << 32, n_rand, dtype=np.uint64); rb = rng.integers(0, 1 << 32, n_rand, dtype=np.uint64)
+    a += ra.tolist(); b += rb.tolist()
+    # pairs sharing long stretches on shifted diagonals
+    for _ in range(n_low):
+        x = int(rng.integers(0, 1 << 32)); sh = int(rng.integers(1, 4)) * 2
+        y = ((x << sh) | int(rng.integers(0, 1 << sh))) & 0xFFFFFFFF if rng.random() < 0.5 else (x >> sh) | (int(rng.integers(0, 1 << sh)) << (32 - sh))
+        if rng.random() < 0.5:
+            y = edit_ops(rng, y, 1)
+        if x != y:
+            a.append(x); b.append(y)
+    a = np.asarray(a, dtype=np.uint32); b = np.asarray(b, dtype=np.uint32)
+    keep = a != b
+    return a[keep], b[keep]
+
+
+def test_core_vs_oracle(shim):
+    a, b = make_pairs(5)
+    res, mult = run(shim, a, b)
+    L = orc.lib()
+    n = a.size
+    ed = np.fromiter((L.orc_ed(int(x), 16, int(y), 16) for x, y in zip(a, b)), np.int32, n)
+    ea = np.fromiter((L.orc_ed(int(x), 15, int(y), 16) for x, y in zip(a, b)), np.int32, n)
+    eb = np.fromiter((L.orc_ed(int(x), 16, int(y), 15) for x, y in zip(a, b)), np.int32, n)
+    D = np.minimum(ed, np.minimum(ea, eb))
+    S = np.fromiter((L.orc_S(int(x), int(y)) for x, y in zip(a, b)), np.int32, n)
+    assert np.array_equal(res["dfull"], ed)
+    assert np.array_equal(res["da15"], ea)
+    assert np.array_equal(res["db15"], eb)
+    assert np.array_equal(res["S"], S)
+    assert np.array_equal(res["dsmall"], np.minimum(D, 3))
+    assert np.array_equal(res["dplain"], np.minimum(ed, 3))
+    # soundness of the prefilters: D<=t  =>  prefilter passes
+    assert res["pre1"][D <= 1].all()
+    assert res["pre2"][D <= 2].all()
+    assert (D <= 1).sum() > 5000 and ((D == 2).sum() > 5000)
+    # the prefilters do reject random pairs
+    rng = np.random.default_rng(1)
+    ra = rng.integers(0, 1 << 32, 1 << 20, dtype=np.uint64).astype(np.uint32)
+    rb = rng.integers(0, 1 << 32, 1 << 20, dtype=np.uint64).astype(np.uint32)
+    rr, _ = run(shim, ra, rb)
+    assert rr["pre1"].mean() < 4e-4      # expected 2*2^-16 + 2*2^-14 = 1.5e-4
+    assert rr["pre2"].mean() < 0.012     # expected 9 * 2^-10   = 0.88 %
+    # symmetry
+    res2, _ = run(shim, b, a)
+    for k in ("pre1", "dsmall", "dplain", "S"):   # pre2 is frame-dependent (sound either way)
+        assert np.array_equal(res[k], res2[k]), k
+    # multiplicities: sum over positions == S, and equal to the oracle's kmer_score multiplicities
+    nib = np.stack([(mult >> np.uint64(4 * p)) & np.uint64(15) for p in range(11)], 1).astype(np.int32)
+    assert np.array_equal(nib.sum(1), S)
+    idx = np.arange(0, n, 97)
+    for i in idx:
+        _, m = orc.kmer_score(a[i:i + 1], b[i:i + 1])
+        assert m[0, 0].tolist() == nib[i].tolist()
+
+
+def test_edge_predicate_on_golden(shim, gold_pairs):
+    for p in gold_pairs["pairs"]:
+        for t in range(0, 5):
+            want = p["D"] if (p["S"] >= orc.T(t) and p["D"] <= t) else 0
+            assert shim.shim_edge(p["ra"], p["rb"], t) == want
+            assert shim.shim_edge(p["rb"], p["ra"], t) == want
+
+
+def test_exhaustive_neighbourhood(shim):
+    """Every string within two edit operations of a few seeds (incl. truncation effects)."""
+    rng = np.random.default_rng(9)
+    seeds = [int(rng.integers(0, 1 << 32)) for _ in range(3)] + [0, 0x11111111 * 0 + 0x44444444, int(synth.rank_many(["ACACACACACACACAC"])[0])]
+    for x in seeds:
+        s = [(x >> (2 * i)) & 3 for i in range(16)]
+        neigh = set()
+
+        def one(seq):
+            out = []
+            for pos in range(len(seq)):
+                for c in range(4):
+                    if c != seq[pos]:
+                        out.append(seq[:pos] + [c] + seq[pos + 1:])
+                out.append(seq[:pos] + seq[pos + 1:])
+            for pos in range(len(seq) + 1):
+                for c in range(4):
+                    out.append(seq[:pos] + [c] + seq[pos:])
+            return out
+
+        lvl1 = one(s)
+        sample = [lvl1[i] for i in rng.choice(len(lvl1), 40, replace=False)]
+        lvl2 = [y for z in sample for y in one(z)]
+        for seq in lvl1 + lvl2:
+            for pad in range(4):
+                q = (seq + [pad, pad])[:16] if len(seq) < 16 else seq[:16]
+                neigh.add(sum(c << (2 * i) for i, c in enumerate(q)))
+        neigh.discard(x)
+        b = np.fromiter(neigh, dtype=np.uint32)
+        a = np.full(b.size, x, dtype=np.uint32)
+        res, _ = run(shim, a, b)
+        L = orc.lib()
+        D = np.fromiter((L.orc_D(int(x), int(y)) for y in b), np.int32, b.size)
+        assert np.array_equal(res["dsmall"], np.minimum(D, 3))
+        assert res["pre1"][D <= 1].all() and res["pre2"][D <= 2].all()
