@@ -1,0 +1,272 @@
+"""Parity tests proper: the CUDA path, called through the C ABI (badger_b200.ops -> libbadger_b200.so), against
+the golden fixtures of the unmodified reference and against the CPU oracle on seeded inputs.
+Bit-exact: all of this path is integer work."""
+import ctypes as C
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import badger_b200
+from badger_b200 import BarcodeGraph, KmerIndexer, QGramIndex, ops, synth
+from badger_b200.parallel import part_pairs, part_rows
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _init():
+    n = badger_b200.init()
+    assert n >= 1
+    yield
+
+
+def edge_rows(a, b, d):
+    a, b, d = ops.canonical(a, b, d)
+    return np.stack([a, b, d], 1).astype(np.int64)
+
+
+def clustered_set(seed, n_cells, reads, perr):
+    rng = synth.rng_for(seed)
+    cells = rng.integers(0, 1 << 32, n_cells, dtype=np.uint64).astype(np.uint32)
+    obs, _ = synth.simulate_reads(cells, reads, perr, rng)
+    return np.unique(obs)
+
+
+# ------------------------------------------------------------------------------------------ golden fixtures
+def test_pack16_and_pairs(gold_pairs):
+    strs = [p["a"] for p in gold_pairs["pairs"]] + [p["b"] for p in gold_pairs["pairs"]]
+    r, v = ops.pack16(strs)
+    assert v.all()
+    assert r.tolist() == [p["ra"] for p in gold_pairs["pairs"]] + [p["rb"] for p in gold_pairs["pairs"]]
+    r2, v2 = ops.pack16(["ACGTACGTACGTACGN", "acgtacgtacgtacgt", "ACGTACGTACGTACGT", "ACGTACGTACGTAC\nT"])
+    assert v2.tolist() == [False, False, True, False] and int(r2[2]) == 3840206052
+    # every golden pair as a two-node graph: edge iff S >= T(t) and D <= t, stored distance D
+    for t in (0, 1, 2, 3, 4):
+        for p in gold_pairs["pairs"][::3]:
+            s = np.sort(np.asarray([p["ra"], p["rb"]], np.uint32))
+            a, b, d = ops.edges_build(s, t)
+            want = p["S"] >= orc.T(t) and p["D"] <= t
+            assert (a.size == 1) == want, (p, t)
+            if want:
+                assert int(d[0]) == p["D"] and (int(a[0]), int(b[0])) == (int(s[0]), int(s[1]))
+
+
+def test_graphs_golden(gold_graphs):
+    for g in gold_graphs:
+        bg = BarcodeGraph(g["t"])
+        bg.graph_construction(g["reads"], 16, 1)
+        assert [(k, v) for k, v in bg.counts.items()] == [tuple(x) for x in g["counts"]], g["name"]
+        a, b, d = bg.edge_arrays()
+        assert np.stack([a, b, d], 1).astype(np.int64).tolist() == g["edges"], g["name"]
+        for gc in g["get_close"]:
+            assert sorted(bg.index.get_close(orc.unrank(gc["query"]), gc["query"])) == gc["close"]
+
+
+def test_pipeline_golden(gold_pipeline, tmp_path, capsys):
+    import importlib.util
+    import logging
+    spec = importlib.util.spec_from_file_location("badger_cli", os.path.join(ROOT, "badger.py"))
+    cli = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cli)
+    g = gold_pipeline
+    out = str(tmp_path / "OUT")
+    cli.main(["-r", g["dir"] + "/reads.tsv", "-l", g["dir"] + "/whitelist.txt", "-d", "tenX_v3", "-t", str(g["t"]),
+              "--n_cells", str(g["n_cells"]), "-i", str(g["interval"]), "-o", out])
+    for h in list(logging.getLogger("BarcodeGraph").handlers):
+        logging.getLogger("BarcodeGraph").removeHandler(h)
+    with open(out + "_output_file.tsv", "rb") as fh, open(g["dir"] + "/expected_output_file.tsv", "rb") as ref:
+        assert fh.read() == ref.read()
+    tail = [ln for ln in capsys.readouterr().out.splitlines() if ln.strip().lstrip("-").isdigit()]
+    assert tail == g["stdout_tail"]
+    # internals + --high_sens with the centre order the reference iterated
+    import pandas as pd
+    df = pd.read_csv(g["dir"] + "/reads.tsv", sep="\t")
+    bcs = df["barcode"].dropna()
+    bcs = bcs[(bcs != "*") & (bcs != "barcode")].tolist()
+    bg = BarcodeGraph(g["t"])
+    bg.graph_construction(bcs, 16, 1)
+    a, b, d = bg.edge_arrays()
+    assert np.stack([a, b, d], 1).astype(np.int64).tolist() == g["edges"]
+    with open(g["dir"] + "/whitelist.txt") as fh:
+        wl = set(fh.read().split("\n"))
+    assert bg.get_cluster_centers(None, 16, wl, g["n_cells"], g["interval"]) == g["centres"]
+    bg.cluster(None, wl, g["n_cells"], 16, g["interval"])
+    assert {k: tuple(v) for k, v in bg.clustering.items()} == {k: (c, l) for k, c, l in g["clustering"]}
+    assign = bg.assign_by_cluster(16)
+    assert dict(assign) == g["assignments"]
+    hs = bg.postprocessing(assign, 16, _centre_order=g["hs_centre_order"])
+    assert {k: v for k, v in hs.items() if v not in ("", "*")} == g["hs_assignments"]
+
+
+def test_c1_golden(gold_c1):
+    wl, cells, obs, valid, cfg = synth.make_dataset("C1")
+    strs = [s.decode() for s in synth.unrank_many(obs[valid]).tolist()]
+    bg = BarcodeGraph(cfg["threshold"])
+    bg.graph_construction(strs, 16, 1)
+    assert len(bg.counts) == gold_c1["n_distinct"]
+    pairs = np.asarray(list(bg.counts.items()), dtype=np.uint64)
+    assert hashlib.sha256(pairs.tobytes()).hexdigest() == gold_c1["counts_sha256"]
+    a, b, d = bg.edge_arrays()
+    assert np.stack([a, b, d], 1).astype(np.int64).tolist() == gold_c1["edges"]
+    wl_set = set(s.decode() for s in synth.unrank_many(wl).tolist()) | {""}
+    centres = bg.get_cluster_centers(None, 16, wl_set, cfg["n_cells"], 25)
+    assert len(centres) == gold_c1["n_centres"]
+    assert hashlib.sha256(np.asarray(centres, dtype=np.uint64).tobytes()).hexdigest() == gold_c1["centres_sha256"]
+    bg.cluster(None, wl_set, cfg["n_cells"], 16, 25)
+    assign = bg.assign_by_cluster(16)
+    h = hashlib.sha256()
+    for k in sorted(assign):
+        h.update(("%s\t%s\n" % (k, assign[k])).encode())
+    assert len(assign) == gold_c1["n_assigned"] and h.hexdigest() == gold_c1["assignments_sha256"]
+
+
+def test_kmer_indexer_golden(gold_kmer):
+    for c in gold_kmer:
+        if len(c["query"]) != 16 or any(len(s) != 16 for s in c["known"]):
+            continue
+        got = KmerIndexer(c["known"], c["k"]).get_occurrences(c["query"], **c["kw"])
+        assert [(k, v[1], list(v[2])) for k, v in got.items()] == [(x[0], x[1], x[2]) for x in c["result"]]
+
+
+# ------------------------------------------------------------------------------------------ oracle, seeded inputs
+@pytest.mark.parametrize("t", [1, 2, 3])
+def test_edges_vs_oracle_clustered(t):
+    s = clustered_set(40 + t, 300, 30000 if t < 3 else 6000, 0.06)
+    a, b, d = ops.edges_build(s, t)
+    ix = orc.Index(s)
+    wa, wb, wd, _ = ix.edges(t)
+    assert np.array_equal(edge_rows(a, b, d), np.stack([wa, wb, wd], 1).astype(np.int64))
+    assert a.size > 1000
+
+
+@pytest.mark.parametrize("t", [1, 2])
+def test_edges_dense_neighbourhoods(t):
+    """Consecutive integers and low-complexity families: every sub-tile next to the diagonal is dense."""
+    rng = np.random.default_rng(5)
+    base = int(rng.integers(0, 1 << 31))
+    s = np.unique(np.concatenate([np.arange(base, base + 3000, dtype=np.uint64),
+                                  (np.arange(0, 2500, dtype=np.uint64) << np.uint64(20)) + np.uint64(0x55555),
+                                  rng.integers(0, 1 << 32, 4000, dtype=np.uint64)]).astype(np.uint32))
+    a, b, d = ops.edges_build(s, t)
+    wa, wb, wd, _ = orc.Index(s).edges(t)
+    assert np.array_equal(edge_rows(a, b, d), np.stack([wa, wb, wd], 1).astype(np.int64))
+
+
+def test_edges_edge_cases():
+    for t in (1, 2, 3):
+        for arr in ([], [7], [0, 0xFFFFFFFF], [0, 1, 2, 3], list(range(2047, 2047 + 5))):
+            s = np.asarray(arr, np.uint32)
+            a, b, d = ops.edges_build(s, t)
+            wa, wb, wd = orc.edges_brute(s, t)
+            assert np.array_equal(edge_rows(a, b, d), np.stack([wa, wb, wd], 1).astype(np.int64))
+    with pytest.raises(badger_b200.BadgerB200Error):
+        ops.edges_build(np.asarray([5, 5, 6], np.uint32), 1)         # not strictly increasing
+    with pytest.raises(badger_b200.BadgerB200Error):
+        ops.edges_build(np.asarray([9, 3], np.uint32), 1)
+    a, _, _ = ops.edges_build(np.arange(100, dtype=np.uint32), 0)    # t = 0: no edges (barcode_graph.py:245)
+    assert a.size == 0
+
+
+@pytest.mark.parametrize("nparts", [2, 3, 8])
+def test_parts_union_equals_full(nparts):
+    s = clustered_set(77, 200, 20000, 0.06)
+    fa, fb, fd = ops.edges_build(s, 2)
+    rows = []
+    total_pairs = 0
+    for p in range(nparts):
+        a, b, d = ops.edges_build_part(s, 2, p, nparts)
+        own = set(s[part_rows(s.size, p, nparts)].tolist())
+        assert all(x in own for x in a.tolist())                      # a part emits edges of its own rows only
+        rows.append(edge_rows(a, b, d))
+        pp = badger_b200.lib().bdg_part_pairs(s.size, p, nparts)
+        assert pp == part_pairs(s.size, p, nparts)
+        total_pairs += pp
+    assert total_pairs == s.size * (s.size - 1) // 2
+    merged = np.concatenate(rows)
+    merged = merged[np.lexsort((merged[:, 1], merged[:, 0]))]
+    assert np.array_equal(merged, edge_rows(fa, fb, fd))
+
+
+def test_member_vs_oracle():
+    rng = np.random.default_rng(8)
+    for W in (0, 1, 5, 1000, 1024, 1025, 300000):
+        wl = np.unique(rng.integers(0, 1 << 32, W, dtype=np.uint64).astype(np.uint32))
+        q = np.concatenate([rng.integers(0, 1 << 32, 5000, dtype=np.uint64).astype(np.uint32), wl[:2000],
+                            np.asarray([0, 0xFFFFFFFF], np.uint32)])
+        assert np.array_equal(ops.member_sorted(wl, q), orc.member(wl, q).astype(bool))
+    assert ops.member_sorted(np.asarray([1, 2], np.uint32), np.empty(0, np.uint32)).size == 0
+
+
+@pytest.mark.parametrize("max_d", [2, 1, 0, 4])
+def test_nearest_vs_oracle(max_d):
+    rng = np.random.default_rng(9)
+    centres = rng.integers(0, 1 << 32, 700, dtype=np.uint64).astype(np.uint32)
+    obs, _ = synth.simulate_reads(centres, 4000, 0.08, rng)
+    q = np.concatenate([obs, centres[:50], rng.integers(0, 1 << 32, 500, dtype=np.uint64).astype(np.uint32)])
+    tg = np.concatenate([centres, centres[:30] ^ np.uint32(1)])       # near-duplicates force ties on distance
+    tg = tg[rng.permutation(tg.size)]
+    am, dist = ops.nearest_bounded(q, tg, max_d)
+    wam, wdist = orc.nearest(q, tg, max_d)
+    assert np.array_equal(am, wam) and np.array_equal(dist, wdist)
+    assert (am >= 0).sum() > 100
+    e_am, e_d = ops.nearest_bounded(q[:10], np.empty(0, np.uint32), 2)
+    assert (e_am == -1).all() and (e_d == 255).all()
+
+
+def test_kmer_score_vs_oracle():
+    rng = np.random.default_rng(10)
+    wl = rng.integers(0, 1 << 32, 3000, dtype=np.uint64).astype(np.uint32)
+    wl[:20] = np.asarray([0, 0x55555555, 0xAAAAAAAA, 0xFFFFFFFF, 0x11111111] * 4, np.uint32)   # low complexity
+    q = np.concatenate([wl[:40], rng.integers(0, 1 << 32, 300, dtype=np.uint64).astype(np.uint32)])
+    for mk in (1, 4, 5):
+        hq, hw, cnt, mult = ops.kmer_score(q, wl, min_kmers=mk)
+        wc, wm = orc.kmer_score(q, wl)
+        wq, ww = np.nonzero(wc >= mk)
+        o = np.lexsort((hw, hq))
+        assert np.array_equal(hq[o], wq) and np.array_equal(hw[o], ww)
+        assert np.array_equal(cnt[o], wc[wq, ww]) and np.array_equal(mult[o], wm[wq, ww])
+    _, hw, _, _ = ops.kmer_score(q[:5], wl, min_kmers=1, cap=3)       # capacity retry path
+    assert hw.size >= 5
+
+
+# ------------------------------------------------------------------------------------------ full size: properties
+def test_c2_full_size_properties():
+    """BASELINE config 2 at full size (1 M reads, t=1): sampled rows against the oracle's index walk, plus
+    structural properties that do not depend on the size."""
+    wl, cells, obs, valid, cfg = synth.make_dataset("C2")
+    s = np.unique(obs[valid])
+    a, b, d = ops.edges_build(s, cfg["threshold"])
+    assert (a < b).all() and ((d >= 1) & (d <= cfg["threshold"])).all()
+    key = (a.astype(np.uint64) << np.uint64(32)) | b.astype(np.uint64)
+    assert np.unique(key).size == key.size                                # no duplicate edges
+    assert np.isin(a, s).all() and np.isin(b, s).all()
+    rng = np.random.default_rng(2)
+    rows = np.sort(rng.choice(s.size, 2000, replace=False)).astype(np.uint32)
+    wa, wb, wd, _ = orc.Index(s).edges(cfg["threshold"], rows=rows)
+    sel = np.isin(a, s[rows])
+    assert np.array_equal(edge_rows(a[sel], b[sel], d[sel]), np.stack([wa, wb, wd], 1).astype(np.int64))
+    # idempotence / determinism: a second run gives the same set
+    a2, b2, d2 = ops.edges_build(s, cfg["threshold"])
+    assert np.array_equal(edge_rows(a, b, d), edge_rows(a2, b2, d2))
+    # whitelist hits at full size: every cell barcode present in the data is found, random words are not
+    hit = ops.member_sorted(np.sort(wl), s)
+    assert np.array_equal(hit, orc.member(np.sort(wl), s).astype(bool))
+
+
+def test_t2_large_sampled_rows():
+    """t=2 at N ~ 4e5 (the shape of configs 4/5, scaled): sampled rows against the oracle."""
+    rng = synth.rng_for(31)
+    wl = synth.make_whitelist(50000, rng)
+    cells = synth.pick_cells(wl, 8000, rng)
+    obs, valid = synth.simulate_reads(cells, 900000, 0.05, rng)
+    s = np.unique(obs[valid])
+    a, b, d = ops.edges_build(s, 2)
+    rows = np.sort(rng.choice(s.size, 1500, replace=False)).astype(np.uint32)
+    wa, wb, wd, _ = orc.Index(s).edges(2, rows=rows)
+    sel = np.isin(a, s[rows])
+    assert np.array_equal(edge_rows(a[sel], b[sel], d[sel]), np.stack([wa, wb, wd], 1).astype(np.int64))
+    assert (d == 2).sum() > 1000 and (d == 1).sum() > 1000
