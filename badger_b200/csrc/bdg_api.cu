@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <ctime>
 #include <new>
 #include <vector>
 
@@ -35,10 +36,31 @@ int fail(int code, const char* fmt, ...)
                         #expr, cudaGetErrorString(e_));                                                \
     } while (0)
 
+// grow-only device buffer: the host-buffer entry points reuse their workspaces from call to call
+// (cudaMalloc / cudaFree per call cost far more than the kernels at BASELINE config-2 sizes)
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes)
+    {
+        if (bytes <= cap) return BDG_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { p = nullptr; return (int)e; }
+        cap = want;
+        return BDG_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
 struct DevCtx {
     int dev = -1;
     cudaStream_t stream = nullptr;
     int sms = 0;
+    Buf sorted, ea, eb, ed, count, plan;   // edge construction
 };
 std::vector<DevCtx> g_ctx;
 
@@ -97,7 +119,7 @@ void build_plan(size_t N, int part, int nparts, int grid, Plan& p)
 
 // Launch the edge kernel for one part on the current device / stream.  d_count is zeroed on the stream.
 int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts, uint32_t* d_a, uint32_t* d_b,
-                 uint8_t* d_d, size_t cap, unsigned long long* d_count, cudaStream_t st)
+                 uint8_t* d_d, size_t cap, unsigned long long* d_count, cudaStream_t st, Buf* plan_ws)
 {
     if (nparts < 1 || part < 0 || part >= nparts) return fail(BDG_ERR_ARG, "part %d of %d is not a valid part", part, nparts);
     if (N > 0xFFFFFFFFull) return fail(BDG_ERR_ARG, "N = %zu exceeds the 2^32 distinct 16-mers", N);
@@ -113,7 +135,15 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
     if (n_items == 0) return BDG_OK;
     const size_t nb_tiles = plan.tile_ids.size() * sizeof(uint32_t), nb_items = plan.item_start.size() * sizeof(uint32_t);
     char* d_plan = nullptr;   // [counter | tile_ids | item_start]
-    CU_TRY(cudaMallocAsync((void**)&d_plan, 16 + nb_tiles + nb_items, st));
+    bool plan_async = true;
+    if (plan_ws) {            // caller-provided grow-only workspace (one in-flight call per device)
+        if (cudaError_t e = (cudaError_t)plan_ws->ensure(16 + nb_tiles + nb_items))
+            return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "plan workspace: %s", cudaGetErrorString(e));
+        d_plan = (char*)plan_ws->p;
+        plan_async = false;
+    } else {
+        CU_TRY(cudaMallocAsync((void**)&d_plan, 16 + nb_tiles + nb_items, st));
+    }
     CU_TRY(cudaMemsetAsync(d_plan, 0, 16, st));
     CU_TRY(cudaMemcpyAsync(d_plan + 16, plan.tile_ids.data(), nb_tiles, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(d_plan + 16 + nb_tiles, plan.item_start.data(), nb_items, cudaMemcpyHostToDevice, st));
@@ -136,8 +166,16 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
     else bdg::edges_kernel<3><<<blocks, bdg::NT, 0, st>>>(w, o);
     g_launches++;
     CU_TRY(cudaGetLastError());
-    CU_TRY(cudaFreeAsync(d_plan, st));
+    if (plan_async) CU_TRY(cudaFreeAsync(d_plan, st));
     return BDG_OK;
+}
+
+DevCtx* ctx_of_current_device()
+{
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    for (auto& c : g_ctx) if (c.dev == dev) return &c;
+    return nullptr;
 }
 
 int need_ctx()
@@ -201,6 +239,11 @@ int bdg_init(const int* device_ids, int n_devices)
         if (prop.major < 10) { bdg_shutdown(); return fail(BDG_ERR_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", id, prop.major, prop.minor); }
         c.sms = prop.multiProcessorCount;
         CU_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        cudaMemPool_t pool;   // keep stream-ordered allocations cached instead of returning them at every sync
+        if (cudaDeviceGetDefaultMemPool(&pool, id) == cudaSuccess) {
+            unsigned long long keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
         g_ctx.push_back(c);
     }
     CU_TRY(cudaSetDevice(g_ctx[0].dev));
@@ -211,6 +254,7 @@ void bdg_shutdown(void)
 {
     for (auto& c : g_ctx) {
         if (c.stream) { cudaSetDevice(c.dev); cudaStreamSynchronize(c.stream); cudaStreamDestroy(c.stream); }
+        c.sorted.release(); c.ea.release(); c.eb.release(); c.ed.release(); c.count.release(); c.plan.release();
     }
     g_ctx.clear();
 }
@@ -228,7 +272,8 @@ int bdg_dev_edges_build(const uint32_t* d_sorted, size_t N, int t, int part, int
                         uint8_t* d_d, size_t cap, unsigned long long* d_count, void* stream)
 {
     if (!d_count || (N && !d_sorted) || (cap && (!d_a || !d_b || !d_d))) return fail(BDG_ERR_ARG, "NULL pointer argument");
-    return launch_edges(d_sorted, N, t, part, nparts, d_a, d_b, d_d, cap, d_count, (cudaStream_t)stream);
+    DevCtx* c = ctx_of_current_device();
+    return launch_edges(d_sorted, N, t, part, nparts, d_a, d_b, d_d, cap, d_count, (cudaStream_t)stream, c ? &c->plan : nullptr);
 }
 
 int bdg_dev_pack16(const char* d_seqs, size_t R, uint32_t* d_out, uint8_t* d_valid, void* stream)
@@ -331,68 +376,76 @@ int bdg_pack16(const char* seqs, size_t R, uint32_t* out, uint8_t* valid)
     return rc;
 }
 
+static double now_ms()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
 static int edges_on_devices(const uint32_t* sorted, size_t N, int t, const std::vector<int>& ctx_idx,
                             const std::vector<int>& parts, int nparts, bdg_edges* res)
 {
-    struct Run { uint32_t* d_sorted = nullptr; uint32_t *d_a = nullptr, *d_b = nullptr; uint8_t* d_d = nullptr;
-                 unsigned long long* d_count = nullptr; size_t cap = 0; unsigned long long count = 0; };
-    std::vector<Run> runs(ctx_idx.size());
-    int rc = BDG_OK;
-    auto cleanup = [&]() {
-        for (size_t g = 0; g < runs.size(); g++) {
-            cudaSetDevice(g_ctx[ctx_idx[g]].dev);
-            cudaFree(runs[g].d_sorted); cudaFree(runs[g].d_a); cudaFree(runs[g].d_b); cudaFree(runs[g].d_d); cudaFree(runs[g].d_count);
-        }
-    };
-    auto alloc_out = [&](Run& r, size_t cap) -> int {
-        cudaFree(r.d_a); cudaFree(r.d_b); cudaFree(r.d_d);
-        r.d_a = r.d_b = nullptr; r.d_d = nullptr;
-        r.cap = cap;
-        CU_TRY(cudaMalloc((void**)&r.d_a, cap * 4));
-        CU_TRY(cudaMalloc((void**)&r.d_b, cap * 4));
-        CU_TRY(cudaMalloc((void**)&r.d_d, cap));
+    const bool trace = getenv("BDG_TRACE") != nullptr;
+    const double t0 = now_ms();
+    std::vector<unsigned long long> counts(ctx_idx.size(), 0);
+    auto ensure = [&](Buf& b, size_t bytes) -> int {
+        if (cudaError_t e = (cudaError_t)b.ensure(bytes))
+            return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation of %zu bytes: %s", bytes, cudaGetErrorString(e));
         return BDG_OK;
     };
+    auto launch = [&](DevCtx& c, int part, size_t cap) -> int {
+        if (int e = ensure(c.ea, cap * 4)) return e;
+        if (int e = ensure(c.eb, cap * 4)) return e;
+        if (int e = ensure(c.ed, cap)) return e;
+        return launch_edges((const uint32_t*)c.sorted.p, N, t, part, nparts, (uint32_t*)c.ea.p, (uint32_t*)c.eb.p, (uint8_t*)c.ed.p,
+                            cap, (unsigned long long*)c.count.p, c.stream, &c.plan);
+    };
+    std::vector<size_t> caps(ctx_idx.size(), 0);
+    int rc = BDG_OK;
     // upload + launch on every device first (asynchronous), then collect
-    for (size_t g = 0; g < runs.size() && rc == BDG_OK; g++) {
+    for (size_t g = 0; g < ctx_idx.size() && rc == BDG_OK; g++) {
         DevCtx& c = g_ctx[ctx_idx[g]];
-        Run& r = runs[g];
         rc = [&]() -> int {
             CU_TRY(cudaSetDevice(c.dev));
-            CU_TRY(cudaMalloc((void**)&r.d_sorted, std::max<size_t>(N, 1) * 4));
-            CU_TRY(cudaMalloc((void**)&r.d_count, sizeof(unsigned long long)));
-            CU_TRY(cudaMemcpyAsync(r.d_sorted, sorted, N * 4, cudaMemcpyHostToDevice, c.stream));
-            if (int e = alloc_out(r, edge_cap_guess(N, nparts))) return e;
-            return launch_edges(r.d_sorted, N, t, parts[g], nparts, r.d_a, r.d_b, r.d_d, r.cap, r.d_count, c.stream);
+            if (int e = ensure(c.sorted, std::max<size_t>(N, 1) * 4)) return e;
+            if (int e = ensure(c.count, sizeof(unsigned long long))) return e;
+            CU_TRY(cudaMemcpyAsync(c.sorted.p, sorted, N * 4, cudaMemcpyHostToDevice, c.stream));
+            caps[g] = std::max(edge_cap_guess(N, nparts), c.ea.cap / 4);
+            return launch(c, parts[g], caps[g]);
         }();
     }
-    for (size_t g = 0; g < runs.size() && rc == BDG_OK; g++) {
+    const double t1 = now_ms();
+    double t2 = t1;
+    for (size_t g = 0; g < ctx_idx.size() && rc == BDG_OK; g++) {
         DevCtx& c = g_ctx[ctx_idx[g]];
-        Run& r = runs[g];
         rc = [&]() -> int {
             CU_TRY(cudaSetDevice(c.dev));
-            CU_TRY(cudaMemcpyAsync(&r.count, r.d_count, sizeof(r.count), cudaMemcpyDeviceToHost, c.stream));
+            CU_TRY(cudaMemcpyAsync(&counts[g], c.count.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
             CU_TRY(cudaStreamSynchronize(c.stream));
-            if (r.count > r.cap) {   // rare: the guess was too small; the edge set is deterministic, so run again
-                if (int e = alloc_out(r, (size_t)r.count)) return e;
-                if (int e = launch_edges(r.d_sorted, N, t, parts[g], nparts, r.d_a, r.d_b, r.d_d, r.cap, r.d_count, c.stream)) return e;
-                CU_TRY(cudaMemcpyAsync(&r.count, r.d_count, sizeof(r.count), cudaMemcpyDeviceToHost, c.stream));
+            if (counts[g] > caps[g]) {   // rare: the guess was too small; the edge set is deterministic, so run again
+                caps[g] = (size_t)counts[g];
+                if (int e = launch(c, parts[g], caps[g])) return e;
+                CU_TRY(cudaMemcpyAsync(&counts[g], c.count.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
                 CU_TRY(cudaStreamSynchronize(c.stream));
-                if (r.count > r.cap) return fail(BDG_ERR_CUDA, "edge count changed between identical launches");
+                if (counts[g] > caps[g]) return fail(BDG_ERR_CUDA, "edge count changed between identical launches");
             }
-            const size_t off = res->a.size(), n = (size_t)r.count;
+            t2 = now_ms();
+            const size_t off = res->a.size(), n = (size_t)counts[g];
             res->a.resize(off + n); res->b.resize(off + n); res->d.resize(off + n);
             if (n) {
-                CU_TRY(cudaMemcpyAsync(res->a.data() + off, r.d_a, n * 4, cudaMemcpyDeviceToHost, c.stream));
-                CU_TRY(cudaMemcpyAsync(res->b.data() + off, r.d_b, n * 4, cudaMemcpyDeviceToHost, c.stream));
-                CU_TRY(cudaMemcpyAsync(res->d.data() + off, r.d_d, n, cudaMemcpyDeviceToHost, c.stream));
+                CU_TRY(cudaMemcpyAsync(res->a.data() + off, c.ea.p, n * 4, cudaMemcpyDeviceToHost, c.stream));
+                CU_TRY(cudaMemcpyAsync(res->b.data() + off, c.eb.p, n * 4, cudaMemcpyDeviceToHost, c.stream));
+                CU_TRY(cudaMemcpyAsync(res->d.data() + off, c.ed.p, n, cudaMemcpyDeviceToHost, c.stream));
                 CU_TRY(cudaStreamSynchronize(c.stream));
             }
             return BDG_OK;
         }();
     }
-    cleanup();
     if (!g_ctx.empty()) cudaSetDevice(g_ctx[0].dev);
+    if (trace)
+        fprintf(stderr, "[bdg] edges N=%zu t=%d devices=%zu: upload+launch %.2f ms, kernels %.2f ms, download %.2f ms, edges %zu\n", N, t,
+                ctx_idx.size(), t1 - t0, t2 - t1, now_ms() - t2, res->a.size());
     return rc;
 }
 

@@ -117,21 +117,29 @@ __device__ __forceinline__ void pair_t2(uint32_t a, uint32_t b0, uint32_t bR, ui
         : "r"(a), "r"(b0), "r"(bR), "r"(bL), "r"(one), "r"(neg_ones), "n"(F10_HIGH), "r"(bit));
 }
 
-// t=1: both test words of one pair folded into the running accumulator of this column
-__device__ __forceinline__ void pair_t1_acc(uint32_t a, uint32_t a2, uint32_t b0, uint32_t b1, uint32_t one, uint32_t neg_ones,
-                                            uint32_t& acc)
+// t=1: both test words of one pair folded into the running accumulators of this column.
+//   word 0 (two 16-bit halves, no spare bit): zero-field test  x = a^b, y = x-ones, accA |= y & ~x   (ALU, FMA, ALU)
+//   word 1 (two 14-bit fields, each with a guard bit above it): equality as two guarded subtractions
+//          d1 = (a2|G) - b1, d2 = (b1|G) - a2; the guard survives in both iff the fields are equal;
+//          accB |= d1 & d2                                                                           (FMA, FMA, ALU)
+// so a pair costs 3 ALU-pipe + 3 FMA-pipe instructions: the two pipes are loaded evenly.
+//   lop3 immLut: C | (A & ~B) = 0xBA;  C | (A & B) = 0xEA.
+constexpr uint32_t T1_GUARD = 0x40004000u;
+
+__device__ __forceinline__ void pair_t1_acc(uint32_t a, uint32_t a2, uint32_t aG, uint32_t b0, uint32_t b1, uint32_t bG,
+                                            uint32_t one, uint32_t mone, uint32_t neg_ones, uint32_t& accA, uint32_t& accB)
 {
     asm("{\n\t"
-        ".reg .b32 x0, x1, y0, y1;\n\t"
-        "xor.b32 x0, %1, %3;\n\t"
-        "xor.b32 x1, %2, %4;\n\t"
-        "mad.lo.u32 y0, x0, %5, %6;\n\t"
-        "mad.lo.u32 y1, x1, %5, %6;\n\t"
+        ".reg .b32 x0, y0, d1, d2;\n\t"
+        "xor.b32 x0, %2, %5;\n\t"
+        "mad.lo.u32 y0, x0, %8, %10;\n\t"
+        "mad.lo.u32 d1, %6, %9, %4;\n\t"
+        "mad.lo.u32 d2, %3, %9, %7;\n\t"
         "lop3.b32 %0, y0, x0, %0, 0xBA;\n\t"
-        "lop3.b32 %0, y1, x1, %0, 0xBA;\n\t"
+        "lop3.b32 %1, d1, d2, %1, 0xEA;\n\t"
         "}"
-        : "+r"(acc)
-        : "r"(a), "r"(a2), "r"(b0), "r"(b1), "r"(one), "r"(neg_ones));
+        : "+r"(accA), "+r"(accB)
+        : "r"(a), "r"(a2), "r"(aG), "r"(b0), "r"(b1), "r"(bG), "r"(one), "r"(mone), "r"(neg_ones));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -150,9 +158,9 @@ constexpr int SB = 128;            // columns per sub-tile
 constexpr int NQ = SB / 4;         // hit-mask words per thread and sub-tile
 
 template <int MODE>
-__global__ void __launch_bounds__(NT, 2) edges_kernel(const EdgeWork w, const EdgeOut out)
+__global__ void __launch_bounds__(NT, 3) edges_kernel(const EdgeWork w, const EdgeOut out)
 {
-    constexpr int NW = MODE == 1 ? 2 : (MODE == 2 ? 3 : 1);
+    constexpr int NW = MODE == 3 ? 1 : 3;
     __shared__ __align__(16) uint32_t s_a[ROW_TILE];
     __shared__ __align__(16) uint32_t s_b[NW][SB];
     __shared__ uint32_t s_mask[NQ * NT];
@@ -160,6 +168,7 @@ __global__ void __launch_bounds__(NT, 2) edges_kernel(const EdgeWork w, const Ed
 
     const int tid = threadIdx.x;
     const uint32_t one = w.one;
+    const uint32_t mone = 0u - one;                                            // runtime -1: a*mone + c is c - a on the FMA pipe
     const uint32_t neg10 = 0u - F10_ONES * one, neg16 = 0u - F16_ONES * one;   // runtime values: not foldable
 
     for (;;) {
@@ -200,7 +209,7 @@ __global__ void __launch_bounds__(NT, 2) edges_kernel(const EdgeWork w, const Ed
                 const uint64_t idx = sub + tid;
                 const uint32_t b = idx < col_hi ? __ldg(&w.sorted[idx]) : 0u;   // pad: never the larger of a pair
                 s_b[0][tid] = b;
-                if constexpr (MODE == 1) s_b[1][tid] = t1_word_b(b);
+                if constexpr (MODE == 1) { s_b[1][tid] = t1_word_b(b); s_b[2][tid] = t1_word_b(b) | T1_GUARD; }
                 if constexpr (MODE == 2) { s_b[1][tid] = b >> 2; s_b[2][tid] = b << 2; }
             }
             __syncthreads();
@@ -212,14 +221,16 @@ __global__ void __launch_bounds__(NT, 2) edges_kernel(const EdgeWork w, const Ed
                 for (int xq = 0; xq < NQ; xq++) {
                     const uint4 B0 = *reinterpret_cast<const uint4*>(&s_b[0][xq * 4]);
                     const uint4 B1 = *reinterpret_cast<const uint4*>(&s_b[1][xq * 4]);
+                    const uint4 BG = *reinterpret_cast<const uint4*>(&s_b[2][xq * 4]);
                     uint32_t hits = 0;
 #pragma unroll
                     for (int k = 0; k < 4; k++) {
-                        const uint32_t b0 = pick4(B0, k), b1 = pick4(B1, k);
-                        uint32_t acc = 0;
+                        const uint32_t b0 = pick4(B0, k), b1 = pick4(B1, k), bG = pick4(BG, k);
+                        uint32_t accA = 0, accB = 0;
 #pragma unroll
-                        for (int r = 0; r < RA; r++) pair_t1_acc(a[r], a2[r], b0, b1, one, neg16, acc);
-                        if (acc & F16_HIGH) {   // ~1.4e-3 per thread and column on random data
+                        for (int r = 0; r < RA; r++) pair_t1_acc(a[r], a2[r], a2[r] | T1_GUARD, b0, b1, bG, one, mone, neg16, accA, accB);
+                        const uint32_t acc = (accA & F16_HIGH) | (accB & T1_GUARD);
+                        if (acc) {   // ~1.4e-3 per thread and column on random data
 #pragma unroll
                             for (int r = 0; r < RA; r++) {
                                 const uint32_t x0 = a[r] ^ b0, x1 = a2[r] ^ b1;

@@ -39,10 +39,10 @@ from badger_b200 import synth  # noqa: E402
 METRIC = "barcode_pairs_scored_per_s"
 UNIT = "pairs/s"
 # integer instructions the edge kernel issues per pair in stage 1 (DESIGN.md "edges_kernel"):
-#   t=1: 2 XOR + 2 IMAD(sub) + 2 LOP3                      (ALU pipe 4, FMA pipe 2)
+#   t=1: XOR + 3 IMAD(sub) + 2 LOP3                        (ALU pipe 3, FMA pipe 3)
 #   t=2: 3 XOR + 3 IMAD(sub) + 3 LOP3 + test + set-bit     (ALU pipe 8, FMA pipe 3)
 A_PAIR = {1: 6, 2: 11}
-A_PAIR_ALU = {1: 4, 2: 8}
+A_PAIR_ALU = {1: 3, 2: 8}
 A_PAIR_SURVEY = {1: 15, 2: 25}   # SURVEY.md §8(d) nominal figure, reported alongside
 
 
@@ -226,6 +226,13 @@ def run_b200(args):
         badger_b200._lib.check(L.bdg_dev_edges_build(d_sorted.data_ptr(), n, t, rank, world, d_a.data_ptr(), d_b.data_ptr(),
                                                      d_d.data_ptr(), cap, d_count.data_ptr(), stream.cuda_stream))
 
+    step_dev()
+    torch.cuda.synchronize()
+    if int(d_count.item()) > cap:          # dense data (t >= 2): size the edge buffers from the first count
+        cap = int(d_count.item()) + 1024
+        d_a = torch.empty(cap, dtype=torch.int32, device=dev)
+        d_b = torch.empty(cap, dtype=torch.int32, device=dev)
+        d_d = torch.empty(cap, dtype=torch.uint8, device=dev)
     for _ in range(max(args.warmup, 3)):
         step_dev()
     torch.cuda.synchronize()

@@ -171,6 +171,18 @@ def test_edges_edge_cases():
     assert a.size == 0
 
 
+def test_edge_buffer_regrow(monkeypatch):
+    """The library sizes its edge buffer from a guess and re-runs the (deterministic) kernel when it was too small."""
+    s = clustered_set(55, 40, 60000, 0.05)
+    want = edge_rows(*ops.edges_build(s, 2))
+    assert want.shape[0] > (1 << 16) + 1024 + s.size          # more edges than the forced guess below
+    badger_b200.lib().bdg_shutdown()                            # drop the grown workspaces
+    monkeypatch.setenv("BDG_EDGE_CAP_PER_ROW", "1")
+    badger_b200.init()
+    got = edge_rows(*ops.edges_build(s, 2))
+    assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize("nparts", [2, 3, 8])
 def test_parts_union_equals_full(nparts):
     s = clustered_set(77, 200, 20000, 0.06)
