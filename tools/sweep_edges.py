@@ -1,0 +1,67 @@
+#!/usr/bin/env python3
+"""Development sweep: time the edge kernel (device-resident input, CUDA events) over sizes, thresholds and the
+BDG_EDGE_* experiment switches.  Not part of the product or of bench.py."""
+import itertools
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import badger_b200  # noqa: E402
+from badger_b200 import synth  # noqa: E402
+
+
+def dataset(reads):
+    wl, cells, obs, valid, cfg = synth.make_dataset("C2", reads=reads)
+    return np.unique(obs[valid])
+
+
+def time_edges(s, t, reps=3):
+    L = badger_b200.lib()
+    dev = torch.device("cuda", 0)
+    n = int(s.size)
+    d_sorted = torch.from_numpy(s.view(np.int32)).to(dev)
+    cap = 64 * n
+    d_a = torch.empty(cap, dtype=torch.int32, device=dev); d_b = torch.empty(cap, dtype=torch.int32, device=dev)
+    d_d = torch.empty(cap, dtype=torch.uint8, device=dev); d_c = torch.zeros(1, dtype=torch.int64, device=dev)
+    st = torch.cuda.current_stream()
+
+    def go():
+        badger_b200._lib.check(L.bdg_dev_edges_build(d_sorted.data_ptr(), n, t, 0, 1, d_a.data_ptr(), d_b.data_ptr(), d_d.data_ptr(),
+                                                     cap, d_c.data_ptr(), st.cuda_stream))
+    go(); go()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record(st); go(); e1.record(st); e1.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return best, int(d_c.item())
+
+
+def main():
+    badger_b200.init([0])
+    sizes = [int(x) for x in os.environ.get("SWEEP_READS", "400000,1000000").split(",")]
+    ts = [int(x) for x in os.environ.get("SWEEP_T", "1,2").split(",")]
+    knobs = {k: os.environ.get("SWEEP_" + k, d).split(",") for k, d in (("IMPL", "0,1"), ("OCC", ""), ("ITEMS", "16"))}
+    data = {r: dataset(r) for r in sizes}
+    for r, t in itertools.product(sizes, ts):
+        s = data[r]
+        n = s.size
+        for impl, occ, items in itertools.product(knobs["IMPL"], knobs["OCC"], knobs["ITEMS"]):
+            os.environ["BDG_EDGE_IMPL"] = impl
+            if occ:
+                os.environ["BDG_EDGE_OCC"] = occ
+            else:
+                os.environ.pop("BDG_EDGE_OCC", None)
+            os.environ["BDG_EDGE_ITEMS"] = items
+            ms, edges = time_edges(s, t)
+            print("reads=%8d N=%8d t=%d impl=%s occ=%-2s items=%-3s  %9.3f ms  %.3e pairs/s  edges=%d" % (
+                r, n, t, impl, occ or "-", items, ms, n * (n - 1) / 2 / (ms * 1e-3), edges), flush=True)
+
+
+if __name__ == "__main__":
+    main()
