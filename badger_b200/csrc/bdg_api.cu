@@ -70,52 +70,59 @@ int owner_of_tile(uint64_t I, int P)
     return (int)(m < (uint64_t)P ? m : 2ull * P - 1 - m);
 }
 
-int grid_for(const void* kernel, int* out)
+int grid_for(const void* kernel, int* out, int threads = bdg::NT)
 {
     int dev = 0, sms = 0, occ = 0;
     CU_TRY(cudaGetDevice(&dev));
     CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, bdg::NT, 0));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, 0));
     if (occ < 1) occ = 1;
     *out = sms * occ;
     return BDG_OK;
 }
 
-// ---- the work plan of one part: owned row tiles, column chunks per tile --------------------------------
+// ---- the work plan of one part: owned row groups (256 rows, one warp each), column chunks per group ----
+// Ownership is dealt in tiles of BDG_ROW_TILE rows (8 groups), boustrophedon over the parts.
 struct Plan {
-    std::vector<uint32_t> tile_ids;
+    std::vector<uint32_t> group_ids;
     std::vector<uint32_t> item_start;
-    uint32_t chunk_cols = 256;
+    uint32_t chunk_cols = bdg::SB_MAX;
     uint64_t pairs = 0;
 };
 
-void build_plan(size_t N, int part, int nparts, int grid, Plan& p)
+void build_plan(size_t N, int part, int nparts, int workers, Plan& p)
 {
     const uint64_t tiles = (N + bdg::ROW_TILE - 1) / bdg::ROW_TILE;
-    p.tile_ids.clear();
+    const uint64_t groups = (N + bdg::GROUP - 1) / bdg::GROUP;
+    constexpr uint64_t GPT = bdg::ROW_TILE / bdg::GROUP;
+    p.group_ids.clear();
     p.pairs = 0;
     for (uint64_t I = 0; I < tiles; I++) {
         if (owner_of_tile(I, nparts) != part) continue;
-        p.tile_ids.push_back((uint32_t)I);
         const uint64_t r0 = I * bdg::ROW_TILE, r1 = std::min<uint64_t>(N, r0 + bdg::ROW_TILE);
         const uint64_t n = r1 - r0;                       // rows i in [r0,r1): N-1-i partners each
         p.pairs += n * (N - 1) - (r0 + r1 - 1) * n / 2;
+        for (uint64_t g = I * GPT; g < std::min(groups, (I + 1) * GPT); g++) p.group_ids.push_back((uint32_t)g);
     }
-    // aim at >= 16 work items per resident CTA so that the dynamic scheduler can level the load
-    const double want_items = 16.0 * std::max(grid, 1);
-    double cols = ((double)p.pairs / bdg::ROW_TILE) / want_items;
-    uint64_t cc = (uint64_t)cols / 256 * 256;
-    cc = std::min<uint64_t>(std::max<uint64_t>(cc, 256), 16384);
+    // aim at >= 16 work items per resident warp so that the dynamic scheduler can level the load
+    double per_worker = 16.0;
+    if (const char* e = getenv("BDG_EDGE_ITEMS")) per_worker = std::max(1.0, atof(e));
+    const double want_items = per_worker * std::max(workers, 1);
+    const double cols = ((double)p.pairs / bdg::GROUP) / want_items;
+    uint64_t cc = (uint64_t)cols / bdg::SB_MAX * bdg::SB_MAX;
+    cc = std::min<uint64_t>(std::max<uint64_t>(cc, 4 * bdg::SB_MAX), 1u << 17);
     p.chunk_cols = (uint32_t)cc;
-    p.item_start.assign(p.tile_ids.size() + 1, 0);
+    p.item_start.assign(p.group_ids.size() + 1, 0);
     uint64_t acc = 0;
-    for (size_t k = 0; k < p.tile_ids.size(); k++) {
+    for (size_t k = 0; k < p.group_ids.size(); k++) {
         p.item_start[k] = (uint32_t)acc;
-        const uint64_t ncols = N - (uint64_t)p.tile_ids[k] * bdg::ROW_TILE;
+        const uint64_t ncols = N - (uint64_t)p.group_ids[k] * bdg::GROUP;
         acc += (ncols + cc - 1) / cc;
     }
-    p.item_start[p.tile_ids.size()] = (uint32_t)acc;
+    p.item_start[p.group_ids.size()] = (uint32_t)acc;
 }
+
+constexpr size_t PLAN_HDR = 32;   // [item counter u32 | pad | sub-tiles u64 | full sub-tiles u64 | pad]
 
 // Launch the edge kernel for one part on the current device / stream.  d_count is zeroed on the stream.
 int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts, uint32_t* d_a, uint32_t* d_b,
@@ -128,42 +135,44 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
     const void* kern = t == 1 ? (const void*)bdg::edges_kernel<1> : t == 2 ? (const void*)bdg::edges_kernel<2>
                                                                            : (const void*)bdg::edges_kernel<3>;
     int grid = 0;
-    if (int rc = grid_for(kern, &grid)) return rc;
+    if (int rc = grid_for(kern, &grid, bdg::ENT)) return rc;
     Plan plan;
-    build_plan(N, part, nparts, grid, plan);
-    const uint32_t n_items = plan.item_start.back();
+    build_plan(N, part, nparts, grid * bdg::EW, plan);
+    const uint64_t n_items64 = plan.item_start.empty() ? 0 : plan.item_start.back();
+    const uint32_t n_items = (uint32_t)n_items64;
     if (n_items == 0) return BDG_OK;
-    const size_t nb_tiles = plan.tile_ids.size() * sizeof(uint32_t), nb_items = plan.item_start.size() * sizeof(uint32_t);
-    char* d_plan = nullptr;   // [counter | tile_ids | item_start]
+    const size_t nb_groups = plan.group_ids.size() * sizeof(uint32_t), nb_items = plan.item_start.size() * sizeof(uint32_t);
+    char* d_plan = nullptr;   // [header | group_ids | item_start]
     bool plan_async = true;
     if (plan_ws) {            // caller-provided grow-only workspace (one in-flight call per device)
-        if (cudaError_t e = (cudaError_t)plan_ws->ensure(16 + nb_tiles + nb_items))
+        if (cudaError_t e = (cudaError_t)plan_ws->ensure(PLAN_HDR + nb_groups + nb_items))
             return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "plan workspace: %s", cudaGetErrorString(e));
         d_plan = (char*)plan_ws->p;
         plan_async = false;
     } else {
-        CU_TRY(cudaMallocAsync((void**)&d_plan, 16 + nb_tiles + nb_items, st));
+        CU_TRY(cudaMallocAsync((void**)&d_plan, PLAN_HDR + nb_groups + nb_items, st));
     }
-    CU_TRY(cudaMemsetAsync(d_plan, 0, 16, st));
-    CU_TRY(cudaMemcpyAsync(d_plan + 16, plan.tile_ids.data(), nb_tiles, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemcpyAsync(d_plan + 16 + nb_tiles, plan.item_start.data(), nb_items, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemsetAsync(d_plan, 0, PLAN_HDR, st));
+    CU_TRY(cudaMemcpyAsync(d_plan + PLAN_HDR, plan.group_ids.data(), nb_groups, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_plan + PLAN_HDR + nb_groups, plan.item_start.data(), nb_items, cudaMemcpyHostToDevice, st));
     bdg::EdgeWork w;
     w.sorted = d_sorted;
     w.N = (uint32_t)N;
     w.t = t;
     w.T = bdg::qgram_threshold(t);
-    w.tile_ids = (const uint32_t*)(d_plan + 16);
-    w.item_start = (const uint32_t*)(d_plan + 16 + nb_tiles);
-    w.K = (uint32_t)plan.tile_ids.size();
+    w.group_ids = (const uint32_t*)(d_plan + PLAN_HDR);
+    w.item_start = (const uint32_t*)(d_plan + PLAN_HDR + nb_groups);
+    w.K = (uint32_t)plan.group_ids.size();
     w.n_items = n_items;
     w.chunk_cols = plan.chunk_cols;
     w.item_counter = (unsigned int*)d_plan;
+    w.stats = plan_async ? nullptr : (unsigned long long*)(d_plan + 8);
     w.one = 1u;
     bdg::EdgeOut o{d_a, d_b, d_d, d_count, (unsigned long long)cap};
-    const int blocks = (int)std::min<uint64_t>((uint64_t)grid, n_items);
-    if (t == 1) bdg::edges_kernel<1><<<blocks, bdg::NT, 0, st>>>(w, o);
-    else if (t == 2) bdg::edges_kernel<2><<<blocks, bdg::NT, 0, st>>>(w, o);
-    else bdg::edges_kernel<3><<<blocks, bdg::NT, 0, st>>>(w, o);
+    const int blocks = (int)std::min<uint64_t>((uint64_t)grid, (n_items + bdg::EW - 1) / bdg::EW);
+    if (t == 1) bdg::edges_kernel<1><<<blocks, bdg::ENT, 0, st>>>(w, o);
+    else if (t == 2) bdg::edges_kernel<2><<<blocks, bdg::ENT, 0, st>>>(w, o);
+    else bdg::edges_kernel<3><<<blocks, bdg::ENT, 0, st>>>(w, o);
     g_launches++;
     CU_TRY(cudaGetLastError());
     if (plan_async) CU_TRY(cudaFreeAsync(d_plan, st));
@@ -274,6 +283,18 @@ int bdg_dev_edges_build(const uint32_t* d_sorted, size_t N, int t, int part, int
     if (!d_count || (N && !d_sorted) || (cap && (!d_a || !d_b || !d_d))) return fail(BDG_ERR_ARG, "NULL pointer argument");
     DevCtx* c = ctx_of_current_device();
     return launch_edges(d_sorted, N, t, part, nparts, d_a, d_b, d_d, cap, d_count, (cudaStream_t)stream, c ? &c->plan : nullptr);
+}
+
+int bdg_dev_edges_stats(unsigned long long* sub_tiles, unsigned long long* full_tiles, void* stream)
+{
+    DevCtx* c = ctx_of_current_device();
+    if (!c || !c->plan.p) return fail(BDG_ERR_ARG, "no edge launch on this device yet");
+    unsigned long long v[2] = {0, 0};
+    CU_TRY(cudaMemcpyAsync(v, (char*)c->plan.p + 8, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    if (sub_tiles) *sub_tiles = v[0];
+    if (full_tiles) *full_tiles = v[1];
+    return BDG_OK;
 }
 
 int bdg_dev_pack16(const char* d_seqs, size_t R, uint32_t* d_out, uint8_t* d_valid, void* stream)

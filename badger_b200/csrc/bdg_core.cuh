@@ -92,6 +92,84 @@ BDG_HD bool prefilter_t2(uint32_t a, uint32_t b)
 }
 
 // ---------------------------------------------------------------------------------------------
+// The prefilters split in two for the tiled edge kernel (bdg_edges.cuh).  The barcode array is SORTED, so
+// inside a tile (a run of consecutive rows x a run of consecutive columns) the high bits of a and of b
+// barely move.  Conditions that compare the TOP block of a with (a shift of) the top of b ("top" part) can
+// therefore be excluded for a whole tile from the first/last element of its rows and columns
+// (tX_top_possible); only the remaining conditions ("light" part) have to be evaluated pair by pair.
+//
+// Which conditions are needed (tighter than the 9/4 fields tested above): an insertion in front of a[i]
+// is charged to the block holding a[i], so every operation touches one block, and an untouched block sits
+// on diagonal (#insertions - #deletions before it).  Block 0 has nothing before it: diagonal 0 only.
+//   t = 1, blocks a[0:8] | a[8:16]:   light  a[0:8]==b[0:8]   (kernel compares 15 of its 16 bits)
+//                                     top    a[8:16]==b[8:16], a[8:15]==b[9:16], a[9:16]==b[8:15]
+//   t = 2, blocks a[0:5] | a[5:10] | a[10:15]:
+//                                     light  a[0:5]==b[0:5], a[5:10]==b[5:10], a[5:10]==b[6:11], a[5:10]==b[4:9]
+//                                     top    a[10:15]==b[10:15], a[10:15]==b[11:16], a[10:15]==b[9:14]
+// tests/test_core_host.py checks  D <= t  =>  light || top  on the oracle's distances, in both frames.
+// ---------------------------------------------------------------------------------------------
+BDG_HD bool t1_light(uint32_t a, uint32_t b) { return ((a ^ b) & 0x7FFFu) == 0; }
+
+BDG_HD bool t1_top(uint32_t a, uint32_t b)
+{
+    return (a >> 16) == (b >> 16) || ((a >> 16) & 0x3FFFu) == (b >> 18) || (a >> 18) == ((b >> 16) & 0x3FFFu);
+}
+
+// t=2 light test words: two 10-bit fields in the two 16-bit lanes, bit 10 of each lane is a guard position
+//   word A:  lane0 = block 0, lane1 = block 1                 (diagonal 0)
+//   word B:  a: block 1 in both lanes;  b: lane0 = b[6:11] (diagonal +1), lane1 = b[4:9] (diagonal -1)
+BDG_HD uint32_t t2_word_aA(uint32_t a) { return (a & 0x3FFu) | (((a >> 10) & 0x3FFu) << 16); }
+BDG_HD uint32_t t2_word_aB(uint32_t a) { return ((a >> 10) & 0x3FFu) * 0x00010001u; }
+BDG_HD uint32_t t2_word_bA(uint32_t b) { return t2_word_aA(b); }
+BDG_HD uint32_t t2_word_bB(uint32_t b) { return ((b >> 12) & 0x3FFu) | (((b >> 8) & 0x3FFu) << 16); }
+constexpr uint32_t T2_GUARD = 0x04000400u;
+
+BDG_HD bool t2_light(uint32_t a, uint32_t b)
+{
+    // G - x keeps the guard bit of a lane iff the lane's field of x is zero (x < 2^10 per lane, no borrow across lanes)
+    const uint32_t yA = T2_GUARD - (t2_word_aA(a) ^ t2_word_bA(b));
+    const uint32_t yB = T2_GUARD - (t2_word_aB(a) ^ t2_word_bB(b));
+    return ((yA | yB) & T2_GUARD) != 0;
+}
+
+BDG_HD bool t2_top(uint32_t a, uint32_t b)
+{
+    const uint32_t f = (a >> 20) & 0x3FFu;
+    return f == ((b >> 20) & 0x3FFu) || f == (b >> 22) || f == ((b >> 18) & 0x3FFu);
+}
+
+// Interval of the field v[x : x+len) over all v in [lo, hi]: exact ends when the bits above the field do
+// not change between lo and hi (the field is then monotone in v), else the whole range.
+BDG_HD void field_range(uint32_t lo, uint32_t hi, int x, int len, uint32_t& flo, uint32_t& fhi)
+{
+    const uint32_t mask = (len >= 32) ? 0xFFFFFFFFu : ((1u << len) - 1u);
+    const bool same_above = (x + len >= 32) || ((lo >> (x + len)) == (hi >> (x + len)));
+    flo = same_above ? ((lo >> x) & mask) : 0u;
+    fhi = same_above ? ((hi >> x) & mask) : mask;
+}
+
+BDG_HD bool fields_may_meet(uint32_t alo, uint32_t ahi, int xa, uint32_t blo, uint32_t bhi, int xb, int len)
+{
+    uint32_t al, ah, bl, bh;
+    field_range(alo, ahi, xa, len, al, ah);
+    field_range(blo, bhi, xb, len, bl, bh);
+    return al <= bh && bl <= ah;
+}
+
+// Can ANY pair (a in [alo,ahi], b in [blo,bhi]) satisfy a top condition?  false => the whole tile skips them.
+BDG_HD bool t1_top_possible(uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi)
+{
+    return fields_may_meet(alo, ahi, 16, blo, bhi, 16, 16) || fields_may_meet(alo, ahi, 16, blo, bhi, 18, 14) ||
+           fields_may_meet(alo, ahi, 18, blo, bhi, 16, 14);
+}
+
+BDG_HD bool t2_top_possible(uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi)
+{
+    return fields_may_meet(alo, ahi, 20, blo, bhi, 20, 10) || fields_may_meet(alo, ahi, 20, blo, bhi, 22, 10) ||
+           fields_may_meet(alo, ahi, 20, blo, bhi, 18, 10);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Stage-2, exact for small distances: returns min(D(a,b), 3) for a != b, i.e. 1, 2, or 3 (= "3 or more").
 // With plain_only it returns min(ed(a,b), 3) instead (no truncated variants; barcode_graph.py:379).
 //

@@ -1,0 +1,357 @@
+// bdg_edges.cuh -- the edge-construction kernel (sm_100a): reference index.py:77-93 (candidate filter) +
+// barcode_graph.py:224-249 (3-way edit-distance verify, emit) over every unordered pair of a SORTED array of
+// distinct packed barcodes.
+//
+// Shape of the computation
+//   * worker = one WARP.  Workers pull (row group, column chunk) items from an atomic counter: a row group is
+//     256 consecutive rows (lane l holds rows row0 + r*32 + l, r = 0..7, in registers), a chunk is a run of
+//     columns right of the group's first row.  No block-level barrier anywhere: a warp stages its own column
+//     sub-tiles in its own slice of shared memory (__syncwarp only), so warps never wait for one another.
+//   * per column sub-tile (SB columns) the warp first asks whether ANY pair of the tile can meet one of the
+//     "top" conditions of the prefilter (bdg_core.cuh: interval test on the first/last row and column - the
+//     array is sorted, so the high bits of a tile's rows and columns barely move).  ~99 % of the tiles cannot:
+//     they run the LIGHT loop, which evaluates only the remaining conditions, pair by pair, in 1.25 (t=1) or
+//     6 (t=2) integer instructions per pair, split over the ALU pipe (LOP3) and the FMA pipe (IMAD).  The rest
+//     (tiles next to the diagonal and the few whose top fields line up) run the FULL prefilter.
+//   * stage 1 leaves one hit bit per pair in registers (32 pairs per word: 4 columns x 8 rows); every
+//     16 columns the warp votes, and lanes with hits append (row, column) codes to the warp's candidate queue
+//     in shared memory.
+//   * stage 2 is warp-cooperative: whenever the queue holds >= 32 candidates, each lane takes one, evaluates
+//     D and S exactly (bdg_core.cuh) and the warp appends the edges it found with one atomic.  The rare,
+//     expensive exact test therefore runs with 32 busy lanes instead of one.
+// MODE 1: t = 1.  MODE 2: t = 2.  MODE 3: any t, no prefilter (every pair goes through stage 2).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "bdg_core.cuh"
+
+namespace bdg {
+
+constexpr int EW = 8;              // warps per CTA
+constexpr int ENT = EW * 32;       // threads per CTA
+constexpr int RA = 8;              // rows per lane
+constexpr int GROUP = 32 * RA;     // rows per work item (one warp)
+constexpr int ROW_TILE = 2048;     // == BDG_ROW_TILE: rows are dealt to parts in tiles of 8 groups
+constexpr int QCAP = 256;          // candidate queue entries per warp
+constexpr unsigned FULL = 0xffffffffu;
+
+template <int MODE> struct EdgeCfg { static constexpr int SB = (MODE == 1) ? 256 : 128; };   // columns per sub-tile
+constexpr int SB_MAX = 256;
+
+struct EdgeOut {
+    uint32_t* a;
+    uint32_t* b;
+    uint8_t* d;
+    unsigned long long* count;
+    unsigned long long cap;
+};
+
+struct EdgeWork {
+    const uint32_t* sorted;     // N strictly increasing barcodes
+    uint32_t N;
+    int t;                      // edit-distance threshold
+    int T;                      // q-gram threshold T(t)
+    const uint32_t* group_ids;  // K row groups (GROUP rows each) owned by this part
+    const uint32_t* item_start; // K+1 prefix sums of column chunks per owned group
+    uint32_t K;
+    uint32_t n_items;
+    uint32_t chunk_cols;        // columns per work item (multiple of SB_MAX, <= 2^17)
+    unsigned int* item_counter; // dynamic scheduler
+    unsigned long long* stats;  // optional [2]: sub-tiles visited, sub-tiles that ran the full prefilter
+    uint32_t one;               // == 1, opaque to the compiler: x*(-one)+c keeps the subtraction on the FMA pipe (IMAD)
+};
+
+// ---- output: warp-aggregated append (one atomic per warp that has anything to emit) ---------------
+__device__ __forceinline__ void emit_warp(bool ok, uint32_t a, uint32_t b, int d, const EdgeOut& out)
+{
+    const unsigned m = __ballot_sync(FULL, ok);
+    if (m == 0) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(m) - 1;
+    unsigned long long base = 0;
+    if (lane == leader) base = atomicAdd(out.count, (unsigned long long)__popc(m));
+    base = __shfl_sync(FULL, base, leader);
+    if (ok) {
+        const unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
+        if (pos < out.cap) {
+            out.a[pos] = a;
+            out.b[pos] = b;
+            out.d[pos] = (uint8_t)d;
+        }
+    }
+}
+
+// exact stage: D (case analysis for t<=2, bit-vector pass otherwise), then S only for survivors
+template <int MODE>
+__device__ __forceinline__ int exact_edge(uint32_t a, uint32_t b, int t, int T)
+{
+    if (!(a < b)) return 0;   // rows are sorted and distinct: index order == value order
+    const int d = (MODE == 3) ? dist3_min(a, b) : dist_small(a, b);
+    if (d > t) return 0;
+    return qgram_score(a, b) >= T ? d : 0;
+}
+
+__device__ __forceinline__ uint32_t pick4(const uint4& v, int k)
+{
+    return k == 0 ? v.x : (k == 1 ? v.y : (k == 2 ? v.z : v.w));
+}
+
+// ---- stage-1 inner steps in PTX (so that the subtraction is an IMAD and the hit bit ONE predicated LOP3) ----
+// t=2 light, one pair: 2 XOR + 2 IMAD + LOP3(->predicate) + predicated OR.  lop3 0xA8 = (A | B) & C.
+__device__ __forceinline__ void pair_t2_light(uint32_t aA, uint32_t aB, uint32_t bA, uint32_t bB, uint32_t mone, uint32_t guard,
+                                              uint32_t& hits, const uint32_t bit)
+{
+    asm("{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b32 xA, xB, yA, yB, m;\n\t"
+        "xor.b32 xA, %1, %3;\n\t"
+        "xor.b32 xB, %2, %4;\n\t"
+        "mad.lo.u32 yA, xA, %5, %6;\n\t"
+        "mad.lo.u32 yB, xB, %5, %6;\n\t"
+        "lop3.b32 m, yA, yB, %7, 0xA8;\n\t"
+        "setp.ne.u32 p, m, 0;\n\t"
+        "@p or.b32 %0, %0, %8;\n\t"
+        "}"
+        : "+r"(hits)
+        : "r"(aA), "r"(aB), "r"(bA), "r"(bB), "r"(mone), "r"(guard), "n"(T2_GUARD), "r"(bit));
+}
+
+// t=1 light, one row against two packed words (= 4 columns): 2 XOR + 2 IMAD + 1 LOP3.  lop3 0xFE = A | B | C.
+constexpr uint32_t T1L_GUARD = 0x80008000u;
+__device__ __forceinline__ void quad_t1_light(uint32_t aw, uint32_t p0, uint32_t p1, uint32_t mone, uint32_t guard, uint32_t& acc)
+{
+    asm("{\n\t"
+        ".reg .b32 x0, x1, y0, y1;\n\t"
+        "xor.b32 x0, %1, %2;\n\t"
+        "xor.b32 x1, %1, %3;\n\t"
+        "mad.lo.u32 y0, x0, %4, %5;\n\t"
+        "mad.lo.u32 y1, x1, %4, %5;\n\t"
+        "lop3.b32 %0, y0, y1, %0, 0xFE;\n\t"
+        "}"
+        : "+r"(acc)
+        : "r"(aw), "r"(p0), "r"(p1), "r"(mone), "r"(guard));
+}
+
+// ---- per-warp context -------------------------------------------------------------------------------
+struct WarpCtx {
+    uint32_t* q;           // candidate queue (shared)
+    int* qn;               // its fill count (shared)
+    const uint32_t* sorted;
+    uint32_t N;
+    uint64_t row0, col_lo, col_hi;
+    int t, T, lane;
+};
+
+// stage 2 on full batches of 32 candidates (all == true: also the partial rest)
+template <int MODE>
+__device__ __forceinline__ void drain(const WarpCtx& c, const EdgeOut& out, bool all)
+{
+    __syncwarp();
+    int n = *(volatile int*)c.qn;
+    n = n < QCAP ? n : QCAP;
+    __syncwarp();
+    while (n >= 32 || (all && n > 0)) {
+        const int take = n >= 32 ? 32 : n;
+        n -= take;
+        bool ok = false;
+        uint32_t a = 0, b = 0;
+        int d = 0;
+        if (c.lane < take) {
+            const uint32_t e = c.q[n + c.lane];
+            const uint64_t row = c.row0 + (e & 255u), col = c.col_lo + (e >> 8);
+            if (row < c.N && col < c.col_hi) {
+                a = __ldg(&c.sorted[row]);
+                b = __ldg(&c.sorted[col]);
+                d = exact_edge<MODE>(a, b, c.t, c.T);
+                ok = d > 0;
+            }
+        }
+        emit_warp(ok, a, b, d, out);
+    }
+    if (c.lane == 0) *c.qn = n;
+    __syncwarp();
+}
+
+// append the set bits of h[0..3] (bit k*8+r of h[s] = column colrel + 4s + k, row r*32+lane) to the queue
+template <int MODE>
+__device__ __forceinline__ void push_hits(uint32_t (&h)[4], uint32_t colrel, const WarpCtx& c, const EdgeOut& out)
+{
+    do {
+        bool room = true;
+#pragma unroll
+        for (int s = 0; s < 4; s++) {
+            while (room && h[s]) {
+                const int j = __ffs(h[s]) - 1;
+                const int slot = atomicAdd(c.qn, 1);
+                if (slot >= QCAP) { room = false; break; }
+                c.q[slot] = ((colrel + 4 * s + (j >> 3)) << 8) | (uint32_t)((j & 7) * 32 + c.lane);
+                h[s] &= h[s] - 1;
+            }
+        }
+        drain<MODE>(c, out, false);
+    } while (__any_sync(FULL, (h[0] | h[1] | h[2] | h[3]) != 0));
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(ENT, 3) edges_kernel(const EdgeWork w, const EdgeOut out)
+{
+    constexpr int SB = EdgeCfg<MODE>::SB;
+    constexpr int NB = SB / 32;                        // staged columns per lane
+    __shared__ __align__(16) uint32_t s_raw[EW][SB];                          // the sub-tile's barcodes
+    __shared__ __align__(16) uint32_t s_w0[EW][MODE == 1 ? SB / 2 : (MODE == 2 ? SB : 4)];   // t1: packed low-15 pairs; t2: word A
+    __shared__ __align__(16) uint32_t s_w1[EW][MODE == 2 ? SB : 4];          // t2: word B
+    __shared__ uint32_t s_q[EW][QCAP];
+    __shared__ int s_qn[EW];
+
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t* const raw = s_raw[wid];
+    uint32_t* const w0 = s_w0[wid];
+    uint32_t* const w1 = s_w1[wid];
+    const uint32_t mone = 0u - w.one;                                         // runtime -1
+    const uint32_t g2 = T2_GUARD * w.one, g1 = T1L_GUARD * w.one;             // runtime guards: keep IMAD from folding
+    (void)g1; (void)g2; (void)w0; (void)w1;
+
+    WarpCtx c;
+    c.q = s_q[wid]; c.qn = &s_qn[wid]; c.sorted = w.sorted; c.N = w.N; c.t = w.t; c.T = w.T; c.lane = lane;
+    if (lane == 0) s_qn[wid] = 0;
+    __syncwarp();
+    unsigned long long n_sub = 0, n_full = 0;
+
+    for (;;) {
+        uint32_t item = 0, k = 0, j = 0;
+        if (lane == 0) {
+            item = atomicAdd(w.item_counter, 1u);
+            if (item < w.n_items) {
+                uint32_t lo = 0, hi = w.K;   // largest k with item_start[k] <= item
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (__ldg(&w.item_start[mid]) <= item) lo = mid; else hi = mid;
+                }
+                k = lo;
+                j = item - __ldg(&w.item_start[k]);
+            }
+        }
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= w.n_items) break;
+        k = __shfl_sync(FULL, k, 0);
+        j = __shfl_sync(FULL, j, 0);
+        c.row0 = (uint64_t)__ldg(&w.group_ids[k]) * GROUP;
+        c.col_lo = c.row0 + (uint64_t)j * w.chunk_cols;
+        c.col_hi = min((uint64_t)w.N, c.col_lo + w.chunk_cols);
+
+        uint32_t a[RA];
+        uint32_t aw0[RA], aw1[RA];   // light-loop row words (t1: aw0 only)
+#pragma unroll
+        for (int r = 0; r < RA; r++) {
+            const uint64_t idx = c.row0 + (uint64_t)r * 32 + lane;
+            a[r] = idx < w.N ? __ldg(&w.sorted[idx]) : 0xFFFFFFFFu;
+            if constexpr (MODE == 1) { aw0[r] = (a[r] & 0x7FFFu) * 0x00010001u; aw1[r] = 0; }
+            else if constexpr (MODE == 2) { aw0[r] = t2_word_aA(a[r]); aw1[r] = t2_word_aB(a[r]); }
+            else { aw0[r] = aw1[r] = 0; }
+        }
+        const uint32_t a_lo = __ldg(&w.sorted[c.row0]);
+        const uint32_t a_hi = __ldg(&w.sorted[min((uint64_t)w.N, c.row0 + GROUP) - 1]);
+
+        uint32_t nb[NB];             // prefetched columns of the next sub-tile
+#pragma unroll
+        for (int i = 0; i < NB; i++) {
+            const uint64_t idx = c.col_lo + (uint64_t)i * 32 + lane;
+            nb[i] = idx < c.col_hi ? __ldg(&w.sorted[idx]) : 0u;
+        }
+
+        for (uint64_t sub = c.col_lo; sub < c.col_hi; sub += SB) {
+            __syncwarp();            // every lane is done with the previous sub-tile's words
+#pragma unroll
+            for (int i = 0; i < NB; i++) {
+                raw[i * 32 + lane] = nb[i];
+                if constexpr (MODE == 2) { w0[i * 32 + lane] = t2_word_bA(nb[i]); w1[i * 32 + lane] = t2_word_bB(nb[i]); }
+            }
+            __syncwarp();
+            if constexpr (MODE == 1) {
+#pragma unroll
+                for (int i = 0; i < NB / 2; i++) {
+                    const uint2 p = *reinterpret_cast<const uint2*>(&raw[2 * (i * 32 + lane)]);
+                    w0[i * 32 + lane] = (p.x & 0x7FFFu) | ((p.y & 0x7FFFu) << 16);
+                }
+                __syncwarp();
+            }
+            if (sub + SB < c.col_hi) {
+#pragma unroll
+                for (int i = 0; i < NB; i++) {
+                    const uint64_t idx = sub + SB + (uint64_t)i * 32 + lane;
+                    nb[i] = idx < c.col_hi ? __ldg(&w.sorted[idx]) : 0u;
+                }
+            }
+            const int ncols = (int)min((uint64_t)SB, c.col_hi - sub);
+            const uint32_t colrel0 = (uint32_t)(sub - c.col_lo);
+            bool full = true;
+            if constexpr (MODE == 1) full = t1_top_possible(a_lo, a_hi, raw[0], raw[ncols - 1]);
+            if constexpr (MODE == 2) full = t2_top_possible(a_lo, a_hi, raw[0], raw[ncols - 1]);
+            n_sub++; n_full += full ? 1 : 0;
+
+            if (!full) {
+                // ------------------------------ light loop: 16 columns per vote ------------------------------
+#pragma unroll 1
+                for (int cb = 0; cb < SB; cb += 16) {
+                    uint32_t h[4] = {0u, 0u, 0u, 0u};
+                    if constexpr (MODE == 1) {
+                        const uint4 P0 = *reinterpret_cast<const uint4*>(&w0[cb / 2]);
+                        const uint4 P1 = *reinterpret_cast<const uint4*>(&w0[cb / 2 + 4]);
+#pragma unroll
+                        for (int s = 0; s < 4; s++) {
+                            const uint32_t p0 = s < 2 ? pick4(P0, 2 * s) : pick4(P1, 2 * s - 4);
+                            const uint32_t p1 = s < 2 ? pick4(P0, 2 * s + 1) : pick4(P1, 2 * s - 3);
+                            uint32_t acc = 0;
+#pragma unroll
+                            for (int r = 0; r < RA; r++) quad_t1_light(aw0[r], p0, p1, mone, g1, acc);
+                            if (acc & T1L_GUARD) {      // ~1e-3 per lane and step on random data
+                                const uint4 B = *reinterpret_cast<const uint4*>(&raw[cb + 4 * s]);
+#pragma unroll
+                                for (int kk = 0; kk < 4; kk++)
+#pragma unroll
+                                    for (int r = 0; r < RA; r++)
+                                        if (t1_light(a[r], pick4(B, kk))) h[s] |= 1u << (kk * 8 + r);
+                            }
+                        }
+                    } else if constexpr (MODE == 2) {
+#pragma unroll
+                        for (int s = 0; s < 4; s++) {
+                            const uint4 A4 = *reinterpret_cast<const uint4*>(&w0[cb + 4 * s]);
+                            const uint4 B4 = *reinterpret_cast<const uint4*>(&w1[cb + 4 * s]);
+#pragma unroll
+                            for (int kk = 0; kk < 4; kk++)
+#pragma unroll
+                                for (int r = 0; r < RA; r++)
+                                    pair_t2_light(aw0[r], aw1[r], pick4(A4, kk), pick4(B4, kk), mone, g2, h[s], 1u << (kk * 8 + r));
+                        }
+                    }
+                    if (__any_sync(FULL, (h[0] | h[1] | h[2] | h[3]) != 0)) push_hits<MODE>(h, colrel0 + cb, c, out);
+                }
+            } else {
+                // ------------------------------ full prefilter (rare tiles; every pair for MODE 3) -----------
+#pragma unroll 1
+                for (int cb = 0; cb < SB; cb += 4) {
+                    const uint4 B = *reinterpret_cast<const uint4*>(&raw[cb]);
+                    uint32_t h[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) {
+                        const uint32_t b = pick4(B, kk);
+#pragma unroll
+                        for (int r = 0; r < RA; r++) {
+                            const bool hit = MODE == 1 ? prefilter_t1(a[r], b) : (MODE == 2 ? prefilter_t2(a[r], b) : true);
+                            h[0] |= (hit ? 1u : 0u) << (kk * 8 + r);
+                        }
+                    }
+                    if (__any_sync(FULL, h[0] != 0)) push_hits<MODE>(h, colrel0 + cb, c, out);
+                }
+            }
+        }
+        drain<MODE>(c, out, true);   // the queue's codes are relative to this item: empty it before the next one
+    }
+    if (w.stats) {
+        if (lane == 0) { atomicAdd(&w.stats[0], n_sub); atomicAdd(&w.stats[1], n_full); }   // uniform per warp
+    }
+}
+
+}  // namespace bdg

@@ -93,6 +93,10 @@ int bdg_kmer_score(const uint32_t* q, size_t Q, const uint32_t* wl, size_t W, in
  * the number of edges found, which may exceed cap (only the first cap are stored). */
 int bdg_dev_edges_build(const uint32_t* d_sorted, size_t N, int t, int part, int nparts, uint32_t* d_a,
                         uint32_t* d_b, uint8_t* d_d, size_t cap, unsigned long long* d_count, void* stream);
+/* Tile statistics of the last bdg_dev_edges_build / bdg_edges_build* launch on the current device: column
+ * sub-tiles visited by the kernel and how many of them had to run the full prefilter (the rest ran the
+ * light loop; DESIGN.md "edges_kernel").  Synchronises the stream. */
+int bdg_dev_edges_stats(unsigned long long* sub_tiles, unsigned long long* full_tiles, void* stream);
 int bdg_dev_pack16(const char* d_seqs, size_t R, uint32_t* d_out, uint8_t* d_valid, void* stream);
 int bdg_dev_member_sorted(const uint32_t* d_sorted_wl, size_t W, const uint32_t* d_q, size_t Q, uint8_t* d_hit,
                           void* stream);

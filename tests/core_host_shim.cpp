@@ -18,4 +18,16 @@ void shim_pairs(const uint32_t* a, const uint32_t* b, size_t n, uint8_t* pre1, u
     }
 }
 int shim_edge(uint32_t a, uint32_t b, int t) { return bdg::edge_dist(a, b, t); }
+// split prefilters of the tiled edge kernel: light (per pair) and top (excluded per tile)
+void shim_split(const uint32_t* a, const uint32_t* b, size_t n, uint8_t* l1, uint8_t* t1, uint8_t* l2, uint8_t* t2)
+{
+    for (size_t i = 0; i < n; i++) {
+        l1[i] = bdg::t1_light(a[i], b[i]); t1[i] = bdg::t1_top(a[i], b[i]);
+        l2[i] = bdg::t2_light(a[i], b[i]); t2[i] = bdg::t2_top(a[i], b[i]);
+    }
+}
+int shim_top_possible(int t, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi)
+{
+    return t == 1 ? bdg::t1_top_possible(alo, ahi, blo, bhi) : bdg::t2_top_possible(alo, ahi, blo, bhi);
+}
 }

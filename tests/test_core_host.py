@@ -28,6 +28,9 @@ def shim(tmp_path_factory):
     L.shim_pairs.argtypes = [u32p, u32p, C.c_size_t] + [u8p] * 8 + [u64p]
     L.shim_edge.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
     L.shim_edge.restype = C.c_int
+    L.shim_split.argtypes = [u32p, u32p, C.c_size_t] + [u8p] * 4
+    L.shim_top_possible.argtypes = [C.c_int] + [C.c_uint32] * 4
+    L.shim_top_possible.restype = C.c_int
     return L
 
 
@@ -167,3 +170,92 @@ def test_exhaustive_neighbourhood(shim):
         D = np.fromiter((L.orc_D(int(x), int(y)) for y in b), np.int32, b.size)
         assert np.array_equal(res["dsmall"], np.minimum(D, 3))
         assert res["pre1"][D <= 1].all() and res["pre2"][D <= 2].all()
+
+
+def split(shim, a, b):
+    outs = [np.zeros(a.size, np.uint8) for _ in range(4)]
+    shim.shim_split(a, b, a.size, *outs)
+    return dict(zip(["l1", "t1", "l2", "t2"], outs))
+
+
+def test_split_filters_sound(shim):
+    """light || top is a necessary condition for D <= t in both frames (bdg_core.cuh, tiled edge kernel)."""
+    L = orc.lib()
+    tot1 = tot2 = 0
+    for seed in (5, 6, 7):
+        a, b = make_pairs(seed)
+        D = np.fromiter((L.orc_D(int(x), int(y)) for x, y in zip(a, b)), np.int32, a.size)
+        for x, y in ((a, b), (b, a)):
+            r = split(shim, x, y)
+            assert (r["l1"] | r["t1"])[D <= 1].all()
+            assert (r["l2"] | r["t2"])[D <= 2].all()
+        tot1 += int((D <= 1).sum()); tot2 += int((D == 2).sum())
+    assert tot1 > 15000 and tot2 > 15000
+    rng = np.random.default_rng(2)
+    ra = rng.integers(0, 1 << 32, 1 << 20, dtype=np.uint64).astype(np.uint32)
+    rb = rng.integers(0, 1 << 32, 1 << 20, dtype=np.uint64).astype(np.uint32)
+    r = split(shim, ra, rb)
+    assert r["l1"].mean() < 6e-5 and r["t1"].mean() < 3e-4         # 2^-15 ; 2^-16 + 2*2^-14
+    assert r["l2"].mean() < 6e-3 and r["t2"].mean() < 4.5e-3       # 4*2^-10 ; 3*2^-10
+
+
+def test_split_filters_exhaustive_neighbourhood(shim):
+    """All strings within two operations of a few seeds, all paddings: no edge candidate is lost."""
+    rng = np.random.default_rng(11)
+    L = orc.lib()
+    seeds = [int(rng.integers(0, 1 << 32)) for _ in range(4)] + [0, 0xFFFFFFFF, 0x44444444, int(synth.rank_many(["ACACACACACACACAC"])[0])]
+    for x in seeds:
+        s = [(x >> (2 * i)) & 3 for i in range(16)]
+
+        def one(seq):
+            out = []
+            for pos in range(len(seq)):
+                for c in range(4):
+                    if c != seq[pos]:
+                        out.append(seq[:pos] + [c] + seq[pos + 1:])
+                out.append(seq[:pos] + seq[pos + 1:])
+            for pos in range(len(seq) + 1):
+                for c in range(4):
+                    out.append(seq[:pos] + [c] + seq[pos:])
+            return out
+
+        lvl1 = one(s)
+        sample = [lvl1[i] for i in rng.choice(len(lvl1), 60, replace=False)]
+        neigh = set()
+        for seq in lvl1 + [y for z in sample for y in one(z)]:
+            for pad in range(16):
+                q = (seq + [pad & 3, pad >> 2])[:16]
+                neigh.add(sum(c << (2 * i) for i, c in enumerate(q)))
+        neigh.discard(x)
+        b = np.fromiter(neigh, dtype=np.uint32)
+        a = np.full(b.size, x, dtype=np.uint32)
+        D = np.fromiter((L.orc_D(int(x), int(y)) for y in b), np.int32, b.size)
+        for p, q in ((a, b), (b, a)):
+            r = split(shim, p, q)
+            assert (r["l1"] | r["t1"])[D <= 1].all()
+            assert (r["l2"] | r["t2"])[D <= 2].all()
+
+
+@pytest.mark.parametrize("t", [1, 2])
+def test_top_possible_is_conservative(shim, t):
+    """If some pair of a (row run) x (column run) tile of a sorted array meets a top condition, the interval test
+    on the runs' end points must say so."""
+    rng = np.random.default_rng(20 + t)
+    checked = hits = skipped = 0
+    for n, rows, cols in ((3000, 64, 32), (20000, 256, 128), (200000, 256, 256)):
+        base = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+        # plant near-duplicates so that top conditions do occur
+        extra = (base[: n // 4] ^ rng.integers(0, 1 << 12, n // 4, dtype=np.uint64).astype(np.uint32))
+        s = np.unique(np.concatenate([base, extra]))
+        for _ in range(300):
+            r0 = int(rng.integers(0, s.size - rows)); c0 = int(rng.integers(0, s.size - cols))
+            if rng.random() < 0.3:
+                c0 = min(s.size - cols, r0 + int(rng.integers(0, rows)))
+            A = s[r0:r0 + rows]; B = s[c0:c0 + cols]
+            aa = np.repeat(A, B.size); bb = np.tile(B, A.size)
+            r = split(shim, aa, bb)
+            any_top = bool(r["t%d" % t].any())
+            poss = bool(shim.shim_top_possible(t, int(A[0]), int(A[-1]), int(B[0]), int(B[-1])))
+            assert poss or not any_top
+            checked += 1; hits += any_top; skipped += (not poss)
+    assert hits > 50 and skipped > 200

@@ -39,28 +39,26 @@ def time_edges(s, t, reps=3):
         e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
         e0.record(st); go(); e1.record(st); e1.synchronize()
         best = min(best, e0.elapsed_time(e1))
-    return best, int(d_c.item())
+    import ctypes as C
+    st0, st1 = C.c_ulonglong(0), C.c_ulonglong(0)
+    L.bdg_dev_edges_stats(C.byref(st0), C.byref(st1), st.cuda_stream)
+    return best, int(d_c.item()), st0.value, st1.value
 
 
 def main():
     badger_b200.init([0])
     sizes = [int(x) for x in os.environ.get("SWEEP_READS", "400000,1000000").split(",")]
     ts = [int(x) for x in os.environ.get("SWEEP_T", "1,2").split(",")]
-    knobs = {k: os.environ.get("SWEEP_" + k, d).split(",") for k, d in (("IMPL", "0,1"), ("OCC", ""), ("ITEMS", "16"))}
+    knobs = {k: os.environ.get("SWEEP_" + k, d).split(",") for k, d in (("ITEMS", "16"),)}
     data = {r: dataset(r) for r in sizes}
     for r, t in itertools.product(sizes, ts):
         s = data[r]
         n = s.size
-        for impl, occ, items in itertools.product(knobs["IMPL"], knobs["OCC"], knobs["ITEMS"]):
-            os.environ["BDG_EDGE_IMPL"] = impl
-            if occ:
-                os.environ["BDG_EDGE_OCC"] = occ
-            else:
-                os.environ.pop("BDG_EDGE_OCC", None)
+        for (items,) in itertools.product(knobs["ITEMS"]):
             os.environ["BDG_EDGE_ITEMS"] = items
-            ms, edges = time_edges(s, t)
-            print("reads=%8d N=%8d t=%d impl=%s occ=%-2s items=%-3s  %9.3f ms  %.3e pairs/s  edges=%d" % (
-                r, n, t, impl, occ or "-", items, ms, n * (n - 1) / 2 / (ms * 1e-3), edges), flush=True)
+            ms, edges, subs, fulls = time_edges(s, t)
+            print("reads=%8d N=%8d t=%d items=%-3s  %9.3f ms  %.3e pairs/s  edges=%d  sub-tiles=%d full=%.2f%%" % (
+                r, n, t, items, ms, n * (n - 1) / 2 / (ms * 1e-3), edges, subs, 100.0 * fulls / max(subs, 1)), flush=True)
 
 
 if __name__ == "__main__":
