@@ -14,6 +14,8 @@
 #include "../../include/badger_b200.h"
 #include "bdg_kernels.cuh"
 
+#include <cub/device/device_radix_sort.cuh>
+
 namespace {
 
 thread_local char g_err[512] = "";
@@ -61,6 +63,7 @@ struct DevCtx {
     cudaStream_t stream = nullptr;
     int sms = 0;
     Buf sorted, ea, eb, ed, count, plan;   // edge construction
+    Buf rot_in, rot_sorted[bdg::MAX_PASSES], sort_tmp;   // sparse passes: rotated keys, their sorted copies, radix-sort scratch
 };
 std::vector<DevCtx> g_ctx;
 
@@ -90,7 +93,7 @@ struct Plan {
     uint64_t pairs = 0;
 };
 
-void build_plan(size_t N, int part, int nparts, int workers, Plan& p)
+void build_plan(size_t N, int part, int nparts, int workers, Plan& p, uint64_t col_quantum = bdg::SB_MAX)
 {
     const uint64_t tiles = (N + bdg::ROW_TILE - 1) / bdg::ROW_TILE;
     const uint64_t groups = (N + bdg::GROUP - 1) / bdg::GROUP;
@@ -109,8 +112,8 @@ void build_plan(size_t N, int part, int nparts, int workers, Plan& p)
     if (const char* e = getenv("BDG_EDGE_ITEMS")) per_worker = std::max(1.0, atof(e));
     const double want_items = per_worker * std::max(workers, 1);
     const double cols = ((double)p.pairs / bdg::GROUP) / want_items;
-    uint64_t cc = (uint64_t)cols / bdg::SB_MAX * bdg::SB_MAX;
-    cc = std::min<uint64_t>(std::max<uint64_t>(cc, 4 * bdg::SB_MAX), 1u << 17);
+    uint64_t cc = (uint64_t)cols / col_quantum * col_quantum;
+    cc = std::min<uint64_t>(std::max<uint64_t>(cc, std::max<uint64_t>(col_quantum, 4 * bdg::SB_MAX)), 1u << 17);
     p.chunk_cols = (uint32_t)cc;
     p.item_start.assign(p.group_ids.size() + 1, 0);
     uint64_t acc = 0;
@@ -122,60 +125,101 @@ void build_plan(size_t N, int part, int nparts, int workers, Plan& p)
     p.item_start[p.group_ids.size()] = (uint32_t)acc;
 }
 
-constexpr size_t PLAN_HDR = 32;   // [item counter u32 | pad | sub-tiles u64 | full sub-tiles u64 | pad]
+constexpr size_t PLAN_HDR = 32;   // per launch: [item counter u32 | pad | sub-tiles u64 | full sub-tiles u64 | pad]
+int g_edge_mode = -1;             // -1: BDG_EDGE_MODE or default (sparse); 0 dense; 1 sparse
 
-// Launch the edge kernel for one part on the current device / stream.  d_count is zeroed on the stream.
+bool sparse_mode(int t)
+{
+    if (t != 1 && t != 2) return false;
+    int m = g_edge_mode;
+    if (m < 0) { const char* e = getenv("BDG_EDGE_MODE"); m = (e && !strcmp(e, "dense")) ? 0 : 1; }
+    return m == 1;
+}
+
+template <int T_, int P_>
+void launch_sparse(int blocks, cudaStream_t st, const bdg::EdgeWork& w, const bdg::EdgeOut& o)
+{
+    bdg::edges_sparse_kernel<T_, P_><<<blocks, bdg::ENT, 0, st>>>(w, o);
+}
+
+// Launch the edge construction of one part on the current device / stream.  d_count is zeroed on the stream.
+// ws: the device's grow-only workspaces (plan, rotated keys, sort scratch); one in-flight call per device.
 int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts, uint32_t* d_a, uint32_t* d_b,
-                 uint8_t* d_d, size_t cap, unsigned long long* d_count, cudaStream_t st, Buf* plan_ws)
+                 uint8_t* d_d, size_t cap, unsigned long long* d_count, cudaStream_t st, DevCtx* ws)
 {
     if (nparts < 1 || part < 0 || part >= nparts) return fail(BDG_ERR_ARG, "part %d of %d is not a valid part", part, nparts);
     if (N > 0xFFFFFFFFull) return fail(BDG_ERR_ARG, "N = %zu exceeds the 2^32 distinct 16-mers", N);
+    if (!ws) return fail(BDG_ERR_NODEVICE, "bdg_init has not claimed the current CUDA device");
     CU_TRY(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
     if (t <= 0 || N < 2) return BDG_OK;   // D >= 1 for distinct barcodes: no edges (barcode_graph.py:245)
-    const void* kern = t == 1 ? (const void*)bdg::edges_kernel<1> : t == 2 ? (const void*)bdg::edges_kernel<2>
-                                                                           : (const void*)bdg::edges_kernel<3>;
+    const bool sparse = sparse_mode(t);
+    const int passes = sparse ? bdg::n_passes(t) : 1;
+    const void* kern = sparse ? (t == 1 ? (const void*)bdg::edges_sparse_kernel<1, 0> : (const void*)bdg::edges_sparse_kernel<2, 0>)
+                              : (t == 1 ? (const void*)bdg::edges_kernel<1> : t == 2 ? (const void*)bdg::edges_kernel<2>
+                                                                                     : (const void*)bdg::edges_kernel<3>);
     int grid = 0;
     if (int rc = grid_for(kern, &grid, bdg::ENT)) return rc;
     Plan plan;
-    build_plan(N, part, nparts, grid * bdg::EW, plan);
-    const uint64_t n_items64 = plan.item_start.empty() ? 0 : plan.item_start.back();
-    const uint32_t n_items = (uint32_t)n_items64;
+    build_plan(N, part, nparts, grid * bdg::EW, plan, sparse ? bdg::SBATCH : bdg::SB_MAX);
+    const uint32_t n_items = plan.item_start.empty() ? 0 : plan.item_start.back();
     if (n_items == 0) return BDG_OK;
     const size_t nb_groups = plan.group_ids.size() * sizeof(uint32_t), nb_items = plan.item_start.size() * sizeof(uint32_t);
-    char* d_plan = nullptr;   // [header | group_ids | item_start]
-    bool plan_async = true;
-    if (plan_ws) {            // caller-provided grow-only workspace (one in-flight call per device)
-        if (cudaError_t e = (cudaError_t)plan_ws->ensure(PLAN_HDR + nb_groups + nb_items))
-            return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "plan workspace: %s", cudaGetErrorString(e));
-        d_plan = (char*)plan_ws->p;
-        plan_async = false;
-    } else {
-        CU_TRY(cudaMallocAsync((void**)&d_plan, PLAN_HDR + nb_groups + nb_items, st));
-    }
-    CU_TRY(cudaMemsetAsync(d_plan, 0, PLAN_HDR, st));
-    CU_TRY(cudaMemcpyAsync(d_plan + PLAN_HDR, plan.group_ids.data(), nb_groups, cudaMemcpyHostToDevice, st));
-    CU_TRY(cudaMemcpyAsync(d_plan + PLAN_HDR + nb_groups, plan.item_start.data(), nb_items, cudaMemcpyHostToDevice, st));
+    const size_t hdr = PLAN_HDR * bdg::MAX_PASSES;
+    if (cudaError_t e = (cudaError_t)ws->plan.ensure(hdr + nb_groups + nb_items))
+        return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "plan workspace: %s", cudaGetErrorString(e));
+    char* d_plan = (char*)ws->plan.p;   // [headers | group_ids | item_start]
+    CU_TRY(cudaMemsetAsync(d_plan, 0, hdr, st));
+    CU_TRY(cudaMemcpyAsync(d_plan + hdr, plan.group_ids.data(), nb_groups, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemcpyAsync(d_plan + hdr + nb_groups, plan.item_start.data(), nb_items, cudaMemcpyHostToDevice, st));
     bdg::EdgeWork w;
-    w.sorted = d_sorted;
     w.N = (uint32_t)N;
     w.t = t;
     w.T = bdg::qgram_threshold(t);
-    w.group_ids = (const uint32_t*)(d_plan + PLAN_HDR);
-    w.item_start = (const uint32_t*)(d_plan + PLAN_HDR + nb_groups);
+    w.group_ids = (const uint32_t*)(d_plan + hdr);
+    w.item_start = (const uint32_t*)(d_plan + hdr + nb_groups);
     w.K = (uint32_t)plan.group_ids.size();
     w.n_items = n_items;
     w.chunk_cols = plan.chunk_cols;
-    w.item_counter = (unsigned int*)d_plan;
-    w.stats = plan_async ? nullptr : (unsigned long long*)(d_plan + 8);
     w.one = 1u;
     bdg::EdgeOut o{d_a, d_b, d_d, d_count, (unsigned long long)cap};
     const int blocks = (int)std::min<uint64_t>((uint64_t)grid, (n_items + bdg::EW - 1) / bdg::EW);
-    if (t == 1) bdg::edges_kernel<1><<<blocks, bdg::ENT, 0, st>>>(w, o);
-    else if (t == 2) bdg::edges_kernel<2><<<blocks, bdg::ENT, 0, st>>>(w, o);
-    else bdg::edges_kernel<3><<<blocks, bdg::ENT, 0, st>>>(w, o);
-    g_launches++;
-    CU_TRY(cudaGetLastError());
-    if (plan_async) CU_TRY(cudaFreeAsync(d_plan, st));
+    for (int p = 0; p < passes; p++) {
+        w.item_counter = (unsigned int*)(d_plan + PLAN_HDR * p);
+        w.stats = (unsigned long long*)(d_plan + PLAN_HDR * p + 8);
+        w.pass = p;
+        w.rot = sparse ? bdg::pass_rot(t, p) : 0;
+        w.sorted = d_sorted;
+        if (w.rot != 0) {   // this pass scans the array in the order of rotl(key, rot): rotate, radix-sort
+            auto ensure = [&](Buf& b, size_t bytes) -> int {
+                if (cudaError_t e = (cudaError_t)b.ensure(bytes))
+                    return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "sort workspace of %zu bytes: %s", bytes, cudaGetErrorString(e));
+                return BDG_OK;
+            };
+            if (int e = ensure(ws->rot_in, N * 4)) return e;
+            if (int e = ensure(ws->rot_sorted[p], N * 4)) return e;
+            size_t tmp_bytes = 0;
+            CU_TRY(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (const uint32_t*)ws->rot_in.p, (uint32_t*)ws->rot_sorted[p].p, (int)N, 0, 32, st));
+            if (int e = ensure(ws->sort_tmp, tmp_bytes)) return e;
+            const int rb = (int)std::min<size_t>((N + 255) / 256, (size_t)ws->sms * 8);
+            bdg::rotate_keys_kernel<<<rb, 256, 0, st>>>(d_sorted, (uint32_t*)ws->rot_in.p, (uint32_t)N, w.rot);
+            g_launches++;
+            CU_TRY(cub::DeviceRadixSort::SortKeys(ws->sort_tmp.p, tmp_bytes, (const uint32_t*)ws->rot_in.p, (uint32_t*)ws->rot_sorted[p].p, (int)N, 0, 32, st));
+            w.sorted = (const uint32_t*)ws->rot_sorted[p].p;
+        }
+        if (!sparse) {
+            if (t == 1) bdg::edges_kernel<1><<<blocks, bdg::ENT, 0, st>>>(w, o);
+            else if (t == 2) bdg::edges_kernel<2><<<blocks, bdg::ENT, 0, st>>>(w, o);
+            else bdg::edges_kernel<3><<<blocks, bdg::ENT, 0, st>>>(w, o);
+        } else if (t == 1) {
+            if (p == 0) launch_sparse<1, 0>(blocks, st, w, o); else launch_sparse<1, 1>(blocks, st, w, o);
+        } else {
+            if (p == 0) launch_sparse<2, 0>(blocks, st, w, o);
+            else if (p == 1) launch_sparse<2, 1>(blocks, st, w, o);
+            else launch_sparse<2, 2>(blocks, st, w, o);
+        }
+        g_launches++;
+        CU_TRY(cudaGetLastError());
+    }
     return BDG_OK;
 }
 
@@ -264,6 +308,8 @@ void bdg_shutdown(void)
     for (auto& c : g_ctx) {
         if (c.stream) { cudaSetDevice(c.dev); cudaStreamSynchronize(c.stream); cudaStreamDestroy(c.stream); }
         c.sorted.release(); c.ea.release(); c.eb.release(); c.ed.release(); c.count.release(); c.plan.release();
+        c.rot_in.release(); c.sort_tmp.release();
+        for (auto& b : c.rot_sorted) b.release();
     }
     g_ctx.clear();
 }
@@ -282,18 +328,27 @@ int bdg_dev_edges_build(const uint32_t* d_sorted, size_t N, int t, int part, int
 {
     if (!d_count || (N && !d_sorted) || (cap && (!d_a || !d_b || !d_d))) return fail(BDG_ERR_ARG, "NULL pointer argument");
     DevCtx* c = ctx_of_current_device();
-    return launch_edges(d_sorted, N, t, part, nparts, d_a, d_b, d_d, cap, d_count, (cudaStream_t)stream, c ? &c->plan : nullptr);
+    return launch_edges(d_sorted, N, t, part, nparts, d_a, d_b, d_d, cap, d_count, (cudaStream_t)stream, c);
+}
+
+int bdg_set_edge_mode(int mode)
+{
+    if (mode < -1 || mode > 1) return fail(BDG_ERR_ARG, "edge mode must be -1 (default), 0 (dense) or 1 (sparse)");
+    g_edge_mode = mode;
+    return BDG_OK;
 }
 
 int bdg_dev_edges_stats(unsigned long long* sub_tiles, unsigned long long* full_tiles, void* stream)
 {
     DevCtx* c = ctx_of_current_device();
     if (!c || !c->plan.p) return fail(BDG_ERR_ARG, "no edge launch on this device yet");
-    unsigned long long v[2] = {0, 0};
-    CU_TRY(cudaMemcpyAsync(v, (char*)c->plan.p + 8, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    unsigned long long v[4 * bdg::MAX_PASSES];
+    CU_TRY(cudaMemcpyAsync(v, c->plan.p, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-    if (sub_tiles) *sub_tiles = v[0];
-    if (full_tiles) *full_tiles = v[1];
+    unsigned long long a = 0, b = 0;
+    for (int p = 0; p < bdg::MAX_PASSES; p++) { a += v[4 * p + 1]; b += v[4 * p + 2]; }
+    if (sub_tiles) *sub_tiles = a;
+    if (full_tiles) *full_tiles = b;
     return BDG_OK;
 }
 
@@ -420,7 +475,7 @@ static int edges_on_devices(const uint32_t* sorted, size_t N, int t, const std::
         if (int e = ensure(c.eb, cap * 4)) return e;
         if (int e = ensure(c.ed, cap)) return e;
         return launch_edges((const uint32_t*)c.sorted.p, N, t, part, nparts, (uint32_t*)c.ea.p, (uint32_t*)c.eb.p, (uint8_t*)c.ed.p,
-                            cap, (unsigned long long*)c.count.p, c.stream, &c.plan);
+                            cap, (unsigned long long*)c.count.p, c.stream, &c);
     };
     std::vector<size_t> caps(ctx_idx.size(), 0);
     int rc = BDG_OK;

@@ -60,6 +60,8 @@ struct EdgeWork {
     unsigned int* item_counter; // dynamic scheduler
     unsigned long long* stats;  // optional [2]: sub-tiles visited, sub-tiles that ran the full prefilter
     uint32_t one;               // == 1, opaque to the compiler: x*(-one)+c keeps the subtraction on the FMA pipe (IMAD)
+    int pass;                   // sparse kernel: pass index p (bdg_core.cuh pass_pred); `sorted` holds rotl(key, rot) sorted
+    int rot;
 };
 
 // ---- output: warp-aggregated append (one atomic per warp that has anything to emit) ---------------
@@ -352,6 +354,177 @@ __global__ void __launch_bounds__(ENT, 3) edges_kernel(const EdgeWork w, const E
     if (w.stats) {
         if (lane == 0) { atomicAdd(&w.stats[0], n_sub); atomicAdd(&w.stats[1], n_full); }   // uniform per warp
     }
+}
+
+
+// =====================================================================================================
+// Sparse multi-pass form (bdg_core.cuh "Multi-pass").  One launch per pass; `w.sorted` is the array sorted by
+// the pass's rotated key.  A warp owns (row group, column chunk) items as above, but instead of testing pairs
+// it tests TILES: lane l takes column sub-tile l of a batch of 32, reads its first and last key and asks
+// pass_possible() against the row group's first/last key.  Only the sub-tiles that survive are staged in
+// shared memory and get the pass predicate evaluated pair by pair (hit bits -> candidate queue -> exact stage,
+// as in the dense kernel).  Candidates that an EARLIER pass also finds are dropped, so the passes' outputs
+// are disjoint and simply share one output cursor.
+// =====================================================================================================
+constexpr int SSB = 128;           // columns per sub-tile
+constexpr int SBATCH = 32 * SSB;   // columns per interval-test batch (one sub-tile per lane)
+constexpr int SQCAP = 64;
+
+struct SparseCtx {
+    uint32_t* q;
+    const uint32_t* sorted;
+    uint32_t N;
+    uint64_t row0, col_lo, col_hi;
+    int t, T, pass, rot, lane;
+};
+
+template <int T_, int P_>
+__device__ __forceinline__ void sparse_process(const SparseCtx& c, const EdgeOut& out, uint32_t e, bool active)
+{
+    bool ok = false;
+    uint32_t x = 0, y = 0;
+    int d = 0;
+    if (active) {
+        const uint64_t row = c.row0 + (e & 255u), col = c.col_lo + (e >> 8);
+        if (row < col && col < c.col_hi) {          // each unordered pair once: row index < column index
+            x = rotr32(__ldg(&c.sorted[row]), c.rot);
+            y = rotr32(__ldg(&c.sorted[col]), c.rot);
+            if (x > y) { const uint32_t tmp = x; x = y; y = tmp; }
+            bool earlier = false;
+#pragma unroll
+            for (int q = 0; q < P_; q++) earlier = earlier || pass_pred(T_, q, x, y);
+            if (!earlier) {
+                d = dist_small(x, y);
+                if (d > c.t || qgram_score(x, y) < c.T) d = 0;
+                ok = d > 0;
+            }
+        }
+    }
+    emit_warp(ok, x, y, d, out);
+}
+
+// append the set bits of h (bit k*8+r = column colrel+k, row r*32+lane); run stage 2 whenever 32 candidates wait
+template <int T_, int P_>
+__device__ __forceinline__ void sparse_push(uint32_t h, uint32_t colrel, int& qn, const SparseCtx& c, const EdgeOut& out)
+{
+    for (;;) {
+        const bool has = h != 0;
+        const unsigned m = __ballot_sync(FULL, has);
+        if (m == 0) break;
+        if (has) {
+            const int j = __ffs(h) - 1;
+            h &= h - 1;
+            c.q[qn + __popc(m & ((1u << c.lane) - 1u))] = ((colrel + (j >> 3)) << 8) | (uint32_t)((j & 7) * 32 + c.lane);
+        }
+        qn += __popc(m);
+        __syncwarp();
+        if (qn >= 32) {
+            qn -= 32;
+            const uint32_t e = c.q[qn + c.lane];
+            sparse_process<T_, P_>(c, out, e, true);
+        }
+        __syncwarp();
+    }
+}
+
+template <int T_, int P_>
+__global__ void __launch_bounds__(ENT, 3) edges_sparse_kernel(const EdgeWork w, const EdgeOut out)
+{
+    __shared__ __align__(16) uint32_t s_raw[EW][SSB];
+    __shared__ uint32_t s_q[EW][SQCAP];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t* const raw = s_raw[wid];
+    SparseCtx c;
+    c.q = s_q[wid]; c.sorted = w.sorted; c.N = w.N; c.t = w.t; c.T = w.T; c.pass = w.pass; c.rot = w.rot; c.lane = lane;
+    int qn = 0;                                   // queue fill, uniform across the warp
+    unsigned long long n_sub = 0, n_full = 0;
+
+    for (;;) {
+        uint32_t item = 0, k = 0, j = 0;
+        if (lane == 0) {
+            item = atomicAdd(w.item_counter, 1u);
+            if (item < w.n_items) {
+                uint32_t lo = 0, hi = w.K;
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (__ldg(&w.item_start[mid]) <= item) lo = mid; else hi = mid;
+                }
+                k = lo;
+                j = item - __ldg(&w.item_start[k]);
+            }
+        }
+        item = __shfl_sync(FULL, item, 0);
+        if (item >= w.n_items) break;
+        k = __shfl_sync(FULL, k, 0);
+        j = __shfl_sync(FULL, j, 0);
+        c.row0 = (uint64_t)__ldg(&w.group_ids[k]) * GROUP;
+        c.col_lo = c.row0 + (uint64_t)j * w.chunk_cols;
+        c.col_hi = min((uint64_t)w.N, c.col_lo + w.chunk_cols);
+
+        uint32_t a[RA];
+#pragma unroll
+        for (int r = 0; r < RA; r++) {
+            const uint64_t idx = c.row0 + (uint64_t)r * 32 + lane;
+            a[r] = idx < w.N ? __ldg(&w.sorted[idx]) : 0xFFFFFFFFu;   // pad rows are dropped in sparse_process (row < col < N)
+        }
+        const uint32_t a_lo = __ldg(&w.sorted[c.row0]);
+        const uint32_t a_hi = __ldg(&w.sorted[min((uint64_t)w.N, c.row0 + GROUP) - 1]);
+
+        for (uint64_t batch = c.col_lo; batch < c.col_hi; batch += SBATCH) {
+            const uint64_t my = batch + (uint64_t)lane * SSB;
+            bool poss = false;
+            if (my < c.col_hi) {
+                const uint32_t b_lo = __ldg(&w.sorted[my]);
+                const uint32_t b_hi = __ldg(&w.sorted[min(c.col_hi, my + SSB) - 1]);
+                poss = pass_possible(T_, P_, a_lo, a_hi, b_lo, b_hi);
+            }
+            unsigned pm = __ballot_sync(FULL, poss);
+            n_sub += __popc(__ballot_sync(FULL, my < c.col_hi));
+            n_full += __popc(pm);
+            while (pm) {
+                const int l0 = __ffs(pm) - 1;
+                pm &= pm - 1;
+                const uint64_t sub = batch + (uint64_t)l0 * SSB;
+                const int ncols = (int)min((uint64_t)SSB, c.col_hi - sub);
+                const uint32_t colrel0 = (uint32_t)(sub - c.col_lo);
+                __syncwarp();
+#pragma unroll
+                for (int i = 0; i < SSB / 32; i++) {
+                    const uint64_t idx = sub + (uint64_t)i * 32 + lane;
+                    raw[i * 32 + lane] = idx < c.col_hi ? __ldg(&w.sorted[idx]) : 0u;
+                }
+                __syncwarp();
+#pragma unroll 1
+                for (int cb = 0; cb < ncols; cb += 4) {
+                    const uint4 B = *reinterpret_cast<const uint4*>(&raw[cb]);
+                    uint32_t h = 0;
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++) {
+                        const uint32_t b = pick4(B, kk);
+#pragma unroll
+                        for (int r = 0; r < RA; r++) h |= (pass_pred_rot(T_, P_, a[r], b) ? 1u : 0u) << (kk * 8 + r);
+                    }
+                    if (cb + 4 > ncols) h &= (1u << (8 * (ncols - cb))) - 1u;      // columns past the chunk end
+                    if (__any_sync(FULL, h != 0)) sparse_push<T_, P_>(h, colrel0 + cb, qn, c, out);
+                }
+            }
+        }
+        // the queue's codes are relative to this item: finish the partial batch before moving on
+        __syncwarp();
+        if (qn > 0) {
+            const uint32_t e = lane < qn ? c.q[lane] : 0u;
+            sparse_process<T_, P_>(c, out, e, lane < qn);
+            qn = 0;
+        }
+        __syncwarp();
+    }
+    if (w.stats && lane == 0) { atomicAdd(&w.stats[0], n_sub); atomicAdd(&w.stats[1], n_full); }
+}
+
+// rotl(key, rot) for a whole array (input of the per-pass radix sort)
+__global__ void rotate_keys_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, int rot)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = rotl32(__ldg(&in[i]), rot);
 }
 
 }  // namespace bdg

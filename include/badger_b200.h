@@ -37,9 +37,10 @@ enum {
 };
 
 /* Rows of the sorted distinct-barcode array are dealt to parts (GPUs / ranks) in tiles of this many
- * rows, boustrophedon order: tile I belongs to part  m<P ? m : 2P-1-m,  m = I mod 2P.  A part emits every
- * edge whose SMALLER barcode lies in one of its tiles.  (Replaces the 10 000-barcode chunks dealt to
- * worker processes in barcode_graph.py:26,164-189.) */
+ * rows, boustrophedon order: tile I belongs to part  m<P ? m : 2P-1-m,  m = I mod 2P.  The parts' edge lists
+ * are disjoint and their union is the full edge set.  (Dense mode: a part emits every edge whose SMALLER
+ * barcode lies in one of its tiles; sparse mode deals the rows of every pass's own sort order the same way.)
+ * Replaces the 10 000-barcode chunks dealt to worker processes in barcode_graph.py:26,164-189. */
 #define BDG_ROW_TILE 2048
 
 /* ---- life cycle ------------------------------------------------------------------------------- */
@@ -93,9 +94,15 @@ int bdg_kmer_score(const uint32_t* q, size_t Q, const uint32_t* wl, size_t W, in
  * the number of edges found, which may exceed cap (only the first cap are stored). */
 int bdg_dev_edges_build(const uint32_t* d_sorted, size_t N, int t, int part, int nparts, uint32_t* d_a,
                         uint32_t* d_b, uint8_t* d_d, size_t cap, unsigned long long* d_count, void* stream);
+/* How the edge set is searched for t = 1, 2 (results are identical; DESIGN.md "edge construction"):
+ *   1 sparse (default): one pass per prefilter block over the array sorted by a rotated key, pairs are decided
+ *     tile by tile from key intervals and scored only inside the tiles that can hold a candidate;
+ *   0 dense: one pass, the low-block conditions are scored for every pair (the all-pairs kernel);
+ *  -1 back to the default / BDG_EDGE_MODE=dense|sparse.  t >= 3 always runs dense without a prefilter. */
+int bdg_set_edge_mode(int mode);
 /* Tile statistics of the last bdg_dev_edges_build / bdg_edges_build* launch on the current device: column
- * sub-tiles visited by the kernel and how many of them had to run the full prefilter (the rest ran the
- * light loop; DESIGN.md "edges_kernel").  Synchronises the stream. */
+ * sub-tiles visited by the kernel and how many of them had to run the pair-by-pair prefilter (sparse: the rest were excluded
+ * by their key intervals; dense: the rest ran the light loop; DESIGN.md "edges_kernel").  Synchronises the stream. */
 int bdg_dev_edges_stats(unsigned long long* sub_tiles, unsigned long long* full_tiles, void* stream);
 int bdg_dev_pack16(const char* d_seqs, size_t R, uint32_t* d_out, uint8_t* d_valid, void* stream);
 int bdg_dev_member_sorted(const uint32_t* d_sorted_wl, size_t W, const uint32_t* d_q, size_t Q, uint8_t* d_hit,

@@ -26,6 +26,23 @@ void shim_split(const uint32_t* a, const uint32_t* b, size_t n, uint8_t* l1, uin
         l2[i] = bdg::t2_light(a[i], b[i]); t2[i] = bdg::t2_top(a[i], b[i]);
     }
 }
+void shim_pass_pred(int t, const uint32_t* a, const uint32_t* b, size_t n, uint8_t* mask /* bit p = pass p fires */)
+{
+    for (size_t i = 0; i < n; i++) {
+        uint8_t m = 0;
+        for (int p = 0; p < bdg::n_passes(t); p++) {
+            const bool f = bdg::pass_pred(t, p, a[i], b[i]);
+            const int r = bdg::pass_rot(t, p);
+            if (f != bdg::pass_pred_rot(t, p, bdg::rotl32(a[i], r), bdg::rotl32(b[i], r))) m |= 0x80;   // must agree
+            if (f) m |= (uint8_t)(1u << p);
+        }
+        mask[i] = m;
+    }
+}
+int shim_pass_possible(int t, int p, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi)
+{
+    return bdg::pass_possible(t, p, alo, ahi, blo, bhi);
+}
 int shim_top_possible(int t, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi)
 {
     return t == 1 ? bdg::t1_top_possible(alo, ahi, blo, bhi) : bdg::t2_top_possible(alo, ahi, blo, bhi);

@@ -29,6 +29,9 @@ def shim(tmp_path_factory):
     L.shim_edge.argtypes = [C.c_uint32, C.c_uint32, C.c_int]
     L.shim_edge.restype = C.c_int
     L.shim_split.argtypes = [u32p, u32p, C.c_size_t] + [u8p] * 4
+    L.shim_pass_pred.argtypes = [C.c_int, u32p, u32p, C.c_size_t, u8p]
+    L.shim_pass_possible.argtypes = [C.c_int, C.c_int] + [C.c_uint32] * 4
+    L.shim_pass_possible.restype = C.c_int
     L.shim_top_possible.argtypes = [C.c_int] + [C.c_uint32] * 4
     L.shim_top_possible.restype = C.c_int
     return L
@@ -259,3 +262,61 @@ def test_top_possible_is_conservative(shim, t):
             assert poss or not any_top
             checked += 1; hits += any_top; skipped += (not poss)
     assert hits > 50 and skipped > 200
+
+
+def pass_mask(shim, t, a, b):
+    m = np.zeros(a.size, np.uint8)
+    shim.shim_pass_pred(t, a, b, a.size, m)
+    assert not (m & 0x80).any(), "pass_pred and pass_pred_rot disagree"
+    return m
+
+
+def rotl(v, r):
+    v = v.astype(np.uint32)
+    return v if r == 0 else ((v << np.uint32(r)) | (v >> np.uint32(32 - r))).astype(np.uint32)
+
+
+PASS_ROT = {1: [0, 16], 2: [0, 10, 20]}
+
+
+@pytest.mark.parametrize("t", [1, 2])
+def test_pass_predicates_cover_and_are_symmetric(shim, t):
+    """Sparse edge passes: every pair with D <= t fires in at least one pass; predicates are orientation-free."""
+    L = orc.lib()
+    tot = 0
+    for seed in (5, 8):
+        a, b = make_pairs(seed)
+        D = np.fromiter((L.orc_D(int(x), int(y)) for x, y in zip(a, b)), np.int32, a.size)
+        m = pass_mask(shim, t, a, b)
+        assert np.array_equal(m, pass_mask(shim, t, b, a))
+        assert (m[D <= t] != 0).all()
+        tot += int((D <= t).sum())
+    assert tot > 10000
+    rng = np.random.default_rng(3)
+    ra = rng.integers(0, 1 << 32, 1 << 20, dtype=np.uint64).astype(np.uint32)
+    rb = rng.integers(0, 1 << 32, 1 << 20, dtype=np.uint64).astype(np.uint32)
+    assert (pass_mask(shim, t, ra, rb) != 0).mean() < (4e-4 if t == 1 else 0.014)
+
+
+@pytest.mark.parametrize("t", [1, 2])
+def test_pass_possible_is_conservative(shim, t):
+    """Interval test of every pass on arrays sorted by that pass's rotated key."""
+    rng = np.random.default_rng(40 + t)
+    for p, rot in enumerate(PASS_ROT[t]):
+        hits = skipped = 0
+        for n, rows, cols in ((3000, 64, 32), (20000, 256, 128), (200000, 256, 128)):
+            base = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+            noise = rng.integers(0, 1 << 12, n // 4, dtype=np.uint64).astype(np.uint32)
+            extra = base[: n // 4] ^ rotl(noise, int(rng.integers(0, 32)))
+            s = np.unique(rotl(np.concatenate([base, extra]), rot))       # sorted by the rotated key
+            for _ in range(250):
+                r0 = int(rng.integers(0, s.size - rows)); c0 = int(rng.integers(0, s.size - cols))
+                if rng.random() < 0.3:
+                    c0 = min(s.size - cols, r0 + int(rng.integers(0, rows)))
+                A = s[r0:r0 + rows]; B = s[c0:c0 + cols]
+                aa = np.repeat(A, B.size); bb = np.tile(B, A.size)
+                fires = ((pass_mask(shim, t, rotl(aa, (32 - rot) % 32), rotl(bb, (32 - rot) % 32)) >> p) & 1).any()
+                poss = bool(shim.shim_pass_possible(t, p, int(A[0]), int(A[-1]), int(B[0]), int(B[-1])))
+                assert poss or not fires, (t, p)
+                hits += bool(fires); skipped += (not poss)
+        assert hits > 30 and skipped > 150, (t, p, hits, skipped)

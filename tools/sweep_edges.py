@@ -49,16 +49,17 @@ def main():
     badger_b200.init([0])
     sizes = [int(x) for x in os.environ.get("SWEEP_READS", "400000,1000000").split(",")]
     ts = [int(x) for x in os.environ.get("SWEEP_T", "1,2").split(",")]
-    knobs = {k: os.environ.get("SWEEP_" + k, d).split(",") for k, d in (("ITEMS", "16"),)}
+    knobs = {k: os.environ.get("SWEEP_" + k, d).split(",") for k, d in (("ITEMS", "16"), ("MODE", "1,0"))}
     data = {r: dataset(r) for r in sizes}
     for r, t in itertools.product(sizes, ts):
         s = data[r]
         n = s.size
-        for (items,) in itertools.product(knobs["ITEMS"]):
+        for items, mode in itertools.product(knobs["ITEMS"], knobs["MODE"]):
             os.environ["BDG_EDGE_ITEMS"] = items
+            badger_b200.lib().bdg_set_edge_mode(int(mode))
             ms, edges, subs, fulls = time_edges(s, t)
-            print("reads=%8d N=%8d t=%d items=%-3s  %9.3f ms  %.3e pairs/s  edges=%d  sub-tiles=%d full=%.2f%%" % (
-                r, n, t, items, ms, n * (n - 1) / 2 / (ms * 1e-3), edges, subs, 100.0 * fulls / max(subs, 1)), flush=True)
+            print("reads=%8d N=%8d t=%d items=%-3s mode=%s  %9.3f ms  %.3e pairs/s  edges=%d  sub-tiles=%d full=%.2f%%" % (
+                r, n, t, items, "sparse" if mode == "1" else "dense ", ms, n * (n - 1) / 2 / (ms * 1e-3), edges, subs, 100.0 * fulls / max(subs, 1)), flush=True)
 
 
 if __name__ == "__main__":
