@@ -196,6 +196,24 @@ BDG_HD bool t2_blk3(uint32_t x, uint32_t y)   // words rotated so that the block
 }
 BDG_HD bool t2_blk1(uint32_t x, uint32_t y) { return (((x ^ y) >> 20) & 0x3FFu) == 0; }
 
+// Per-pair test of the sparse passes inside a surviving tile: NOT the pass predicate (that is re-checked on
+// the few survivors, for the duplicate-free hand-over between passes) but the stronger necessary condition
+// "at most t columns of a[0:15] mismatch on all three diagonals" (see dist_small's quick reject): with <= t
+// operations every other column is matched on diagonal 0, +1 or -1.  Marks live on the ODD bits here
+// (x | x<<1), so the shift is a multiply by two on the FMA pipe.  bP = b >> 2, bM = b << 2.
+constexpr uint32_t QUICK_VALID = 0x2AAAAAAAu;   // columns 0..14, odd bits
+BDG_HD uint32_t quick_marks(uint32_t a, uint32_t b0, uint32_t bP, uint32_t bM)
+{
+    const uint32_t x0 = a ^ b0, xp = a ^ bP, xm = a ^ bM;
+    return (x0 | (x0 << 1)) & (xp | (xp << 1)) & (xm | (xm << 1)) & QUICK_VALID;
+}
+BDG_HD bool quick_pass(uint32_t a, uint32_t b, int t)
+{
+    uint32_t u = quick_marks(a, b, b >> 2, b << 2);
+    for (int i = 0; i < t; i++) u &= u - 1;      // drop the t lowest marks
+    return u == 0;
+}
+
 constexpr int MAX_PASSES = 3;
 BDG_HD int n_passes(int t) { return t == 1 ? 2 : (t == 2 ? 3 : 0); }
 BDG_HD int pass_rot(int t, int p) { return t == 1 ? (p == 1 ? 16 : 0) : 10 * p; }

@@ -362,9 +362,10 @@ __global__ void __launch_bounds__(ENT, 3) edges_kernel(const EdgeWork w, const E
 // the pass's rotated key.  A warp owns (row group, column chunk) items as above, but instead of testing pairs
 // it tests TILES: lane l takes column sub-tile l of a batch of 32, reads its first and last key and asks
 // pass_possible() against the row group's first/last key.  Only the sub-tiles that survive are staged in
-// shared memory and get the pass predicate evaluated pair by pair (hit bits -> candidate queue -> exact stage,
-// as in the dense kernel).  Candidates that an EARLIER pass also finds are dropped, so the passes' outputs
-// are disjoint and simply share one output cursor.
+// shared memory; inside them every pair gets the quick test of bdg_core.cuh (<= t columns mismatching on all
+// three diagonals: 9 ALU + 5 FMA-pipe instructions), hit bits -> candidate queue -> exact stage as in the
+// dense kernel.  The exact stage keeps a candidate only if THIS pass's predicate holds and no EARLIER pass's
+// does, so the passes' outputs are disjoint and simply share one output cursor.
 // =====================================================================================================
 constexpr int SSB = 128;           // columns per sub-tile
 constexpr int SBATCH = 32 * SSB;   // columns per interval-test batch (one sub-tile per lane)
@@ -390,10 +391,10 @@ __device__ __forceinline__ void sparse_process(const SparseCtx& c, const EdgeOut
             x = rotr32(__ldg(&c.sorted[row]), c.rot);
             y = rotr32(__ldg(&c.sorted[col]), c.rot);
             if (x > y) { const uint32_t tmp = x; x = y; y = tmp; }
-            bool earlier = false;
+            bool mine = pass_pred(T_, P_, x, y);      // found by this pass and by no earlier one
 #pragma unroll
-            for (int q = 0; q < P_; q++) earlier = earlier || pass_pred(T_, q, x, y);
-            if (!earlier) {
+            for (int q = 0; q < P_; q++) mine = mine && !pass_pred(T_, q, x, y);
+            if (mine) {
                 d = dist_small(x, y);
                 if (d > c.t || qgram_score(x, y) < c.T) d = 0;
                 ok = d > 0;
@@ -430,10 +431,12 @@ __device__ __forceinline__ void sparse_push(uint32_t h, uint32_t colrel, int& qn
 template <int T_, int P_>
 __global__ void __launch_bounds__(ENT, 3) edges_sparse_kernel(const EdgeWork w, const EdgeOut out)
 {
-    __shared__ __align__(16) uint32_t s_raw[EW][SSB];
+    __shared__ __align__(16) uint32_t s_b[EW][3][SSB];   // unrotated b, b >> 2, b << 2 of the staged sub-tile
     __shared__ uint32_t s_q[EW][SQCAP];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    uint32_t* const raw = s_raw[wid];
+    uint32_t* const b0s = s_b[wid][0];
+    uint32_t* const bPs = s_b[wid][1];
+    uint32_t* const bMs = s_b[wid][2];
     SparseCtx c;
     c.q = s_q[wid]; c.sorted = w.sorted; c.N = w.N; c.t = w.t; c.T = w.T; c.pass = w.pass; c.rot = w.rot; c.lane = lane;
     int qn = 0;                                   // queue fill, uniform across the warp
@@ -461,14 +464,23 @@ __global__ void __launch_bounds__(ENT, 3) edges_sparse_kernel(const EdgeWork w, 
         c.col_lo = c.row0 + (uint64_t)j * w.chunk_cols;
         c.col_hi = min((uint64_t)w.N, c.col_lo + w.chunk_cols);
 
-        uint32_t a[RA];
+        uint32_t a[RA];              // UNROTATED rows (the interval test below uses the rotated end points)
 #pragma unroll
         for (int r = 0; r < RA; r++) {
             const uint64_t idx = c.row0 + (uint64_t)r * 32 + lane;
-            a[r] = idx < w.N ? __ldg(&w.sorted[idx]) : 0xFFFFFFFFu;   // pad rows are dropped in sparse_process (row < col < N)
+            a[r] = idx < w.N ? rotr32(__ldg(&w.sorted[idx]), w.rot) : 0xFFFFFFFFu;   // pad rows are dropped in sparse_process
         }
         const uint32_t a_lo = __ldg(&w.sorted[c.row0]);
         const uint32_t a_hi = __ldg(&w.sorted[min((uint64_t)w.N, c.row0 + GROUP) - 1]);
+        // second-level intervals: lane l owns the combination (row slab r = l & 7, column quarter c = l >> 3).
+        // Slab r = the 32 consecutive rows row0 + 32r .. +31 (one per lane); its rotated end points sit in lanes 0 / 31.
+        uint32_t my_alo = 0, my_ahi = 0;
+#pragma unroll
+        for (int r = 0; r < RA; r++) {
+            const uint32_t ar = rotl32(a[r], w.rot);                  // pad rows are 0xFFFFFFFF: they only widen the interval
+            const uint32_t lo = __shfl_sync(FULL, ar, 0), hi = __shfl_sync(FULL, ar, 31);
+            if ((lane & 7) == r) { my_alo = lo; my_ahi = hi; }
+        }
 
         for (uint64_t batch = c.col_lo; batch < c.col_hi; batch += SBATCH) {
             const uint64_t my = batch + (uint64_t)lane * SSB;
@@ -488,24 +500,47 @@ __global__ void __launch_bounds__(ENT, 3) edges_sparse_kernel(const EdgeWork w, 
                 const int ncols = (int)min((uint64_t)SSB, c.col_hi - sub);
                 const uint32_t colrel0 = (uint32_t)(sub - c.col_lo);
                 __syncwarp();
+                uint32_t my_blo = 0, my_bhi = 0;
 #pragma unroll
-                for (int i = 0; i < SSB / 32; i++) {
+                for (int i = 0; i < SSB / 32; i++) {                     // quarter i = columns sub + 32i .. +31
                     const uint64_t idx = sub + (uint64_t)i * 32 + lane;
-                    raw[i * 32 + lane] = idx < c.col_hi ? __ldg(&w.sorted[idx]) : 0u;
+                    const uint32_t br = idx < c.col_hi ? __ldg(&w.sorted[idx]) : 0xFFFFFFFFu;   // pads only widen the interval
+                    const uint32_t b = idx < c.col_hi ? rotr32(br, w.rot) : 0u;
+                    b0s[i * 32 + lane] = b;
+                    bPs[i * 32 + lane] = b >> 2;
+                    bMs[i * 32 + lane] = b << 2;
+                    const uint32_t lo = __shfl_sync(FULL, br, 0), hi = __shfl_sync(FULL, br, 31);
+                    if ((lane >> 3) == i) { my_blo = lo; my_bhi = hi; }
                 }
                 __syncwarp();
+                const bool mine = (32 * (lane >> 3) < ncols) && pass_possible(T_, P_, my_alo, my_ahi, my_blo, my_bhi);
+                const unsigned cm = __ballot_sync(FULL, mine);             // bit 8c + r: slab r x quarter c can hold a candidate
 #pragma unroll 1
-                for (int cb = 0; cb < ncols; cb += 4) {
-                    const uint4 B = *reinterpret_cast<const uint4*>(&raw[cb]);
-                    uint32_t h = 0;
+                for (int q4 = 0; q4 < SSB / 32; q4++) {
+                    const unsigned sm = (cm >> (8 * q4)) & 0xFFu;
+                    if (sm == 0) continue;
+                    const int cend = min(ncols, 32 * q4 + 32);
+#pragma unroll 1
+                    for (int cb = 32 * q4; cb < cend; cb += 4) {
+                        const uint4 B0 = *reinterpret_cast<const uint4*>(&b0s[cb]);
+                        const uint4 BP = *reinterpret_cast<const uint4*>(&bPs[cb]);
+                        const uint4 BM = *reinterpret_cast<const uint4*>(&bMs[cb]);
+                        uint32_t h = 0;
 #pragma unroll
-                    for (int kk = 0; kk < 4; kk++) {
-                        const uint32_t b = pick4(B, kk);
+                        for (int r = 0; r < RA; r++) {
+                            if (sm & (1u << r)) {
 #pragma unroll
-                        for (int r = 0; r < RA; r++) h |= (pass_pred_rot(T_, P_, a[r], b) ? 1u : 0u) << (kk * 8 + r);
+                                for (int kk = 0; kk < 4; kk++) {
+                                    uint32_t u = quick_marks(a[r], pick4(B0, kk), pick4(BP, kk), pick4(BM, kk));
+                                    u &= u - 1;
+                                    if (T_ == 2) u &= u - 1;
+                                    h |= (u == 0 ? 1u : 0u) << (kk * 8 + r);
+                                }
+                            }
+                        }
+                        if (cb + 4 > ncols) h &= (1u << (8 * (ncols - cb))) - 1u;      // columns past the chunk end
+                        if (__any_sync(FULL, h != 0)) sparse_push<T_, P_>(h, colrel0 + cb, qn, c, out);
                     }
-                    if (cb + 4 > ncols) h &= (1u << (8 * (ncols - cb))) - 1u;      // columns past the chunk end
-                    if (__any_sync(FULL, h != 0)) sparse_push<T_, P_>(h, colrel0 + cb, qn, c, out);
                 }
             }
         }

@@ -43,6 +43,10 @@ int shim_pass_possible(int t, int p, uint32_t alo, uint32_t ahi, uint32_t blo, u
 {
     return bdg::pass_possible(t, p, alo, ahi, blo, bhi);
 }
+void shim_quick(int t, const uint32_t* a, const uint32_t* b, size_t n, uint8_t* out)
+{
+    for (size_t i = 0; i < n; i++) out[i] = bdg::quick_pass(a[i], b[i], t);
+}
 int shim_top_possible(int t, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi)
 {
     return t == 1 ? bdg::t1_top_possible(alo, ahi, blo, bhi) : bdg::t2_top_possible(alo, ahi, blo, bhi);

@@ -32,6 +32,7 @@ def shim(tmp_path_factory):
     L.shim_pass_pred.argtypes = [C.c_int, u32p, u32p, C.c_size_t, u8p]
     L.shim_pass_possible.argtypes = [C.c_int, C.c_int] + [C.c_uint32] * 4
     L.shim_pass_possible.restype = C.c_int
+    L.shim_quick.argtypes = [C.c_int, u32p, u32p, C.c_size_t, u8p]
     L.shim_top_possible.argtypes = [C.c_int] + [C.c_uint32] * 4
     L.shim_top_possible.restype = C.c_int
     return L
@@ -320,3 +321,22 @@ def test_pass_possible_is_conservative(shim, t):
                 assert poss or not fires, (t, p)
                 hits += bool(fires); skipped += (not poss)
         assert hits > 30 and skipped > 150, (t, p, hits, skipped)
+
+
+@pytest.mark.parametrize("t", [1, 2])
+def test_quick_pass_sound(shim, t):
+    """The per-pair test of the sparse passes never rejects a pair with D <= t (both frames), and rejects most others."""
+    L = orc.lib()
+    for seed in (5, 12):
+        a, b = make_pairs(seed)
+        D = np.fromiter((L.orc_D(int(x), int(y)) for x, y in zip(a, b)), np.int32, a.size)
+        for x, y in ((a, b), (b, a)):
+            out = np.zeros(x.size, np.uint8)
+            shim.shim_quick(t, x, y, x.size, out)
+            assert out[D <= t].all()
+    rng = np.random.default_rng(4)
+    ra = rng.integers(0, 1 << 32, 1 << 20, dtype=np.uint64).astype(np.uint32)
+    rb = rng.integers(0, 1 << 32, 1 << 20, dtype=np.uint64).astype(np.uint32)
+    out = np.zeros(ra.size, np.uint8)
+    shim.shim_quick(t, ra, rb, ra.size, out)
+    assert out.mean() < (0.004 if t == 1 else 0.03)

@@ -1,12 +1,16 @@
 #!/usr/bin/env python3
 """Basic-block view of an ncu source page: consecutive SASS instructions with the same execution count are
 folded into one line (first instruction, length, warp-level executions, share of all issued instructions).
-usage: ncu_blocks.py <file.ncu-rep> [min_share_percent]"""
+usage: ncu_blocks.py <file.ncu-rep> [min_share_percent] [launch index in the report]"""
 import csv, io, subprocess, sys
 raw = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "source", "--csv"], capture_output=True, text=True).stdout
 lines = raw.splitlines()
-start = next(i for i, l in enumerate(lines) if l.startswith('"Address"'))
-rows = list(csv.DictReader(io.StringIO("\n".join(lines[start:]))))
+starts = [i for i, l in enumerate(lines) if l.startswith('"Address"')]
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+start = starts[which]
+end = starts[which + 1] - 1 if which + 1 < len(starts) else len(lines)
+print(lines[start - 1][:120])
+rows = list(csv.DictReader(io.StringIO("\n".join(lines[start:end]))))
 minshare = float(sys.argv[2]) if len(sys.argv) > 2 else 0.5
 tot = sum(int(r["Instructions Executed"]) for r in rows)
 ttot = sum(int(r["Thread Instructions Executed"]) for r in rows)
