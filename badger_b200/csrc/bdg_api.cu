@@ -125,7 +125,7 @@ void build_plan(size_t N, int part, int nparts, int workers, Plan& p, uint64_t c
     p.item_start[p.group_ids.size()] = (uint32_t)acc;
 }
 
-constexpr size_t PLAN_HDR = 32;   // per launch: [item counter u32 | pad | sub-tiles u64 | full sub-tiles u64 | pad]
+constexpr size_t PLAN_HDR = 64;   // per launch: [item counter u32 | pad | 6 x u64 statistics | earliest warp start (ns)]
 int g_edge_mode = -1;             // -1: BDG_EDGE_MODE or default (sparse); 0 dense; 1 sparse
 
 bool sparse_mode(int t)
@@ -169,6 +169,8 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
         return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "plan workspace: %s", cudaGetErrorString(e));
     char* d_plan = (char*)ws->plan.p;   // [headers | group_ids | item_start]
     CU_TRY(cudaMemsetAsync(d_plan, 0, hdr, st));
+    for (int p = 0; p < bdg::MAX_PASSES; p++)   // the "earliest warp start" slots are minima: prime them with all ones
+        CU_TRY(cudaMemsetAsync(d_plan + PLAN_HDR * p + 56, 0xFF, 8, st));
     CU_TRY(cudaMemcpyAsync(d_plan + hdr, plan.group_ids.data(), nb_groups, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(d_plan + hdr + nb_groups, plan.item_start.data(), nb_items, cudaMemcpyHostToDevice, st));
     bdg::EdgeWork w;
@@ -338,17 +340,30 @@ int bdg_set_edge_mode(int mode)
     return BDG_OK;
 }
 
-int bdg_dev_edges_stats(unsigned long long* sub_tiles, unsigned long long* full_tiles, void* stream)
+int bdg_dev_edges_stats(unsigned long long* out4, void* stream)
 {
     DevCtx* c = ctx_of_current_device();
-    if (!c || !c->plan.p) return fail(BDG_ERR_ARG, "no edge launch on this device yet");
-    unsigned long long v[4 * bdg::MAX_PASSES];
+    if (!c || !c->plan.p || !out4) return fail(BDG_ERR_ARG, "no edge launch on this device yet");
+    unsigned long long v[(PLAN_HDR / 8) * bdg::MAX_PASSES];
     CU_TRY(cudaMemcpyAsync(v, c->plan.p, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-    unsigned long long a = 0, b = 0;
-    for (int p = 0; p < bdg::MAX_PASSES; p++) { a += v[4 * p + 1]; b += v[4 * p + 2]; }
-    if (sub_tiles) *sub_tiles = a;
-    if (full_tiles) *full_tiles = b;
+    for (int k = 0; k < 4; k++) {
+        out4[k] = 0;
+        for (int p = 0; p < bdg::MAX_PASSES; p++) out4[k] += v[(PLAN_HDR / 8) * p + 1 + k];
+    }
+    return BDG_OK;
+}
+
+// Development aid (tools/sweep_edges.py): per pass, sum and max over warps of the warp's exit time in ns
+// measured from the first warp's start - the load-balance picture of the last edge launch.
+int bdg_dev_edges_balance(unsigned long long* out /* 2 * MAX_PASSES */, void* stream)
+{
+    DevCtx* c = ctx_of_current_device();
+    if (!c || !c->plan.p || !out) return fail(BDG_ERR_ARG, "no edge launch on this device yet");
+    unsigned long long v[(PLAN_HDR / 8) * bdg::MAX_PASSES];
+    CU_TRY(cudaMemcpyAsync(v, c->plan.p, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int p = 0; p < bdg::MAX_PASSES; p++) { out[2 * p] = v[(PLAN_HDR / 8) * p + 5]; out[2 * p + 1] = v[(PLAN_HDR / 8) * p + 6]; }
     return BDG_OK;
 }
 

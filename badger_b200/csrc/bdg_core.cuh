@@ -138,22 +138,15 @@ BDG_HD bool t2_top(uint32_t a, uint32_t b)
     return f == ((b >> 20) & 0x3FFu) || f == (b >> 22) || f == ((b >> 18) & 0x3FFu);
 }
 
-// Interval of the field v[x : x+len) over all v in [lo, hi]: exact ends when the bits above the field do
-// not change between lo and hi (the field is then monotone in v), else the whole range.
-BDG_HD void field_range(uint32_t lo, uint32_t hi, int x, int len, uint32_t& flo, uint32_t& fhi)
-{
-    const uint32_t mask = (len >= 32) ? 0xFFFFFFFFu : ((1u << len) - 1u);
-    const bool same_above = (x + len >= 32) || ((lo >> (x + len)) == (hi >> (x + len)));
-    flo = same_above ? ((lo >> x) & mask) : 0u;
-    fhi = same_above ? ((hi >> x) & mask) : mask;
-}
-
+// Values of the field v[x : x+len) over all v in [lo, hi]: v >> x runs through consecutive integers, so the field
+// runs through a CYCLIC interval of the field's range: start = field(lo), length = (hi>>x) - (lo>>x) + 1, capped
+// at the whole range.  Two such intervals meet iff either start lies inside the other one.
 BDG_HD bool fields_may_meet(uint32_t alo, uint32_t ahi, int xa, uint32_t blo, uint32_t bhi, int xb, int len)
 {
-    uint32_t al, ah, bl, bh;
-    field_range(alo, ahi, xa, len, al, ah);
-    field_range(blo, bhi, xb, len, bl, bh);
-    return al <= bh && bl <= ah;
+    const uint32_t mask = (1u << len) - 1u;          // len <= 16 here
+    const uint32_t sa = (alo >> xa) & mask, sb = (blo >> xb) & mask;
+    const uint32_t la = (ahi >> xa) - (alo >> xa) + 1u, lb = (bhi >> xb) - (blo >> xb) + 1u;
+    return ((sb - sa) & mask) < la || ((sa - sb) & mask) < lb;
 }
 
 // Can ANY pair (a in [alo,ahi], b in [blo,bhi]) satisfy a top condition?  false => the whole tile skips them.

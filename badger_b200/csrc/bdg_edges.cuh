@@ -58,11 +58,51 @@ struct EdgeWork {
     uint32_t n_items;
     uint32_t chunk_cols;        // columns per work item (multiple of SB_MAX, <= 2^17)
     unsigned int* item_counter; // dynamic scheduler
-    unsigned long long* stats;  // optional [2]: sub-tiles visited, sub-tiles that ran the full prefilter
+    unsigned long long* stats;  // optional [6]: sub-tiles visited, sub-tiles scored pair by pair, pairs scored, candidates,
+                                //               sum / max over warps of the time from the first warp's start to the warp's exit (ns)
     uint32_t one;               // == 1, opaque to the compiler: x*(-one)+c keeps the subtraction on the FMA pipe (IMAD)
     int pass;                   // sparse kernel: pass index p (bdg_core.cuh pass_pred); `sorted` holds rotl(key, rot) sorted
     int rot;
 };
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// warp exit bookkeeping for the load-balance statistics: stats[6] holds the earliest start (atomicMin, primed to ~0)
+__device__ __forceinline__ void warp_exit_stats(unsigned long long* stats, unsigned long long t_start)
+{
+    const unsigned long long t0 = atomicMin(&stats[6], t_start);
+    const unsigned long long base = t0 < t_start ? t0 : t_start;
+    const unsigned long long dt = global_ns() - base;
+    atomicAdd(&stats[4], dt);
+    atomicMax(&stats[5], dt);
+}
+
+// Next work item of the dynamic scheduler: (k, j) = owned group index, column chunk.  The position of the item in
+// the prefix sums is found by a 32-ary search (one probe per lane and step: 3 round trips for 2k groups, 4 for 200k).
+__device__ __forceinline__ bool fetch_item(const EdgeWork& w, int lane, uint32_t& k, uint32_t& j)
+{
+    uint32_t item = 0;
+    if (lane == 0) item = atomicAdd(w.item_counter, 1u);
+    item = __shfl_sync(FULL, item, 0);
+    if (item >= w.n_items) return false;
+    uint32_t lo = 0, hi = w.K;                        // item_start[lo] <= item < item_start[hi]
+    while (hi - lo > 1) {
+        const uint32_t step = (hi - lo + 32) / 33;
+        const uint32_t pos = lo + (uint32_t)(lane + 1) * step;
+        const bool le = pos < hi && __ldg(&w.item_start[pos]) <= item;
+        const uint32_t c = (uint32_t)__popc(__ballot_sync(FULL, le));   // item_start is increasing: a prefix of the lanes
+        hi = min(hi, lo + (c + 1) * step);
+        lo = lo + c * step;
+    }
+    k = lo;
+    j = item - __ldg(&w.item_start[lo]);
+    return true;
+}
 
 // ---- output: warp-aggregated append (one atomic per warp that has anything to emit) ---------------
 __device__ __forceinline__ void emit_warp(bool ok, uint32_t a, uint32_t b, int d, const EdgeOut& out)
@@ -218,26 +258,12 @@ __global__ void __launch_bounds__(ENT, 3) edges_kernel(const EdgeWork w, const E
     c.q = s_q[wid]; c.qn = &s_qn[wid]; c.sorted = w.sorted; c.N = w.N; c.t = w.t; c.T = w.T; c.lane = lane;
     if (lane == 0) s_qn[wid] = 0;
     __syncwarp();
-    unsigned long long n_sub = 0, n_full = 0;
+    const unsigned long long t_start = global_ns();
+    unsigned long long n_sub = 0, n_full = 0, n_cand = 0;
 
     for (;;) {
-        uint32_t item = 0, k = 0, j = 0;
-        if (lane == 0) {
-            item = atomicAdd(w.item_counter, 1u);
-            if (item < w.n_items) {
-                uint32_t lo = 0, hi = w.K;   // largest k with item_start[k] <= item
-                while (hi - lo > 1) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (__ldg(&w.item_start[mid]) <= item) lo = mid; else hi = mid;
-                }
-                k = lo;
-                j = item - __ldg(&w.item_start[k]);
-            }
-        }
-        item = __shfl_sync(FULL, item, 0);
-        if (item >= w.n_items) break;
-        k = __shfl_sync(FULL, k, 0);
-        j = __shfl_sync(FULL, j, 0);
+        uint32_t k = 0, j = 0;
+        if (!fetch_item(w, lane, k, j)) break;
         c.row0 = (uint64_t)__ldg(&w.group_ids[k]) * GROUP;
         c.col_lo = c.row0 + (uint64_t)j * w.chunk_cols;
         c.col_hi = min((uint64_t)w.N, c.col_lo + w.chunk_cols);
@@ -328,7 +354,10 @@ __global__ void __launch_bounds__(ENT, 3) edges_kernel(const EdgeWork w, const E
                                     pair_t2_light(aw0[r], aw1[r], pick4(A4, kk), pick4(B4, kk), mone, g2, h[s], 1u << (kk * 8 + r));
                         }
                     }
-                    if (__any_sync(FULL, (h[0] | h[1] | h[2] | h[3]) != 0)) push_hits<MODE>(h, colrel0 + cb, c, out);
+                    if (__any_sync(FULL, (h[0] | h[1] | h[2] | h[3]) != 0)) {
+                        n_cand += __popc(h[0]) + __popc(h[1]) + __popc(h[2]) + __popc(h[3]);
+                        push_hits<MODE>(h, colrel0 + cb, c, out);
+                    }
                 }
             } else {
                 // ------------------------------ full prefilter (rare tiles; every pair for MODE 3) -----------
@@ -345,14 +374,19 @@ __global__ void __launch_bounds__(ENT, 3) edges_kernel(const EdgeWork w, const E
                             h[0] |= (hit ? 1u : 0u) << (kk * 8 + r);
                         }
                     }
-                    if (__any_sync(FULL, h[0] != 0)) push_hits<MODE>(h, colrel0 + cb, c, out);
+                    if (__any_sync(FULL, h[0] != 0)) { n_cand += __popc(h[0]); push_hits<MODE>(h, colrel0 + cb, c, out); }
                 }
             }
         }
         drain<MODE>(c, out, true);   // the queue's codes are relative to this item: empty it before the next one
     }
     if (w.stats) {
-        if (lane == 0) { atomicAdd(&w.stats[0], n_sub); atomicAdd(&w.stats[1], n_full); }   // uniform per warp
+        for (int o = 16; o; o >>= 1) n_cand += __shfl_down_sync(FULL, n_cand, o);           // per-lane counts
+        if (lane == 0) {                                                                  // n_sub / n_full are uniform per warp
+            atomicAdd(&w.stats[0], n_sub); atomicAdd(&w.stats[1], n_full);
+            atomicAdd(&w.stats[2], n_sub * (unsigned long long)(SB * GROUP)); atomicAdd(&w.stats[3], n_cand);
+            warp_exit_stats(w.stats, t_start);
+        }
     }
 }
 
@@ -440,29 +474,21 @@ __global__ void __launch_bounds__(ENT, 3) edges_sparse_kernel(const EdgeWork w, 
     SparseCtx c;
     c.q = s_q[wid]; c.sorted = w.sorted; c.N = w.N; c.t = w.t; c.T = w.T; c.pass = w.pass; c.rot = w.rot; c.lane = lane;
     int qn = 0;                                   // queue fill, uniform across the warp
-    unsigned long long n_sub = 0, n_full = 0;
+    const unsigned long long t_start = global_ns();
+    unsigned long long n_sub = 0, n_full = 0, n_combo = 0, n_cand = 0;
+#ifdef BDG_ITEM_TRACE
+    unsigned long long n_items_done = 0, t_item_max = 0;
+#endif
 
     for (;;) {
-        uint32_t item = 0, k = 0, j = 0;
-        if (lane == 0) {
-            item = atomicAdd(w.item_counter, 1u);
-            if (item < w.n_items) {
-                uint32_t lo = 0, hi = w.K;
-                while (hi - lo > 1) {
-                    const uint32_t mid = (lo + hi) >> 1;
-                    if (__ldg(&w.item_start[mid]) <= item) lo = mid; else hi = mid;
-                }
-                k = lo;
-                j = item - __ldg(&w.item_start[k]);
-            }
-        }
-        item = __shfl_sync(FULL, item, 0);
-        if (item >= w.n_items) break;
-        k = __shfl_sync(FULL, k, 0);
-        j = __shfl_sync(FULL, j, 0);
+        uint32_t k = 0, j = 0;
+        if (!fetch_item(w, lane, k, j)) break;
         c.row0 = (uint64_t)__ldg(&w.group_ids[k]) * GROUP;
         c.col_lo = c.row0 + (uint64_t)j * w.chunk_cols;
         c.col_hi = min((uint64_t)w.N, c.col_lo + w.chunk_cols);
+#ifdef BDG_ITEM_TRACE
+        const unsigned long long it0 = global_ns(), combo0 = n_combo, cand0 = n_cand, full0 = n_full;
+#endif
 
         uint32_t a[RA];              // UNROTATED rows (the interval test below uses the rotated end points)
 #pragma unroll
@@ -482,17 +508,27 @@ __global__ void __launch_bounds__(ENT, 3) edges_sparse_kernel(const EdgeWork w, 
             if ((lane & 7) == r) { my_alo = lo; my_ahi = hi; }
         }
 
-        for (uint64_t batch = c.col_lo; batch < c.col_hi; batch += SBATCH) {
-            const uint64_t my = batch + (uint64_t)lane * SSB;
+        for (uint64_t batch2 = c.col_lo; batch2 < c.col_hi; batch2 += 2 * SBATCH) {
+          // two batches of 32 interval tests in flight (their 4 loads per lane overlap)
+          unsigned pm_a = 0, pm_b = 0;
+#pragma unroll
+          for (int u = 0; u < 2; u++) {
+            const uint64_t my = batch2 + (uint64_t)u * SBATCH + (uint64_t)lane * SSB;
             bool poss = false;
             if (my < c.col_hi) {
                 const uint32_t b_lo = __ldg(&w.sorted[my]);
                 const uint32_t b_hi = __ldg(&w.sorted[min(c.col_hi, my + SSB) - 1]);
                 poss = pass_possible(T_, P_, a_lo, a_hi, b_lo, b_hi);
             }
-            unsigned pm = __ballot_sync(FULL, poss);
+            const unsigned pmu = __ballot_sync(FULL, poss);
+            if (u == 0) pm_a = pmu; else pm_b = pmu;
             n_sub += __popc(__ballot_sync(FULL, my < c.col_hi));
-            n_full += __popc(pm);
+            n_full += __popc(pmu);
+          }
+#pragma unroll 1
+          for (int u = 0; u < 2; u++) {
+            unsigned pm = u == 0 ? pm_a : pm_b;
+            const uint64_t batch = batch2 + (uint64_t)u * SBATCH;
             while (pm) {
                 const int l0 = __ffs(pm) - 1;
                 pm &= pm - 1;
@@ -515,6 +551,7 @@ __global__ void __launch_bounds__(ENT, 3) edges_sparse_kernel(const EdgeWork w, 
                 __syncwarp();
                 const bool mine = (32 * (lane >> 3) < ncols) && pass_possible(T_, P_, my_alo, my_ahi, my_blo, my_bhi);
                 const unsigned cm = __ballot_sync(FULL, mine);             // bit 8c + r: slab r x quarter c can hold a candidate
+                n_combo += __popc(cm);
 #pragma unroll 1
                 for (int q4 = 0; q4 < SSB / 32; q4++) {
                     const unsigned sm = (cm >> (8 * q4)) & 0xFFu;
@@ -539,10 +576,11 @@ __global__ void __launch_bounds__(ENT, 3) edges_sparse_kernel(const EdgeWork w, 
                             }
                         }
                         if (cb + 4 > ncols) h &= (1u << (8 * (ncols - cb))) - 1u;      // columns past the chunk end
-                        if (__any_sync(FULL, h != 0)) sparse_push<T_, P_>(h, colrel0 + cb, qn, c, out);
+                        if (__any_sync(FULL, h != 0)) { n_cand += __popc(h); sparse_push<T_, P_>(h, colrel0 + cb, qn, c, out); }
                     }
                 }
             }
+          }
         }
         // the queue's codes are relative to this item: finish the partial batch before moving on
         __syncwarp();
@@ -552,8 +590,22 @@ __global__ void __launch_bounds__(ENT, 3) edges_sparse_kernel(const EdgeWork w, 
             qn = 0;
         }
         __syncwarp();
+#ifdef BDG_ITEM_TRACE
+        n_items_done++; { const unsigned long long dt = global_ns() - it0; if (dt > t_item_max) t_item_max = dt; }
+#endif
     }
-    if (w.stats && lane == 0) { atomicAdd(&w.stats[0], n_sub); atomicAdd(&w.stats[1], n_full); }
+    if (w.stats) {
+        for (int o = 16; o; o >>= 1) n_cand += __shfl_down_sync(FULL, n_cand, o);           // per-lane counts
+#ifdef BDG_ITEM_TRACE
+        if (lane == 0) printf("warpexit pass %d sm %d busy_us %llu items %llu longest_item_us %llu combos %llu cands %llu\n", P_, (int)(blockIdx.x % 148),
+                              (global_ns() - t_start) / 1000ull, n_items_done, t_item_max / 1000ull, n_combo, n_cand);
+#endif
+        if (lane == 0) {                                                                  // the others are uniform per warp
+            atomicAdd(&w.stats[0], n_sub); atomicAdd(&w.stats[1], n_full);
+            atomicAdd(&w.stats[2], n_combo * 1024ull); atomicAdd(&w.stats[3], n_cand);
+            warp_exit_stats(w.stats, t_start);
+        }
+    }
 }
 
 // rotl(key, rot) for a whole array (input of the per-pass radix sort)

@@ -100,10 +100,13 @@ int bdg_dev_edges_build(const uint32_t* d_sorted, size_t N, int t, int part, int
  *   0 dense: one pass, the low-block conditions are scored for every pair (the all-pairs kernel);
  *  -1 back to the default / BDG_EDGE_MODE=dense|sparse.  t >= 3 always runs dense without a prefilter. */
 int bdg_set_edge_mode(int mode);
-/* Tile statistics of the last bdg_dev_edges_build / bdg_edges_build* launch on the current device: column
- * sub-tiles visited by the kernel and how many of them had to run the pair-by-pair prefilter (sparse: the rest were excluded
- * by their key intervals; dense: the rest ran the light loop; DESIGN.md "edges_kernel").  Synchronises the stream. */
-int bdg_dev_edges_stats(unsigned long long* sub_tiles, unsigned long long* full_tiles, void* stream);
+/* Work statistics of the last bdg_dev_edges_build / bdg_edges_build* launch on the current device, summed over
+ * its passes: out4[0] column sub-tiles whose key interval was tested, out4[1] sub-tiles that could hold a
+ * candidate, out4[2] pairs scored pair by pair (sparse: quick test; dense: light loop or full prefilter),
+ * out4[3] candidates handed to the exact stage.  Synchronises the stream.  (bench.py's roofline numerator.) */
+int bdg_dev_edges_stats(unsigned long long* out4, void* stream);
+/* Development aid: out[2p], out[2p+1] = sum and max over the warps of pass p of (warp exit - first warp start), ns. */
+int bdg_dev_edges_balance(unsigned long long* out6, void* stream);
 int bdg_dev_pack16(const char* d_seqs, size_t R, uint32_t* d_out, uint8_t* d_valid, void* stream);
 int bdg_dev_member_sorted(const uint32_t* d_sorted_wl, size_t W, const uint32_t* d_q, size_t Q, uint8_t* d_hit,
                           void* stream);
