@@ -81,7 +81,8 @@ def workload(args, world):
 def cpu_sample(s, t, seconds, seed=7):
     """Oracle port of the reference algorithm (6-mer index walk + 3-way verify) on a bounded row sample."""
     from oracle import oracle as orc
-    threads = orc.num_threads()
+    # all the host cores this process may run on (torchrun exports OMP_NUM_THREADS=1, which is not a property of the box)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or orc.num_threads())
     ix = orc.Index(s)
     rng = np.random.default_rng(seed)
     n = s.size
@@ -281,7 +282,13 @@ def run_b200(args):
     for _ in range(3):
         step_dev()
     torch.cuda.synchronize()
-    assert int(d_count.item()) == n_edges_part, "the two edge modes disagree on the edge count"
+    n_other = int(d_count.item())          # per-part counts differ between the modes (different row orders), totals must not
+    if world > 1:
+        tt = torch.tensor([n_edges_part, n_other], dtype=torch.int64, device=dev)
+        dist.all_reduce(tt)
+        assert int(tt[0].item()) == int(tt[1].item()), "the two edge modes disagree on the total edge count"
+    else:
+        assert n_other == n_edges_part, "the two edge modes disagree on the edge count"
     ms_other = timed_steps(max(2, min(args.steps, 3))) / max(2, min(args.steps, 3))
     stats_other = work_stats()
     badger_b200._lib.check(L.bdg_set_edge_mode(1 if args.mode == "sparse" else 0))
