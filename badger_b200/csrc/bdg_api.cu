@@ -9,6 +9,8 @@
 #include <cstring>
 #include <ctime>
 #include <new>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/badger_b200.h"
@@ -64,6 +66,9 @@ struct DevCtx {
     int sms = 0;
     Buf sorted, ea, eb, ed, count, plan;   // edge construction
     Buf rot_in, rot_sorted[bdg::MAX_PASSES], sort_tmp;   // sparse passes: rotated keys, their sorted copies, radix-sort scratch
+    Buf tile_bnd, tile_list;                             // sparse passes: sub-tile end keys, list of tiles that survive level 1
+    unsigned long long host_stats[bdg::MAX_PASSES][2] = {};   // interval tests done / tiles listed per pass of the last launch
+    unsigned long long generation = 0;                        // bumped by every host-buffer edge build on this device
 };
 std::vector<DevCtx> g_ctx;
 
@@ -125,7 +130,8 @@ void build_plan(size_t N, int part, int nparts, int workers, Plan& p, uint64_t c
     p.item_start[p.group_ids.size()] = (uint32_t)acc;
 }
 
-constexpr size_t PLAN_HDR = 64;   // per launch: [item counter u32 | pad | 6 x u64 statistics | earliest warp start (ns)]
+constexpr size_t PLAN_HDR = 128;  // per launch: [work cursor u64 | tile-list count u64 | 7 x u64 statistics (last: earliest warp start) | pad]
+constexpr size_t HDR_LIST = 8, HDR_STATS = 16;
 int g_edge_mode = -1;             // -1: BDG_EDGE_MODE or default (sparse); 0 dense; 1 sparse
 
 bool sparse_mode(int t)
@@ -137,10 +143,22 @@ bool sparse_mode(int t)
 }
 
 template <int T_, int P_>
-void launch_sparse(int blocks, cudaStream_t st, const bdg::EdgeWork& w, const bdg::EdgeOut& o)
+void launch_scan(int blocks, cudaStream_t st, const bdg::EdgeWork& w, const uint2* bnd, uint32_t NS, const bdg::TileList& l)
 {
-    bdg::edges_sparse_kernel<T_, P_><<<blocks, bdg::ENT, 0, st>>>(w, o);
+    bdg::sparse_scan_kernel<T_, P_><<<blocks, 256, 0, st>>>(w.sorted, w.N, w.group_ids, w.K, bnd, NS, l);
 }
+template <int T_, int P_>
+void launch_tiles(int blocks, cudaStream_t st, const bdg::EdgeWork& w, const bdg::EdgeOut& o, const bdg::TileList& l)
+{
+    bdg::sparse_tile_kernel<T_, P_><<<blocks, bdg::ENT, 0, st>>>(w, o, l);
+}
+#define BDG_PASS_DISPATCH(FN, ...)                                                    \
+    do {                                                                              \
+        if (t == 1) { if (p == 0) FN<1, 0>(__VA_ARGS__); else FN<1, 1>(__VA_ARGS__); } \
+        else if (p == 0) FN<2, 0>(__VA_ARGS__);                                       \
+        else if (p == 1) FN<2, 1>(__VA_ARGS__);                                       \
+        else FN<2, 2>(__VA_ARGS__);                                                   \
+    } while (0)
 
 // Launch the edge construction of one part on the current device / stream.  d_count is zeroed on the stream.
 // ws: the device's grow-only workspaces (plan, rotated keys, sort scratch); one in-flight call per device.
@@ -154,13 +172,13 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
     if (t <= 0 || N < 2) return BDG_OK;   // D >= 1 for distinct barcodes: no edges (barcode_graph.py:245)
     const bool sparse = sparse_mode(t);
     const int passes = sparse ? bdg::n_passes(t) : 1;
-    const void* kern = sparse ? (t == 1 ? (const void*)bdg::edges_sparse_kernel<1, 0> : (const void*)bdg::edges_sparse_kernel<2, 0>)
+    const void* kern = sparse ? (t == 1 ? (const void*)bdg::sparse_tile_kernel<1, 0> : (const void*)bdg::sparse_tile_kernel<2, 0>)
                               : (t == 1 ? (const void*)bdg::edges_kernel<1> : t == 2 ? (const void*)bdg::edges_kernel<2>
                                                                                      : (const void*)bdg::edges_kernel<3>);
     int grid = 0;
     if (int rc = grid_for(kern, &grid, bdg::ENT)) return rc;
     Plan plan;
-    build_plan(N, part, nparts, grid * bdg::EW, plan, sparse ? bdg::SBATCH : bdg::SB_MAX);
+    build_plan(N, part, nparts, grid * bdg::EW, plan, bdg::SB_MAX);
     const uint32_t n_items = plan.item_start.empty() ? 0 : plan.item_start.back();
     if (n_items == 0) return BDG_OK;
     const size_t nb_groups = plan.group_ids.size() * sizeof(uint32_t), nb_items = plan.item_start.size() * sizeof(uint32_t);
@@ -169,8 +187,10 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
         return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "plan workspace: %s", cudaGetErrorString(e));
     char* d_plan = (char*)ws->plan.p;   // [headers | group_ids | item_start]
     CU_TRY(cudaMemsetAsync(d_plan, 0, hdr, st));
-    for (int p = 0; p < bdg::MAX_PASSES; p++)   // the "earliest warp start" slots are minima: prime them with all ones
-        CU_TRY(cudaMemsetAsync(d_plan + PLAN_HDR * p + 56, 0xFF, 8, st));
+    for (int p = 0; p < bdg::MAX_PASSES; p++) {   // the "earliest warp start" slots are minima: prime them with all ones
+        CU_TRY(cudaMemsetAsync(d_plan + PLAN_HDR * p + HDR_STATS + 48, 0xFF, 8, st));
+        ws->host_stats[p][0] = ws->host_stats[p][1] = 0;
+    }
     CU_TRY(cudaMemcpyAsync(d_plan + hdr, plan.group_ids.data(), nb_groups, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(d_plan + hdr + nb_groups, plan.item_start.data(), nb_items, cudaMemcpyHostToDevice, st));
     bdg::EdgeWork w;
@@ -187,16 +207,16 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
     const int blocks = (int)std::min<uint64_t>((uint64_t)grid, (n_items + bdg::EW - 1) / bdg::EW);
     for (int p = 0; p < passes; p++) {
         w.item_counter = (unsigned int*)(d_plan + PLAN_HDR * p);
-        w.stats = (unsigned long long*)(d_plan + PLAN_HDR * p + 8);
+        w.stats = (unsigned long long*)(d_plan + PLAN_HDR * p + HDR_STATS);
         w.pass = p;
         w.rot = sparse ? bdg::pass_rot(t, p) : 0;
         w.sorted = d_sorted;
+        auto ensure = [&](Buf& b, size_t bytes) -> int {
+            if (cudaError_t e = (cudaError_t)b.ensure(bytes))
+                return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "workspace of %zu bytes: %s", bytes, cudaGetErrorString(e));
+            return BDG_OK;
+        };
         if (w.rot != 0) {   // this pass scans the array in the order of rotl(key, rot): rotate, radix-sort
-            auto ensure = [&](Buf& b, size_t bytes) -> int {
-                if (cudaError_t e = (cudaError_t)b.ensure(bytes))
-                    return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "sort workspace of %zu bytes: %s", bytes, cudaGetErrorString(e));
-                return BDG_OK;
-            };
             if (int e = ensure(ws->rot_in, N * 4)) return e;
             if (int e = ensure(ws->rot_sorted[p], N * 4)) return e;
             size_t tmp_bytes = 0;
@@ -212,12 +232,37 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
             if (t == 1) bdg::edges_kernel<1><<<blocks, bdg::ENT, 0, st>>>(w, o);
             else if (t == 2) bdg::edges_kernel<2><<<blocks, bdg::ENT, 0, st>>>(w, o);
             else bdg::edges_kernel<3><<<blocks, bdg::ENT, 0, st>>>(w, o);
-        } else if (t == 1) {
-            if (p == 0) launch_sparse<1, 0>(blocks, st, w, o); else launch_sparse<1, 1>(blocks, st, w, o);
         } else {
-            if (p == 0) launch_sparse<2, 0>(blocks, st, w, o);
-            else if (p == 1) launch_sparse<2, 1>(blocks, st, w, o);
-            else launch_sparse<2, 2>(blocks, st, w, o);
+            // level 1: interval scan of every (owned row group, sub-tile right of it) -> compact tile list
+            const uint32_t NS = (uint32_t)((N + bdg::SSB - 1) / bdg::SSB);
+            if (int e = ensure(ws->tile_bnd, (size_t)NS * sizeof(uint2))) return e;
+            if (ws->tile_list.cap == 0)
+                if (int e = ensure(ws->tile_list, std::max<size_t>((size_t)1 << 22, 4 * N) * sizeof(uint2))) return e;
+            bdg::tile_bounds_kernel<<<std::min<uint32_t>((NS + 255) / 256, (uint32_t)ws->sms * 8), 256, 0, st>>>(w.sorted, w.N, (uint2*)ws->tile_bnd.p, NS);
+            g_launches++;
+            unsigned long long n_tiles = 0;
+            for (int attempt = 0; attempt < 2; attempt++) {
+                bdg::TileList l{(uint2*)ws->tile_list.p, (unsigned long long*)(d_plan + PLAN_HDR * p + HDR_LIST), ws->tile_list.cap / sizeof(uint2)};
+                CU_TRY(cudaMemsetAsync(l.count, 0, 8, st));
+                const int sblocks = (int)std::min<uint64_t>(w.K, (uint64_t)ws->sms * 16);
+                BDG_PASS_DISPATCH(launch_scan, sblocks, st, w, (const uint2*)ws->tile_bnd.p, NS, l);
+                g_launches++;
+                CU_TRY(cudaGetLastError());
+                // the list length sizes the next launch (and tells whether the list was large enough): one 8-byte read-back
+                CU_TRY(cudaMemcpyAsync(&n_tiles, l.count, 8, cudaMemcpyDeviceToHost, st));
+                CU_TRY(cudaStreamSynchronize(st));
+                if (n_tiles <= l.cap) break;
+                if (attempt == 1) return fail(BDG_ERR_CUDA, "tile list count changed between identical scans");
+                if (int e = ensure(ws->tile_list, (size_t)n_tiles * sizeof(uint2))) return e;   // grow-only; rescan into the larger list
+            }
+            uint64_t tests = 0;
+            for (uint32_t g : plan.group_ids) tests += NS - std::min<uint64_t>(NS, (uint64_t)g * (bdg::GROUP / bdg::SSB));
+            ws->host_stats[p][0] = tests;
+            ws->host_stats[p][1] = n_tiles;
+            if (n_tiles == 0) continue;
+            bdg::TileList l{(uint2*)ws->tile_list.p, (unsigned long long*)(d_plan + PLAN_HDR * p + HDR_LIST), ws->tile_list.cap / sizeof(uint2)};
+            const int tblocks = (int)std::min<uint64_t>((uint64_t)grid, (n_tiles + bdg::EW - 1) / bdg::EW);
+            BDG_PASS_DISPATCH(launch_tiles, tblocks, st, w, o, l);
         }
         g_launches++;
         CU_TRY(cudaGetLastError());
@@ -258,9 +303,13 @@ size_t edge_cap_guess(size_t N, int nparts)
 
 }  // namespace
 
+// Handle of one edge construction: the edges stay in the devices' grow-only workspaces until the caller copies them
+// out (bdg_edges_copy: ONE device-to-host copy per array, straight into the caller's buffers).  A later build on the
+// same device reuses those workspaces, which makes older handles stale (checked through the generation numbers).
 struct bdg_edges {
-    std::vector<uint32_t> a, b;
-    std::vector<uint8_t> d;
+    std::vector<int> ctx;                 // indices into g_ctx
+    std::vector<size_t> count;            // edges held by each of them
+    std::vector<unsigned long long> gen;  // workspace generation at build time
 };
 
 extern "C" {
@@ -310,7 +359,7 @@ void bdg_shutdown(void)
     for (auto& c : g_ctx) {
         if (c.stream) { cudaSetDevice(c.dev); cudaStreamSynchronize(c.stream); cudaStreamDestroy(c.stream); }
         c.sorted.release(); c.ea.release(); c.eb.release(); c.ed.release(); c.count.release(); c.plan.release();
-        c.rot_in.release(); c.sort_tmp.release();
+        c.rot_in.release(); c.sort_tmp.release(); c.tile_bnd.release(); c.tile_list.release();
         for (auto& b : c.rot_sorted) b.release();
     }
     g_ctx.clear();
@@ -349,7 +398,7 @@ int bdg_dev_edges_stats(unsigned long long* out4, void* stream)
     CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
     for (int k = 0; k < 4; k++) {
         out4[k] = 0;
-        for (int p = 0; p < bdg::MAX_PASSES; p++) out4[k] += v[(PLAN_HDR / 8) * p + 1 + k];
+        for (int p = 0; p < bdg::MAX_PASSES; p++) out4[k] += v[(PLAN_HDR / 8) * p + HDR_STATS / 8 + k] + (k < 2 ? c->host_stats[p][k] : 0);
     }
     return BDG_OK;
 }
@@ -363,7 +412,10 @@ int bdg_dev_edges_balance(unsigned long long* out /* 2 * MAX_PASSES */, void* st
     unsigned long long v[(PLAN_HDR / 8) * bdg::MAX_PASSES];
     CU_TRY(cudaMemcpyAsync(v, c->plan.p, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-    for (int p = 0; p < bdg::MAX_PASSES; p++) { out[2 * p] = v[(PLAN_HDR / 8) * p + 5]; out[2 * p + 1] = v[(PLAN_HDR / 8) * p + 6]; }
+    for (int p = 0; p < bdg::MAX_PASSES; p++) {
+        out[2 * p] = v[(PLAN_HDR / 8) * p + HDR_STATS / 8 + 4];
+        out[2 * p + 1] = v[(PLAN_HDR / 8) * p + HDR_STATS / 8 + 5];
+    }
     return BDG_OK;
 }
 
@@ -467,6 +519,40 @@ int bdg_pack16(const char* seqs, size_t R, uint32_t* out, uint8_t* valid)
     return rc;
 }
 
+
+// One device's share of a host-buffer edge build: upload, launch, read the count back (re-run once with the exact
+// size when the guess was too small).  Runs on its own host thread when several devices take part, because the
+// sparse passes read a tile count back between their kernels.
+static int edges_on_device(DevCtx& c, const uint32_t* sorted, size_t N, int t, int part, int nparts, size_t* n_out)
+{
+    auto ensure = [&](Buf& b, size_t bytes) -> int {
+        if (cudaError_t e = (cudaError_t)b.ensure(bytes))
+            return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation of %zu bytes: %s", bytes, cudaGetErrorString(e));
+        return BDG_OK;
+    };
+    CU_TRY(cudaSetDevice(c.dev));
+    if (int e = ensure(c.sorted, std::max<size_t>(N, 1) * 4)) return e;
+    if (int e = ensure(c.count, sizeof(unsigned long long))) return e;
+    CU_TRY(cudaMemcpyAsync(c.sorted.p, sorted, N * 4, cudaMemcpyHostToDevice, c.stream));
+    size_t cap = std::max(edge_cap_guess(N, nparts), c.ea.cap / 4);
+    unsigned long long count = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (int e = ensure(c.ea, cap * 4)) return e;
+        if (int e = ensure(c.eb, cap * 4)) return e;
+        if (int e = ensure(c.ed, cap)) return e;
+        if (int e = launch_edges((const uint32_t*)c.sorted.p, N, t, part, nparts, (uint32_t*)c.ea.p, (uint32_t*)c.eb.p, (uint8_t*)c.ed.p, cap,
+                                 (unsigned long long*)c.count.p, c.stream, &c)) return e;
+        CU_TRY(cudaMemcpyAsync(&count, c.count.p, sizeof(count), cudaMemcpyDeviceToHost, c.stream));
+        CU_TRY(cudaStreamSynchronize(c.stream));
+        if (count <= cap) break;               // rare: the guess was too small; the edge set is deterministic, so run again
+        if (attempt == 1) return fail(BDG_ERR_CUDA, "edge count changed between identical launches");
+        cap = (size_t)count;
+    }
+    c.generation++;
+    *n_out = (size_t)count;
+    return BDG_OK;
+}
+
 static double now_ms()
 {
     timespec ts;
@@ -477,67 +563,34 @@ static double now_ms()
 static int edges_on_devices(const uint32_t* sorted, size_t N, int t, const std::vector<int>& ctx_idx,
                             const std::vector<int>& parts, int nparts, bdg_edges* res)
 {
-    const bool trace = getenv("BDG_TRACE") != nullptr;
     const double t0 = now_ms();
-    std::vector<unsigned long long> counts(ctx_idx.size(), 0);
-    auto ensure = [&](Buf& b, size_t bytes) -> int {
-        if (cudaError_t e = (cudaError_t)b.ensure(bytes))
-            return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation of %zu bytes: %s", bytes, cudaGetErrorString(e));
-        return BDG_OK;
+    const size_t G = ctx_idx.size();
+    std::vector<int> rcs(G, BDG_OK);
+    std::vector<std::string> errs(G);
+    std::vector<size_t> counts(G, 0);
+    auto work = [&](size_t g) {
+        rcs[g] = edges_on_device(g_ctx[ctx_idx[g]], sorted, N, t, parts[g], nparts, &counts[g]);
+        if (rcs[g]) errs[g] = g_err;       // g_err is thread-local
     };
-    auto launch = [&](DevCtx& c, int part, size_t cap) -> int {
-        if (int e = ensure(c.ea, cap * 4)) return e;
-        if (int e = ensure(c.eb, cap * 4)) return e;
-        if (int e = ensure(c.ed, cap)) return e;
-        return launch_edges((const uint32_t*)c.sorted.p, N, t, part, nparts, (uint32_t*)c.ea.p, (uint32_t*)c.eb.p, (uint8_t*)c.ed.p,
-                            cap, (unsigned long long*)c.count.p, c.stream, &c);
-    };
-    std::vector<size_t> caps(ctx_idx.size(), 0);
-    int rc = BDG_OK;
-    // upload + launch on every device first (asynchronous), then collect
-    for (size_t g = 0; g < ctx_idx.size() && rc == BDG_OK; g++) {
-        DevCtx& c = g_ctx[ctx_idx[g]];
-        rc = [&]() -> int {
-            CU_TRY(cudaSetDevice(c.dev));
-            if (int e = ensure(c.sorted, std::max<size_t>(N, 1) * 4)) return e;
-            if (int e = ensure(c.count, sizeof(unsigned long long))) return e;
-            CU_TRY(cudaMemcpyAsync(c.sorted.p, sorted, N * 4, cudaMemcpyHostToDevice, c.stream));
-            caps[g] = std::max(edge_cap_guess(N, nparts), c.ea.cap / 4);
-            return launch(c, parts[g], caps[g]);
-        }();
-    }
-    const double t1 = now_ms();
-    double t2 = t1;
-    for (size_t g = 0; g < ctx_idx.size() && rc == BDG_OK; g++) {
-        DevCtx& c = g_ctx[ctx_idx[g]];
-        rc = [&]() -> int {
-            CU_TRY(cudaSetDevice(c.dev));
-            CU_TRY(cudaMemcpyAsync(&counts[g], c.count.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
-            CU_TRY(cudaStreamSynchronize(c.stream));
-            if (counts[g] > caps[g]) {   // rare: the guess was too small; the edge set is deterministic, so run again
-                caps[g] = (size_t)counts[g];
-                if (int e = launch(c, parts[g], caps[g])) return e;
-                CU_TRY(cudaMemcpyAsync(&counts[g], c.count.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
-                CU_TRY(cudaStreamSynchronize(c.stream));
-                if (counts[g] > caps[g]) return fail(BDG_ERR_CUDA, "edge count changed between identical launches");
-            }
-            t2 = now_ms();
-            const size_t off = res->a.size(), n = (size_t)counts[g];
-            res->a.resize(off + n); res->b.resize(off + n); res->d.resize(off + n);
-            if (n) {
-                CU_TRY(cudaMemcpyAsync(res->a.data() + off, c.ea.p, n * 4, cudaMemcpyDeviceToHost, c.stream));
-                CU_TRY(cudaMemcpyAsync(res->b.data() + off, c.eb.p, n * 4, cudaMemcpyDeviceToHost, c.stream));
-                CU_TRY(cudaMemcpyAsync(res->d.data() + off, c.ed.p, n, cudaMemcpyDeviceToHost, c.stream));
-                CU_TRY(cudaStreamSynchronize(c.stream));
-            }
-            return BDG_OK;
-        }();
+    if (G == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (size_t g = 0; g < G; g++) th.emplace_back(work, g);
+        for (auto& x : th) x.join();
     }
     if (!g_ctx.empty()) cudaSetDevice(g_ctx[0].dev);
-    if (trace)
-        fprintf(stderr, "[bdg] edges N=%zu t=%d devices=%zu: upload+launch %.2f ms, kernels %.2f ms, download %.2f ms, edges %zu\n", N, t,
-                ctx_idx.size(), t1 - t0, t2 - t1, now_ms() - t2, res->a.size());
-    return rc;
+    for (size_t g = 0; g < G; g++)
+        if (rcs[g]) return fail(rcs[g], "%s", errs[g].c_str());
+    size_t total = 0;
+    for (size_t g = 0; g < G; g++) {
+        res->ctx.push_back(ctx_idx[g]);
+        res->count.push_back(counts[g]);
+        res->gen.push_back(g_ctx[ctx_idx[g]].generation);
+        total += counts[g];
+    }
+    if (getenv("BDG_TRACE"))
+        fprintf(stderr, "[bdg] edges N=%zu t=%d devices=%zu: upload + kernels %.2f ms, edges %zu\n", N, t, G, now_ms() - t0, total);
+    return BDG_OK;
 }
 
 int bdg_edges_build(const uint32_t* sorted_unique, size_t N, int t, bdg_edges** out)
@@ -554,6 +607,7 @@ int bdg_edges_build(const uint32_t* sorted_unique, size_t N, int t, bdg_edges** 
     int rc = BDG_OK;
     try { rc = edges_on_devices(sorted_unique, N, t, idx, parts, G, res); }
     catch (const std::bad_alloc&) { rc = fail(BDG_ERR_OOM, "host allocation failed"); }
+    catch (const std::exception& e) { rc = fail(BDG_ERR_CUDA, "host thread failure: %s", e.what()); }
     if (rc) { delete res; return rc; }
     *out = res;
     return BDG_OK;
@@ -576,14 +630,35 @@ int bdg_edges_build_part(const uint32_t* sorted_unique, size_t N, int t, int par
     return BDG_OK;
 }
 
-size_t bdg_edges_count(const bdg_edges* e) { return e ? e->a.size() : 0; }
+size_t bdg_edges_count(const bdg_edges* e)
+{
+    size_t n = 0;
+    if (e) for (size_t c : e->count) n += c;
+    return n;
+}
 
 int bdg_edges_copy(const bdg_edges* e, uint32_t* a, uint32_t* b, uint8_t* d)
 {
     if (!e) return fail(BDG_ERR_ARG, "NULL edge handle");
-    const size_t n = e->a.size();
+    const size_t n = bdg_edges_count(e);
     if (n && (!a || !b || !d)) return fail(BDG_ERR_ARG, "NULL output pointer");
-    if (n) { memcpy(a, e->a.data(), n * 4); memcpy(b, e->b.data(), n * 4); memcpy(d, e->d.data(), n); }
+    size_t off = 0;
+    for (size_t g = 0; g < e->ctx.size(); g++) {
+        if (e->ctx[g] < 0 || (size_t)e->ctx[g] >= g_ctx.size() || g_ctx[e->ctx[g]].generation != e->gen[g])
+            return fail(BDG_ERR_ARG, "stale edge handle: a later edge build on the same device has reused its buffers");
+        DevCtx& c = g_ctx[e->ctx[g]];
+        const size_t k = e->count[g];
+        if (k) {
+            CU_TRY(cudaSetDevice(c.dev));
+            CU_TRY(cudaMemcpyAsync(a + off, c.ea.p, k * 4, cudaMemcpyDeviceToHost, c.stream));
+            CU_TRY(cudaMemcpyAsync(b + off, c.eb.p, k * 4, cudaMemcpyDeviceToHost, c.stream));
+            CU_TRY(cudaMemcpyAsync(d + off, c.ed.p, k, cudaMemcpyDeviceToHost, c.stream));
+        }
+        off += k;
+    }
+    for (size_t g = 0; g < e->ctx.size(); g++)
+        if (e->count[g]) { CU_TRY(cudaSetDevice(g_ctx[e->ctx[g]].dev)); CU_TRY(cudaStreamSynchronize(g_ctx[e->ctx[g]].stream)); }
+    if (!g_ctx.empty()) cudaSetDevice(g_ctx[0].dev);
     return BDG_OK;
 }
 

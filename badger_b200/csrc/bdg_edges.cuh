@@ -392,55 +392,101 @@ __global__ void __launch_bounds__(ENT, 3) edges_kernel(const EdgeWork w, const E
 
 
 // =====================================================================================================
-// Sparse multi-pass form (bdg_core.cuh "Multi-pass").  One launch per pass; `w.sorted` is the array sorted by
-// the pass's rotated key.  A warp owns (row group, column chunk) items as above, but instead of testing pairs
-// it tests TILES: lane l takes column sub-tile l of a batch of 32, reads its first and last key and asks
-// pass_possible() against the row group's first/last key.  Only the sub-tiles that survive are staged in
-// shared memory; inside them every pair gets the quick test of bdg_core.cuh (<= t columns mismatching on all
-// three diagonals: 9 ALU + 5 FMA-pipe instructions), hit bits -> candidate queue -> exact stage as in the
-// dense kernel.  The exact stage keeps a candidate only if THIS pass's predicate holds and no EARLIER pass's
-// does, so the passes' outputs are disjoint and simply share one output cursor.
+// Sparse multi-pass form (bdg_core.cuh "Multi-pass").  `sorted` is the array sorted by the pass's rotated key.
+// Three small kernels per pass:
+//   tile_bounds_kernel   first / last key of every 128-column sub-tile (8 B per sub-tile, stays in L2)
+//   sparse_scan_kernel   LEVEL 1: one interval test (pass_possible) per (row group of 256 rows, sub-tile right of
+//                        it); the (group, sub-tile) pairs that can hold a candidate are appended to a compact
+//                        tile list.  Pure streaming, every pair of the matrix is decided here or handed on.
+//   sparse_tile_kernel   persistent warps pull tiles from the list (small uniform units: no load imbalance):
+//                        LEVEL 2 - lane l tests (32-row slab l&7, 32-column quarter l>>3) -> mask of 32x32 blocks;
+//                        inside those every pair gets the quick test of bdg_core.cuh (<= t columns mismatching
+//                        on all three diagonals: ~9 ALU-pipe + 5 FMA-pipe instructions), hit bits -> the warp's
+//                        candidate queue (ballot/popc slots) -> warp-cooperative exact stage whenever 32 wait.
+// The exact stage keeps a candidate only if THIS pass's predicate holds and no EARLIER pass's does, so the
+// passes' outputs are disjoint and simply share one output cursor.
 // =====================================================================================================
 constexpr int SSB = 128;           // columns per sub-tile
-constexpr int SBATCH = 32 * SSB;   // columns per interval-test batch (one sub-tile per lane)
-constexpr int SQCAP = 64;
+constexpr int SQCAP = 64;          // candidate queue entries per warp (31 left over + 32 new)
+
+struct TileList {
+    uint2* tiles;                  // (group, sub-tile)
+    unsigned long long* count;     // tiles appended (may exceed cap: the host then grows the list and rescans)
+    unsigned long long cap;
+};
+
+__global__ void tile_bounds_kernel(const uint32_t* __restrict__ sorted, uint32_t N, uint2* __restrict__ bnd, uint32_t NS)
+{
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < NS; s += gridDim.x * blockDim.x) {
+        const uint64_t c0 = (uint64_t)s * SSB, c1 = min((uint64_t)N, c0 + SSB) - 1;
+        bnd[s] = make_uint2(__ldg(&sorted[c0]), __ldg(&sorted[c1]));
+    }
+}
+
+template <int T_, int P_>
+__global__ void __launch_bounds__(256) sparse_scan_kernel(const uint32_t* __restrict__ sorted, uint32_t N,
+                                                          const uint32_t* __restrict__ group_ids, uint32_t K,
+                                                          const uint2* __restrict__ bnd, uint32_t NS, TileList list)
+{
+    const int lane = threadIdx.x & 31;
+    for (uint32_t k = blockIdx.x; k < K; k += gridDim.x) {
+        const uint32_t g = __ldg(&group_ids[k]);
+        const uint64_t row0 = (uint64_t)g * GROUP;
+        const uint32_t a_lo = __ldg(&sorted[row0]);
+        const uint32_t a_hi = __ldg(&sorted[min((uint64_t)N, row0 + GROUP) - 1]);
+        const uint32_t s0 = g * (GROUP / SSB);                      // first sub-tile that reaches past the group's first row
+        for (uint32_t sb = s0; sb < NS; sb += blockDim.x) {        // whole warps stay in the loop together
+            const uint32_t sidx = sb + threadIdx.x;
+            bool poss = false;
+            if (sidx < NS) {
+                const uint2 b = __ldg(&bnd[sidx]);
+                poss = pass_possible(T_, P_, a_lo, a_hi, b.x, b.y);
+            }
+            const unsigned m = __ballot_sync(FULL, poss);
+            if (m) {
+                unsigned long long base = 0;
+                const int leader = __ffs(m) - 1;
+                if (lane == leader) base = atomicAdd(list.count, (unsigned long long)__popc(m));
+                base = __shfl_sync(FULL, base, leader);
+                const unsigned long long pos = base + __popc(m & ((1u << lane) - 1u));
+                if (poss && pos < list.cap) list.tiles[pos] = make_uint2(g, sidx);
+            }
+        }
+    }
+}
 
 struct SparseCtx {
-    uint32_t* q;
+    uint2* q;                      // candidate queue: (row, column) indices into `sorted`
     const uint32_t* sorted;
     uint32_t N;
-    uint64_t row0, col_lo, col_hi;
-    int t, T, pass, rot, lane;
+    int t, T, rot, lane;
 };
 
 template <int T_, int P_>
-__device__ __forceinline__ void sparse_process(const SparseCtx& c, const EdgeOut& out, uint32_t e, bool active)
+__device__ __forceinline__ void sparse_process(const SparseCtx& c, const EdgeOut& out, uint2 e, bool active)
 {
     bool ok = false;
     uint32_t x = 0, y = 0;
     int d = 0;
-    if (active) {
-        const uint64_t row = c.row0 + (e & 255u), col = c.col_lo + (e >> 8);
-        if (row < col && col < c.col_hi) {          // each unordered pair once: row index < column index
-            x = rotr32(__ldg(&c.sorted[row]), c.rot);
-            y = rotr32(__ldg(&c.sorted[col]), c.rot);
-            if (x > y) { const uint32_t tmp = x; x = y; y = tmp; }
-            bool mine = pass_pred(T_, P_, x, y);      // found by this pass and by no earlier one
+    if (active && e.x < e.y && e.y < c.N) {             // each unordered pair once: row index < column index
+        x = rotr32(__ldg(&c.sorted[e.x]), c.rot);
+        y = rotr32(__ldg(&c.sorted[e.y]), c.rot);
+        if (x > y) { const uint32_t tmp = x; x = y; y = tmp; }
+        bool mine = pass_pred(T_, P_, x, y);            // found by this pass and by no earlier one
 #pragma unroll
-            for (int q = 0; q < P_; q++) mine = mine && !pass_pred(T_, q, x, y);
-            if (mine) {
-                d = dist_small(x, y);
-                if (d > c.t || qgram_score(x, y) < c.T) d = 0;
-                ok = d > 0;
-            }
+        for (int q = 0; q < P_; q++) mine = mine && !pass_pred(T_, q, x, y);
+        if (mine) {
+            d = dist_small(x, y);
+            if (d > c.t || qgram_score(x, y) < c.T) d = 0;
+            ok = d > 0;
         }
     }
     emit_warp(ok, x, y, d, out);
 }
 
-// append the set bits of h (bit k*8+r = column colrel+k, row r*32+lane); run stage 2 whenever 32 candidates wait
+// append the set bits of h (bit k*8+r = column col0+k, row row0 + r*32 + lane); run stage 2 whenever 32 candidates wait
 template <int T_, int P_>
-__device__ __forceinline__ void sparse_push(uint32_t h, uint32_t colrel, int& qn, const SparseCtx& c, const EdgeOut& out)
+__device__ __forceinline__ void sparse_push(uint32_t h, uint32_t row0, uint32_t col0, int& qn, const SparseCtx& c, const EdgeOut& out)
 {
     for (;;) {
         const bool has = h != 0;
@@ -449,13 +495,13 @@ __device__ __forceinline__ void sparse_push(uint32_t h, uint32_t colrel, int& qn
         if (has) {
             const int j = __ffs(h) - 1;
             h &= h - 1;
-            c.q[qn + __popc(m & ((1u << c.lane) - 1u))] = ((colrel + (j >> 3)) << 8) | (uint32_t)((j & 7) * 32 + c.lane);
+            c.q[qn + __popc(m & ((1u << c.lane) - 1u))] = make_uint2(row0 + (uint32_t)((j & 7) * 32 + c.lane), col0 + (uint32_t)(j >> 3));
         }
         qn += __popc(m);
         __syncwarp();
         if (qn >= 32) {
             qn -= 32;
-            const uint32_t e = c.q[qn + c.lane];
+            const uint2 e = c.q[qn + c.lane];
             sparse_process<T_, P_>(c, out, e, true);
         }
         __syncwarp();
@@ -463,145 +509,97 @@ __device__ __forceinline__ void sparse_push(uint32_t h, uint32_t colrel, int& qn
 }
 
 template <int T_, int P_>
-__global__ void __launch_bounds__(ENT, 3) edges_sparse_kernel(const EdgeWork w, const EdgeOut out)
+__global__ void __launch_bounds__(ENT, 3) sparse_tile_kernel(const EdgeWork w, const EdgeOut out, const TileList list)
 {
     __shared__ __align__(16) uint32_t s_b[EW][3][SSB];   // unrotated b, b >> 2, b << 2 of the staged sub-tile
-    __shared__ uint32_t s_q[EW][SQCAP];
+    __shared__ uint2 s_q[EW][SQCAP];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t* const b0s = s_b[wid][0];
     uint32_t* const bPs = s_b[wid][1];
     uint32_t* const bMs = s_b[wid][2];
     SparseCtx c;
-    c.q = s_q[wid]; c.sorted = w.sorted; c.N = w.N; c.t = w.t; c.T = w.T; c.pass = w.pass; c.rot = w.rot; c.lane = lane;
+    c.q = s_q[wid]; c.sorted = w.sorted; c.N = w.N; c.t = w.t; c.T = w.T; c.rot = w.rot; c.lane = lane;
     int qn = 0;                                   // queue fill, uniform across the warp
     const unsigned long long t_start = global_ns();
-    unsigned long long n_sub = 0, n_full = 0, n_combo = 0, n_cand = 0;
-#ifdef BDG_ITEM_TRACE
-    unsigned long long n_items_done = 0, t_item_max = 0;
-#endif
+    unsigned long long n_combo = 0, n_cand = 0;
+    const unsigned long long n_tiles = min(*list.count, list.cap);
+    uint32_t g_cur = 0xFFFFFFFFu;
+    uint32_t a[RA];                               // UNROTATED rows of the current group
+    uint32_t my_alo = 0, my_ahi = 0;              // rotated end points of this lane's slab (lane & 7)
 
     for (;;) {
-        uint32_t k = 0, j = 0;
-        if (!fetch_item(w, lane, k, j)) break;
-        c.row0 = (uint64_t)__ldg(&w.group_ids[k]) * GROUP;
-        c.col_lo = c.row0 + (uint64_t)j * w.chunk_cols;
-        c.col_hi = min((uint64_t)w.N, c.col_lo + w.chunk_cols);
-#ifdef BDG_ITEM_TRACE
-        const unsigned long long it0 = global_ns(), combo0 = n_combo, cand0 = n_cand, full0 = n_full;
-#endif
-
-        uint32_t a[RA];              // UNROTATED rows (the interval test below uses the rotated end points)
+        unsigned long long ti = 0;
+        if (lane == 0) ti = atomicAdd((unsigned long long*)w.item_counter, 1ull);
+        ti = __shfl_sync(FULL, ti, 0);
+        if (ti >= n_tiles) break;
+        const uint2 tile = list.tiles[ti];
+        const uint32_t row0 = tile.x * GROUP;
+        if (tile.x != g_cur) {                    // consecutive list entries mostly share the group
+            g_cur = tile.x;
 #pragma unroll
-        for (int r = 0; r < RA; r++) {
-            const uint64_t idx = c.row0 + (uint64_t)r * 32 + lane;
-            a[r] = idx < w.N ? rotr32(__ldg(&w.sorted[idx]), w.rot) : 0xFFFFFFFFu;   // pad rows are dropped in sparse_process
-        }
-        const uint32_t a_lo = __ldg(&w.sorted[c.row0]);
-        const uint32_t a_hi = __ldg(&w.sorted[min((uint64_t)w.N, c.row0 + GROUP) - 1]);
-        // second-level intervals: lane l owns the combination (row slab r = l & 7, column quarter c = l >> 3).
-        // Slab r = the 32 consecutive rows row0 + 32r .. +31 (one per lane); its rotated end points sit in lanes 0 / 31.
-        uint32_t my_alo = 0, my_ahi = 0;
-#pragma unroll
-        for (int r = 0; r < RA; r++) {
-            const uint32_t ar = rotl32(a[r], w.rot);                  // pad rows are 0xFFFFFFFF: they only widen the interval
-            const uint32_t lo = __shfl_sync(FULL, ar, 0), hi = __shfl_sync(FULL, ar, 31);
-            if ((lane & 7) == r) { my_alo = lo; my_ahi = hi; }
-        }
-
-        for (uint64_t batch2 = c.col_lo; batch2 < c.col_hi; batch2 += 2 * SBATCH) {
-          // two batches of 32 interval tests in flight (their 4 loads per lane overlap)
-          unsigned pm_a = 0, pm_b = 0;
-#pragma unroll
-          for (int u = 0; u < 2; u++) {
-            const uint64_t my = batch2 + (uint64_t)u * SBATCH + (uint64_t)lane * SSB;
-            bool poss = false;
-            if (my < c.col_hi) {
-                const uint32_t b_lo = __ldg(&w.sorted[my]);
-                const uint32_t b_hi = __ldg(&w.sorted[min(c.col_hi, my + SSB) - 1]);
-                poss = pass_possible(T_, P_, a_lo, a_hi, b_lo, b_hi);
+            for (int r = 0; r < RA; r++) {
+                const uint32_t idx = row0 + (uint32_t)r * 32 + lane;
+                const uint32_t ar = idx < w.N ? __ldg(&w.sorted[idx]) : 0xFFFFFFFFu;    // pad rows only widen the interval;
+                a[r] = rotr32(ar, w.rot);                                               // they are dropped in sparse_process
+                const uint32_t lo = __shfl_sync(FULL, ar, 0), hi = __shfl_sync(FULL, ar, 31);
+                if ((lane & 7) == r) { my_alo = lo; my_ahi = hi; }
             }
-            const unsigned pmu = __ballot_sync(FULL, poss);
-            if (u == 0) pm_a = pmu; else pm_b = pmu;
-            n_sub += __popc(__ballot_sync(FULL, my < c.col_hi));
-            n_full += __popc(pmu);
-          }
-#pragma unroll 1
-          for (int u = 0; u < 2; u++) {
-            unsigned pm = u == 0 ? pm_a : pm_b;
-            const uint64_t batch = batch2 + (uint64_t)u * SBATCH;
-            while (pm) {
-                const int l0 = __ffs(pm) - 1;
-                pm &= pm - 1;
-                const uint64_t sub = batch + (uint64_t)l0 * SSB;
-                const int ncols = (int)min((uint64_t)SSB, c.col_hi - sub);
-                const uint32_t colrel0 = (uint32_t)(sub - c.col_lo);
-                __syncwarp();
-                uint32_t my_blo = 0, my_bhi = 0;
+        }
+        const uint32_t sub = tile.y * SSB;
+        const int ncols = (int)min((uint32_t)SSB, w.N - sub);
+        __syncwarp();
+        uint32_t my_blo = 0, my_bhi = 0;
 #pragma unroll
-                for (int i = 0; i < SSB / 32; i++) {                     // quarter i = columns sub + 32i .. +31
-                    const uint64_t idx = sub + (uint64_t)i * 32 + lane;
-                    const uint32_t br = idx < c.col_hi ? __ldg(&w.sorted[idx]) : 0xFFFFFFFFu;   // pads only widen the interval
-                    const uint32_t b = idx < c.col_hi ? rotr32(br, w.rot) : 0u;
-                    b0s[i * 32 + lane] = b;
-                    bPs[i * 32 + lane] = b >> 2;
-                    bMs[i * 32 + lane] = b << 2;
-                    const uint32_t lo = __shfl_sync(FULL, br, 0), hi = __shfl_sync(FULL, br, 31);
-                    if ((lane >> 3) == i) { my_blo = lo; my_bhi = hi; }
-                }
-                __syncwarp();
-                const bool mine = (32 * (lane >> 3) < ncols) && pass_possible(T_, P_, my_alo, my_ahi, my_blo, my_bhi);
-                const unsigned cm = __ballot_sync(FULL, mine);             // bit 8c + r: slab r x quarter c can hold a candidate
-                n_combo += __popc(cm);
+        for (int i = 0; i < SSB / 32; i++) {                     // quarter i = columns sub + 32i .. +31
+            const uint32_t idx = sub + (uint32_t)i * 32 + lane;
+            const uint32_t br = idx < w.N ? __ldg(&w.sorted[idx]) : 0xFFFFFFFFu;   // pads only widen the interval
+            const uint32_t b = idx < w.N ? rotr32(br, w.rot) : 0u;
+            b0s[i * 32 + lane] = b;
+            bPs[i * 32 + lane] = b >> 2;
+            bMs[i * 32 + lane] = b << 2;
+            const uint32_t lo = __shfl_sync(FULL, br, 0), hi = __shfl_sync(FULL, br, 31);
+            if ((lane >> 3) == i) { my_blo = lo; my_bhi = hi; }
+        }
+        __syncwarp();
+        const bool mine = (32 * (lane >> 3) < ncols) && pass_possible(T_, P_, my_alo, my_ahi, my_blo, my_bhi);
+        const unsigned cm = __ballot_sync(FULL, mine);             // bit 8c + r: slab r x quarter c can hold a candidate
+        n_combo += __popc(cm);
 #pragma unroll 1
-                for (int q4 = 0; q4 < SSB / 32; q4++) {
-                    const unsigned sm = (cm >> (8 * q4)) & 0xFFu;
-                    if (sm == 0) continue;
-                    const int cend = min(ncols, 32 * q4 + 32);
+        for (int q4 = 0; q4 < SSB / 32; q4++) {
+            const unsigned sm = (cm >> (8 * q4)) & 0xFFu;
+            if (sm == 0) continue;
+            const int cend = min(ncols, 32 * q4 + 32);
 #pragma unroll 1
-                    for (int cb = 32 * q4; cb < cend; cb += 4) {
-                        const uint4 B0 = *reinterpret_cast<const uint4*>(&b0s[cb]);
-                        const uint4 BP = *reinterpret_cast<const uint4*>(&bPs[cb]);
-                        const uint4 BM = *reinterpret_cast<const uint4*>(&bMs[cb]);
-                        uint32_t h = 0;
+            for (int cb = 32 * q4; cb < cend; cb += 4) {
+                const uint4 B0 = *reinterpret_cast<const uint4*>(&b0s[cb]);
+                const uint4 BP = *reinterpret_cast<const uint4*>(&bPs[cb]);
+                const uint4 BM = *reinterpret_cast<const uint4*>(&bMs[cb]);
+                uint32_t h = 0;
 #pragma unroll
-                        for (int r = 0; r < RA; r++) {
-                            if (sm & (1u << r)) {
+                for (int r = 0; r < RA; r++) {
+                    if (sm & (1u << r)) {
 #pragma unroll
-                                for (int kk = 0; kk < 4; kk++) {
-                                    uint32_t u = quick_marks(a[r], pick4(B0, kk), pick4(BP, kk), pick4(BM, kk));
-                                    u &= u - 1;
-                                    if (T_ == 2) u &= u - 1;
-                                    h |= (u == 0 ? 1u : 0u) << (kk * 8 + r);
-                                }
-                            }
+                        for (int kk = 0; kk < 4; kk++) {
+                            uint32_t u = quick_marks(a[r], pick4(B0, kk), pick4(BP, kk), pick4(BM, kk));
+                            u &= u - 1;
+                            if (T_ == 2) u &= u - 1;
+                            h |= (u == 0 ? 1u : 0u) << (kk * 8 + r);
                         }
-                        if (cb + 4 > ncols) h &= (1u << (8 * (ncols - cb))) - 1u;      // columns past the chunk end
-                        if (__any_sync(FULL, h != 0)) { n_cand += __popc(h); sparse_push<T_, P_>(h, colrel0 + cb, qn, c, out); }
                     }
                 }
+                if (cb + 4 > ncols) h &= (1u << (8 * (ncols - cb))) - 1u;      // columns past the end of the array
+                if (__any_sync(FULL, h != 0)) { n_cand += __popc(h); sparse_push<T_, P_>(h, row0, sub + cb, qn, c, out); }
             }
-          }
         }
-        // the queue's codes are relative to this item: finish the partial batch before moving on
-        __syncwarp();
-        if (qn > 0) {
-            const uint32_t e = lane < qn ? c.q[lane] : 0u;
-            sparse_process<T_, P_>(c, out, e, lane < qn);
-            qn = 0;
-        }
-        __syncwarp();
-#ifdef BDG_ITEM_TRACE
-        n_items_done++; { const unsigned long long dt = global_ns() - it0; if (dt > t_item_max) t_item_max = dt; }
-#endif
+    }
+    __syncwarp();
+    if (qn > 0) {                                  // the partial batch left in the queue
+        const uint2 e = lane < qn ? c.q[lane] : make_uint2(0u, 0u);
+        sparse_process<T_, P_>(c, out, e, lane < qn);
     }
     if (w.stats) {
         for (int o = 16; o; o >>= 1) n_cand += __shfl_down_sync(FULL, n_cand, o);           // per-lane counts
-#ifdef BDG_ITEM_TRACE
-        if (lane == 0) printf("warpexit pass %d sm %d busy_us %llu items %llu longest_item_us %llu combos %llu cands %llu\n", P_, (int)(blockIdx.x % 148),
-                              (global_ns() - t_start) / 1000ull, n_items_done, t_item_max / 1000ull, n_combo, n_cand);
-#endif
-        if (lane == 0) {                                                                  // the others are uniform per warp
-            atomicAdd(&w.stats[0], n_sub); atomicAdd(&w.stats[1], n_full);
+        if (lane == 0) {                                                                  // n_combo is uniform per warp
             atomicAdd(&w.stats[2], n_combo * 1024ull); atomicAdd(&w.stats[3], n_cand);
             warp_exit_stats(w.stats, t_start);
         }

@@ -63,6 +63,8 @@ int bdg_pack16(const char* seqs, size_t R, uint32_t* out, uint8_t* valid);
  * barcodes (checked).  bdg_edges_build uses every initialised device (rows dealt per BDG_ROW_TILE) and
  * returns the union; bdg_edges_build_part computes one part on the first initialised device (one process
  * per GPU).  Edge order is unspecified.  t <= 0 yields the empty set, as in the reference. */
+/* The handle keeps the edges in device memory until bdg_edges_copy moves them straight into the caller's arrays; it
+ * becomes stale (BDG_ERR_ARG from bdg_edges_copy) once another edge build runs on the same device - copy first. */
 typedef struct bdg_edges bdg_edges;
 int bdg_edges_build(const uint32_t* sorted_unique, size_t N, int t, bdg_edges** out);
 int bdg_edges_build_part(const uint32_t* sorted_unique, size_t N, int t, int part, int nparts, bdg_edges** out);
@@ -90,8 +92,10 @@ int bdg_kmer_score(const uint32_t* q, size_t Q, const uint32_t* wl, size_t W, in
                    uint32_t* hit_q, uint32_t* hit_w, uint8_t* cnt, uint64_t* mult, size_t* total);
 
 /* ---- device-resident variants (bench.py "value" path; torch owns the memory and the stream) -------- */
-/* Edge kernel over rows of part/nparts.  d_count (one uint64, device) is zeroed by the call and receives
- * the number of edges found, which may exceed cap (only the first cap are stored). */
+/* Edge construction over rows of part/nparts.  d_count (one uint64, device) is zeroed by the call and receives
+ * the number of edges found, which may exceed cap (only the first cap are stored).  The current device must have
+ * been claimed by bdg_init (the call uses its workspaces).  In sparse mode the call synchronises the stream once per
+ * pass (an 8-byte read-back of the tile count that sizes the next launch); the last kernel is left in flight. */
 int bdg_dev_edges_build(const uint32_t* d_sorted, size_t N, int t, int part, int nparts, uint32_t* d_a,
                         uint32_t* d_b, uint8_t* d_d, size_t cap, unsigned long long* d_count, void* stream);
 /* How the edge set is searched for t = 1, 2 (results are identical; DESIGN.md "edge construction"):
