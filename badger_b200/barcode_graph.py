@@ -8,7 +8,9 @@ rounds of ``cluster`` (vectorised, order-free restatement), dict-shaped views fo
 from __future__ import annotations
 
 import logging
+import time
 from collections import defaultdict
+from contextlib import contextmanager
 from statistics import StatisticsError
 
 import numpy as np
@@ -110,9 +112,18 @@ class BarcodeGraph:
         self.clustering = dict()
         self.clustered = defaultdict(bool)
         self.index = None
+        self.timings = defaultdict(float)          # seconds per stage of this graph's life (tools/pipeline_bench.py)
         self._ranks = np.empty(0, np.uint32)      # distinct ranks, first-seen order
         self._cnt = np.empty(0, np.int64)
         self._edge_arrays = (np.empty(0, np.uint32), np.empty(0, np.uint32), np.empty(0, np.uint8))
+
+    @contextmanager
+    def _timed(self, stage):
+        t0 = time.perf_counter()
+        try:
+            yield
+        finally:
+            self.timings[stage] += time.perf_counter() - t0
 
     @classmethod
     def from_arrays(cls, threshold, ranks_first_seen, counts, edges=None):
@@ -132,22 +143,23 @@ class BarcodeGraph:
         ranked (GPU, ops.pack16) and counted in first-seen order."""
         if bc_len != 16:
             raise NotImplementedError("the B200 path packs 16-bp barcodes into uint32; bc_len=%r is not supported" % bc_len)
-        keep = []
-        for s in barcodes:
-            n = len(s)
-            if n == bc_len + 1:
-                keep.append(s[:-1])
-            elif n == bc_len:
-                keep.append(s)
+        with self._timed("index: length filter (python loop)"):
+            keep = []
+            for s in barcodes:
+                n = len(s)
+                if n == bc_len + 1:
+                    keep.append(s[:-1])
+                elif n == bc_len:
+                    keep.append(s)
         if not keep:
             return
-        ranks, valid = ops.pack16(keep)
+        with self._timed("index: pack16 (join + GPU)"):
+            ranks, valid = ops.pack16(keep)
         if not valid.all():
             bad = keep[int(np.argmin(valid))]
             raise KeyError(next(c for c in bad if c not in "ACGT"))      # common.py:24 raises KeyError(letter)
-        uniq, first, cnt = np.unique(ranks, return_index=True, return_counts=True)
-        order = np.argsort(first, kind="stable")
-        new_r, new_c = uniq[order], cnt[order].astype(np.int64)
+        with self._timed("index: dedup/count first-seen (GPU)"):
+            new_r, new_c = ops.dedup_first_seen(ranks)
         if self._ranks.size:                                               # merge with an earlier call
             for r, c in zip(new_r.tolist(), new_c.tolist()):
                 self.counts[r] += c
@@ -155,7 +167,8 @@ class BarcodeGraph:
             self._cnt = np.fromiter(self.counts.values(), dtype=np.int64, count=len(self.counts))
         else:
             self._ranks, self._cnt = new_r, new_c
-            self.counts.update(zip(new_r.tolist(), new_c.tolist()))
+            with self._timed("index: counts dict"):
+                self.counts.update(zip(new_r.tolist(), new_c.tolist()))
 
     index_bc_in_parallel = lambda self, barcodes, bc_len, threads: self.index_bc_single_thread(barcodes, bc_len)  # noqa: E731
 
@@ -166,8 +179,10 @@ class BarcodeGraph:
         self.index = QGramIndex(self.threshold, bc_len, 6)
         self.index_bc_single_thread(barcodes, bc_len)
         self.index._adopt(self._ranks)
-        a, b, d = ops.edges_build(np.sort(self._ranks), self.threshold)
-        self._set_edges(a, b, d)
+        with self._timed("edges: sort + GPU edge construction"):
+            a, b, d = ops.edges_build(np.sort(self._ranks), self.threshold)
+        with self._timed("edges: canonical order + CSR views"):
+            self._set_edges(a, b, d)
 
     def compare_in_parallel(self, bc_len, threads):
         a, b, d = ops.edges_build(np.sort(self._ranks), self.threshold)
@@ -195,8 +210,13 @@ class BarcodeGraph:
         packed once, sorted, and probed on the GPU (ops.member_sorted)."""
         cache = getattr(self, "_wl_cache", None)
         if cache is None or cache[0] is not barcode_list:
-            good = [s for s in barcode_list if len(s) == bc_len and not (set(s) - set("ACGT"))]
-            wl = np.sort(ops.pack16(good)[0]) if good else np.empty(0, np.uint32)
+            with self._timed("centres: pack + sort whitelist"):
+                good = [s for s in barcode_list if len(s) == bc_len]       # other lengths can never equal an unranked barcode
+                if good:
+                    r, ok = ops.pack16(good)                                # entries with letters outside ACGT are flagged invalid
+                    wl = np.sort(r[ok])
+                else:
+                    wl = np.empty(0, np.uint32)
             self._wl_cache = cache = (barcode_list, wl)
         return ops.member_sorted(cache[1], self._ranks)
 

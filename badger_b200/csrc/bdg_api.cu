@@ -17,6 +17,7 @@
 #include "bdg_kernels.cuh"
 
 #include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
 
 namespace {
 
@@ -69,6 +70,7 @@ struct DevCtx {
     Buf tile_bnd, tile_list;                             // sparse passes: sub-tile end keys, list of tiles that survive level 1
     unsigned long long host_stats[bdg::MAX_PASSES][2] = {};   // interval tests done / tiles listed per pass of the last launch
     unsigned long long generation = 0;                        // bumped by every host-buffer edge build on this device
+    Buf dd[10];                                               // dedup: keys, idx, sorted keys/idx, heads, scan, run arrays, cub scratch
 };
 std::vector<DevCtx> g_ctx;
 
@@ -360,6 +362,7 @@ void bdg_shutdown(void)
         if (c.stream) { cudaSetDevice(c.dev); cudaStreamSynchronize(c.stream); cudaStreamDestroy(c.stream); }
         c.sorted.release(); c.ea.release(); c.eb.release(); c.ed.release(); c.count.release(); c.plan.release();
         c.rot_in.release(); c.sort_tmp.release(); c.tile_bnd.release(); c.tile_list.release();
+        for (auto& b : c.dd) b.release();
         for (auto& b : c.rot_sorted) b.release();
     }
     g_ctx.clear();
@@ -497,6 +500,63 @@ int bdg_dev_pipe_probe(int kind, int blocks, int iters, uint32_t* d_sink, unsign
 }
 
 // ---------------------------------------------------------------- host-buffer entry points
+// ---- a-2  dedup + count in first-seen order (barcode_graph.py:192-204) ------------------------------------
+int bdg_dedup_first_seen(const uint32_t* ranks, size_t R, uint32_t* distinct, uint32_t* counts, uint32_t* read_to_distinct, size_t* n_distinct)
+{
+    if (!n_distinct) return fail(BDG_ERR_ARG, "NULL n_distinct pointer");
+    *n_distinct = 0;
+    if (R == 0) return BDG_OK;
+    if (!ranks || !distinct || !counts) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if (R > 0x7FFFFFFFull) return fail(BDG_ERR_ARG, "more than 2^31 reads in one call");
+    if (int rc = need_ctx()) return rc;
+    DevCtx& c = g_ctx[0];
+    CU_TRY(cudaSetDevice(c.dev));
+    cudaStream_t st = c.stream;
+    const uint32_t n = (uint32_t)R;
+    auto ensure = [&](Buf& b, size_t bytes) -> int {
+        if (cudaError_t e = (cudaError_t)b.ensure(bytes))
+            return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation of %zu bytes: %s", bytes, cudaGetErrorString(e));
+        return BDG_OK;
+    };
+    // dd[0] keys, [1] idx, [2] sorted keys, [3] sorted idx, [4] heads, [5] inclusive scan, [6] run key, [7] run first, [8] run start, [9] scratch
+    for (int k = 0; k < 9; k++) if (int e = ensure(c.dd[k], R * 4)) return e;
+    uint32_t *d_k = (uint32_t*)c.dd[0].p, *d_i = (uint32_t*)c.dd[1].p, *d_sk = (uint32_t*)c.dd[2].p, *d_si = (uint32_t*)c.dd[3].p;
+    uint32_t *d_head = (uint32_t*)c.dd[4].p, *d_scan = (uint32_t*)c.dd[5].p, *d_rk = (uint32_t*)c.dd[6].p, *d_rf = (uint32_t*)c.dd[7].p, *d_rs = (uint32_t*)c.dd[8].p;
+    size_t tmp1 = 0, tmp2 = 0;
+    CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp1, d_k, d_sk, d_i, d_si, (int)n, 0, 32, st));
+    CU_TRY(cub::DeviceScan::InclusiveSum(nullptr, tmp2, d_head, d_scan, (int)n, st));
+    if (int e = ensure(c.dd[9], std::max(tmp1, tmp2))) return e;
+    const int blocks = (int)std::min<size_t>((R + 255) / 256, (size_t)c.sms * 8);
+    CU_TRY(cudaMemcpyAsync(d_k, ranks, R * 4, cudaMemcpyHostToDevice, st));
+    bdg::iota_kernel<<<blocks, 256, 0, st>>>(d_i, n);
+    CU_TRY(cub::DeviceRadixSort::SortPairs(c.dd[9].p, tmp1, d_k, d_sk, d_i, d_si, (int)n, 0, 32, st));
+    bdg::dedup_heads_kernel<<<blocks, 256, 0, st>>>(d_sk, n, d_head);
+    CU_TRY(cub::DeviceScan::InclusiveSum(c.dd[9].p, tmp2, d_head, d_scan, (int)n, st));
+    bdg::dedup_runs_kernel<<<blocks, 256, 0, st>>>(d_sk, d_si, d_head, d_scan, n, d_rk, d_rf, d_rs);
+    uint32_t n_runs = 0;
+    CU_TRY(cudaMemcpyAsync(&n_runs, d_scan + (n - 1), 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    g_launches += 3;
+    // order the runs by their first read index: reuse keys/idx buffers (d_k := sorted first indices, d_i := order), heads := iota
+    bdg::iota_kernel<<<blocks, 256, 0, st>>>(d_head, n_runs);
+    CU_TRY(cub::DeviceRadixSort::SortPairs(c.dd[9].p, tmp1, d_rf, d_k, d_head, d_i, (int)n_runs, 0, 32, st));
+    // d_sk is free again after dedup_runs: distinct / counts / pos_of_run live in d_sk, d_k, d_head
+    uint32_t *d_distinct = d_sk, *d_counts = d_k, *d_pos = d_head;
+    bdg::dedup_finish_kernel<<<blocks, 256, 0, st>>>(d_i, d_rk, d_rs, n_runs, n, d_distinct, d_counts, d_pos);
+    g_launches += 2;
+    CU_TRY(cudaMemcpyAsync(distinct, d_distinct, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(counts, d_counts, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st));
+    if (read_to_distinct) {
+        bdg::dedup_scatter_kernel<<<blocks, 256, 0, st>>>(d_si, d_scan, d_pos, n, d_rf);   // d_rf is free after the run sort
+        g_launches++;
+        CU_TRY(cudaMemcpyAsync(read_to_distinct, d_rf, R * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(st));
+    *n_distinct = n_runs;
+    return BDG_OK;
+}
+
 int bdg_pack16(const char* seqs, size_t R, uint32_t* out, uint8_t* valid)
 {
     if (R == 0) return BDG_OK;

@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(ENT, 3) edges_kernel(const EdgeWork w, const E
 // passes' outputs are disjoint and simply share one output cursor.
 // =====================================================================================================
 constexpr int SSB = 128;           // columns per sub-tile
-constexpr int SQCAP = 64;          // candidate queue entries per warp (31 left over + 32 new)
+constexpr int SQCAP = 128;         // entries per warp of the candidate queue and of the second (scoring) queue
 
 struct TileList {
     uint2* tiles;                  // (group, sub-tile)
@@ -457,13 +457,31 @@ __global__ void __launch_bounds__(256) sparse_scan_kernel(const uint32_t* __rest
 
 struct SparseCtx {
     uint2* q;                      // candidate queue: (row, column) indices into `sorted`
+    uint2* q2;                     // second queue: (x, y) values with D <= t that still need S
+    uint8_t* q2d;                  // their distances
     const uint32_t* sorted;
     uint32_t N;
     int t, T, rot, lane;
 };
 
+// stage 3 on a batch: S = shared 6-mer count (the dearest test: 21 diagonals) for pairs that already have D <= t
+__device__ __forceinline__ void sparse_score(const SparseCtx& c, const EdgeOut& out, int n)
+{
+    bool ok = false;
+    uint32_t x = 0, y = 0;
+    int d = 0;
+    if (c.lane < n) {
+        const uint2 e = c.q2[c.lane];
+        x = e.x; y = e.y; d = c.q2d[c.lane];
+        ok = qgram_score(x, y) >= c.T;
+    }
+    emit_warp(ok, x, y, d, out);
+}
+
+// stage 2 on a batch of candidates: pass predicates (this pass yes, earlier passes no) and exact D; survivors
+// wait in the second queue so that stage 3 also runs with full warps
 template <int T_, int P_>
-__device__ __forceinline__ void sparse_process(const SparseCtx& c, const EdgeOut& out, uint2 e, bool active)
+__device__ __forceinline__ void sparse_process(const SparseCtx& c, const EdgeOut& out, uint2 e, bool active, int& q2n)
 {
     bool ok = false;
     uint32_t x = 0, y = 0;
@@ -477,17 +495,60 @@ __device__ __forceinline__ void sparse_process(const SparseCtx& c, const EdgeOut
         for (int q = 0; q < P_; q++) mine = mine && !pass_pred(T_, q, x, y);
         if (mine) {
             d = dist_small(x, y);
-            if (d > c.t || qgram_score(x, y) < c.T) d = 0;
-            ok = d > 0;
+            ok = d <= c.t;
         }
     }
-    emit_warp(ok, x, y, d, out);
+    const unsigned m = __ballot_sync(FULL, ok);
+    if (m == 0) return;
+    // fewer than 32 entries wait on entry (full batches are scored right below), so 32 more always fit
+    if (ok) {
+        const int slot = q2n + __popc(m & ((1u << c.lane) - 1u));
+        c.q2[slot] = make_uint2(x, y);
+        c.q2d[slot] = (uint8_t)d;
+    }
+    q2n += __popc(m);
+    __syncwarp();
+    while (q2n >= 32) {                                 // stage 3 on full batches, taken from the top
+        q2n -= 32;
+        const uint2 mv = c.q2[q2n + c.lane];
+        const uint8_t md = c.q2d[q2n + c.lane];
+        const bool good = qgram_score(mv.x, mv.y) >= c.T;
+        emit_warp(good, mv.x, mv.y, md, out);
+        __syncwarp();
+    }
 }
 
 // append the set bits of h (bit k*8+r = column col0+k, row row0 + r*32 + lane); run stage 2 whenever 32 candidates wait
 template <int T_, int P_>
-__device__ __forceinline__ void sparse_push(uint32_t h, uint32_t row0, uint32_t col0, int& qn, const SparseCtx& c, const EdgeOut& out)
+__device__ __forceinline__ void sparse_push(uint32_t h, uint32_t row0, uint32_t col0, int& qn, int& q2n, const SparseCtx& c, const EdgeOut& out)
 {
+    // common case: every lane writes all its hits at once at offsets from a warp prefix sum of the hit counts
+    const int cnt = __popc(h);
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(FULL, incl, o);
+        if (c.lane >= o) incl += v;
+    }
+    const int total = __shfl_sync(FULL, incl, 31);
+    if (qn + total <= SQCAP) {
+        int slot = qn + incl - cnt;
+        while (h) {
+            const int j = __ffs(h) - 1;
+            h &= h - 1;
+            c.q[slot++] = make_uint2(row0 + (uint32_t)((j & 7) * 32 + c.lane), col0 + (uint32_t)(j >> 3));
+        }
+        qn += total;
+        __syncwarp();
+        while (qn >= 32) {
+            qn -= 32;
+            const uint2 e = c.q[qn + c.lane];
+            sparse_process<T_, P_>(c, out, e, true, q2n);
+            __syncwarp();
+        }
+        return;
+    }
+    // burst larger than the queue: one hit per lane and round
     for (;;) {
         const bool has = h != 0;
         const unsigned m = __ballot_sync(FULL, has);
@@ -499,12 +560,12 @@ __device__ __forceinline__ void sparse_push(uint32_t h, uint32_t row0, uint32_t 
         }
         qn += __popc(m);
         __syncwarp();
-        if (qn >= 32) {
+        while (qn >= 32) {
             qn -= 32;
             const uint2 e = c.q[qn + c.lane];
-            sparse_process<T_, P_>(c, out, e, true);
+            sparse_process<T_, P_>(c, out, e, true, q2n);
+            __syncwarp();
         }
-        __syncwarp();
     }
 }
 
@@ -513,13 +574,17 @@ __global__ void __launch_bounds__(ENT, 3) sparse_tile_kernel(const EdgeWork w, c
 {
     __shared__ __align__(16) uint32_t s_b[EW][3][SSB];   // unrotated b, b >> 2, b << 2 of the staged sub-tile
     __shared__ uint2 s_q[EW][SQCAP];
+    __shared__ uint2 s_q2[EW][SQCAP];
+    __shared__ uint8_t s_q2d[EW][SQCAP];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t* const b0s = s_b[wid][0];
     uint32_t* const bPs = s_b[wid][1];
     uint32_t* const bMs = s_b[wid][2];
     SparseCtx c;
-    c.q = s_q[wid]; c.sorted = w.sorted; c.N = w.N; c.t = w.t; c.T = w.T; c.rot = w.rot; c.lane = lane;
-    int qn = 0;                                   // queue fill, uniform across the warp
+    c.q = s_q[wid]; c.q2 = s_q2[wid]; c.q2d = s_q2d[wid];
+    c.sorted = w.sorted; c.N = w.N; c.t = w.t; c.T = w.T; c.rot = w.rot; c.lane = lane;
+    int qn = 0, q2n = 0;                          // queue fills, uniform across the warp
+    const uint32_t mone = 0u - w.one;             // runtime -1: u*one + mone is u - 1 on the FMA pipe
     const unsigned long long t_start = global_ns();
     unsigned long long n_combo = 0, n_cand = 0;
     const unsigned long long n_tiles = min(*list.count, list.cap);
@@ -581,22 +646,26 @@ __global__ void __launch_bounds__(ENT, 3) sparse_tile_kernel(const EdgeWork w, c
 #pragma unroll
                         for (int kk = 0; kk < 4; kk++) {
                             uint32_t u = quick_marks(a[r], pick4(B0, kk), pick4(BP, kk), pick4(BM, kk));
-                            u &= u - 1;
-                            if (T_ == 2) u &= u - 1;
+                            u &= u * w.one + mone;               // drop the lowest mark (IMAD keeps the -1 off the ALU pipe)
+                            if (T_ == 2) u &= u * w.one + mone;
                             h |= (u == 0 ? 1u : 0u) << (kk * 8 + r);
                         }
                     }
                 }
                 if (cb + 4 > ncols) h &= (1u << (8 * (ncols - cb))) - 1u;      // columns past the end of the array
-                if (__any_sync(FULL, h != 0)) { n_cand += __popc(h); sparse_push<T_, P_>(h, row0, sub + cb, qn, c, out); }
+                if (__any_sync(FULL, h != 0)) { n_cand += __popc(h); sparse_push<T_, P_>(h, row0, sub + cb, qn, q2n, c, out); }
             }
         }
     }
     __syncwarp();
-    if (qn > 0) {                                  // the partial batch left in the queue
-        const uint2 e = lane < qn ? c.q[lane] : make_uint2(0u, 0u);
-        sparse_process<T_, P_>(c, out, e, lane < qn);
+    while (qn > 0) {                               // what is left in the queues: partial batches
+        const int take = min(qn, 32);
+        qn -= take;
+        const uint2 e = lane < take ? c.q[qn + lane] : make_uint2(0u, 0u);
+        sparse_process<T_, P_>(c, out, e, lane < take, q2n);
+        __syncwarp();
     }
+    if (q2n > 0) sparse_score(c, out, q2n);         // fewer than 32 by construction
     if (w.stats) {
         for (int o = 16; o; o >>= 1) n_cand += __shfl_down_sync(FULL, n_cand, o);           // per-lane counts
         if (lane == 0) {                                                                  // n_combo is uniform per warp

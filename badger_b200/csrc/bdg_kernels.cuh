@@ -224,4 +224,63 @@ __global__ void __launch_bounds__(NT) pipe_probe_kernel(int iters, uint32_t* __r
     if (s == 0x12345678u) sink[2] = s;   // practically never; keeps the chains live
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Dedup + count in FIRST-SEEN order (a-2, reference barcode_graph.py:192-204: `counts[rank] += 1`, dict order =
+// order of first sighting).  The reads are radix-sorted by (key) with their read index as payload (stable: equal
+// keys keep ascending indices, so the head of a run is the first sighting), then:
+//   dedup_heads_kernel    head flags of the runs of equal keys
+//   dedup_runs_kernel     per run (numbered by the exclusive scan of the heads): key, first read index, start
+//   dedup_finish_kernel   after the runs are sorted by first read index: first-seen position of every run,
+//                         distinct[] / counts[] in that order
+//   dedup_scatter_kernel  read -> first-seen position of its barcode
+// HBM bound: 4 B in per read for the flags, 4+4 B out for the per-read map; the sorts are cub (library, 2 passes).
+// ---------------------------------------------------------------------------------------------------
+__global__ void iota_kernel(uint32_t* __restrict__ v, uint32_t n)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = i;
+}
+
+__global__ void dedup_heads_kernel(const uint32_t* __restrict__ sk, uint32_t n, uint32_t* __restrict__ head)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        head[i] = (i == 0 || __ldg(&sk[i]) != __ldg(&sk[i - 1])) ? 1u : 0u;
+}
+
+// run_of[i] = inclusive scan of head - 1
+__global__ void dedup_runs_kernel(const uint32_t* __restrict__ sk, const uint32_t* __restrict__ si, const uint32_t* __restrict__ head,
+                                  const uint32_t* __restrict__ scan_incl, uint32_t n, uint32_t* __restrict__ run_key,
+                                  uint32_t* __restrict__ run_first, uint32_t* __restrict__ run_start)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        if (__ldg(&head[i])) {
+            const uint32_t r = __ldg(&scan_incl[i]) - 1u;
+            run_key[r] = __ldg(&sk[i]);
+            run_first[r] = __ldg(&si[i]);
+            run_start[r] = i;
+        }
+    }
+}
+
+// order[pos] = run with the pos-th smallest first read index
+__global__ void dedup_finish_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ run_key,
+                                    const uint32_t* __restrict__ run_start, uint32_t n_runs, uint32_t n_reads,
+                                    uint32_t* __restrict__ distinct, uint32_t* __restrict__ counts, uint32_t* __restrict__ pos_of_run)
+{
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n_runs; p += gridDim.x * blockDim.x) {
+        const uint32_t r = __ldg(&order[p]);
+        const uint32_t s0 = __ldg(&run_start[r]);
+        const uint32_t s1 = r + 1 < n_runs ? __ldg(&run_start[r + 1]) : n_reads;
+        distinct[p] = __ldg(&run_key[r]);
+        counts[p] = s1 - s0;
+        pos_of_run[r] = p;
+    }
+}
+
+__global__ void dedup_scatter_kernel(const uint32_t* __restrict__ si, const uint32_t* __restrict__ scan_incl,
+                                     const uint32_t* __restrict__ pos_of_run, uint32_t n, uint32_t* __restrict__ read_to_distinct)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        read_to_distinct[__ldg(&si[i])] = __ldg(&pos_of_run[__ldg(&scan_incl[i]) - 1u]);
+}
+
 }  // namespace bdg

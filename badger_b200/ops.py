@@ -31,6 +31,21 @@ def pack16(seqs) -> tuple[np.ndarray, np.ndarray]:
     return out, valid.astype(bool)
 
 
+def dedup_first_seen(ranks: np.ndarray, want_map: bool = False):
+    """barcode_graph.py:192-204: distinct barcodes in first-seen order with their counts
+    (and, with want_map, the position in that order of every read)."""
+    r = np.ascontiguousarray(ranks, dtype=np.uint32)
+    distinct = np.empty(r.size, np.uint32)
+    counts = np.empty(r.size, np.uint32)
+    rmap = np.empty(r.size, np.uint32) if want_map else None
+    n = C.c_size_t(0)
+    if r.size:
+        check(lib().bdg_dedup_first_seen(ptr(r), r.size, ptr(distinct), ptr(counts), ptr(rmap) if want_map else None, C.byref(n)))
+    k = int(n.value)
+    out = (distinct[:k].copy(), counts[:k].astype(np.int64))
+    return out + (rmap,) if want_map else out
+
+
 def _collect_edges(handle):
     L = lib()
     try:

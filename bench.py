@@ -358,6 +358,8 @@ def run_b200(args):
                           "partition": "2048-row tiles dealt boustrophedon to ranks; no data-path collective"},
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
                "reads_per_s": reads * args.steps / (ms_total * 1e-3)}
+    if rank == 0 and world == 1:
+        out["stages"] = other_stages(torch, dev, stream, L, s, args)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"], _ = cpu_sample(s, t, args.cpu_seconds)
     if world > 1:
@@ -365,6 +367,81 @@ def run_b200(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out))
+
+
+def other_stages(torch, dev, stream, L, s, args):
+    """The other rows of the hot path, each timed on its own: device-resident inputs and CUDA events
+    for the kernels that have a device entry point, wall clock through the host-buffer call otherwise."""
+    import ctypes as C
+    import badger_b200
+    from badger_b200 import ops
+    chk = badger_b200._lib.check
+    hbm = 6451.8
+    try:
+        hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+        hbm_src = "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        hbm_src = "MEASURED_PEAKS.json value recorded in BASELINE.md (file absent on this box)"
+    rng = np.random.default_rng(11)
+    res = {}
+
+    def dev_time(fn, reps=5):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    # a-1 pack16: 16 B in + 5 B out per read
+    R = 8_000_000
+    seqs = torch.from_numpy(np.frombuffer(b"ACGT", np.uint8)[rng.integers(0, 4, R * 16)].copy()).to(dev)
+    d_out = torch.empty(R, dtype=torch.int32, device=dev); d_ok = torch.empty(R, dtype=torch.uint8, device=dev)
+    dt = dev_time(lambda: chk(L.bdg_dev_pack16(seqs.data_ptr(), R, d_out.data_ptr(), d_ok.data_ptr(), stream.cuda_stream)))
+    res["pack16"] = {"reads_per_s": R / dt, "GBps": 21 * R / dt / 1e9, "frac_of_hbm": 21 * R / dt / 1e9 / hbm, "n": R, "bytes_per_read": 21}
+    # a-6 membership: 4 B in + 1 B out per query, 3 M-entry whitelist resident
+    wl = np.unique(rng.integers(0, 1 << 32, 3_000_000, dtype=np.uint64).astype(np.uint32))
+    Q = 8_000_000
+    q = rng.integers(0, 1 << 32, Q, dtype=np.uint64).astype(np.uint32)
+    q[::3] = wl[rng.integers(0, wl.size, q[::3].size)]
+    d_wl = torch.from_numpy(wl.view(np.int32)).to(dev); d_q = torch.from_numpy(q.view(np.int32)).to(dev)
+    d_hit = torch.empty(Q, dtype=torch.uint8, device=dev)
+    dt = dev_time(lambda: chk(L.bdg_dev_member_sorted(d_wl.data_ptr(), wl.size, d_q.data_ptr(), Q, d_hit.data_ptr(), stream.cuda_stream)))
+    res["member_sorted"] = {"queries_per_s": Q / dt, "GBps": 5 * Q / dt / 1e9, "frac_of_hbm": 5 * Q / dt / 1e9 / hbm, "n": Q, "whitelist": int(wl.size),
+                            "note": "random probes of a 12 MB sorted table: L2-latency bound, not HBM bound"}
+    # a-7 post-processing: Q unassigned x W centres, first minimum of the plain edit distance, bound 2
+    W7, Q7 = 10_000, 400_000
+    tg = rng.integers(0, 1 << 32, W7, dtype=np.uint64).astype(np.uint32)
+    q7 = s[rng.integers(0, s.size, Q7)]
+    d_t = torch.from_numpy(tg.view(np.int32)).to(dev); d_q7 = torch.from_numpy(q7.view(np.int32)).to(dev)
+    d_keys = torch.empty(Q7, dtype=torch.int32, device=dev); d_am = torch.empty(Q7, dtype=torch.int32, device=dev)
+    d_di = torch.empty(Q7, dtype=torch.uint8, device=dev)
+    dt = dev_time(lambda: chk(L.bdg_dev_nearest_bounded(d_q7.data_ptr(), Q7, d_t.data_ptr(), W7, 2, d_keys.data_ptr(), d_am.data_ptr(),
+                                                        d_di.data_ptr(), stream.cuda_stream)))
+    res["nearest_bounded"] = {"pairs_per_s": Q7 * W7 / dt, "queries": Q7, "targets": W7, "ms": dt * 1e3,
+                              "int_Tinst_per_s": 11 * Q7 * W7 / dt / 1e12, "note": "11 prefilter instructions per pair (DESIGN.md 4)"}
+    # a-2 dedup in first-seen order and a-5 k-mer scoring: host-buffer calls, wall clock (copies included)
+    reads = s[rng.integers(0, s.size, 2_000_000)]
+    ops.dedup_first_seen(reads, want_map=True)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        ops.dedup_first_seen(reads, want_map=True)
+    dt = (time.perf_counter() - t0) / 3
+    res["dedup_first_seen"] = {"reads_per_s": reads.size / dt, "n": int(reads.size), "ms": dt * 1e3, "timing": "host-buffer call, wall clock"}
+    qk = s[:64]
+    ops.kmer_score(qk, wl, min_kmers=4)
+    t0 = time.perf_counter()
+    ops.kmer_score(qk, wl, min_kmers=4)
+    dt = time.perf_counter() - t0
+    res["kmer_score"] = {"pairs_per_s": qk.size * wl.size / dt, "queries": int(qk.size), "whitelist": int(wl.size), "ms": dt * 1e3,
+                         "timing": "host-buffer call, wall clock"}
+    res["hbm_peak_GBps"] = hbm
+    res["hbm_peak_source"] = hbm_src
+    return res
 
 
 def main():

@@ -214,6 +214,22 @@ def test_parts_union_equals_full(nparts, mode):
     assert np.array_equal(merged, edge_rows(fa, fb, fd))
 
 
+def test_dedup_first_seen_vs_oracle():
+    """Row a-2 on the device: same distinct order (first sighting), counts and read map as the oracle's restatement of
+    barcode_graph.py:192-204."""
+    rng = np.random.default_rng(21)
+    for R, pool in ((1, 1), (2, 1), (1000, 10), (5000, 5000), (300000, 20000), (1 << 20, 1 << 18)):
+        src = rng.integers(0, 1 << 32, pool, dtype=np.uint64).astype(np.uint32)
+        src[: min(4, pool)] = np.asarray([0, 0xFFFFFFFF, 1, 0x80000000], np.uint32)[: min(4, pool)]
+        reads = src[rng.integers(0, pool, R)]
+        d, c, m = ops.dedup_first_seen(reads, want_map=True)
+        wd, wc = orc.dedup_count(reads)
+        assert np.array_equal(d, wd) and np.array_equal(c, np.asarray(wc, np.int64))
+        assert np.array_equal(d[m], reads)                      # the map sends every read to its own barcode
+    d, c = ops.dedup_first_seen(np.empty(0, np.uint32))
+    assert d.size == 0 and c.size == 0
+
+
 def test_member_vs_oracle():
     rng = np.random.default_rng(8)
     for W in (0, 1, 5, 1000, 1024, 1025, 300000):
