@@ -429,7 +429,7 @@ int bdg_dev_pack16(const char* d_seqs, size_t R, uint32_t* d_out, uint8_t* d_val
     if ((uintptr_t)d_seqs % 16) return fail(BDG_ERR_ARG, "sequence buffer must be 16-byte aligned");
     int grid = 0;
     if (int rc = grid_for((const void*)bdg::pack16_kernel, &grid)) return rc;
-    const int blocks = (int)std::min<uint64_t>((uint64_t)grid, (R + bdg::NT - 1) / bdg::NT);
+    const int blocks = (int)std::min<uint64_t>((uint64_t)grid, (R + 4 * bdg::NT - 1) / (4 * bdg::NT));
     bdg::pack16_kernel<<<blocks, bdg::NT, 0, (cudaStream_t)stream>>>((const uint4*)d_seqs, R, d_out, d_valid);
     g_launches++;
     CU_TRY(cudaGetLastError());

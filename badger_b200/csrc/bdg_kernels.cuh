@@ -183,13 +183,26 @@ __device__ __forceinline__ void pack4(uint32_t wrd, int base_pos, uint32_t& r, b
 __global__ void __launch_bounds__(NT) pack16_kernel(const uint4* __restrict__ seqs, uint64_t R, uint32_t* __restrict__ out,
                                                     uint8_t* __restrict__ valid)
 {
-    for (uint64_t i = (uint64_t)blockIdx.x * NT + threadIdx.x; i < R; i += (uint64_t)gridDim.x * NT) {
-        const uint4 v = __ldg(&seqs[i]);
-        uint32_t r = 0;
-        bool ok = true;
-        pack4(v.x, 0, r, ok); pack4(v.y, 4, r, ok); pack4(v.z, 8, r, ok); pack4(v.w, 12, r, ok);
-        out[i] = r;
-        valid[i] = ok ? 1 : 0;
+    // four independent 128-bit loads in flight per thread (one per 256-read row of a 1024-read block)
+    constexpr int U = 4;
+    for (uint64_t base = (uint64_t)blockIdx.x * NT * U; base < R; base += (uint64_t)gridDim.x * NT * U) {
+        uint4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t i = base + (uint64_t)u * NT + threadIdx.x;
+            v[u] = i < R ? __ldg(&seqs[i]) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const uint64_t i = base + (uint64_t)u * NT + threadIdx.x;
+            if (i < R) {
+                uint32_t r = 0;
+                bool ok = true;
+                pack4(v[u].x, 0, r, ok); pack4(v[u].y, 4, r, ok); pack4(v[u].z, 8, r, ok); pack4(v[u].w, 12, r, ok);
+                out[i] = r;
+                valid[i] = ok ? 1 : 0;
+            }
+        }
     }
 }
 

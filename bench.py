@@ -332,7 +332,7 @@ def run_b200(args):
             achieved = alg / (step_ms * 1e-3) / 1e12
             alg_o = algorithmic(other, stats_other)
             roof = {"bound": "int_issue",
-                    "kernel": ("edges_sparse_kernel<%d,p>, %d passes per step" % (t, 2 if t == 1 else 3)) if args.mode == "sparse" else "edges_kernel<%d>" % t,
+                    "kernel": ("sparse_scan_kernel + sparse_tile_kernel<%d,p>, %d passes per step" % (t, 2 if t == 1 else 3)) if args.mode == "sparse" else "edges_kernel<%d>" % t,
                     "achieved": achieved, "peak": peak, "unit": "Tinst/s", "frac": achieved / peak if peak else None, "traffic": None,
                     "how": "achieved = algorithmic integer instructions of rank 0's step (%d interval tests x %d + %d pairs scored x %s + "
                            "%d candidates x %d; unit counts from the kernel's own counters, per-unit costs from its SASS, DESIGN.md) / "
