@@ -71,6 +71,7 @@ struct DevCtx {
     unsigned long long host_stats[bdg::MAX_PASSES][2] = {};   // interval tests done / tiles listed per pass of the last launch
     unsigned long long generation = 0;                        // bumped by every host-buffer edge build on this device
     Buf dd[10];                                               // dedup: keys, idx, sorted keys/idx, heads, scan, run arrays, cub scratch
+    Buf nn[9];                                                // sparse nearest: rotated keys + payload (in/out) of queries and targets, scratch
 };
 std::vector<DevCtx> g_ctx;
 
@@ -147,12 +148,22 @@ bool sparse_mode(int t)
 template <int T_, int P_>
 void launch_scan(int blocks, cudaStream_t st, const bdg::EdgeWork& w, const uint2* bnd, uint32_t NS, const bdg::TileList& l)
 {
-    bdg::sparse_scan_kernel<T_, P_><<<blocks, 256, 0, st>>>(w.sorted, w.N, w.group_ids, w.K, bnd, NS, l);
+    bdg::sparse_scan_kernel<T_, P_, false><<<blocks, 256, 0, st>>>(w.sorted, w.N, w.group_ids, w.K, bnd, NS, l);
 }
 template <int T_, int P_>
 void launch_tiles(int blocks, cudaStream_t st, const bdg::EdgeWork& w, const bdg::EdgeOut& o, const bdg::TileList& l)
 {
-    bdg::sparse_tile_kernel<T_, P_><<<blocks, bdg::ENT, 0, st>>>(w, o, l);
+    bdg::sparse_tile_kernel<T_, P_, false><<<blocks, bdg::ENT, 0, st>>>(w, o, l);
+}
+template <int T_, int P_>
+void launch_scan_bip(int blocks, cudaStream_t st, const bdg::EdgeWork& w, const uint2* bnd, uint32_t NS, const bdg::TileList& l)
+{
+    bdg::sparse_scan_kernel<T_, P_, true><<<blocks, 256, 0, st>>>(w.sorted, w.N, nullptr, w.K, bnd, NS, l);
+}
+template <int T_, int P_>
+void launch_tiles_bip(int blocks, cudaStream_t st, const bdg::EdgeWork& w, const bdg::EdgeOut& o, const bdg::TileList& l)
+{
+    bdg::sparse_tile_kernel<T_, P_, true><<<blocks, bdg::ENT, 0, st>>>(w, o, l);
 }
 #define BDG_PASS_DISPATCH(FN, ...)                                                    \
     do {                                                                              \
@@ -174,7 +185,7 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
     if (t <= 0 || N < 2) return BDG_OK;   // D >= 1 for distinct barcodes: no edges (barcode_graph.py:245)
     const bool sparse = sparse_mode(t);
     const int passes = sparse ? bdg::n_passes(t) : 1;
-    const void* kern = sparse ? (t == 1 ? (const void*)bdg::sparse_tile_kernel<1, 0> : (const void*)bdg::sparse_tile_kernel<2, 0>)
+    const void* kern = sparse ? (t == 1 ? (const void*)bdg::sparse_tile_kernel<1, 0, false> : (const void*)bdg::sparse_tile_kernel<2, 0, false>)
                               : (t == 1 ? (const void*)bdg::edges_kernel<1> : t == 2 ? (const void*)bdg::edges_kernel<2>
                                                                                      : (const void*)bdg::edges_kernel<3>);
     int grid = 0;
@@ -272,6 +283,80 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
     return BDG_OK;
 }
 
+
+// Q x W scoring through the sparse machinery (max_d <= 2): queries and targets are each sorted by the pass's rotated
+// key (original indices ride along), tiles of (256 queries x 128 targets) whose key intervals cannot meet are decided
+// by the scan, the rest get the quick test, survivors the exact plain distance and an atomicMin on the query's key.
+int launch_nearest_sparse(const uint32_t* d_q, size_t Q, const uint32_t* d_t, size_t W, int max_d, uint32_t* d_keys, cudaStream_t st, DevCtx* ws)
+{
+    const int T_ = max_d <= 1 ? 1 : 2;
+    const int passes = bdg::n_passes(T_);
+    auto ensure = [&](Buf& b, size_t bytes) -> int {
+        if (cudaError_t e = (cudaError_t)b.ensure(bytes))
+            return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "workspace of %zu bytes: %s", bytes, cudaGetErrorString(e));
+        return BDG_OK;
+    };
+    // nn[0..3]: query keys in / payload in / keys sorted / payload sorted; nn[4..7]: the same for the targets; nn[8]: sort scratch
+    for (int k = 0; k < 4; k++) if (int e = ensure(ws->nn[k], Q * 4)) return e;
+    for (int k = 4; k < 8; k++) if (int e = ensure(ws->nn[k], W * 4)) return e;
+    uint32_t *qk = (uint32_t*)ws->nn[0].p, *qp = (uint32_t*)ws->nn[1].p, *qks = (uint32_t*)ws->nn[2].p, *qps = (uint32_t*)ws->nn[3].p;
+    uint32_t *tk = (uint32_t*)ws->nn[4].p, *tp = (uint32_t*)ws->nn[5].p, *tks = (uint32_t*)ws->nn[6].p, *tps = (uint32_t*)ws->nn[7].p;
+    size_t tmp_q = 0, tmp_t = 0;
+    CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_q, qk, qks, qp, qps, (int)Q, 0, 32, st));
+    CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_t, tk, tks, tp, tps, (int)W, 0, 32, st));
+    if (int e = ensure(ws->nn[8], std::max(tmp_q, tmp_t))) return e;
+    const uint32_t NS = (uint32_t)((W + bdg::SSB - 1) / bdg::SSB);
+    const uint32_t K = (uint32_t)((Q + bdg::GROUP - 1) / bdg::GROUP);
+    if (int e = ensure(ws->tile_bnd, (size_t)NS * sizeof(uint2))) return e;
+    if (ws->tile_list.cap == 0)
+        if (int e = ensure(ws->tile_list, ((size_t)1 << 22) * sizeof(uint2))) return e;
+    if (int e = ensure(ws->plan, PLAN_HDR * bdg::MAX_PASSES)) return e;
+    char* d_plan = (char*)ws->plan.p;
+    CU_TRY(cudaMemsetAsync(d_plan, 0, PLAN_HDR * bdg::MAX_PASSES, st));
+    int grid = 0;
+    if (int rc = grid_for(T_ == 1 ? (const void*)bdg::sparse_tile_kernel<1, 0, true> : (const void*)bdg::sparse_tile_kernel<2, 0, true>, &grid, bdg::ENT)) return rc;
+    const int t = T_;   // BDG_PASS_DISPATCH reads `t` and `p`
+    for (int p = 0; p < passes; p++) {
+        const int rot = bdg::pass_rot(T_, p);
+        const int qb = (int)std::min<size_t>((Q + 255) / 256, (size_t)ws->sms * 8), tb = (int)std::min<size_t>((W + 255) / 256, (size_t)ws->sms * 8);
+        bdg::rotate_keys_iota_kernel<<<qb, 256, 0, st>>>(d_q, qk, qp, (uint32_t)Q, rot);
+        bdg::rotate_keys_iota_kernel<<<tb, 256, 0, st>>>(d_t, tk, tp, (uint32_t)W, rot);
+        CU_TRY(cub::DeviceRadixSort::SortPairs(ws->nn[8].p, tmp_q, qk, qks, qp, qps, (int)Q, 0, 32, st));
+        CU_TRY(cub::DeviceRadixSort::SortPairs(ws->nn[8].p, tmp_t, tk, tks, tp, tps, (int)W, 0, 32, st));
+        bdg::tile_bounds_kernel<<<std::min<uint32_t>((NS + 255) / 256, (uint32_t)ws->sms * 8), 256, 0, st>>>(tks, (uint32_t)W, (uint2*)ws->tile_bnd.p, NS);
+        g_launches += 3;
+        bdg::EdgeWork w{};
+        w.sorted = qks; w.N = (uint32_t)Q; w.t = max_d; w.T = 0; w.group_ids = nullptr; w.item_start = nullptr; w.K = K;
+        w.item_counter = (unsigned int*)(d_plan + PLAN_HDR * p);
+        w.stats = nullptr; w.one = 1u; w.pass = p; w.rot = rot;
+        w.cols = tks; w.NC = (uint32_t)W; w.row_pay = qps; w.col_pay = tps; w.near_keys = d_keys;
+        unsigned long long n_tiles = 0;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            bdg::TileList l{(uint2*)ws->tile_list.p, (unsigned long long*)(d_plan + PLAN_HDR * p + HDR_LIST), ws->tile_list.cap / sizeof(uint2)};
+            CU_TRY(cudaMemsetAsync(l.count, 0, 8, st));
+            const int sblocks = (int)std::min<uint64_t>(K, (uint64_t)ws->sms * 16);
+            BDG_PASS_DISPATCH(launch_scan_bip, sblocks, st, w, (const uint2*)ws->tile_bnd.p, NS, l);
+            g_launches++;
+            CU_TRY(cudaGetLastError());
+            CU_TRY(cudaMemcpyAsync(&n_tiles, l.count, 8, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            if (n_tiles <= l.cap) break;
+            if (attempt == 1) return fail(BDG_ERR_CUDA, "tile list count changed between identical scans");
+            if (int e = ensure(ws->tile_list, (size_t)n_tiles * sizeof(uint2))) return e;
+        }
+        if (n_tiles == 0) continue;
+        bdg::TileList l{(uint2*)ws->tile_list.p, (unsigned long long*)(d_plan + PLAN_HDR * p + HDR_LIST), ws->tile_list.cap / sizeof(uint2)};
+        const int tblocks = (int)std::min<uint64_t>((uint64_t)grid, (n_tiles + bdg::EW - 1) / bdg::EW);
+        bdg::EdgeOut o{nullptr, nullptr, nullptr, nullptr, 0};
+        BDG_PASS_DISPATCH(launch_tiles_bip, tblocks, st, w, o, l);
+        g_launches++;
+        CU_TRY(cudaGetLastError());
+    }
+    return BDG_OK;
+}
+
+DevCtx* ctx_of_current_device();
+
 DevCtx* ctx_of_current_device()
 {
     int dev = -1;
@@ -363,6 +448,7 @@ void bdg_shutdown(void)
         c.sorted.release(); c.ea.release(); c.eb.release(); c.ed.release(); c.count.release(); c.plan.release();
         c.rot_in.release(); c.sort_tmp.release(); c.tile_bnd.release(); c.tile_list.release();
         for (auto& b : c.dd) b.release();
+        for (auto& b : c.nn) b.release();
         for (auto& b : c.rot_sorted) b.release();
     }
     g_ctx.clear();
@@ -459,7 +545,11 @@ int bdg_dev_nearest_bounded(const uint32_t* d_q, size_t Q, const uint32_t* d_t, 
     if (W >= (1ull << bdg::NEAR_IDX_BITS) || Q > 0xFFFFFFFFull) return fail(BDG_ERR_ARG, "W must be < 2^28 and Q < 2^32");
     cudaStream_t st = (cudaStream_t)stream;
     CU_TRY(cudaMemsetAsync(d_keys, 0xFF, Q * sizeof(uint32_t), st));
-    if (W > 0 && max_d >= 0) {
+    DevCtx* ws = ctx_of_current_device();
+    const bool sparse = ws && W > 0 && max_d >= 0 && max_d <= 2 && (unsigned long long)Q * W >= (1ull << 24) && !getenv("BDG_NEAREST_DENSE");
+    if (sparse) {
+        if (int rc = launch_nearest_sparse(d_q, Q, d_t, W, max_d, d_keys, st, ws)) return rc;
+    } else if (W > 0 && max_d >= 0) {
         int sms = 0, dev = 0;
         CU_TRY(cudaGetDevice(&dev));
         CU_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

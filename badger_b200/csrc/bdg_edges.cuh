@@ -63,6 +63,12 @@ struct EdgeWork {
     uint32_t one;               // == 1, opaque to the compiler: x*(-one)+c keeps the subtraction on the FMA pipe (IMAD)
     int pass;                   // sparse kernel: pass index p (bdg_core.cuh pass_pred); `sorted` holds rotl(key, rot) sorted
     int rot;
+    // bipartite form (queries x targets, bdg_nearest_bounded): rows come from `sorted` (N queries), columns from `cols`
+    const uint32_t* cols;       // NC target keys sorted by the same rotated key
+    uint32_t NC;
+    const uint32_t* row_pay;    // original index of every sorted query / target
+    const uint32_t* col_pay;
+    uint32_t* near_keys;        // per query: min over targets of (plain distance << 28 | target index)
 };
 
 __device__ __forceinline__ unsigned long long global_ns()
@@ -423,18 +429,18 @@ __global__ void tile_bounds_kernel(const uint32_t* __restrict__ sorted, uint32_t
     }
 }
 
-template <int T_, int P_>
+template <int T_, int P_, bool BIP>
 __global__ void __launch_bounds__(256) sparse_scan_kernel(const uint32_t* __restrict__ sorted, uint32_t N,
                                                           const uint32_t* __restrict__ group_ids, uint32_t K,
                                                           const uint2* __restrict__ bnd, uint32_t NS, TileList list)
 {
     const int lane = threadIdx.x & 31;
     for (uint32_t k = blockIdx.x; k < K; k += gridDim.x) {
-        const uint32_t g = __ldg(&group_ids[k]);
+        const uint32_t g = group_ids ? __ldg(&group_ids[k]) : k;
         const uint64_t row0 = (uint64_t)g * GROUP;
         const uint32_t a_lo = __ldg(&sorted[row0]);
         const uint32_t a_hi = __ldg(&sorted[min((uint64_t)N, row0 + GROUP) - 1]);
-        const uint32_t s0 = g * (GROUP / SSB);                      // first sub-tile that reaches past the group's first row
+        const uint32_t s0 = BIP ? 0u : g * (GROUP / SSB);         // triangular: first sub-tile that reaches past the group's first row
         for (uint32_t sb = s0; sb < NS; sb += blockDim.x) {        // whole warps stay in the loop together
             const uint32_t sidx = sb + threadIdx.x;
             bool poss = false;
@@ -462,6 +468,11 @@ struct SparseCtx {
     const uint32_t* sorted;
     uint32_t N;
     int t, T, rot, lane;
+    const uint32_t* cols;          // bipartite form only
+    uint32_t NC;
+    const uint32_t* row_pay;
+    const uint32_t* col_pay;
+    uint32_t* near_keys;
 };
 
 // stage 3 on a batch: S = shared 6-mer count (the dearest test: 21 diagonals) for pairs that already have D <= t
@@ -480,9 +491,22 @@ __device__ __forceinline__ void sparse_score(const SparseCtx& c, const EdgeOut& 
 
 // stage 2 on a batch of candidates: pass predicates (this pass yes, earlier passes no) and exact D; survivors
 // wait in the second queue so that stage 3 also runs with full warps
-template <int T_, int P_>
+// bipartite stage 2: plain edit distance of (query, target); the best (distance, target index) per query is kept with
+// an atomicMin, which also absorbs pairs that several passes find
+__device__ __forceinline__ void near_process(const SparseCtx& c, uint2 e, bool active)
+{
+    if (active && e.x < c.N && e.y < c.NC) {
+        const uint32_t x = rotr32(__ldg(&c.sorted[e.x]), c.rot);
+        const uint32_t y = rotr32(__ldg(&c.cols[e.y]), c.rot);
+        const int d = dist_small(x, y, true);
+        if (d <= c.t) atomicMin(&c.near_keys[__ldg(&c.row_pay[e.x])], ((uint32_t)d << 28) | __ldg(&c.col_pay[e.y]));
+    }
+}
+
+template <int T_, int P_, bool BIP>
 __device__ __forceinline__ void sparse_process(const SparseCtx& c, const EdgeOut& out, uint2 e, bool active, int& q2n)
 {
+    if constexpr (BIP) { near_process(c, e, active); return; }
     bool ok = false;
     uint32_t x = 0, y = 0;
     int d = 0;
@@ -519,7 +543,7 @@ __device__ __forceinline__ void sparse_process(const SparseCtx& c, const EdgeOut
 }
 
 // append the set bits of h (bit k*8+r = column col0+k, row row0 + r*32 + lane); run stage 2 whenever 32 candidates wait
-template <int T_, int P_>
+template <int T_, int P_, bool BIP>
 __device__ __forceinline__ void sparse_push(uint32_t h, uint32_t row0, uint32_t col0, int& qn, int& q2n, const SparseCtx& c, const EdgeOut& out)
 {
     // common case: every lane writes all its hits at once at offsets from a warp prefix sum of the hit counts
@@ -543,7 +567,7 @@ __device__ __forceinline__ void sparse_push(uint32_t h, uint32_t row0, uint32_t 
         while (qn >= 32) {
             qn -= 32;
             const uint2 e = c.q[qn + c.lane];
-            sparse_process<T_, P_>(c, out, e, true, q2n);
+            sparse_process<T_, P_, BIP>(c, out, e, true, q2n);
             __syncwarp();
         }
         return;
@@ -563,13 +587,13 @@ __device__ __forceinline__ void sparse_push(uint32_t h, uint32_t row0, uint32_t 
         while (qn >= 32) {
             qn -= 32;
             const uint2 e = c.q[qn + c.lane];
-            sparse_process<T_, P_>(c, out, e, true, q2n);
+            sparse_process<T_, P_, BIP>(c, out, e, true, q2n);
             __syncwarp();
         }
     }
 }
 
-template <int T_, int P_>
+template <int T_, int P_, bool BIP>
 __global__ void __launch_bounds__(ENT, 3) sparse_tile_kernel(const EdgeWork w, const EdgeOut out, const TileList list)
 {
     __shared__ __align__(16) uint32_t s_b[EW][3][SSB];   // unrotated b, b >> 2, b << 2 of the staged sub-tile
@@ -583,6 +607,7 @@ __global__ void __launch_bounds__(ENT, 3) sparse_tile_kernel(const EdgeWork w, c
     SparseCtx c;
     c.q = s_q[wid]; c.q2 = s_q2[wid]; c.q2d = s_q2d[wid];
     c.sorted = w.sorted; c.N = w.N; c.t = w.t; c.T = w.T; c.rot = w.rot; c.lane = lane;
+    c.cols = BIP ? w.cols : w.sorted; c.NC = BIP ? w.NC : w.N; c.row_pay = w.row_pay; c.col_pay = w.col_pay; c.near_keys = w.near_keys;
     int qn = 0, q2n = 0;                          // queue fills, uniform across the warp
     const uint32_t mone = 0u - w.one;             // runtime -1: u*one + mone is u - 1 on the FMA pipe
     const unsigned long long t_start = global_ns();
@@ -611,14 +636,14 @@ __global__ void __launch_bounds__(ENT, 3) sparse_tile_kernel(const EdgeWork w, c
             }
         }
         const uint32_t sub = tile.y * SSB;
-        const int ncols = (int)min((uint32_t)SSB, w.N - sub);
+        const int ncols = (int)min((uint32_t)SSB, c.NC - sub);
         __syncwarp();
         uint32_t my_blo = 0, my_bhi = 0;
 #pragma unroll
         for (int i = 0; i < SSB / 32; i++) {                     // quarter i = columns sub + 32i .. +31
             const uint32_t idx = sub + (uint32_t)i * 32 + lane;
-            const uint32_t br = idx < w.N ? __ldg(&w.sorted[idx]) : 0xFFFFFFFFu;   // pads only widen the interval
-            const uint32_t b = idx < w.N ? rotr32(br, w.rot) : 0u;
+            const uint32_t br = idx < c.NC ? __ldg(&c.cols[idx]) : 0xFFFFFFFFu;    // pads only widen the interval
+            const uint32_t b = idx < c.NC ? rotr32(br, w.rot) : 0u;
             b0s[i * 32 + lane] = b;
             bPs[i * 32 + lane] = b >> 2;
             bMs[i * 32 + lane] = b << 2;
@@ -653,7 +678,7 @@ __global__ void __launch_bounds__(ENT, 3) sparse_tile_kernel(const EdgeWork w, c
                     }
                 }
                 if (cb + 4 > ncols) h &= (1u << (8 * (ncols - cb))) - 1u;      // columns past the end of the array
-                if (__any_sync(FULL, h != 0)) { n_cand += __popc(h); sparse_push<T_, P_>(h, row0, sub + cb, qn, q2n, c, out); }
+                if (__any_sync(FULL, h != 0)) { n_cand += __popc(h); sparse_push<T_, P_, BIP>(h, row0, sub + cb, qn, q2n, c, out); }
             }
         }
     }
@@ -662,7 +687,7 @@ __global__ void __launch_bounds__(ENT, 3) sparse_tile_kernel(const EdgeWork w, c
         const int take = min(qn, 32);
         qn -= take;
         const uint2 e = lane < take ? c.q[qn + lane] : make_uint2(0u, 0u);
-        sparse_process<T_, P_>(c, out, e, lane < take, q2n);
+        sparse_process<T_, P_, BIP>(c, out, e, lane < take, q2n);
         __syncwarp();
     }
     if (q2n > 0) sparse_score(c, out, q2n);         // fewer than 32 by construction
@@ -673,6 +698,12 @@ __global__ void __launch_bounds__(ENT, 3) sparse_tile_kernel(const EdgeWork w, c
             warp_exit_stats(w.stats, t_start);
         }
     }
+}
+
+// rotl(key, rot) and the identity payload for a whole array (input of the per-pass radix sort of the bipartite form)
+__global__ void rotate_keys_iota_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t* __restrict__ pay, uint32_t n, int rot)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) { out[i] = rotl32(__ldg(&in[i]), rot); pay[i] = i; }
 }
 
 // rotl(key, rot) for a whole array (input of the per-pass radix sort)

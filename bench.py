@@ -423,7 +423,13 @@ def other_stages(torch, dev, stream, L, s, args):
     dt = dev_time(lambda: chk(L.bdg_dev_nearest_bounded(d_q7.data_ptr(), Q7, d_t.data_ptr(), W7, 2, d_keys.data_ptr(), d_am.data_ptr(),
                                                         d_di.data_ptr(), stream.cuda_stream)))
     res["nearest_bounded"] = {"pairs_per_s": Q7 * W7 / dt, "queries": Q7, "targets": W7, "ms": dt * 1e3,
-                              "int_Tinst_per_s": 11 * Q7 * W7 / dt / 1e12, "note": "11 prefilter instructions per pair (DESIGN.md 4)"}
+                              "note": "sorted/tiled form (same scan + tile kernels as the edges, bipartite)"}
+    os.environ["BDG_NEAREST_DENSE"] = "1"
+    dt = dev_time(lambda: chk(L.bdg_dev_nearest_bounded(d_q7.data_ptr(), Q7, d_t.data_ptr(), W7, 2, d_keys.data_ptr(), d_am.data_ptr(),
+                                                        d_di.data_ptr(), stream.cuda_stream)))
+    os.environ.pop("BDG_NEAREST_DENSE", None)
+    res["nearest_bounded"]["brute_force_kernel"] = {"pairs_per_s": Q7 * W7 / dt, "ms": dt * 1e3, "int_Tinst_per_s": 11 * Q7 * W7 / dt / 1e12,
+                                                    "note": "11 prefilter instructions per pair"}
     # a-2 dedup in first-seen order and a-5 k-mer scoring: host-buffer calls, wall clock (copies included)
     reads = s[rng.integers(0, s.size, 2_000_000)]
     ops.dedup_first_seen(reads, want_map=True)

@@ -256,6 +256,28 @@ def test_nearest_vs_oracle(max_d):
     assert (e_am == -1).all() and (e_d == 255).all()
 
 
+@pytest.mark.parametrize("max_d", [2, 1, 0])
+def test_nearest_large_sparse_path(max_d, monkeypatch):
+    """Q x W large enough for the sorted / tiled form of the scorer (bdg_api.cu launch_nearest_sparse): same answers as the
+    brute-force kernel and as the oracle, including ties on distance (first index in caller order wins) and duplicates."""
+    rng = np.random.default_rng(19 + max_d)
+    centres = rng.integers(0, 1 << 32, 6000, dtype=np.uint64).astype(np.uint32)
+    obs, _ = synth.simulate_reads(centres, 70000, 0.07, rng)
+    q = np.concatenate([obs, centres[:500], rng.integers(0, 1 << 32, 3000, dtype=np.uint64).astype(np.uint32),
+                        np.asarray([0, 0xFFFFFFFF, 0x55555555], np.uint32)])
+    tg = np.concatenate([centres, centres[:200] ^ np.uint32(1), centres[:100], np.asarray([0, 0xFFFFFFFF], np.uint32)])
+    tg = tg[rng.permutation(tg.size)]
+    assert q.size * tg.size >= 1 << 24
+    am, dist = ops.nearest_bounded(q, tg, max_d)
+    monkeypatch.setenv("BDG_NEAREST_DENSE", "1")
+    am2, dist2 = ops.nearest_bounded(q, tg, max_d)
+    assert np.array_equal(am, am2) and np.array_equal(dist, dist2)
+    sel = rng.choice(q.size, 6000, replace=False)
+    wam, wdist = orc.nearest(q[sel], tg, max_d)
+    assert np.array_equal(am[sel], wam) and np.array_equal(dist[sel], wdist)
+    assert (am >= 0).sum() > 1000
+
+
 def test_kmer_score_vs_oracle():
     rng = np.random.default_rng(10)
     wl = rng.integers(0, 1 << 32, 3000, dtype=np.uint64).astype(np.uint32)
