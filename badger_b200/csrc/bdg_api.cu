@@ -249,8 +249,11 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
             // level 1: interval scan of every (owned row group, sub-tile right of it) -> compact tile list
             const uint32_t NS = (uint32_t)((N + bdg::SSB - 1) / bdg::SSB);
             if (int e = ensure(ws->tile_bnd, (size_t)NS * sizeof(uint2))) return e;
-            if (ws->tile_list.cap == 0)
-                if (int e = ensure(ws->tile_list, std::max<size_t>((size_t)1 << 22, 4 * N) * sizeof(uint2))) return e;
+            if (ws->tile_list.cap == 0) {
+                size_t want = std::max<size_t>((size_t)1 << 22, 4 * N);
+                if (const char* e = getenv("BDG_TILE_LIST_CAP")) want = (size_t)std::max(1ll, atoll(e));   // tests: force the regrow path
+                if (int e = ensure(ws->tile_list, want * sizeof(uint2))) return e;
+            }
             bdg::tile_bounds_kernel<<<std::min<uint32_t>((NS + 255) / 256, (uint32_t)ws->sms * 8), 256, 0, st>>>(w.sorted, w.N, (uint2*)ws->tile_bnd.p, NS);
             g_launches++;
             unsigned long long n_tiles = 0;

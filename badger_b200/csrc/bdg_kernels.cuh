@@ -170,14 +170,17 @@ __global__ void __launch_bounds__(NT) member_kernel(const uint32_t* __restrict__
 // pack16_kernel (a-1): one 128-bit load per read, 16 B in + 5 B out.  code = ((c>>1) ^ (c>>2)) & 3 maps
 // A,C,G,T -> 0,1,2,3; validity is an exact match against the four upper-case letters.
 // ---------------------------------------------------------------------------------------------------
+// four characters at once (SWAR): x = codes in the low two bits of every byte; a multiply gathers them into one
+// byte (c0 | c1<<2 | c2<<4 | c3<<6 lands in bits 24..31, no carries: every partial product has its own 2-bit slot);
+// validity = the four letters those codes stand for, looked up with byte permutes (the selector nibbles 0 and 2 of
+// x and of x >> 16 are the codes, nibbles 1 and 3 are zero), equal the input word.
 __device__ __forceinline__ void pack4(uint32_t wrd, int base_pos, uint32_t& r, bool& ok)
 {
-#pragma unroll
-    for (int i = 0; i < 4; i++) {
-        const uint32_t c = (wrd >> (8 * i)) & 0xFFu;
-        ok = ok && (c == 'A' || c == 'C' || c == 'G' || c == 'T');
-        r |= (((c >> 1) ^ (c >> 2)) & 3u) << (2 * (base_pos + i));
-    }
+    const uint32_t x = ((wrd >> 1) ^ (wrd >> 2)) & 0x03030303u;
+    r |= ((x * 0x01041040u) >> 24) << (2 * base_pos);
+    const uint32_t e01 = __byte_perm(0x54474341u /* "ACGT" */, 0u, x);          // bytes 0, 2 = letters of characters 0, 1
+    const uint32_t e23 = __byte_perm(0x54474341u, 0u, x >> 16);                 // bytes 0, 2 = letters of characters 2, 3
+    ok = ok && (__byte_perm(e01, e23, 0x6420u) == wrd);
 }
 
 __global__ void __launch_bounds__(NT) pack16_kernel(const uint4* __restrict__ seqs, uint64_t R, uint32_t* __restrict__ out,

@@ -193,6 +193,34 @@ def test_edge_buffer_regrow(monkeypatch, mode):
     assert np.array_equal(got, want)
 
 
+def test_tile_list_regrow(monkeypatch):
+    """Sparse mode sizes its tile list from a guess; when the scan finds more tiles the list grows and the scan repeats."""
+    s = clustered_set(56, 60, 50000, 0.05)
+    L = badger_b200.lib()
+    badger_b200._lib.check(L.bdg_set_edge_mode(1))
+    want = edge_rows(*ops.edges_build(s, 2))
+    L.bdg_shutdown()                                            # drop the grown workspaces
+    monkeypatch.setenv("BDG_TILE_LIST_CAP", "8")
+    badger_b200.init()
+    got = edge_rows(*ops.edges_build(s, 2))
+    badger_b200._lib.check(L.bdg_set_edge_mode(-1))
+    assert want.shape[0] > 10000 and np.array_equal(got, want)
+
+
+def test_stale_edge_handle_is_refused():
+    """A handle's edges live in the device workspaces until copied; a later build on the device invalidates it."""
+    s = clustered_set(57, 20, 3000, 0.05)
+    L = badger_b200.lib()
+    h1, h2 = C.c_void_p(), C.c_void_p()
+    badger_b200._lib.check(L.bdg_edges_build(s.ctypes.data, s.size, 1, C.byref(h1)))
+    n1 = L.bdg_edges_count(h1)
+    badger_b200._lib.check(L.bdg_edges_build(s.ctypes.data, s.size, 1, C.byref(h2)))
+    a = np.empty(n1, np.uint32); b = np.empty(n1, np.uint32); d = np.empty(n1, np.uint8)
+    assert n1 > 0 and L.bdg_edges_copy(h1, a.ctypes.data, b.ctypes.data, d.ctypes.data) == badger_b200._lib.BDG_ERR_ARG
+    assert L.bdg_edges_copy(h2, a.ctypes.data, b.ctypes.data, d.ctypes.data) == 0
+    L.bdg_edges_free(h1); L.bdg_edges_free(h2)
+
+
 @pytest.mark.parametrize("nparts", [2, 3, 8])
 def test_parts_union_equals_full(nparts, mode):
     s = clustered_set(77, 200, 20000, 0.06)
