@@ -44,7 +44,9 @@ class _EdgeView:
         self._touched = set()
 
     def _slot(self, key):
-        i = int(np.searchsorted(self._nodes, key))
+        if not 0 <= int(key) <= 0xFFFFFFFF:
+            return -1
+        i = int(np.searchsorted(self._nodes, np.uint32(key)))     # typed key: a Python int would upcast the whole array per call
         return i if i < self._nodes.size and int(self._nodes[i]) == int(key) else -1
 
     def __getitem__(self, key):
@@ -262,72 +264,39 @@ class BarcodeGraph:
             n += 1
         return tbcs
 
-    # ------------------------------------------------------------------ clustering (host, order-free)
+    # ------------------------------------------------------------------ clustering (GPU rounds, dict views on the host)
     def cluster(self, true_barcodes, barcode_list, n_cells, bc_len, interval):
         """barcode_graph.py:279-301.  The reference's two rounds are level-synchronous and independent of the
-        adjacency order: a node joins centre c at level i iff, among the nodes expanded in
-        round i, its neighbours all belong to c; two different centres in the same round evict it."""
+        adjacency order: a node joins centre c in round i iff every claim it receives in that round
+        comes from c; two different centres in the same round evict it.  The rounds run edge-parallel on the GPU
+        (ops.cluster_levels); this method fills the reference's dict attributes from the resulting arrays."""
         tbcs = self.get_cluster_centers(true_barcodes, bc_len, barcode_list, n_cells, interval)
-        nodes, indptr, nbrs = getattr(self, "_csr", (np.empty(0, np.uint32), np.zeros(1, np.int64), np.empty(0, np.uint32)))
         centres = list(dict.fromkeys(int(t) for t in tbcs))
         for t in centres:
             self.clusters[t] = [t]
             self.clustering[t] = (t, 0)
             self.clustered[t] = True
             _ = self.edges[t]                       # the reference touches edges[centre] (:293)
-        # universe: every node with an edge, plus the centres
-        uni = np.unique(np.concatenate([nodes, np.asarray(centres, dtype=np.uint32)]))
-        centre_of = np.full(uni.size, -2, dtype=np.int64)      # -2 unclustered, -1 evicted, else index into uni
-        level = np.full(uni.size, -1, dtype=np.int64)
-        cidx = np.searchsorted(uni, np.asarray(centres, dtype=np.uint32))
-        centre_of[cidx] = cidx
-        level[cidx] = 0
-        node_pos = np.searchsorted(uni, nodes)                  # CSR row -> universe slot
-        row_of = np.full(uni.size, -1, dtype=np.int64)
-        row_of[node_pos] = np.arange(nodes.size)
-        frontier = cidx
-        for i in (1, 2):
-            print(i)                                             # barcode_graph.py:289
-            rows = row_of[frontier]
-            ok = rows >= 0
-            rows, src = rows[ok], frontier[ok]
-            if rows.size == 0:
-                frontier = np.empty(0, dtype=np.int64)
-                continue
-            lens = indptr[rows + 1] - indptr[rows]
-            tot = int(lens.sum())
-            offs = np.repeat(indptr[rows] - np.concatenate([[0], np.cumsum(lens)[:-1]]), lens) + np.arange(tot)
-            nb = np.searchsorted(uni, nbrs[offs])
-            who = np.repeat(centre_of[src], lens)                # centre (universe slot) claiming nb
-            free = centre_of[nb] == -2
-            nb, who = nb[free], who[free]
-            if nb.size == 0:
-                frontier = np.empty(0, dtype=np.int64)
-                continue
-            o = np.lexsort((who, nb))
-            nb, who = nb[o], who[o]
-            first = np.concatenate([[True], nb[1:] != nb[:-1]])
-            start = np.nonzero(first)[0]
-            end = np.append(start[1:], nb.size)
-            single = who[start] == who[end - 1]                 # sorted by who inside a node: one centre iff min == max
-            tgt = nb[start]
-            centre_of[tgt] = np.where(single, who[start], -1)
-            level[tgt] = np.where(single, i, -1)
-            frontier = tgt[single]
-        # materialise the reference's dict attributes
-        got = np.nonzero(centre_of != -2)[0]
-        got = got[level[got] != 0]
-        uni_l = uni.tolist()
-        for slot in got.tolist():
-            node = uni_l[slot]
-            c = int(centre_of[slot])
-            if c >= 0:
-                cen = uni_l[c]
-                self.clusters[cen].append(node)
-                self.clustering[node] = (cen, int(level[slot]))
-            else:
-                self.clustering[node] = (-1, -1)
-            self.clustered[node] = True
+        print(1)                                     # barcode_graph.py:289 prints the round number
+        print(2)
+        a, b, _d = self._edge_arrays
+        with self._timed("cluster: GPU rounds"):
+            s = np.sort(self._ranks)
+            ci, lv = ops.cluster_levels(s, a, b, np.asarray(centres, dtype=np.uint32), 2)
+        self._cluster_arrays = (s, ci, lv)
+        with self._timed("cluster: dict views"):
+            got = np.nonzero((ci != -2) & (lv != 0))[0]
+            nodes = s[got].tolist()
+            cen = np.where(ci[got] >= 0, s[np.maximum(ci[got], 0)], 0).tolist()
+            ok = (ci[got] >= 0).tolist()
+            lvl = lv[got].tolist()
+            for node, c, good, l in zip(nodes, cen, ok, lvl):
+                if good:
+                    self.clusters[c].append(node)
+                    self.clustering[node] = (c, l)
+                else:
+                    self.clustering[node] = (-1, -1)
+                self.clustered[node] = True
 
     # ------------------------------------------------------------------ assignment / post-processing / output
     def assign_by_cluster(self, bc_len):

@@ -71,6 +71,7 @@ struct DevCtx {
     unsigned long long host_stats[bdg::MAX_PASSES][2] = {};   // interval tests done / tiles listed per pass of the last launch
     unsigned long long generation = 0;                        // bumped by every host-buffer edge build on this device
     Buf dd[10];                                               // dedup: keys, idx, sorted keys/idx, heads, scan, run arrays, cub scratch
+    Buf cl[6];                                                // clustering: centres, centre index, level, claim min / max, index scratch
     Buf nn[9];                                                // sparse nearest: rotated keys + payload (in/out) of queries and targets, scratch
 };
 std::vector<DevCtx> g_ctx;
@@ -133,7 +134,7 @@ void build_plan(size_t N, int part, int nparts, int workers, Plan& p, uint64_t c
     p.item_start[p.group_ids.size()] = (uint32_t)acc;
 }
 
-constexpr size_t PLAN_HDR = 128;  // per launch: [work cursor u64 | tile-list count u64 | 7 x u64 statistics (last: earliest warp start) | pad]
+constexpr size_t PLAN_HDR = 128;  // per launch: [work cursor u64 | tile-list count u64 | 8 x u64 statistics | pad]
 constexpr size_t HDR_LIST = 8, HDR_STATS = 16;
 int g_edge_mode = -1;             // -1: BDG_EDGE_MODE or default (sparse); 0 dense; 1 sparse
 
@@ -452,6 +453,7 @@ void bdg_shutdown(void)
         c.rot_in.release(); c.sort_tmp.release(); c.tile_bnd.release(); c.tile_list.release();
         for (auto& b : c.dd) b.release();
         for (auto& b : c.nn) b.release();
+        for (auto& b : c.cl) b.release();
         for (auto& b : c.rot_sorted) b.release();
     }
     g_ctx.clear();
@@ -481,16 +483,17 @@ int bdg_set_edge_mode(int mode)
     return BDG_OK;
 }
 
-int bdg_dev_edges_stats(unsigned long long* out4, void* stream)
+int bdg_dev_edges_stats(unsigned long long* out5, void* stream)
 {
     DevCtx* c = ctx_of_current_device();
-    if (!c || !c->plan.p || !out4) return fail(BDG_ERR_ARG, "no edge launch on this device yet");
+    if (!c || !c->plan.p || !out5) return fail(BDG_ERR_ARG, "no edge launch on this device yet");
     unsigned long long v[(PLAN_HDR / 8) * bdg::MAX_PASSES];
     CU_TRY(cudaMemcpyAsync(v, c->plan.p, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
     CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-    for (int k = 0; k < 4; k++) {
-        out4[k] = 0;
-        for (int p = 0; p < bdg::MAX_PASSES; p++) out4[k] += v[(PLAN_HDR / 8) * p + HDR_STATS / 8 + k] + (k < 2 ? c->host_stats[p][k] : 0);
+    for (int k = 0; k < 5; k++) {
+        out5[k] = 0;
+        const int slot = k < 4 ? k : 7;
+        for (int p = 0; p < bdg::MAX_PASSES; p++) out5[k] += v[(PLAN_HDR / 8) * p + HDR_STATS / 8 + slot] + (k < 2 ? c->host_stats[p][k] : 0);
     }
     return BDG_OK;
 }
@@ -816,6 +819,90 @@ int bdg_edges_copy(const bdg_edges* e, uint32_t* a, uint32_t* b, uint8_t* d)
 }
 
 void bdg_edges_free(bdg_edges* e) { delete e; }
+
+
+// ---- f-3  cluster(): barcode_graph.py:279-301 -------------------------------------------------------------
+// d_ea / d_eb hold barcode VALUES on entry and node indices on return (converted in place).
+static int cluster_on_device(DevCtx& c, const uint32_t* d_sorted, size_t N, uint32_t* d_ea, uint32_t* d_eb, size_t E,
+                             const uint32_t* centres, size_t C, int rounds, int32_t* centre_idx, uint8_t* level)
+{
+    auto ensure = [&](Buf& b, size_t bytes) -> int {
+        if (cudaError_t e = (cudaError_t)b.ensure(bytes))
+            return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation of %zu bytes: %s", bytes, cudaGetErrorString(e));
+        return BDG_OK;
+    };
+    cudaStream_t st = c.stream;
+    if (int e = ensure(c.cl[0], std::max<size_t>(C, 1) * 4)) return e;
+    if (int e = ensure(c.cl[1], N * 4)) return e;
+    if (int e = ensure(c.cl[2], N)) return e;
+    if (int e = ensure(c.cl[3], N * 4)) return e;
+    if (int e = ensure(c.cl[4], N * 4)) return e;
+    uint32_t* d_cen = (uint32_t*)c.cl[0].p;
+    int32_t *d_ci = (int32_t*)c.cl[1].p, *d_min = (int32_t*)c.cl[3].p, *d_max = (int32_t*)c.cl[4].p;
+    uint8_t* d_lv = (uint8_t*)c.cl[2].p;
+    const int nb = (int)std::min<size_t>((N + 255) / 256, (size_t)c.sms * 8);
+    const int eb = (int)std::min<size_t>((E + 255) / 256, (size_t)c.sms * 16);
+    CU_TRY(cudaMemcpyAsync(d_cen, centres, C * 4, cudaMemcpyHostToDevice, st));
+    bdg::cluster_init_kernel<<<nb, 256, 0, st>>>(d_ci, d_lv, d_min, d_max, (uint32_t)N);
+    if (C) bdg::cluster_seed_kernel<<<(int)std::min<size_t>((C + 255) / 256, (size_t)c.sms * 8), 256, 0, st>>>(d_sorted, (uint32_t)N, d_cen, (uint32_t)C, d_ci, d_lv);
+    g_launches += 2;
+    if (E) {
+        bdg::cluster_index_kernel<<<eb, 256, 0, st>>>(d_sorted, (uint32_t)N, d_ea, d_eb, E);
+        g_launches++;
+        for (int r = 1; r <= rounds; r++) {
+            bdg::cluster_claim_kernel<<<eb, 256, 0, st>>>(d_ea, d_eb, E, r, d_ci, d_lv, d_min, d_max);
+            bdg::cluster_resolve_kernel<<<nb, 256, 0, st>>>(d_ci, d_lv, d_min, d_max, (uint32_t)N, r);
+            g_launches += 2;
+        }
+    }
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(centre_idx, d_ci, N * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(level, d_lv, N, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return BDG_OK;
+}
+
+int bdg_cluster_levels(const uint32_t* sorted_unique, size_t N, const uint32_t* ea, const uint32_t* eb, size_t E, const uint32_t* centres,
+                       size_t C, int rounds, int32_t* centre_idx, uint8_t* level)
+{
+    if (N == 0) return BDG_OK;
+    if (!sorted_unique || !centre_idx || !level || (E && (!ea || !eb)) || (C && !centres)) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if (N > 0x7FFFFFFFull || rounds < 0 || rounds > 254) return fail(BDG_ERR_ARG, "N must be < 2^31 and 0 <= rounds <= 254");
+    if (int rc = check_sorted(sorted_unique, N)) return rc;
+    if (int rc = need_ctx()) return rc;
+    DevCtx& c = g_ctx[0];
+    CU_TRY(cudaSetDevice(c.dev));
+    auto ensure = [&](Buf& b, size_t bytes) -> int {
+        if (cudaError_t e = (cudaError_t)b.ensure(bytes))
+            return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation of %zu bytes: %s", bytes, cudaGetErrorString(e));
+        return BDG_OK;
+    };
+    // the edge workspaces of an earlier build are reused for the index arrays: older handles become stale
+    if (int e = ensure(c.sorted, N * 4)) return e;
+    if (int e = ensure(c.ea, std::max<size_t>(E, 1) * 4)) return e;
+    if (int e = ensure(c.eb, std::max<size_t>(E, 1) * 4)) return e;
+    c.generation++;
+    CU_TRY(cudaMemcpyAsync(c.sorted.p, sorted_unique, N * 4, cudaMemcpyHostToDevice, c.stream));
+    CU_TRY(cudaMemcpyAsync(c.ea.p, ea, E * 4, cudaMemcpyHostToDevice, c.stream));
+    CU_TRY(cudaMemcpyAsync(c.eb.p, eb, E * 4, cudaMemcpyHostToDevice, c.stream));
+    return cluster_on_device(c, (const uint32_t*)c.sorted.p, N, (uint32_t*)c.ea.p, (uint32_t*)c.eb.p, E, centres, C, rounds, centre_idx, level);
+}
+
+int bdg_cluster_levels_from_edges(bdg_edges* e, size_t N, const uint32_t* centres, size_t C, int rounds, int32_t* centre_idx, uint8_t* level)
+{
+    if (!e) return fail(BDG_ERR_ARG, "NULL edge handle");
+    if (N == 0) return BDG_OK;
+    if (!centre_idx || !level || (C && !centres)) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if (e->ctx.size() != 1) return fail(BDG_ERR_ARG, "edge handle spans %zu devices; copy the edges out and use bdg_cluster_levels", e->ctx.size());
+    if (N > 0x7FFFFFFFull || rounds < 0 || rounds > 254) return fail(BDG_ERR_ARG, "N must be < 2^31 and 0 <= rounds <= 254");
+    DevCtx& c = g_ctx[e->ctx[0]];
+    if (c.generation != e->gen[0]) return fail(BDG_ERR_ARG, "stale edge handle: a later edge build on the same device has reused its buffers");
+    if (c.sorted.cap < N * 4) return fail(BDG_ERR_ARG, "N does not match the array the edges were built from");
+    CU_TRY(cudaSetDevice(c.dev));
+    // the handle's edge VALUES are turned into node indices in place: the handle is consumed (stale afterwards)
+    c.generation++;
+    return cluster_on_device(c, (const uint32_t*)c.sorted.p, N, (uint32_t*)c.ea.p, (uint32_t*)c.eb.p, e->count[0], centres, C, rounds, centre_idx, level);
+}
 
 int bdg_member_sorted(const uint32_t* sorted_wl, size_t W, const uint32_t* q, size_t Q, uint8_t* hit)
 {

@@ -58,8 +58,8 @@ struct EdgeWork {
     uint32_t n_items;
     uint32_t chunk_cols;        // columns per work item (multiple of SB_MAX, <= 2^17)
     unsigned int* item_counter; // dynamic scheduler
-    unsigned long long* stats;  // optional [6]: sub-tiles visited, sub-tiles scored pair by pair, pairs scored, candidates,
-                                //               sum / max over warps of the time from the first warp's start to the warp's exit (ns)
+    unsigned long long* stats;  // optional [8]: sub-tiles visited, sub-tiles scored pair by pair, pairs scored, candidates,
+                                //               sum / max over warps of (warp exit - first warp start) in ns, earliest start, pairs that reached S
     uint32_t one;               // == 1, opaque to the compiler: x*(-one)+c keeps the subtraction on the FMA pipe (IMAD)
     int pass;                   // sparse kernel: pass index p (bdg_core.cuh pass_pred); `sorted` holds rotl(key, rot) sorted
     int rot;
@@ -473,6 +473,7 @@ struct SparseCtx {
     const uint32_t* row_pay;
     const uint32_t* col_pay;
     uint32_t* near_keys;
+    unsigned long long* n_score;   // this warp's count of pairs that reached stage 3 (statistics)
 };
 
 // stage 3 on a batch: S = shared 6-mer count (the dearest test: 21 diagonals) for pairs that already have D <= t
@@ -524,6 +525,7 @@ __device__ __forceinline__ void sparse_process(const SparseCtx& c, const EdgeOut
     }
     const unsigned m = __ballot_sync(FULL, ok);
     if (m == 0) return;
+    *c.n_score += __popc(m);
     // fewer than 32 entries wait on entry (full batches are scored right below), so 32 more always fit
     if (ok) {
         const int slot = q2n + __popc(m & ((1u << c.lane) - 1u));
@@ -611,7 +613,8 @@ __global__ void __launch_bounds__(ENT, 3) sparse_tile_kernel(const EdgeWork w, c
     int qn = 0, q2n = 0;                          // queue fills, uniform across the warp
     const uint32_t mone = 0u - w.one;             // runtime -1: u*one + mone is u - 1 on the FMA pipe
     const unsigned long long t_start = global_ns();
-    unsigned long long n_combo = 0, n_cand = 0;
+    unsigned long long n_combo = 0, n_cand = 0, n_score = 0;
+    c.n_score = &n_score;
     const unsigned long long n_tiles = min(*list.count, list.cap);
     uint32_t g_cur = 0xFFFFFFFFu;
     uint32_t a[RA];                               // UNROTATED rows of the current group
@@ -694,7 +697,7 @@ __global__ void __launch_bounds__(ENT, 3) sparse_tile_kernel(const EdgeWork w, c
     if (w.stats) {
         for (int o = 16; o; o >>= 1) n_cand += __shfl_down_sync(FULL, n_cand, o);           // per-lane counts
         if (lane == 0) {                                                                  // n_combo is uniform per warp
-            atomicAdd(&w.stats[2], n_combo * 1024ull); atomicAdd(&w.stats[3], n_cand);
+            atomicAdd(&w.stats[2], n_combo * 1024ull); atomicAdd(&w.stats[3], n_cand); atomicAdd(&w.stats[7], n_score);
             warp_exit_stats(w.stats, t_start);
         }
     }

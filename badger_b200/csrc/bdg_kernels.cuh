@@ -299,4 +299,76 @@ __global__ void dedup_scatter_kernel(const uint32_t* __restrict__ si, const uint
         read_to_distinct[__ldg(&si[i])] = __ldg(&pos_of_run[__ldg(&scan_incl[i]) - 1u]);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Clustering rounds (row f-3, reference barcode_graph.py:279-301): level-synchronous and edge-parallel.
+//   round i: every edge (u,v), both directions: if u joined a centre at level i-1 and v is still free, u's
+//   centre claims v (atomicMin / atomicMax of the centre index);  then every claimed v joins the centre if all
+//   claims of this round agree, and is evicted (centre -1) if two different centres claimed it - exactly the
+//   reference's same-round conflict rule, which does not depend on the adjacency order.
+// Nodes are positions in the sorted distinct-barcode array; centre_idx: -2 free, -1 evicted, else a node.
+// HBM/L2-latency bound: per edge and round two index pairs in, a few random 4-byte reads.
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lower_bound_u32(const uint32_t* __restrict__ v, uint32_t n, uint32_t x)
+{
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&v[mid]) < x) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void cluster_init_kernel(int32_t* __restrict__ centre_idx, uint8_t* __restrict__ level, int32_t* __restrict__ cmin,
+                                    int32_t* __restrict__ cmax, uint32_t n)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        centre_idx[i] = -2; level[i] = 255; cmin[i] = 0x7FFFFFFF; cmax[i] = -1;
+    }
+}
+
+__global__ void cluster_seed_kernel(const uint32_t* __restrict__ sorted, uint32_t n, const uint32_t* __restrict__ centres, uint32_t n_centres,
+                                    int32_t* __restrict__ centre_idx, uint8_t* __restrict__ level)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_centres; i += gridDim.x * blockDim.x) {
+        const uint32_t c = __ldg(&centres[i]);
+        const uint32_t p = lower_bound_u32(sorted, n, c);
+        if (p < n && __ldg(&sorted[p]) == c) { centre_idx[p] = (int32_t)p; level[p] = 0; }   // centres that were never observed have no node
+    }
+}
+
+// barcode values of the edge list -> node indices, in place
+__global__ void cluster_index_kernel(const uint32_t* __restrict__ sorted, uint32_t n, uint32_t* __restrict__ ea, uint32_t* __restrict__ eb, uint64_t n_edges)
+{
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (uint64_t)gridDim.x * blockDim.x) {
+        ea[e] = lower_bound_u32(sorted, n, ea[e]);
+        eb[e] = lower_bound_u32(sorted, n, eb[e]);
+    }
+}
+
+__global__ void cluster_claim_kernel(const uint32_t* __restrict__ ia, const uint32_t* __restrict__ ib, uint64_t n_edges, int round,
+                                     const int32_t* __restrict__ centre_idx, const uint8_t* __restrict__ level,
+                                     int32_t* __restrict__ cmin, int32_t* __restrict__ cmax)
+{
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t u = __ldg(&ia[e]), v = __ldg(&ib[e]);
+        const int32_t cu = centre_idx[u], cv = centre_idx[v];
+        if (cu >= 0 && cv == -2 && level[u] == round - 1) { atomicMin(&cmin[v], cu); atomicMax(&cmax[v], cu); }
+        if (cv >= 0 && cu == -2 && level[v] == round - 1) { atomicMin(&cmin[u], cv); atomicMax(&cmax[u], cv); }
+    }
+}
+
+__global__ void cluster_resolve_kernel(int32_t* __restrict__ centre_idx, uint8_t* __restrict__ level, int32_t* __restrict__ cmin,
+                                       int32_t* __restrict__ cmax, uint32_t n, int round)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int32_t lo = cmin[i];
+        if (lo != 0x7FFFFFFF) {
+            const bool single = lo == cmax[i];
+            centre_idx[i] = single ? lo : -1;
+            level[i] = single ? (uint8_t)round : (uint8_t)255;
+            cmin[i] = 0x7FFFFFFF; cmax[i] = -1;
+        }
+    }
+}
+
 }  // namespace bdg

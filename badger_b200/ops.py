@@ -74,6 +74,19 @@ def edges_build_part(sorted_unique: np.ndarray, t: int, part: int, nparts: int):
     return _collect_edges(h)
 
 
+def cluster_levels(sorted_unique: np.ndarray, ea: np.ndarray, eb: np.ndarray, centres: np.ndarray, rounds: int = 2):
+    """barcode_graph.py:279-301 on node positions of the sorted array: (centre_idx int32[N], level uint8[N]);
+    centre_idx -2 = untouched, -1 = evicted by a same-round conflict, level 255 = none."""
+    s = np.ascontiguousarray(sorted_unique, dtype=np.uint32)
+    ea = np.ascontiguousarray(ea, dtype=np.uint32); eb = np.ascontiguousarray(eb, dtype=np.uint32)
+    cen = np.ascontiguousarray(centres, dtype=np.uint32)
+    ci = np.full(s.size, -2, np.int32)
+    lv = np.full(s.size, 255, np.uint8)
+    if s.size:
+        check(lib().bdg_cluster_levels(ptr(s), s.size, ptr(ea), ptr(eb), ea.size, ptr(cen), cen.size, int(rounds), ptr(ci), ptr(lv)))
+    return ci, lv
+
+
 def canonical(a, b, d):
     """Sort an edge list by (a, b) - the order-free comparison form."""
     order = np.lexsort((b, a))

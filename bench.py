@@ -44,9 +44,10 @@ UNIT = "pairs/s"
 #           test per pair of a surviving 32x32 block; one exact stage (D, then S) per candidate
 #   dense:  one light-loop step per pair (1.25 instr at t=1, 6 at t=2), exact stage per candidate
 A_TILE = 40
-A_QUICK = {1: 14, 2: 16}
+A_QUICK = {1: 14.5, 2: 16.5}       # 58 / 66 SASS instructions per 4 pairs
 A_LIGHT = {1: 1.25, 2: 6.0}
-A_EXACT = 60
+A_EXACT = 110                      # loads, un-rotation, pass predicates, dist_small
+A_SCORE = 220                      # qgram_score, only for pairs with D <= t
 A_PAIR_SURVEY = {1: 15, 2: 25}   # SURVEY.md §8(d) nominal per-pair figure of a plain all-pairs kernel, reported alongside
 
 
@@ -245,9 +246,9 @@ def run_b200(args):
         return ms
 
     def work_stats():
-        v = (C.c_ulonglong * 4)()
+        v = (C.c_ulonglong * 5)()
         badger_b200._lib.check(L.bdg_dev_edges_stats(v, stream.cuda_stream))
-        return dict(zip(("sub_tiles", "sub_tiles_scored", "pairs_scored", "candidates"), (int(x) for x in v)))
+        return dict(zip(("sub_tiles", "sub_tiles_scored", "pairs_scored", "candidates", "pairs_S_scored"), (int(x) for x in v)))
 
     sampler = ClockSampler(local)
     sampler.start()                        # covers warm-up, the timed steps and the e2e loop (a step is ~1 ms)
@@ -321,7 +322,8 @@ def run_b200(args):
             return None
         per_pair = A_QUICK[t] if mode == "sparse" else A_LIGHT[t]
         tiles = (st["sub_tiles"] + 32 * st["sub_tiles_scored"]) if mode == "sparse" else 0
-        return A_TILE * tiles + per_pair * st["pairs_scored"] + A_EXACT * st["candidates"]
+        score = st["pairs_S_scored"] if mode == "sparse" else n_edges_part     # dense counts S inside the exact stage: at least the edges
+        return A_TILE * tiles + per_pair * st["pairs_scored"] + A_EXACT * st["candidates"] + A_SCORE * score
 
     out = None
     if rank == 0:
@@ -335,7 +337,7 @@ def run_b200(args):
                     "kernel": ("sparse_scan_kernel + sparse_tile_kernel<%d,p>, %d passes per step" % (t, 2 if t == 1 else 3)) if args.mode == "sparse" else "edges_kernel<%d>" % t,
                     "achieved": achieved, "peak": peak, "unit": "Tinst/s", "frac": achieved / peak if peak else None, "traffic": None,
                     "how": "achieved = algorithmic integer instructions of rank 0's step (%d interval tests x %d + %d pairs scored x %s + "
-                           "%d candidates x %d; unit counts from the kernel's own counters, per-unit costs from its SASS, DESIGN.md) / "
+                           "%d candidates x %d + pairs S-scored x 220; unit counts from the kernel's own counters, per-unit costs from its SASS, DESIGN.md) / "
                            "%.3f ms (CUDA events, this run); peak = measured issue rate of an independent LOP3+IMAD 1:1 stream on this GPU "
                            "(bdg_dev_pipe_probe, this run)" % (stats["sub_tiles"] + 32 * stats["sub_tiles_scored"] if args.mode == "sparse" else 0,
                                                                A_TILE, stats["pairs_scored"], A_QUICK[t] if args.mode == "sparse" else A_LIGHT[t],

@@ -80,6 +80,19 @@ size_t bdg_edges_count(const bdg_edges* e);
 int bdg_edges_copy(const bdg_edges* e, uint32_t* a, uint32_t* b, uint8_t* d); /* caller-allocated, length = count */
 void bdg_edges_free(bdg_edges* e);
 
+/* ---- f-3  cluster(): barcode_graph.py:279-301 (the two level-synchronous rounds with same-round conflict eviction) -- */
+/* Nodes are positions in sorted_unique[N].  centres[C]: barcode values of the cluster centres (values that are not in
+ * sorted_unique are ignored: a centre that was never observed has no node).  On return centre_idx[i] = position of the
+ * centre node i joined, -1 if two centres claimed it in the same round (the reference's (-1,-1)), -2 if no round reached
+ * it; level[i] = 0 for centres, the round number for joined nodes, 255 otherwise.  The reference runs rounds = 2.
+ * bdg_cluster_levels takes the edge list from host arrays (barcode values, each undirected edge once);
+ * bdg_cluster_levels_from_edges takes it from a single-device edge handle without copying anything (N = the size of
+ * the array the handle was built from) and CONSUMES the handle's edges: copy them out first if they are still needed. */
+int bdg_cluster_levels(const uint32_t* sorted_unique, size_t N, const uint32_t* ea, const uint32_t* eb, size_t E,
+                       const uint32_t* centres, size_t C, int rounds, int32_t* centre_idx, uint8_t* level);
+int bdg_cluster_levels_from_edges(bdg_edges* e, size_t N, const uint32_t* centres, size_t C, int rounds, int32_t* centre_idx,
+                                  uint8_t* level);
+
 /* ---- a-6  whitelist membership: `unrank(r) in barcode_list`, barcode_graph.py:262-267 -------------- */
 int bdg_member_sorted(const uint32_t* sorted_wl, size_t W, const uint32_t* q, size_t Q, uint8_t* hit);
 
@@ -113,10 +126,11 @@ int bdg_dev_edges_build(const uint32_t* d_sorted, size_t N, int t, int part, int
  *  -1 back to the default / BDG_EDGE_MODE=dense|sparse.  t >= 3 always runs dense without a prefilter. */
 int bdg_set_edge_mode(int mode);
 /* Work statistics of the last bdg_dev_edges_build / bdg_edges_build* launch on the current device, summed over
- * its passes: out4[0] column sub-tiles whose key interval was tested, out4[1] sub-tiles that could hold a
- * candidate, out4[2] pairs scored pair by pair (sparse: quick test; dense: light loop or full prefilter),
- * out4[3] candidates handed to the exact stage.  Synchronises the stream.  (bench.py's roofline numerator.) */
-int bdg_dev_edges_stats(unsigned long long* out4, void* stream);
+ * its passes: out5[0] column sub-tiles whose key interval was tested, out5[1] sub-tiles that could hold a
+ * candidate, out5[2] pairs scored pair by pair (sparse: quick test; dense: light loop or full prefilter),
+ * out5[3] candidates handed to the exact stage, out5[4] pairs with D <= t whose 6-mer score S was computed (sparse
+ * mode only).  Synchronises the stream.  (bench.py's roofline numerator.) */
+int bdg_dev_edges_stats(unsigned long long* out5, void* stream);
 /* Development aid: out[2p], out[2p+1] = sum and max over the warps of pass p of (warp exit - first warp start), ns. */
 int bdg_dev_edges_balance(unsigned long long* out6, void* stream);
 int bdg_dev_pack16(const char* d_seqs, size_t R, uint32_t* d_out, uint8_t* d_valid, void* stream);

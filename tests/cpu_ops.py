@@ -51,7 +51,36 @@ def kmer_score(q, wl, min_kmers=1, cap=None):
     return qi.astype(np.uint32), wi.astype(np.uint32), cnt[qi, wi], mult[qi, wi]
 
 
+def dedup_first_seen(ranks, want_map=False):
+    r, c = orc.dedup_count(np.ascontiguousarray(ranks, dtype=np.uint32))
+    if not want_map:
+        return r, c.astype(np.int64)
+    pos = {int(v): i for i, v in enumerate(r.tolist())}
+    return r, c.astype(np.int64), np.asarray([pos[int(v)] for v in np.asarray(ranks).tolist()], np.uint32)
+
+
+def cluster_levels(sorted_unique, ea, eb, centres, rounds=2):
+    """Literal restatement of the reference's rounds (oracle.cluster) turned into the operator's array form."""
+    assert rounds == 2
+    s = np.ascontiguousarray(sorted_unique, dtype=np.uint32)
+    adj = {}
+    for x, y in zip(np.asarray(ea).tolist(), np.asarray(eb).tolist()):
+        adj.setdefault(int(x), []).append(int(y)); adj.setdefault(int(y), []).append(int(x))
+    res = orc.cluster(adj, [int(c) for c in np.asarray(centres).tolist()])
+    ci = np.full(s.size, -2, np.int32); lv = np.full(s.size, 255, np.uint8)
+    pos = {int(v): i for i, v in enumerate(s.tolist())}
+    for node, (cen, level) in res.items():
+        if node not in pos:
+            continue                                   # a centre that was never observed has no node
+        if cen == -1:
+            ci[pos[node]] = -1
+        else:
+            ci[pos[node]] = pos[cen]; lv[pos[node]] = level
+    return ci, lv
+
+
 def install(monkeypatch):
     from badger_b200 import ops
-    for name in ("pack16", "edges_build", "edges_build_part", "member_sorted", "nearest_bounded", "kmer_score"):
+    for name in ("pack16", "edges_build", "edges_build_part", "member_sorted", "nearest_bounded", "kmer_score", "dedup_first_seen",
+                 "cluster_levels"):
         monkeypatch.setattr(ops, name, globals()[name])

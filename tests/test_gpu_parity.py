@@ -258,6 +258,40 @@ def test_dedup_first_seen_vs_oracle():
     assert d.size == 0 and c.size == 0
 
 
+def test_cluster_levels_vs_reference_rounds():
+    """Row f-3 on the device against the literal restatement of barcode_graph.py:283-301 (oracle.cluster): random graphs
+    with many same-round conflicts, centres that are not nodes, and a clustered barcode set with its real edges."""
+    rng = np.random.default_rng(33)
+    cases = []
+    for trial in range(25):
+        n = int(rng.integers(5, 400))
+        s = np.sort(rng.choice(1 << 24, n, replace=False).astype(np.uint32))
+        m = int(rng.integers(0, 5 * n))
+        x = rng.integers(0, n, m); y = rng.integers(0, n, m)
+        pairs = sorted({(min(i, j), max(i, j)) for i, j in zip(x.tolist(), y.tolist()) if i != j})
+        ea = s[[p[0] for p in pairs]] if pairs else np.empty(0, np.uint32)
+        eb = s[[p[1] for p in pairs]] if pairs else np.empty(0, np.uint32)
+        cen = s[rng.choice(n, int(rng.integers(1, max(2, n // 3))), replace=False)]
+        if trial % 3 == 0:
+            cen = np.concatenate([cen, np.asarray([(1 << 24) + 5, (1 << 24) + 9], np.uint32)])     # never observed
+        cases.append((s, ea, eb, cen))
+    big = clustered_set(91, 300, 30000, 0.06)
+    ba, bb, _ = ops.edges_build(big, 2)
+    cases.append((big, ba, bb, big[rng.choice(big.size, 250, replace=False)]))
+    for s, ea, eb, cen in cases:
+        ci, lv = ops.cluster_levels(s, ea, eb, cen, 2)
+        adj = {}
+        for u, v in zip(ea.tolist(), eb.tolist()):
+            adj.setdefault(u, []).append(v); adj.setdefault(v, []).append(u)
+        want = orc.cluster(adj, [int(c) for c in cen.tolist()])
+        pos = {int(v): i for i, v in enumerate(s.tolist())}
+        got = {}
+        for i in np.nonzero(ci != -2)[0].tolist():
+            got[int(s[i])] = (int(s[ci[i]]), int(lv[i])) if ci[i] >= 0 else (-1, -1)
+        assert got == {k: tuple(v) for k, v in want.items() if k in pos}
+    assert any((ci == -1).any() for ci, _ in [ops.cluster_levels(*c, 2) for c in cases[:10]])      # conflicts were exercised
+
+
 def test_member_vs_oracle():
     rng = np.random.default_rng(8)
     for W in (0, 1, 5, 1000, 1024, 1025, 300000):

@@ -40,7 +40,7 @@ def time_edges(s, t, reps=3):
         e0.record(st); go(); e1.record(st); e1.synchronize()
         best = min(best, e0.elapsed_time(e1))
     import ctypes as C
-    v = (C.c_ulonglong * 4)()
+    v = (C.c_ulonglong * 5)()
     L.bdg_dev_edges_stats(v, st.cuda_stream)
     bal = (C.c_ulonglong * 6)()
     L.bdg_dev_edges_balance(bal, st.cuda_stream)
@@ -62,7 +62,7 @@ def main():
         for items, mode in itertools.product(knobs["ITEMS"], knobs["MODE"]):
             os.environ["BDG_EDGE_ITEMS"] = items
             badger_b200.lib().bdg_set_edge_mode(int(mode))
-            ms, edges, (subs, fulls, scored, cand) = time_edges(s, t)
+            ms, edges, (subs, fulls, scored, cand, nS) = time_edges(s, t)
             print("reads=%8d N=%8d t=%d items=%-3s mode=%s  %9.3f ms  %.3e pairs/s  edges=%d  sub-tiles=%d full=%.2f%% scored=%.3e cand=%.3e" % (
                 r, n, t, items, "sparse" if mode == "1" else "dense ", ms, n * (n - 1) / 2 / (ms * 1e-3), edges, subs, 100.0 * fulls / max(subs, 1), scored, cand), flush=True)
             print("      balance (warp exit times): " + BALANCE, flush=True)
