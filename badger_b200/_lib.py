@@ -42,7 +42,7 @@ def lib():
     L.bdg_device_count.restype = _i
     L.bdg_launch_count.restype = C.c_ulonglong
     L.bdg_pack16.argtypes = [_vp, _sz, _vp, _vp]
-    L.bdg_dedup_first_seen.argtypes = [_vp, _sz, _vp, _vp, _vp, C.POINTER(_sz)]
+    L.bdg_dedup_first_seen.argtypes = [_vp, _sz, _vp, _vp, _vp, _vp, C.POINTER(_sz)]
     L.bdg_edges_build.argtypes = [_vp, _sz, _i, C.POINTER(_vp)]
     L.bdg_edges_build_part.argtypes = [_vp, _sz, _i, _i, _i, C.POINTER(_vp)]
     L.bdg_edges_count.argtypes = [_vp]

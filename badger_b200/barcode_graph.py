@@ -128,13 +128,15 @@ class BarcodeGraph:
             self.timings[stage] += time.perf_counter() - t0
 
     @classmethod
-    def from_arrays(cls, threshold, ranks_first_seen, counts, edges=None):
+    def from_arrays(cls, threshold, ranks_first_seen, counts, edges=None, with_dict=True):
         """Array entry point: distinct ranks in first-seen order with their counts, optionally an edge list
-        (a, b, d).  Used by bench.py / tests and by callers that already hold packed barcodes."""
+        (a, b, d).  Used by bench.py / tests and by callers that already hold packed barcodes (with_dict=False skips
+        the `counts` dict, which only the dict-shaped readers of the reference need)."""
         g = cls(threshold)
         g._ranks = np.ascontiguousarray(ranks_first_seen, dtype=np.uint32)
         g._cnt = np.ascontiguousarray(counts, dtype=np.int64)
-        g.counts.update(zip(g._ranks.tolist(), g._cnt.tolist()))
+        if with_dict:
+            g.counts.update(zip(g._ranks.tolist(), g._cnt.tolist()))
         if edges is not None:
             g._set_edges(*edges)
         return g
@@ -239,7 +241,7 @@ class BarcodeGraph:
         tbcs, n, i = [], 0, 0
         n_above = int(np.searchsorted(-cnt_sorted, -cutoff, side="left"))        # entries with count > cutoff
         if true_barcodes:
-            tbcs = [rank(bc, bc_len) for bc in true_barcodes]
+            tbcs = [bc if isinstance(bc, int) else rank(bc, bc_len) for bc in true_barcodes]   # packed callers pass ranks
         elif barcode_list:
             hits = self._whitelist_hits(barcode_list, bc_len)[order][:n_above]
             csum = np.cumsum(hits)

@@ -597,7 +597,8 @@ int bdg_dev_pipe_probe(int kind, int blocks, int iters, uint32_t* d_sink, unsign
 
 // ---------------------------------------------------------------- host-buffer entry points
 // ---- a-2  dedup + count in first-seen order (barcode_graph.py:192-204) ------------------------------------
-int bdg_dedup_first_seen(const uint32_t* ranks, size_t R, uint32_t* distinct, uint32_t* counts, uint32_t* read_to_distinct, size_t* n_distinct)
+int bdg_dedup_first_seen(const uint32_t* ranks, size_t R, uint32_t* distinct, uint32_t* counts, uint32_t* read_to_distinct,
+                         uint32_t* sorted_pos, size_t* n_distinct)
 {
     if (!n_distinct) return fail(BDG_ERR_ARG, "NULL n_distinct pointer");
     *n_distinct = 0;
@@ -642,6 +643,7 @@ int bdg_dedup_first_seen(const uint32_t* ranks, size_t R, uint32_t* distinct, ui
     g_launches += 2;
     CU_TRY(cudaMemcpyAsync(distinct, d_distinct, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(counts, d_counts, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st));
+    if (sorted_pos) CU_TRY(cudaMemcpyAsync(sorted_pos, d_i, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st));   // order[pos] = run = ascending position
     if (read_to_distinct) {
         bdg::dedup_scatter_kernel<<<blocks, 256, 0, st>>>(d_si, d_scan, d_pos, n, d_rf);   // d_rf is free after the run sort
         g_launches++;

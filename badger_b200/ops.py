@@ -31,19 +31,26 @@ def pack16(seqs) -> tuple[np.ndarray, np.ndarray]:
     return out, valid.astype(bool)
 
 
-def dedup_first_seen(ranks: np.ndarray, want_map: bool = False):
+def dedup_first_seen(ranks: np.ndarray, want_map: bool = False, want_sorted_pos: bool = False):
     """barcode_graph.py:192-204: distinct barcodes in first-seen order with their counts
-    (and, with want_map, the position in that order of every read)."""
+    (with want_map also the position in that order of every read; with want_sorted_pos also the position of every
+    distinct barcode in ascending order)."""
     r = np.ascontiguousarray(ranks, dtype=np.uint32)
     distinct = np.empty(r.size, np.uint32)
     counts = np.empty(r.size, np.uint32)
     rmap = np.empty(r.size, np.uint32) if want_map else None
+    spos = np.empty(r.size, np.uint32) if want_sorted_pos else None
     n = C.c_size_t(0)
     if r.size:
-        check(lib().bdg_dedup_first_seen(ptr(r), r.size, ptr(distinct), ptr(counts), ptr(rmap) if want_map else None, C.byref(n)))
+        check(lib().bdg_dedup_first_seen(ptr(r), r.size, ptr(distinct), ptr(counts), ptr(rmap) if want_map else None,
+                                         ptr(spos) if want_sorted_pos else None, C.byref(n)))
     k = int(n.value)
     out = (distinct[:k].copy(), counts[:k].astype(np.int64))
-    return out + (rmap,) if want_map else out
+    if want_map:
+        out += (rmap,)
+    if want_sorted_pos:
+        out += (spos[:k].copy(),)
+    return out
 
 
 def _collect_edges(handle):
@@ -55,6 +62,46 @@ def _collect_edges(handle):
     finally:
         L.bdg_edges_free(handle)
     return a, b, d
+
+
+class EdgeHandle:
+    """Edges of one construction, still on the device (include/badger_b200.h bdg_edges)."""
+
+    def __init__(self, handle, n_nodes):
+        self._h, self.n_nodes = handle, n_nodes
+        self.count = int(lib().bdg_edges_count(handle))
+
+    def copy(self):
+        a = np.empty(self.count, np.uint32); b = np.empty(self.count, np.uint32); d = np.empty(self.count, np.uint8)
+        check(lib().bdg_edges_copy(self._h, ptr(a), ptr(b), ptr(d)))
+        return a, b, d
+
+    def cluster_levels(self, centres: np.ndarray, rounds: int = 2):
+        """barcode_graph.py:279-301 straight from the device-resident edge list; CONSUMES the edges."""
+        cen = np.ascontiguousarray(centres, dtype=np.uint32)
+        ci = np.full(self.n_nodes, -2, np.int32); lv = np.full(self.n_nodes, 255, np.uint8)
+        if self.n_nodes:
+            check(lib().bdg_cluster_levels_from_edges(self._h, self.n_nodes, ptr(cen), cen.size, int(rounds), ptr(ci), ptr(lv)))
+        return ci, lv
+
+    def free(self):
+        if self._h is not None:
+            lib().bdg_edges_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def edges_handle(sorted_unique: np.ndarray, t: int) -> EdgeHandle:
+    """Edge construction on the FIRST claimed device, results left on it (single-device handle)."""
+    s = np.ascontiguousarray(sorted_unique, dtype=np.uint32)
+    h = C.c_void_p()
+    check(lib().bdg_edges_build_part(ptr(s), s.size, int(t), 0, 1, C.byref(h)))
+    return EdgeHandle(h, s.size)
 
 
 def edges_build(sorted_unique: np.ndarray, t: int):

@@ -1,0 +1,98 @@
+"""Array form of the correction step (reference badger.py:120-129 with barcode_graph.py:192-410 behind it): packed
+barcodes per read in, cluster-centre barcode per read out, every stage on the GPU operators, no per-read Python.
+
+    read barcodes (uint32 per read + valid mask)
+      -> ops.dedup_first_seen            barcode_graph.py:192-204   distinct barcodes in first-seen order, counts, read map
+      -> ops.edges_handle                index.py:77-93 + barcode_graph.py:224-249   (edges stay on the device)
+      -> BarcodeGraph.get_cluster_centers   barcode_graph.py:252-277   (count-sorted scan, whitelist membership on the GPU)
+      -> EdgeHandle.cluster_levels       barcode_graph.py:279-301   two rounds, same-round conflicts evict
+      -> ops.nearest_bounded             barcode_graph.py:370-385   only with high_sens
+      -> gather                          barcode_graph.py:322-329,395-404   centre of every read
+
+The string-based mirror (``BarcodeGraph`` + ``badger.py``) gives the same assignments; this module exists for callers
+that already hold packed barcodes and for the reads/s figure of ``bench.py``.
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+from . import ops
+from .barcode_graph import BarcodeGraph
+
+NONE = np.uint64(1) << np.uint64(32)      # "no centre" marker in the uint64 result (every uint32 is a valid barcode)
+
+
+class _Token:
+    """Stands in for the whitelist set the string API passes around (truthy, compared by identity)."""
+
+    def __bool__(self):
+        return True
+
+
+def assign_packed(ranks, valid=None, *, threshold, n_cells, interval=25, whitelist_sorted=None, true_barcodes=None,
+                  high_sens=False, centre_order=None, timings=None):
+    """Returns (centre uint64[R], info).  centre[i] == pipeline.NONE where the reference would write ``*``.
+
+    ranks / valid: packed barcode and validity per read (valid=None: all valid); whitelist_sorted: ascending uint32 array
+    or None; true_barcodes: iterable of packed centres or None (badger.py --true_barcodes); centre_order: order in which
+    --high_sens tries the centres (the reference iterates a Python set, barcode_graph.py:372; default: ascending)."""
+    T = timings if timings is not None else {}
+
+    def tick(name, t0):
+        T[name] = T.get(name, 0.0) + time.perf_counter() - t0
+
+    ranks = np.ascontiguousarray(ranks, dtype=np.uint32)
+    R = ranks.size
+    idx = np.arange(R) if valid is None else np.nonzero(valid)[0]
+    reads = ranks if valid is None else ranks[idx]
+    out = np.full(R, NONE, dtype=np.uint64)
+    info = {"reads": int(R), "valid_reads": int(reads.size)}
+    if reads.size == 0:
+        return out, info
+
+    t0 = time.perf_counter()
+    distinct, counts, rmap, spos = ops.dedup_first_seen(reads, want_map=True, want_sorted_pos=True)
+    tick("dedup_first_seen", t0)
+    t0 = time.perf_counter()
+    s = np.empty_like(distinct)
+    s[spos] = distinct                                    # ascending order, no host sort
+    handle = ops.edges_handle(s, threshold)
+    tick("edges", t0)
+    info.update(distinct=int(distinct.size), edges=int(handle.count))
+
+    t0 = time.perf_counter()
+    g = BarcodeGraph.from_arrays(threshold, distinct, counts, with_dict=False)
+    token = None
+    if whitelist_sorted is not None:
+        token = _Token()
+        g._wl_cache = (token, np.ascontiguousarray(whitelist_sorted, dtype=np.uint32))
+    tb = None if true_barcodes is None else [int(x) for x in true_barcodes]
+    centres = np.asarray(list(dict.fromkeys(g.get_cluster_centers(tb, 16, token, n_cells, interval))), dtype=np.uint32)
+    tick("centres", t0)
+    info["centres"] = int(centres.size)
+
+    t0 = time.perf_counter()
+    ci, lv = handle.cluster_levels(centres, 2)            # consumes the handle's edges (no copy to the host)
+    handle.free()
+    centre_sorted = np.where(ci >= 0, s[np.maximum(ci, 0)].astype(np.uint64), NONE)
+    centre_distinct = centre_sorted[spos]
+    tick("cluster", t0)
+
+    if high_sens:
+        t0 = time.perf_counter()
+        todo = np.nonzero(centre_distinct == NONE)[0]
+        used = np.unique(centre_distinct[centre_distinct != NONE]).astype(np.uint32)     # set(assignments.values())
+        targets = used if centre_order is None else np.asarray([c for c in centre_order if c in set(used.tolist())], np.uint32)
+        if todo.size and targets.size:
+            am, _ = ops.nearest_bounded(distinct[todo], targets, 2)
+            hit = am >= 0
+            centre_distinct[todo[hit]] = targets[am[hit]].astype(np.uint64)
+        tick("high_sens", t0)
+
+    t0 = time.perf_counter()
+    out[idx] = centre_distinct[rmap]
+    tick("gather", t0)
+    info["assigned_reads"] = int((out != NONE).sum())
+    return out, info

@@ -75,6 +75,7 @@ def workload(args, world):
     s = np.unique(obs[valid])
     name = "%s: %d simulated ONT reads, %d cells, %d-entry whitelist, %.0f%% error, threshold %d" % (
         args.config, reads, cfg["n_cells"], cfg["whitelist"], 100 * cfg["perr"], cfg["threshold"])
+    workload.dataset = (wl, obs, valid, cfg)          # for the whole-pipeline reads/s figure
     return s, cfg["threshold"], reads, name
 
 
@@ -362,6 +363,7 @@ def run_b200(args):
                "reads_per_s": reads * args.steps / (ms_total * 1e-3)}
     if rank == 0 and world == 1:
         out["stages"] = other_stages(torch, dev, stream, L, s, args)
+        out["pipeline"] = whole_pipeline(t)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"], _ = cpu_sample(s, t, args.cpu_seconds)
     if world > 1:
@@ -369,6 +371,22 @@ def run_b200(args):
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out))
+
+
+def whole_pipeline(t):
+    """reads/s of the array form of the whole correction step (badger_b200.pipeline.assign_packed: dedup, edges, centre
+    selection with whitelist membership, clustering rounds, per-read gather), host arrays in and out, wall clock."""
+    from badger_b200 import pipeline
+    wl, obs, valid, cfg = workload.dataset
+    wls = np.sort(wl)
+    pipeline.assign_packed(obs, valid, threshold=t, n_cells=cfg["n_cells"], whitelist_sorted=wls)      # warm
+    reps, T = 3, {}
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        out, info = pipeline.assign_packed(obs, valid, threshold=t, n_cells=cfg["n_cells"], whitelist_sorted=wls, timings=T)
+    dt = (time.perf_counter() - t0) / reps
+    return {"reads_per_s": obs.size / dt, "ms": dt * 1e3, "stages_ms": {k: 1e3 * v / reps for k, v in T.items()}, **info,
+            "api": "badger_b200.pipeline.assign_packed (packed barcodes per read in, centre per read out)"}
 
 
 def other_stages(torch, dev, stream, L, s, args):

@@ -61,10 +61,12 @@ int bdg_pack16(const char* seqs, size_t R, uint32_t* out, uint8_t* valid);
 /* ---- a-2  index_bc_single_thread: barcode_graph.py:192-204 ------------------------------------------ */
 /* Dedup + count of R packed barcodes in read order (already length-filtered and valid).  distinct[] receives the
  * distinct barcodes in the order of their FIRST sighting (the iteration order of the reference's `counts` dict),
- * counts[] their multiplicities, read_to_distinct[] (optional, may be NULL) the position in distinct[] of every read.
- * Outputs are caller-allocated with room for R entries; *n_distinct receives the number of distinct barcodes. */
+ * counts[] their multiplicities, read_to_distinct[] (optional, may be NULL) the position in distinct[] of every read,
+ * sorted_pos[] (optional) the position each distinct barcode has in ASCENDING order (so the sorted array the edge
+ * construction wants is sorted[sorted_pos[p]] = distinct[p]).  Outputs are caller-allocated with room for R entries;
+ * *n_distinct receives the number of distinct barcodes. */
 int bdg_dedup_first_seen(const uint32_t* ranks, size_t R, uint32_t* distinct, uint32_t* counts, uint32_t* read_to_distinct,
-                         size_t* n_distinct);
+                         uint32_t* sorted_pos, size_t* n_distinct);
 
 /* ---- a-3 + a-4  QGramIndex.get_close + verify/emit: index.py:77-93, barcode_graph.py:224-249 ------ */
 /* Edge set {(a,b,D): a<b, S(a,b) >= T(t), D(a,b) <= t} over a STRICTLY INCREASING array of distinct

@@ -51,12 +51,15 @@ def kmer_score(q, wl, min_kmers=1, cap=None):
     return qi.astype(np.uint32), wi.astype(np.uint32), cnt[qi, wi], mult[qi, wi]
 
 
-def dedup_first_seen(ranks, want_map=False):
+def dedup_first_seen(ranks, want_map=False, want_sorted_pos=False):
     r, c = orc.dedup_count(np.ascontiguousarray(ranks, dtype=np.uint32))
-    if not want_map:
-        return r, c.astype(np.int64)
-    pos = {int(v): i for i, v in enumerate(r.tolist())}
-    return r, c.astype(np.int64), np.asarray([pos[int(v)] for v in np.asarray(ranks).tolist()], np.uint32)
+    out = (r, c.astype(np.int64))
+    if want_map:
+        pos = {int(v): i for i, v in enumerate(r.tolist())}
+        out += (np.asarray([pos[int(v)] for v in np.asarray(ranks).tolist()], np.uint32),)
+    if want_sorted_pos:
+        out += (np.argsort(np.argsort(r, kind="stable"), kind="stable").astype(np.uint32),)
+    return out
 
 
 def cluster_levels(sorted_unique, ea, eb, centres, rounds=2):

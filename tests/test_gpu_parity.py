@@ -112,6 +112,36 @@ def test_pipeline_golden(gold_pipeline, tmp_path, capsys):
     assert {k: v for k, v in hs.items() if v not in ("", "*")} == g["hs_assignments"]
 
 
+def test_packed_pipeline_golden(gold_pipeline):
+    """Array form of the whole correction step (badger_b200.pipeline.assign_packed: dedup, edges, centres, clustering rounds
+    and the per-read gather all on the GPU operators) against the output TSV of the unmodified reference."""
+    import pandas as pd
+    from badger_b200 import pipeline
+    g = gold_pipeline
+    df = pd.read_csv(g["dir"] + "/reads.tsv", sep="\t")
+    obs = df["barcode"].fillna("*").tolist()
+    keep = [o[:-1] if len(o) == 17 else o for o in obs]
+    valid = np.asarray([len(o) == 16 and not (set(o) - set("ACGT")) for o in keep])
+    ranks = np.zeros(len(keep), np.uint32)
+    ranks[valid] = synth.rank_many([o for o, v in zip(keep, valid) if v])
+    with open(g["dir"] + "/whitelist.txt") as fh:
+        wl = [w for w in fh.read().split("\n") if len(w) == 16]
+    out, info = pipeline.assign_packed(ranks, valid, threshold=g["t"], n_cells=g["n_cells"], interval=g["interval"],
+                                       whitelist_sorted=np.sort(synth.rank_many(wl)))
+    want = pd.read_csv(g["dir"] + "/expected_output_file.tsv", sep="\t")["barcode"].tolist()
+    got = ["*" if c == pipeline.NONE else orc.unrank(int(c)) for c in out.tolist()]
+    assert got == want
+    assert info["edges"] == len(g["edges"]) and info["centres"] == len(g["centres"])
+    # --high_sens with the centre order the reference iterated
+    out_hs, _ = pipeline.assign_packed(ranks, valid, threshold=g["t"], n_cells=g["n_cells"], interval=g["interval"],
+                                       whitelist_sorted=np.sort(synth.rank_many(wl)), high_sens=True,
+                                       centre_order=[orc.rank(c) for c in g["hs_centre_order"]])
+    want_hs = dict(g["hs_assignments"])
+    for o, v, c in zip(keep, valid, out_hs.tolist()):
+        if v:
+            assert (orc.unrank(int(c)) if c != pipeline.NONE else None) == want_hs.get(o), o
+
+
 def test_c1_golden(gold_c1):
     wl, cells, obs, valid, cfg = synth.make_dataset("C1")
     strs = [s.decode() for s in synth.unrank_many(obs[valid]).tolist()]
@@ -250,10 +280,12 @@ def test_dedup_first_seen_vs_oracle():
         src = rng.integers(0, 1 << 32, pool, dtype=np.uint64).astype(np.uint32)
         src[: min(4, pool)] = np.asarray([0, 0xFFFFFFFF, 1, 0x80000000], np.uint32)[: min(4, pool)]
         reads = src[rng.integers(0, pool, R)]
-        d, c, m = ops.dedup_first_seen(reads, want_map=True)
+        d, c, m, sp = ops.dedup_first_seen(reads, want_map=True, want_sorted_pos=True)
         wd, wc = orc.dedup_count(reads)
         assert np.array_equal(d, wd) and np.array_equal(c, np.asarray(wc, np.int64))
         assert np.array_equal(d[m], reads)                      # the map sends every read to its own barcode
+        srt = np.empty_like(d); srt[sp] = d
+        assert np.array_equal(srt, np.sort(d))                  # sorted_pos = position in ascending order
     d, c = ops.dedup_first_seen(np.empty(0, np.uint32))
     assert d.size == 0 and c.size == 0
 
