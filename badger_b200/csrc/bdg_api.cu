@@ -257,29 +257,17 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
             }
             bdg::tile_bounds_kernel<<<std::min<uint32_t>((NS + 255) / 256, (uint32_t)ws->sms * 8), 256, 0, st>>>(w.sorted, w.N, (uint2*)ws->tile_bnd.p, NS);
             g_launches++;
-            unsigned long long n_tiles = 0;
-            for (int attempt = 0; attempt < 2; attempt++) {
-                bdg::TileList l{(uint2*)ws->tile_list.p, (unsigned long long*)(d_plan + PLAN_HDR * p + HDR_LIST), ws->tile_list.cap / sizeof(uint2)};
-                CU_TRY(cudaMemsetAsync(l.count, 0, 8, st));
-                const int sblocks = (int)std::min<uint64_t>(w.K, (uint64_t)ws->sms * 16);
-                BDG_PASS_DISPATCH(launch_scan, sblocks, st, w, (const uint2*)ws->tile_bnd.p, NS, l);
-                g_launches++;
-                CU_TRY(cudaGetLastError());
-                // the list length sizes the next launch (and tells whether the list was large enough): one 8-byte read-back
-                CU_TRY(cudaMemcpyAsync(&n_tiles, l.count, 8, cudaMemcpyDeviceToHost, st));
-                CU_TRY(cudaStreamSynchronize(st));
-                if (n_tiles <= l.cap) break;
-                if (attempt == 1) return fail(BDG_ERR_CUDA, "tile list count changed between identical scans");
-                if (int e = ensure(ws->tile_list, (size_t)n_tiles * sizeof(uint2))) return e;   // grow-only; rescan into the larger list
-            }
+            // no read-back between the scan and the tile kernel: the tile kernel reads the list length on the device and, if
+            // the list was too small, poisons the edge count (bit 63), which every caller inspects before using the edges
+            bdg::TileList l{(uint2*)ws->tile_list.p, (unsigned long long*)(d_plan + PLAN_HDR * p + HDR_LIST), ws->tile_list.cap / sizeof(uint2)};
+            const int sblocks = (int)std::min<uint64_t>(w.K, (uint64_t)ws->sms * 16);
+            BDG_PASS_DISPATCH(launch_scan, sblocks, st, w, (const uint2*)ws->tile_bnd.p, NS, l);
+            g_launches++;
+            CU_TRY(cudaGetLastError());
             uint64_t tests = 0;
             for (uint32_t g : plan.group_ids) tests += NS - std::min<uint64_t>(NS, (uint64_t)g * (bdg::GROUP / bdg::SSB));
             ws->host_stats[p][0] = tests;
-            ws->host_stats[p][1] = n_tiles;
-            if (n_tiles == 0) continue;
-            bdg::TileList l{(uint2*)ws->tile_list.p, (unsigned long long*)(d_plan + PLAN_HDR * p + HDR_LIST), ws->tile_list.cap / sizeof(uint2)};
-            const int tblocks = (int)std::min<uint64_t>((uint64_t)grid, (n_tiles + bdg::EW - 1) / bdg::EW);
-            BDG_PASS_DISPATCH(launch_tiles, tblocks, st, w, o, l);
+            BDG_PASS_DISPATCH(launch_tiles, grid, st, w, o, l);
         }
         g_launches++;
         CU_TRY(cudaGetLastError());
@@ -493,7 +481,11 @@ int bdg_dev_edges_stats(unsigned long long* out5, void* stream)
     for (int k = 0; k < 5; k++) {
         out5[k] = 0;
         const int slot = k < 4 ? k : 7;
-        for (int p = 0; p < bdg::MAX_PASSES; p++) out5[k] += v[(PLAN_HDR / 8) * p + HDR_STATS / 8 + slot] + (k < 2 ? c->host_stats[p][k] : 0);
+        for (int p = 0; p < bdg::MAX_PASSES; p++) {
+            out5[k] += v[(PLAN_HDR / 8) * p + HDR_STATS / 8 + slot];
+            if (k == 0) out5[k] += c->host_stats[p][0];                       // interval tests of the sparse scans (counted on the host)
+            if (k == 1) out5[k] += v[(PLAN_HDR / 8) * p + HDR_LIST / 8];      // tiles the scans listed
+        }
     }
     return BDG_OK;
 }
@@ -694,7 +686,8 @@ static int edges_on_device(DevCtx& c, const uint32_t* sorted, size_t N, int t, i
     CU_TRY(cudaMemcpyAsync(c.sorted.p, sorted, N * 4, cudaMemcpyHostToDevice, c.stream));
     size_t cap = std::max(edge_cap_guess(N, nparts), c.ea.cap / 4);
     unsigned long long count = 0;
-    for (int attempt = 0; attempt < 2; attempt++) {
+    bool done = false;
+    for (int attempt = 0; attempt < 4 && !done; attempt++) {
         if (int e = ensure(c.ea, cap * 4)) return e;
         if (int e = ensure(c.eb, cap * 4)) return e;
         if (int e = ensure(c.ed, cap)) return e;
@@ -702,10 +695,19 @@ static int edges_on_device(DevCtx& c, const uint32_t* sorted, size_t N, int t, i
                                  (unsigned long long*)c.count.p, c.stream, &c)) return e;
         CU_TRY(cudaMemcpyAsync(&count, c.count.p, sizeof(count), cudaMemcpyDeviceToHost, c.stream));
         CU_TRY(cudaStreamSynchronize(c.stream));
-        if (count <= cap) break;               // rare: the guess was too small; the edge set is deterministic, so run again
-        if (attempt == 1) return fail(BDG_ERR_CUDA, "edge count changed between identical launches");
-        cap = (size_t)count;
+        if (count >> 63) {                     // rare: a sparse pass listed more tiles than the list holds; grow it and run again
+            unsigned long long hdr[(PLAN_HDR / 8) * bdg::MAX_PASSES];
+            CU_TRY(cudaMemcpy(hdr, c.plan.p, sizeof(hdr), cudaMemcpyDeviceToHost));
+            unsigned long long need = 0;
+            for (int p = 0; p < bdg::MAX_PASSES; p++) need = std::max(need, hdr[(PLAN_HDR / 8) * p + HDR_LIST / 8]);
+            if (int e = ensure(c.tile_list, (size_t)need * sizeof(uint2))) return e;
+        } else if (count > cap) {              // rare: the capacity guess was too small; the edge set is deterministic, so run again
+            cap = (size_t)count;
+        } else {
+            done = true;
+        }
     }
+    if (!done) return fail(BDG_ERR_CUDA, "edge construction did not settle after growing its buffers (count %llu)", count);
     c.generation++;
     *n_out = (size_t)count;
     return BDG_OK;

@@ -615,7 +615,10 @@ __global__ void __launch_bounds__(ENT, 3) sparse_tile_kernel(const EdgeWork w, c
     const unsigned long long t_start = global_ns();
     unsigned long long n_combo = 0, n_cand = 0, n_score = 0;
     c.n_score = &n_score;
-    const unsigned long long n_tiles = min(*list.count, list.cap);
+    const unsigned long long n_listed = *list.count;
+    const unsigned long long n_tiles = min(n_listed, list.cap);
+    if (n_listed > list.cap && !BIP && blockIdx.x == 0 && threadIdx.x == 0)
+        atomicOr(out.count, 1ull << 63);          // the tile list was too small: poison the edge count, the host grows the list and reruns
     uint32_t g_cur = 0xFFFFFFFFu;
     uint32_t a[RA];                               // UNROTATED rows of the current group
     uint32_t my_alo = 0, my_ahi = 0;              // rotated end points of this lane's slab (lane & 7)

@@ -266,7 +266,7 @@ def run_b200(args):
         step_dev()
     torch.cuda.synchronize()
     n_edges_part = int(d_count.item())
-    assert n_edges_part <= cap, "edge buffer too small: %d > %d" % (n_edges_part, cap)
+    assert 0 <= n_edges_part <= cap, "edge buffer or tile list too small: count %d, capacity %d" % (n_edges_part, cap)
 
     launches0 = L.bdg_launch_count()
     barrier()

@@ -117,8 +117,9 @@ int bdg_kmer_score(const uint32_t* q, size_t Q, const uint32_t* wl, size_t W, in
 /* ---- device-resident variants (bench.py "value" path; torch owns the memory and the stream) -------- */
 /* Edge construction over rows of part/nparts.  d_count (one uint64, device) is zeroed by the call and receives
  * the number of edges found, which may exceed cap (only the first cap are stored).  The current device must have
- * been claimed by bdg_init (the call uses its workspaces).  In sparse mode the call synchronises the stream once per
- * pass (an 8-byte read-back of the tile count that sizes the next launch); the last kernel is left in flight. */
+ * been claimed by bdg_init (the call uses its workspaces).  Fully asynchronous.  If bit 63 of *d_count is set after
+ * the stream has drained, a sparse pass found more candidate tiles than the device's tile list holds (adversarial,
+ * extremely dense inputs): call bdg_edges_build_part once (it grows the list) or use dense mode, then repeat. */
 int bdg_dev_edges_build(const uint32_t* d_sorted, size_t N, int t, int part, int nparts, uint32_t* d_a,
                         uint32_t* d_b, uint8_t* d_d, size_t cap, unsigned long long* d_count, void* stream);
 /* How the edge set is searched for t = 1, 2 (results are identical; DESIGN.md "edge construction"):
