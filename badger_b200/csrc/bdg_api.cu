@@ -61,6 +61,14 @@ struct Buf {
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
 
+// the work plan of one part (built by build_plan below)
+struct Plan {
+    std::vector<uint32_t> group_ids;
+    std::vector<uint32_t> item_start;
+    uint32_t chunk_cols = 256;
+    uint64_t pairs = 0;
+};
+
 struct DevCtx {
     int dev = -1;
     cudaStream_t stream = nullptr;
@@ -71,6 +79,9 @@ struct DevCtx {
     unsigned long long host_stats[bdg::MAX_PASSES][2] = {};   // interval tests done / tiles listed per pass of the last launch
     unsigned long long generation = 0;                        // bumped by every host-buffer edge build on this device
     Buf dd[10];                                               // dedup: keys, idx, sorted keys/idx, heads, scan, run arrays, cub scratch
+    Plan plan_host;                                           // cached work plan (host copy; the device copy lives in `plan`)
+    uint64_t plan_key[4] = {0, 0, 0, 0};
+    bool plan_valid = false;
     Buf cl[6];                                                // clustering: centres, centre index, level, claim min / max, index scratch
     Buf nn[9];                                                // sparse nearest: rotated keys + payload (in/out) of queries and targets, scratch
 };
@@ -95,13 +106,6 @@ int grid_for(const void* kernel, int* out, int threads = bdg::NT)
 
 // ---- the work plan of one part: owned row groups (256 rows, one warp each), column chunks per group ----
 // Ownership is dealt in tiles of BDG_ROW_TILE rows (8 groups), boustrophedon over the parts.
-struct Plan {
-    std::vector<uint32_t> group_ids;
-    std::vector<uint32_t> item_start;
-    uint32_t chunk_cols = bdg::SB_MAX;
-    uint64_t pairs = 0;
-};
-
 void build_plan(size_t N, int part, int nparts, int workers, Plan& p, uint64_t col_quantum = bdg::SB_MAX)
 {
     const uint64_t tiles = (N + bdg::ROW_TILE - 1) / bdg::ROW_TILE;
@@ -201,10 +205,7 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
         return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "plan workspace: %s", cudaGetErrorString(e));
     char* d_plan = (char*)ws->plan.p;   // [headers | group_ids | item_start]
     CU_TRY(cudaMemsetAsync(d_plan, 0, hdr, st));
-    for (int p = 0; p < bdg::MAX_PASSES; p++) {   // the "earliest warp start" slots are minima: prime them with all ones
-        CU_TRY(cudaMemsetAsync(d_plan + PLAN_HDR * p + HDR_STATS + 48, 0xFF, 8, st));
-        ws->host_stats[p][0] = ws->host_stats[p][1] = 0;
-    }
+    for (int p = 0; p < bdg::MAX_PASSES; p++) ws->host_stats[p][0] = ws->host_stats[p][1] = 0;
     CU_TRY(cudaMemcpyAsync(d_plan + hdr, plan.group_ids.data(), nb_groups, cudaMemcpyHostToDevice, st));
     CU_TRY(cudaMemcpyAsync(d_plan + hdr + nb_groups, plan.item_start.data(), nb_items, cudaMemcpyHostToDevice, st));
     bdg::EdgeWork w;
@@ -303,7 +304,7 @@ int launch_nearest_sparse(const uint32_t* d_q, size_t Q, const uint32_t* d_t, si
     if (ws->tile_list.cap == 0)
         if (int e = ensure(ws->tile_list, ((size_t)1 << 22) * sizeof(uint2))) return e;
     if (int e = ensure(ws->plan, PLAN_HDR * bdg::MAX_PASSES)) return e;
-    char* d_plan = (char*)ws->plan.p;
+    char* d_plan = (char*)ws->plan.p;   // only the headers are used here; a cached edge plan behind them stays valid
     CU_TRY(cudaMemsetAsync(d_plan, 0, PLAN_HDR * bdg::MAX_PASSES, st));
     int grid = 0;
     if (int rc = grid_for(T_ == 1 ? (const void*)bdg::sparse_tile_kernel<1, 0, true> : (const void*)bdg::sparse_tile_kernel<2, 0, true>, &grid, bdg::ENT)) return rc;

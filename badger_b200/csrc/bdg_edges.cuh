@@ -59,7 +59,7 @@ struct EdgeWork {
     uint32_t chunk_cols;        // columns per work item (multiple of SB_MAX, <= 2^17)
     unsigned int* item_counter; // dynamic scheduler
     unsigned long long* stats;  // optional [8]: sub-tiles visited, sub-tiles scored pair by pair, pairs scored, candidates,
-                                //               sum / max over warps of (warp exit - first warp start) in ns, earliest start, pairs that reached S
+                                //               sum / max over warps of the warp's busy time in ns, (unused), pairs that reached S
     uint32_t one;               // == 1, opaque to the compiler: x*(-one)+c keeps the subtraction on the FMA pipe (IMAD)
     int pass;                   // sparse kernel: pass index p (bdg_core.cuh pass_pred); `sorted` holds rotl(key, rot) sorted
     int rot;
@@ -78,12 +78,10 @@ __device__ __forceinline__ unsigned long long global_ns()
     return t;
 }
 
-// warp exit bookkeeping for the load-balance statistics: stats[6] holds the earliest start (atomicMin, primed to ~0)
+// warp exit bookkeeping for the load-balance statistics: sum and max over the warps of the time each one was busy
 __device__ __forceinline__ void warp_exit_stats(unsigned long long* stats, unsigned long long t_start)
 {
-    const unsigned long long t0 = atomicMin(&stats[6], t_start);
-    const unsigned long long base = t0 < t_start ? t0 : t_start;
-    const unsigned long long dt = global_ns() - base;
+    const unsigned long long dt = global_ns() - t_start;
     atomicAdd(&stats[4], dt);
     atomicMax(&stats[5], dt);
 }
