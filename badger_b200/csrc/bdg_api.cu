@@ -218,6 +218,7 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
     w.n_items = n_items;
     w.chunk_cols = plan.chunk_cols;
     w.one = 1u;
+    w.mone = 0xFFFFFFFFu;
     bdg::EdgeOut o{d_a, d_b, d_d, d_count, (unsigned long long)cap};
     const int blocks = (int)std::min<uint64_t>((uint64_t)grid, (n_items + bdg::EW - 1) / bdg::EW);
     for (int p = 0; p < passes; p++) {
@@ -321,7 +322,7 @@ int launch_nearest_sparse(const uint32_t* d_q, size_t Q, const uint32_t* d_t, si
         bdg::EdgeWork w{};
         w.sorted = qks; w.N = (uint32_t)Q; w.t = max_d; w.T = 0; w.group_ids = nullptr; w.item_start = nullptr; w.K = K;
         w.item_counter = (unsigned int*)(d_plan + PLAN_HDR * p);
-        w.stats = nullptr; w.one = 1u; w.pass = p; w.rot = rot;
+        w.stats = nullptr; w.one = 1u; w.mone = 0xFFFFFFFFu; w.pass = p; w.rot = rot;
         w.cols = tks; w.NC = (uint32_t)W; w.row_pay = qps; w.col_pay = tps; w.near_keys = d_keys;
         unsigned long long n_tiles = 0;
         for (int attempt = 0; attempt < 2; attempt++) {
@@ -374,9 +375,10 @@ int check_sorted(const uint32_t* v, size_t N)
     return BDG_OK;
 }
 
-size_t edge_cap_guess(size_t N, int nparts)
+size_t edge_cap_guess(size_t N, int t, int nparts)
 {
-    size_t per_row = 16;
+    // a too small guess costs a whole second run (the kernel only counts what it cannot store); 9 bytes per slot are cheap
+    size_t per_row = t <= 1 ? 16 : 64;
     if (const char* e = getenv("BDG_EDGE_CAP_PER_ROW")) per_row = (size_t)std::max(1ll, atoll(e));
     return std::max<size_t>(1u << 16, per_row * N / (size_t)nparts + 1024);
 }
@@ -685,7 +687,7 @@ static int edges_on_device(DevCtx& c, const uint32_t* sorted, size_t N, int t, i
     if (int e = ensure(c.sorted, std::max<size_t>(N, 1) * 4)) return e;
     if (int e = ensure(c.count, sizeof(unsigned long long))) return e;
     CU_TRY(cudaMemcpyAsync(c.sorted.p, sorted, N * 4, cudaMemcpyHostToDevice, c.stream));
-    size_t cap = std::max(edge_cap_guess(N, nparts), c.ea.cap / 4);
+    size_t cap = std::max(edge_cap_guess(N, t, nparts), c.ea.cap / 4);
     unsigned long long count = 0;
     bool done = false;
     for (int attempt = 0; attempt < 4 && !done; attempt++) {

@@ -61,6 +61,8 @@ struct EdgeWork {
     unsigned long long* stats;  // optional [8]: sub-tiles visited, sub-tiles scored pair by pair, pairs scored, candidates,
                                 //               sum / max over warps of the warp's busy time in ns, (unused), pairs that reached S
     uint32_t one;               // == 1, opaque to the compiler: x*(-one)+c keeps the subtraction on the FMA pipe (IMAD)
+    uint32_t mone;              // == 0xFFFFFFFF, a SEPARATE opaque value: u*one + mone is u - 1 as one IMAD (derived from `one`
+                                // the compiler would rewrite it as (u-1)*one, an add on the ALU pipe plus a multiply)
     int pass;                   // sparse kernel: pass index p (bdg_core.cuh pass_pred); `sorted` holds rotl(key, rot) sorted
     int rot;
     // bipartite form (queries x targets, bdg_nearest_bounded): rows come from `sorted` (N queries), columns from `cols`
@@ -609,7 +611,7 @@ __global__ void __launch_bounds__(ENT, 3) sparse_tile_kernel(const EdgeWork w, c
     c.sorted = w.sorted; c.N = w.N; c.t = w.t; c.T = w.T; c.rot = w.rot; c.lane = lane;
     c.cols = BIP ? w.cols : w.sorted; c.NC = BIP ? w.NC : w.N; c.row_pay = w.row_pay; c.col_pay = w.col_pay; c.near_keys = w.near_keys;
     int qn = 0, q2n = 0;                          // queue fills, uniform across the warp
-    const uint32_t mone = 0u - w.one;             // runtime -1: u*one + mone is u - 1 on the FMA pipe
+    const uint32_t mone = w.mone;                 // runtime -1: u*one + mone is u - 1 on the FMA pipe
     const unsigned long long t_start = global_ns();
     unsigned long long n_combo = 0, n_cand = 0, n_score = 0;
     c.n_score = &n_score;
