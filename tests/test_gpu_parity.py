@@ -196,6 +196,55 @@ def test_edges_dense_neighbourhoods(t, mode):
     assert np.array_equal(edge_rows(a, b, d), np.stack([wa, wb, wd], 1).astype(np.int64))
 
 
+def _structured_set(rng, kind, n):
+    """Small barcode sets with structure that stresses the interval tests, the candidate queues and the pass hand-over."""
+    if kind == 0:      # uniform random
+        v = rng.integers(0, 1 << 32, n, dtype=np.uint64)
+    elif kind == 1:    # one dense run of consecutive integers (every tile next to the diagonal is full of candidates)
+        v = np.arange(n, dtype=np.uint64) + np.uint64(int(rng.integers(0, (1 << 32) - n)))
+    elif kind == 2:    # few cells, many errors: real clusters
+        cells = rng.integers(0, 1 << 32, max(2, n // 40), dtype=np.uint64).astype(np.uint32)
+        v, _ = synth.simulate_reads(cells, n, 0.10, rng, star_frac=0.0)
+        v = v.astype(np.uint64)
+    elif kind == 3:    # shared high half / shared low half / shared middle: one block constant, the rest random
+        which = int(rng.integers(0, 3))
+        mask = [np.uint64(0xFFFF0000), np.uint64(0x0000FFFF), np.uint64(0x00FFFF00)][which]
+        v = (rng.integers(0, 1 << 32, n, dtype=np.uint64) & ~mask) | (np.uint64(int(rng.integers(0, 1 << 32))) & mask)
+    elif kind == 4:    # low complexity: periodic words with a few edits
+        out = []
+        for _ in range(n):
+            unit = int(rng.integers(0, 1 << (2 * int(rng.integers(1, 4)))))
+            ul = int(rng.integers(1, 4))
+            w = 0
+            for i in range(16):
+                w |= ((unit >> (2 * (i % ul))) & 3) << (2 * i)
+            for _e in range(int(rng.integers(0, 3))):
+                w ^= int(rng.integers(1, 4)) << (2 * int(rng.integers(0, 16)))
+            out.append(w)
+        v = np.asarray(out, dtype=np.uint64)
+    else:              # values at the ends of the range and around field boundaries of the rotated keys
+        base = np.asarray([0, 1, 2, 3, 0xFFFFFFFF, 0xFFFFFFFE, 0x3FFFFFFF, 0x40000000, 0x7FFFFFFF, 0x80000000, 0xBFFFFFFF, 0xC0000000,
+                           0x000FFFFF, 0x00100000, 0x0000FFFF, 0x00010000, 0x003FFFFF, 0x00400000], dtype=np.uint64)
+        v = np.concatenate([base, base ^ np.uint64(0x55555555), rng.integers(0, 1 << 32, n, dtype=np.uint64)])
+    return np.unique(v.astype(np.uint32))
+
+
+@pytest.mark.parametrize("t", [1, 2])
+def test_edges_many_small_structured_sets(t, mode):
+    """Every pair decided by brute force (oracle predicate on all pairs) on many small sets of each structure."""
+    rng = np.random.default_rng(100 + t)
+    total = 0
+    for trial in range(36):
+        kind = trial % 6
+        n = int(rng.integers(2, 1500)) if trial % 5 else int(rng.integers(1500, 3500))
+        s = _structured_set(rng, kind, n)
+        a, b, d = ops.edges_build(s, t)
+        wa, wb, wd = orc.edges_brute(s, t)
+        assert np.array_equal(edge_rows(a, b, d), np.stack([wa, wb, wd], 1).astype(np.int64)), (trial, kind, s.size)
+        total += a.size
+    assert total > 10000
+
+
 def test_edges_edge_cases(mode):
     for t in (1, 2, 3):
         for arr in ([], [7], [0, 0xFFFFFFFF], [0, 1, 2, 3], list(range(2047, 2047 + 5))):
