@@ -48,6 +48,9 @@ A_QUICK = {1: 14.5, 2: 16.5}       # 58 / 66 SASS instructions per 4 pairs
 A_LIGHT = {1: 1.25, 2: 6.0}
 A_EXACT = 110                      # loads, un-rotation, pass predicates, dist_small
 A_SCORE = 220                      # qgram_score, only for pairs with D <= t
+# DRAM traffic of one step's dominant kernels from the ncu --set full capture of this round (profiles/r1d_sparse_t*_ncu_full.txt:
+# dram__bytes_read.sum + dram__bytes_write.sum of the scan + tile kernels of all passes, C2, N = 492 093).  Writes stay in L2.
+NCU_TRAFFIC_BYTES = {1: 536064 + 2174976 + 535040 + 2056704, 2: 3 * 535808 + 2710528 + 2709760 + 2153728 + 1280}
 A_PAIR_SURVEY = {1: 15, 2: 25}   # SURVEY.md §8(d) nominal per-pair figure of a plain all-pairs kernel, reported alongside
 
 
@@ -336,7 +339,10 @@ def run_b200(args):
             alg_o = algorithmic(other, stats_other)
             roof = {"bound": "int_issue",
                     "kernel": ("sparse_scan_kernel + sparse_tile_kernel<%d,p>, %d passes per step" % (t, 2 if t == 1 else 3)) if args.mode == "sparse" else "edges_kernel<%d>" % t,
-                    "achieved": achieved, "peak": peak, "unit": "Tinst/s", "frac": achieved / peak if peak else None, "traffic": None,
+                    "achieved": achieved, "peak": peak, "unit": "Tinst/s", "frac": achieved / peak if peak else None,
+                    "traffic": NCU_TRAFFIC_BYTES.get(t) if (args.mode == "sparse" and args.config == "C2" and args.reads is None and world == 1) else None,
+                    "traffic_note": "bytes per step, dram read+write of the scan and tile kernels from the committed ncu capture (profiles/); the "
+                                    "algorithmic bytes are hbm.algorithmic_bytes_per_launch",
                     "how": "achieved = algorithmic integer instructions of rank 0's step (%d interval tests x %d + %d pairs scored x %s + "
                            "%d candidates x %d + pairs S-scored x 220; unit counts from the kernel's own counters, per-unit costs from its SASS, DESIGN.md) / "
                            "%.3f ms (CUDA events, this run); peak = measured issue rate of an independent LOP3+IMAD 1:1 stream on this GPU "
@@ -352,7 +358,10 @@ def run_b200(args):
                                    "achieved": alg_o / (ms_other * 1e-3) / 1e12, "frac": alg_o / (ms_other * 1e-3) / 1e12 / peak if peak else None},
                     "probe_Tinst_per_s": probe,
                     "hbm": {"algorithmic_bytes_per_launch": int(4 * n * (2 if t == 1 else 3) + 9 * n_edges_part),
-                            "note": "negligible: operands live in registers / shared memory"}}
+                            "achieved_GBps": (4 * n * (2 if t == 1 else 3) + 9 * n_edges_part) / (step_ms * 1e-3) / 1e9,
+                            "peak_GBps": 6451.8, "frac": (4 * n * (2 if t == 1 else 3) + 9 * n_edges_part) / (step_ms * 1e-3) / 1e9 / 6451.8,
+                            "note": "not the bound: operands live in registers / shared memory, the kernels are integer-issue bound "
+                                    "(north_star asks for the INT-pipe roofline; MEASURED_PEAKS.json has no integer figure, so it is probed live)"}}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "u32", "data": "synthetic",
