@@ -74,8 +74,11 @@ struct DevCtx {
     cudaStream_t stream = nullptr;
     int sms = 0;
     Buf sorted, ea, eb, ed, count, plan;   // edge construction
-    Buf rot_in, rot_sorted[bdg::MAX_PASSES], sort_tmp;   // sparse passes: rotated keys, their sorted copies, radix-sort scratch
-    Buf tile_bnd, tile_list;                             // sparse passes: sub-tile end keys, list of tiles that survive level 1
+    // sparse passes run side by side on their own streams, so each has its own rotated keys, sorted copy, radix-sort scratch,
+    // sub-tile end keys and list of tiles that survive level 1
+    Buf rot_in[bdg::MAX_PASSES], rot_sorted[bdg::MAX_PASSES], sort_tmp[bdg::MAX_PASSES], tile_bnd[bdg::MAX_PASSES], tile_list[bdg::MAX_PASSES];
+    cudaStream_t aux[bdg::MAX_PASSES] = {nullptr, nullptr, nullptr};   // aux[p]: stream of pass p (pass 0 stays on the caller's stream)
+    cudaEvent_t ev_start = nullptr, ev_done[bdg::MAX_PASSES] = {nullptr, nullptr, nullptr};
     unsigned long long host_stats[bdg::MAX_PASSES][2] = {};   // interval tests done / tiles listed per pass of the last launch
     unsigned long long generation = 0;                        // bumped by every host-buffer edge build on this device
     Buf dd[10];                                               // dedup: keys, idx, sorted keys/idx, heads, scan, run arrays, cub scratch
@@ -221,7 +224,14 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
     w.mone = 0xFFFFFFFFu;
     bdg::EdgeOut o{d_a, d_b, d_d, d_count, (unsigned long long)cap};
     const int blocks = (int)std::min<uint64_t>((uint64_t)grid, (n_items + bdg::EW - 1) / bdg::EW);
+    // sparse passes are independent (disjoint outputs through one atomic cursor): pass 0 runs on the caller's stream, the others
+    // on the device's auxiliary streams, so that one pass's sort / scan and its tail overlap the neighbour's tile kernel
+    const bool fork = sparse && passes > 1 && !getenv("BDG_EDGE_SERIAL");
+    cudaStream_t caller = st;
+    if (fork) CU_TRY(cudaEventRecord(ws->ev_start, caller));
     for (int p = 0; p < passes; p++) {
+        st = (fork && p > 0) ? ws->aux[p] : caller;
+        if (fork && p > 0) CU_TRY(cudaStreamWaitEvent(st, ws->ev_start, 0));
         w.item_counter = (unsigned int*)(d_plan + PLAN_HDR * p);
         w.stats = (unsigned long long*)(d_plan + PLAN_HDR * p + HDR_STATS);
         w.pass = p;
@@ -233,15 +243,15 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
             return BDG_OK;
         };
         if (w.rot != 0) {   // this pass scans the array in the order of rotl(key, rot): rotate, radix-sort
-            if (int e = ensure(ws->rot_in, N * 4)) return e;
+            if (int e = ensure(ws->rot_in[p], N * 4)) return e;
             if (int e = ensure(ws->rot_sorted[p], N * 4)) return e;
             size_t tmp_bytes = 0;
-            CU_TRY(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (const uint32_t*)ws->rot_in.p, (uint32_t*)ws->rot_sorted[p].p, (int)N, 0, 32, st));
-            if (int e = ensure(ws->sort_tmp, tmp_bytes)) return e;
+            CU_TRY(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, (const uint32_t*)ws->rot_in[p].p, (uint32_t*)ws->rot_sorted[p].p, (int)N, 0, 32, st));
+            if (int e = ensure(ws->sort_tmp[p], tmp_bytes)) return e;
             const int rb = (int)std::min<size_t>((N + 255) / 256, (size_t)ws->sms * 8);
-            bdg::rotate_keys_kernel<<<rb, 256, 0, st>>>(d_sorted, (uint32_t*)ws->rot_in.p, (uint32_t)N, w.rot);
+            bdg::rotate_keys_kernel<<<rb, 256, 0, st>>>(d_sorted, (uint32_t*)ws->rot_in[p].p, (uint32_t)N, w.rot);
             g_launches++;
-            CU_TRY(cub::DeviceRadixSort::SortKeys(ws->sort_tmp.p, tmp_bytes, (const uint32_t*)ws->rot_in.p, (uint32_t*)ws->rot_sorted[p].p, (int)N, 0, 32, st));
+            CU_TRY(cub::DeviceRadixSort::SortKeys(ws->sort_tmp[p].p, tmp_bytes, (const uint32_t*)ws->rot_in[p].p, (uint32_t*)ws->rot_sorted[p].p, (int)N, 0, 32, st));
             w.sorted = (const uint32_t*)ws->rot_sorted[p].p;
         }
         if (!sparse) {
@@ -251,19 +261,19 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
         } else {
             // level 1: interval scan of every (owned row group, sub-tile right of it) -> compact tile list
             const uint32_t NS = (uint32_t)((N + bdg::SSB - 1) / bdg::SSB);
-            if (int e = ensure(ws->tile_bnd, (size_t)NS * sizeof(uint2))) return e;
-            if (ws->tile_list.cap == 0) {
+            if (int e = ensure(ws->tile_bnd[p], (size_t)NS * sizeof(uint2))) return e;
+            if (ws->tile_list[p].cap == 0) {
                 size_t want = std::max<size_t>((size_t)1 << 22, 4 * N);
                 if (const char* e = getenv("BDG_TILE_LIST_CAP")) want = (size_t)std::max(1ll, atoll(e));   // tests: force the regrow path
-                if (int e = ensure(ws->tile_list, want * sizeof(uint2))) return e;
+                if (int e = ensure(ws->tile_list[p], want * sizeof(uint2))) return e;
             }
-            bdg::tile_bounds_kernel<<<std::min<uint32_t>((NS + 255) / 256, (uint32_t)ws->sms * 8), 256, 0, st>>>(w.sorted, w.N, (uint2*)ws->tile_bnd.p, NS);
+            bdg::tile_bounds_kernel<<<std::min<uint32_t>((NS + 255) / 256, (uint32_t)ws->sms * 8), 256, 0, st>>>(w.sorted, w.N, (uint2*)ws->tile_bnd[p].p, NS);
             g_launches++;
             // no read-back between the scan and the tile kernel: the tile kernel reads the list length on the device and, if
             // the list was too small, poisons the edge count (bit 63), which every caller inspects before using the edges
-            bdg::TileList l{(uint2*)ws->tile_list.p, (unsigned long long*)(d_plan + PLAN_HDR * p + HDR_LIST), ws->tile_list.cap / sizeof(uint2)};
+            bdg::TileList l{(uint2*)ws->tile_list[p].p, (unsigned long long*)(d_plan + PLAN_HDR * p + HDR_LIST), ws->tile_list[p].cap / sizeof(uint2)};
             const int sblocks = (int)std::min<uint64_t>(w.K, (uint64_t)ws->sms * 16);
-            BDG_PASS_DISPATCH(launch_scan, sblocks, st, w, (const uint2*)ws->tile_bnd.p, NS, l);
+            BDG_PASS_DISPATCH(launch_scan, sblocks, st, w, (const uint2*)ws->tile_bnd[p].p, NS, l);
             g_launches++;
             CU_TRY(cudaGetLastError());
             uint64_t tests = 0;
@@ -273,7 +283,10 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
         }
         g_launches++;
         CU_TRY(cudaGetLastError());
+        if (fork && p > 0) CU_TRY(cudaEventRecord(ws->ev_done[p], st));
     }
+    if (fork)
+        for (int p = 1; p < passes; p++) CU_TRY(cudaStreamWaitEvent(caller, ws->ev_done[p], 0));
     return BDG_OK;
 }
 
@@ -301,9 +314,9 @@ int launch_nearest_sparse(const uint32_t* d_q, size_t Q, const uint32_t* d_t, si
     if (int e = ensure(ws->nn[8], std::max(tmp_q, tmp_t))) return e;
     const uint32_t NS = (uint32_t)((W + bdg::SSB - 1) / bdg::SSB);
     const uint32_t K = (uint32_t)((Q + bdg::GROUP - 1) / bdg::GROUP);
-    if (int e = ensure(ws->tile_bnd, (size_t)NS * sizeof(uint2))) return e;
-    if (ws->tile_list.cap == 0)
-        if (int e = ensure(ws->tile_list, ((size_t)1 << 22) * sizeof(uint2))) return e;
+    if (int e = ensure(ws->tile_bnd[0], (size_t)NS * sizeof(uint2))) return e;
+    if (ws->tile_list[0].cap == 0)
+        if (int e = ensure(ws->tile_list[0], ((size_t)1 << 22) * sizeof(uint2))) return e;
     if (int e = ensure(ws->plan, PLAN_HDR * bdg::MAX_PASSES)) return e;
     char* d_plan = (char*)ws->plan.p;   // only the headers are used here; a cached edge plan behind them stays valid
     CU_TRY(cudaMemsetAsync(d_plan, 0, PLAN_HDR * bdg::MAX_PASSES, st));
@@ -317,7 +330,7 @@ int launch_nearest_sparse(const uint32_t* d_q, size_t Q, const uint32_t* d_t, si
         bdg::rotate_keys_iota_kernel<<<tb, 256, 0, st>>>(d_t, tk, tp, (uint32_t)W, rot);
         CU_TRY(cub::DeviceRadixSort::SortPairs(ws->nn[8].p, tmp_q, qk, qks, qp, qps, (int)Q, 0, 32, st));
         CU_TRY(cub::DeviceRadixSort::SortPairs(ws->nn[8].p, tmp_t, tk, tks, tp, tps, (int)W, 0, 32, st));
-        bdg::tile_bounds_kernel<<<std::min<uint32_t>((NS + 255) / 256, (uint32_t)ws->sms * 8), 256, 0, st>>>(tks, (uint32_t)W, (uint2*)ws->tile_bnd.p, NS);
+        bdg::tile_bounds_kernel<<<std::min<uint32_t>((NS + 255) / 256, (uint32_t)ws->sms * 8), 256, 0, st>>>(tks, (uint32_t)W, (uint2*)ws->tile_bnd[0].p, NS);
         g_launches += 3;
         bdg::EdgeWork w{};
         w.sorted = qks; w.N = (uint32_t)Q; w.t = max_d; w.T = 0; w.group_ids = nullptr; w.item_start = nullptr; w.K = K;
@@ -326,20 +339,20 @@ int launch_nearest_sparse(const uint32_t* d_q, size_t Q, const uint32_t* d_t, si
         w.cols = tks; w.NC = (uint32_t)W; w.row_pay = qps; w.col_pay = tps; w.near_keys = d_keys;
         unsigned long long n_tiles = 0;
         for (int attempt = 0; attempt < 2; attempt++) {
-            bdg::TileList l{(uint2*)ws->tile_list.p, (unsigned long long*)(d_plan + PLAN_HDR * p + HDR_LIST), ws->tile_list.cap / sizeof(uint2)};
+            bdg::TileList l{(uint2*)ws->tile_list[0].p, (unsigned long long*)(d_plan + PLAN_HDR * p + HDR_LIST), ws->tile_list[0].cap / sizeof(uint2)};
             CU_TRY(cudaMemsetAsync(l.count, 0, 8, st));
             const int sblocks = (int)std::min<uint64_t>(K, (uint64_t)ws->sms * 16);
-            BDG_PASS_DISPATCH(launch_scan_bip, sblocks, st, w, (const uint2*)ws->tile_bnd.p, NS, l);
+            BDG_PASS_DISPATCH(launch_scan_bip, sblocks, st, w, (const uint2*)ws->tile_bnd[0].p, NS, l);
             g_launches++;
             CU_TRY(cudaGetLastError());
             CU_TRY(cudaMemcpyAsync(&n_tiles, l.count, 8, cudaMemcpyDeviceToHost, st));
             CU_TRY(cudaStreamSynchronize(st));
             if (n_tiles <= l.cap) break;
             if (attempt == 1) return fail(BDG_ERR_CUDA, "tile list count changed between identical scans");
-            if (int e = ensure(ws->tile_list, (size_t)n_tiles * sizeof(uint2))) return e;
+            if (int e = ensure(ws->tile_list[0], (size_t)n_tiles * sizeof(uint2))) return e;
         }
         if (n_tiles == 0) continue;
-        bdg::TileList l{(uint2*)ws->tile_list.p, (unsigned long long*)(d_plan + PLAN_HDR * p + HDR_LIST), ws->tile_list.cap / sizeof(uint2)};
+        bdg::TileList l{(uint2*)ws->tile_list[0].p, (unsigned long long*)(d_plan + PLAN_HDR * p + HDR_LIST), ws->tile_list[0].cap / sizeof(uint2)};
         const int tblocks = (int)std::min<uint64_t>((uint64_t)grid, (n_tiles + bdg::EW - 1) / bdg::EW);
         bdg::EdgeOut o{nullptr, nullptr, nullptr, nullptr, 0};
         BDG_PASS_DISPATCH(launch_tiles_bip, tblocks, st, w, o, l);
@@ -425,6 +438,11 @@ int bdg_init(const int* device_ids, int n_devices)
         if (prop.major < 10) { bdg_shutdown(); return fail(BDG_ERR_NODEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", id, prop.major, prop.minor); }
         c.sms = prop.multiProcessorCount;
         CU_TRY(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+        CU_TRY(cudaEventCreateWithFlags(&c.ev_start, cudaEventDisableTiming));
+        for (int p = 1; p < bdg::MAX_PASSES; p++) {
+            CU_TRY(cudaStreamCreateWithFlags(&c.aux[p], cudaStreamNonBlocking));
+            CU_TRY(cudaEventCreateWithFlags(&c.ev_done[p], cudaEventDisableTiming));
+        }
         cudaMemPool_t pool;   // keep stream-ordered allocations cached instead of returning them at every sync
         if (cudaDeviceGetDefaultMemPool(&pool, id) == cudaSuccess) {
             unsigned long long keep = ~0ull;
@@ -441,7 +459,12 @@ void bdg_shutdown(void)
     for (auto& c : g_ctx) {
         if (c.stream) { cudaSetDevice(c.dev); cudaStreamSynchronize(c.stream); cudaStreamDestroy(c.stream); }
         c.sorted.release(); c.ea.release(); c.eb.release(); c.ed.release(); c.count.release(); c.plan.release();
-        c.rot_in.release(); c.sort_tmp.release(); c.tile_bnd.release(); c.tile_list.release();
+        for (int p = 0; p < bdg::MAX_PASSES; p++) {
+            c.rot_in[p].release(); c.sort_tmp[p].release(); c.tile_bnd[p].release(); c.tile_list[p].release();
+            if (c.aux[p]) cudaStreamDestroy(c.aux[p]);
+            if (c.ev_done[p]) cudaEventDestroy(c.ev_done[p]);
+        }
+        if (c.ev_start) cudaEventDestroy(c.ev_start);
         for (auto& b : c.dd) b.release();
         for (auto& b : c.nn) b.release();
         for (auto& b : c.cl) b.release();
@@ -703,7 +726,8 @@ static int edges_on_device(DevCtx& c, const uint32_t* sorted, size_t N, int t, i
             CU_TRY(cudaMemcpy(hdr, c.plan.p, sizeof(hdr), cudaMemcpyDeviceToHost));
             unsigned long long need = 0;
             for (int p = 0; p < bdg::MAX_PASSES; p++) need = std::max(need, hdr[(PLAN_HDR / 8) * p + HDR_LIST / 8]);
-            if (int e = ensure(c.tile_list, (size_t)need * sizeof(uint2))) return e;
+            for (int p = 0; p < bdg::MAX_PASSES; p++)
+                if (int e = ensure(c.tile_list[p], (size_t)need * sizeof(uint2))) return e;
         } else if (count > cap) {              // rare: the capacity guess was too small; the edge set is deterministic, so run again
             cap = (size_t)count;
         } else {

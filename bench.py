@@ -12,8 +12,9 @@ barcodes of BASELINE.json's config 2 (1 M simulated ONT reads, 10 k cells, 3 M w
   roofline    dominant kernel (the edge kernel's passes) against the MEASURED integer issue rate of this GPU
   cpu_baseline  the oracle's restatement of the reference algorithm on the box's host cores (rank 0, N=1)
 
-N > 1 (torchrun): weak scaling - the read count grows with sqrt(N) so that the pairs per GPU stay fixed; rows
-are dealt to ranks in 2048-row tiles, no data-path collective.
+N > 1 (torchrun): weak scaling - the read count is raised until the distinct barcodes are sqrt(N) times the one-GPU
+count, so that the pairs per GPU stay fixed; rows are dealt to ranks in 2048-row tiles, no data-path collective
+(SURVEY.md §8e).
 
 `--impl reference` times the reference's own algorithm (oracle port, all host threads) on a bounded sample
 of the same workload; /root/reference (pure Python) cannot travel to the GPU box.
@@ -70,15 +71,36 @@ def parse():
 
 
 def workload(args, world):
+    """C2 at one GPU.  For N GPUs (weak scaling) the read count is raised until the number of DISTINCT barcodes is
+    sqrt(N) times the one-GPU count, so that the pairs per GPU stay fixed (distinct barcodes grow slower than reads:
+    sqrt(N) times the reads alone would hand every rank less work than the one-GPU run has)."""
     cfg = dict(synth.CONFIGS[args.config])
-    reads = args.reads if args.reads is not None else int(round(cfg["reads"] * math.sqrt(world)))
     if args.threshold is not None:
         cfg["threshold"] = args.threshold
-    wl, cells, obs, valid, cfg2 = synth.make_dataset(cfg, reads=reads)
-    s = np.unique(obs[valid])
+
+    def distinct_of(reads):
+        wl, cells, obs, valid, _ = synth.make_dataset(cfg, reads=reads)
+        return np.unique(obs[valid]), (wl, obs, valid)
+
+    base_reads = args.reads if args.reads is not None else cfg["reads"]
+    reads = base_reads
+    s, data = distinct_of(reads)
+    if world > 1:
+        n1 = s.size
+        target = n1 * math.sqrt(world)
+        r_prev, n_prev = reads, n1
+        reads = int(round(base_reads * math.sqrt(world)))
+        for _ in range(3):
+            s, data = distinct_of(reads)
+            if abs(s.size - target) <= 0.01 * target:
+                break
+            alpha = math.log(s.size / n_prev) / math.log(reads / r_prev) if reads != r_prev and s.size != n_prev else 0.8
+            alpha = min(max(alpha, 0.3), 1.0)
+            r_prev, n_prev = reads, s.size
+            reads = int(round(reads * (target / s.size) ** (1.0 / alpha)))
     name = "%s: %d simulated ONT reads, %d cells, %d-entry whitelist, %.0f%% error, threshold %d" % (
         args.config, reads, cfg["n_cells"], cfg["whitelist"], 100 * cfg["perr"], cfg["threshold"])
-    workload.dataset = (wl, obs, valid, cfg)          # for the whole-pipeline reads/s figure
+    workload.dataset = (data[0], data[1], data[2], cfg)          # for the whole-pipeline reads/s figure
     return s, cfg["threshold"], reads, name
 
 
