@@ -209,7 +209,7 @@ class BarcodeGraph:
         return self._edge_arrays
 
     # ------------------------------------------------------------------ a-6: centres
-    def _whitelist_hits(self, barcode_list, bc_len):
+    def _whitelist_hits(self, barcode_list, bc_len, ranks=None):
         """`unrank(r, bc_len) in barcode_list` (barcode_graph.py:264) for every distinct barcode: the set is
         packed once, sorted, and probed on the GPU (ops.member_sorted)."""
         cache = getattr(self, "_wl_cache", None)
@@ -222,28 +222,47 @@ class BarcodeGraph:
                 else:
                     wl = np.empty(0, np.uint32)
             self._wl_cache = cache = (barcode_list, wl)
-        return ops.member_sorted(cache[1], self._ranks)
+        return ops.member_sorted(cache[1], self._ranks if ranks is None else ranks)
 
     def get_cluster_centers(self, true_barcodes, bc_len, barcode_list, n_cells, interval):
-        """barcode_graph.py:252-277, vectorised; same list, same order, same IndexError when N is too small."""
+        """barcode_graph.py:252-277; same list, same order, same IndexError when N is too small.  The reference sorts
+        all barcodes by count (stable, so ties keep first-seen order) and walks the list; only the entries above the
+        cutoff - a few thousand - and, rarely, a short stretch below it are ever looked at, so only those are sorted."""
         N = self._ranks.size
         if N == 0:
             raise StatisticsError("mean requires at least one data point")      # statistics.mean([]) at :255
-        order = np.argsort(-self._cnt, kind="stable")                           # sorted(..., reverse=True) is stable
-        by_counts = self._ranks[order]
-        cnt_sorted = self._cnt[order]
         first = self._cnt[:n_cells]
         if first.size == 0:
             raise StatisticsError("mean requires at least one data point")
         cutoff = max((int(first.sum()) / first.size) / 5.0, 5)
         hi = n_cells + n_cells * interval * 0.01
         lo = n_cells - n_cells * interval * 0.01
+        above = np.nonzero(self._cnt > cutoff)[0]                               # first-seen order
+        above = above[np.argsort(-self._cnt[above], kind="stable")]             # count-descending, ties by first sighting
+        n_above = int(above.size)
+        top = self._ranks[above]                                                # bc_by_counts[:n_above]
+        rest_sorted = []                                                        # bc_by_counts[n_above:], built on demand
+
+        def by_counts_at(i, need):
+            """bc_by_counts[i] with the guarantee that the next `need` positions are sorted as well."""
+            if i < n_above:
+                return int(top[i])
+            if not rest_sorted:
+                rest = np.nonzero(self._cnt <= cutoff)[0]
+                m = min(rest.size, max(int(need) + 1, 1))
+                key = -self._cnt[rest] * np.int64(N) + rest                    # unique: count-descending, then first-seen
+                pick = np.argpartition(key, m - 1)[:m] if m < rest.size else np.arange(rest.size)
+                rest_sorted.append(self._ranks[rest[pick[np.argsort(key[pick], kind="stable")]]])
+            j = i - n_above
+            if j >= rest_sorted[0].size:
+                raise IndexError("list index out of range")                     # :274 in the reference
+            return int(rest_sorted[0][j])
+
         tbcs, n, i = [], 0, 0
-        n_above = int(np.searchsorted(-cnt_sorted, -cutoff, side="left"))        # entries with count > cutoff
         if true_barcodes:
             tbcs = [bc if isinstance(bc, int) else rank(bc, bc_len) for bc in true_barcodes]   # packed callers pass ranks
         elif barcode_list:
-            hits = self._whitelist_hits(barcode_list, bc_len)[order][:n_above]
+            hits = self._whitelist_hits(barcode_list, bc_len, top) if n_above else np.zeros(0, bool)
             csum = np.cumsum(hits)
             want = int(np.floor(hi)) + 1                                         # loop runs while n <= hi
             if csum.size and csum[-1] >= want:
@@ -252,16 +271,17 @@ class BarcodeGraph:
             else:
                 i = n_above
                 n = int(csum[-1]) if csum.size else 0
-            tbcs = by_counts[:i][hits[:i]].tolist()
+            tbcs = top[:i][hits[:i]].tolist()
         else:
             if n_above >= N and N <= int(np.floor(hi)) + 1:
                 raise IndexError("list index out of range")                     # :269 runs off the list
             n = i = min(n_above, int(np.floor(hi)) + 1)
-            tbcs = by_counts[:i].tolist()
+            tbcs = top[:i].tolist()
+        missing = int(np.ceil(lo - n)) if n < lo else 0
         while n < lo:
             if i >= N:
                 raise IndexError("list index out of range")                     # :274 in the reference
-            tbcs.append(int(by_counts[i]))
+            tbcs.append(by_counts_at(i, missing))
             i += 1
             n += 1
         return tbcs

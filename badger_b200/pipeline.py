@@ -45,8 +45,9 @@ def assign_packed(ranks, valid=None, *, threshold, n_cells, interval=25, whiteli
 
     ranks = np.ascontiguousarray(ranks, dtype=np.uint32)
     R = ranks.size
-    idx = np.arange(R) if valid is None else np.nonzero(valid)[0]
-    reads = ranks if valid is None else ranks[idx]
+    if valid is not None:
+        valid = np.ascontiguousarray(valid, dtype=bool)
+    reads = ranks if valid is None else ranks[valid]
     out = np.full(R, NONE, dtype=np.uint64)
     info = {"reads": int(R), "valid_reads": int(reads.size)}
     if reads.size == 0:
@@ -92,7 +93,10 @@ def assign_packed(ranks, valid=None, *, threshold, n_cells, interval=25, whiteli
         tick("high_sens", t0)
 
     t0 = time.perf_counter()
-    out[idx] = centre_distinct[rmap]
+    if valid is None:
+        out[:] = centre_distinct[rmap]
+    else:
+        out[valid] = centre_distinct[rmap]
     tick("gather", t0)
     info["assigned_reads"] = int((out != NONE).sum())
     return out, info

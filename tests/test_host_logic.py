@@ -187,3 +187,33 @@ def test_qgram_index_interface(monkeypatch, capsys):
     assert ix.get_close("ATTACAGATTCCATGC", 1818173756) == [2977727730]
     assert ix.get_close("GATTACAGATTCCATG", 2977727730) == []
     assert ix.rank("ACGTAC") == orc.rank("ACGTAC" + "A" * 10) & 0xFFF
+
+
+def test_centres_random_counts_vs_literal_restatement(monkeypatch):
+    """get_cluster_centers (lazy count order) == the literal restatement of barcode_graph.py:252-277 on random count
+    vectors: ties, tiny N (IndexError paths), whitelist hits, top-up below the cutoff."""
+    cpu_ops.install(monkeypatch)
+    rng = np.random.default_rng(17)
+    checked = raised = 0
+    for trial in range(300):
+        n = int(rng.integers(1, 400))
+        ranks = rng.choice(1 << 24, n, replace=False).astype(np.uint32)
+        style = trial % 3
+        counts = (rng.integers(1, 8, n) if style == 0 else rng.integers(1, 200, n) if style == 1
+                  else np.concatenate([rng.integers(50, 500, n // 3 + 1), rng.integers(1, 6, n)])[:n])
+        n_cells = int(rng.integers(1, max(2, n)))
+        interval = int(rng.choice([0, 10, 25, 50]))
+        use_wl = trial % 2 == 0
+        wl_ranks = set(ranks[rng.random(n) < 0.6].tolist()) if use_wl else None
+        bg = BarcodeGraph.from_arrays(1, ranks, counts)
+        wl_strs = set(orc.unrank(int(r)) for r in wl_ranks) if use_wl else None
+        try:
+            want = orc.cluster_centers(dict(zip(ranks.tolist(), counts.tolist())), n_cells, interval, None, wl_ranks)
+        except IndexError:
+            with pytest.raises(IndexError):
+                bg.get_cluster_centers(None, 16, wl_strs, n_cells, interval)
+            raised += 1
+            continue
+        assert bg.get_cluster_centers(None, 16, wl_strs, n_cells, interval) == want, (trial, n, n_cells, interval)
+        checked += 1
+    assert checked > 150 and raised > 5
