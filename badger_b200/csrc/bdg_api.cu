@@ -407,6 +407,14 @@ struct bdg_edges {
     std::vector<unsigned long long> gen;  // workspace generation at build time
 };
 
+// Known strings of a KmerIndexer / QGramIndex, resident on one device, plus grow-only query / result buffers.
+struct bdg_kmer_index {
+    int dev = -1;
+    size_t W = 0;
+    Buf wl;
+    Buf outb[6];
+};
+
 extern "C" {
 
 const char* bdg_version(void) { return "badger_b200 0.1 (sm_100a)"; }
@@ -1003,6 +1011,85 @@ int bdg_nearest_bounded(const uint32_t* q, size_t Q, const uint32_t* targets, si
     return rc;
 }
 
+// ---- a-5  KmerIndexer / QGramIndex: the known strings stay on the device between queries ------------------
+int bdg_kmer_index_create(const uint32_t* wl, size_t W, bdg_kmer_index** out)
+{
+    if (!out || (W && !wl)) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    *out = nullptr;
+    if (W > 0xFFFFFFFFull) return fail(BDG_ERR_ARG, "size exceeds 2^32");
+    if (int rc = need_ctx()) return rc;
+    bdg_kmer_index* ix = new (std::nothrow) bdg_kmer_index();
+    if (!ix) return fail(BDG_ERR_OOM, "host allocation failed");
+    ix->dev = g_ctx[0].dev;
+    ix->W = W;
+    CU_TRY(cudaSetDevice(ix->dev));
+    if (cudaError_t e = (cudaError_t)ix->wl.ensure(std::max<size_t>(W, 1) * 4)) {
+        delete ix;
+        return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation of %zu bytes: %s", W * 4, cudaGetErrorString(e));
+    }
+    cudaError_t e = cudaMemcpyAsync(ix->wl.p, wl, W * 4, cudaMemcpyHostToDevice, g_ctx[0].stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx[0].stream);
+    if (e != cudaSuccess) { bdg_kmer_index_free(ix); return fail(BDG_ERR_CUDA, "upload of the index failed: %s", cudaGetErrorString(e)); }
+    *out = ix;
+    return BDG_OK;
+}
+
+void bdg_kmer_index_free(bdg_kmer_index* ix)
+{
+    if (!ix) return;
+    cudaSetDevice(ix->dev);
+    ix->wl.release();
+    for (auto& b : ix->outb) b.release();
+    delete ix;
+}
+
+int bdg_kmer_index_query(bdg_kmer_index* ix, const uint32_t* q, size_t Q, int min_kmers, size_t cap, uint32_t* hit_q, uint32_t* hit_w,
+                         uint8_t* cnt, uint64_t* mult, size_t* total)
+{
+    if (!total) return fail(BDG_ERR_ARG, "NULL total pointer");
+    *total = 0;
+    if (!ix) return fail(BDG_ERR_ARG, "NULL index handle");
+    const size_t W = ix->W;
+    if (Q == 0 || W == 0) return BDG_OK;
+    if (!q || (cap && (!hit_q || !hit_w || !cnt || !mult))) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if (Q > 0xFFFFFFFFull) return fail(BDG_ERR_ARG, "size exceeds 2^32");
+    DevCtx* c = nullptr;
+    for (auto& x : g_ctx) if (x.dev == ix->dev) c = &x;
+    if (!c) return fail(BDG_ERR_NODEVICE, "the device the index lives on is no longer claimed (bdg_shutdown?)");
+    CU_TRY(cudaSetDevice(c->dev));
+    const size_t capa = std::max<size_t>(cap, 1);
+    const size_t sizes[6] = {Q * 4, capa * 4, capa * 4, capa, capa * 8, 8};     // queries, hit_q, hit_w, cnt, mult, total
+    for (int k = 0; k < 6; k++)
+        if (cudaError_t e = (cudaError_t)ix->outb[k].ensure(sizes[k]))
+            return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation of %zu bytes: %s", sizes[k], cudaGetErrorString(e));
+    uint32_t *d_q = (uint32_t*)ix->outb[0].p, *d_hq = (uint32_t*)ix->outb[1].p, *d_hw = (uint32_t*)ix->outb[2].p;
+    uint8_t* d_cnt = (uint8_t*)ix->outb[3].p;
+    unsigned long long *d_mult = (unsigned long long*)ix->outb[4].p, *d_total = (unsigned long long*)ix->outb[5].p;
+    CU_TRY(cudaMemsetAsync(d_total, 0, 8, c->stream));
+    CU_TRY(cudaMemcpyAsync(d_q, q, Q * 4, cudaMemcpyHostToDevice, c->stream));
+    const uint32_t gy_total = (uint32_t)((Q + bdg::KS_QB - 1) / bdg::KS_QB);
+    const uint32_t gx = (uint32_t)((W + bdg::NT - 1) / bdg::NT);
+    if (gy_total > 65535u) return fail(BDG_ERR_ARG, "Q too large for one call (> 65535*256 queries)");
+    bdg::kmer_score_kernel<<<dim3(gx, gy_total), bdg::NT, 0, c->stream>>>(d_q, (uint32_t)Q, (const uint32_t*)ix->wl.p, (uint32_t)W, min_kmers,
+                                                                       (unsigned long long)cap, d_hq, d_hw, d_cnt, d_mult, d_total);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    unsigned long long tot = 0;
+    CU_TRY(cudaMemcpyAsync(&tot, d_total, 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(cudaStreamSynchronize(c->stream));
+    const size_t n = (size_t)std::min<unsigned long long>(tot, cap);
+    if (n) {
+        CU_TRY(cudaMemcpyAsync(hit_q, d_hq, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaMemcpyAsync(hit_w, d_hw, n * 4, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaMemcpyAsync(cnt, d_cnt, n, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaMemcpyAsync(mult, d_mult, n * 8, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(cudaStreamSynchronize(c->stream));
+    }
+    *total = (size_t)tot;
+    if (tot > cap) return fail(BDG_ERR_CAPACITY, "%llu hits but room for %zu", tot, cap);
+    return BDG_OK;
+}
+
 int bdg_kmer_score(const uint32_t* q, size_t Q, const uint32_t* wl, size_t W, int min_kmers, size_t cap, uint32_t* hit_q,
                    uint32_t* hit_w, uint8_t* cnt, uint64_t* mult, size_t* total)
 {
@@ -1010,46 +1097,11 @@ int bdg_kmer_score(const uint32_t* q, size_t Q, const uint32_t* wl, size_t W, in
     *total = 0;
     if (Q == 0 || W == 0) return BDG_OK;
     if (!q || !wl || (cap && (!hit_q || !hit_w || !cnt || !mult))) return fail(BDG_ERR_ARG, "NULL pointer argument");
-    if (W > 0xFFFFFFFFull || Q > 0xFFFFFFFFull) return fail(BDG_ERR_ARG, "size exceeds 2^32");
-    if (int rc = need_ctx()) return rc;
-    DevCtx& c = g_ctx[0];
-    CU_TRY(cudaSetDevice(c.dev));
-    uint32_t *d_q = nullptr, *d_wl = nullptr, *d_hq = nullptr, *d_hw = nullptr; uint8_t* d_cnt = nullptr;
-    unsigned long long *d_mult = nullptr, *d_total = nullptr;
-    const size_t capa = std::max<size_t>(cap, 1);
-    CU_TRY(cudaMallocAsync((void**)&d_q, Q * 4, c.stream));
-    CU_TRY(cudaMallocAsync((void**)&d_wl, W * 4, c.stream));
-    CU_TRY(cudaMallocAsync((void**)&d_hq, capa * 4, c.stream));
-    CU_TRY(cudaMallocAsync((void**)&d_hw, capa * 4, c.stream));
-    CU_TRY(cudaMallocAsync((void**)&d_cnt, capa, c.stream));
-    CU_TRY(cudaMallocAsync((void**)&d_mult, capa * 8, c.stream));
-    CU_TRY(cudaMallocAsync((void**)&d_total, 8, c.stream));
-    CU_TRY(cudaMemsetAsync(d_total, 0, 8, c.stream));
-    CU_TRY(cudaMemcpyAsync(d_q, q, Q * 4, cudaMemcpyHostToDevice, c.stream));
-    CU_TRY(cudaMemcpyAsync(d_wl, wl, W * 4, cudaMemcpyHostToDevice, c.stream));
-    const uint32_t gy_total = (uint32_t)((Q + bdg::KS_QB - 1) / bdg::KS_QB);
-    const uint32_t gx = (uint32_t)((W + bdg::NT - 1) / bdg::NT);
-    if (gy_total > 65535u) return fail(BDG_ERR_ARG, "Q too large for one call (> 65535*256 queries)");
-    bdg::kmer_score_kernel<<<dim3(gx, gy_total), bdg::NT, 0, c.stream>>>(d_q, (uint32_t)Q, d_wl, (uint32_t)W, min_kmers,
-                                                                      (unsigned long long)cap, d_hq, d_hw, d_cnt, d_mult, d_total);
-    g_launches++;
-    CU_TRY(cudaGetLastError());
-    unsigned long long tot = 0;
-    CU_TRY(cudaMemcpyAsync(&tot, d_total, 8, cudaMemcpyDeviceToHost, c.stream));
-    CU_TRY(cudaStreamSynchronize(c.stream));
-    const size_t n = (size_t)std::min<unsigned long long>(tot, cap);
-    if (n) {
-        CU_TRY(cudaMemcpyAsync(hit_q, d_hq, n * 4, cudaMemcpyDeviceToHost, c.stream));
-        CU_TRY(cudaMemcpyAsync(hit_w, d_hw, n * 4, cudaMemcpyDeviceToHost, c.stream));
-        CU_TRY(cudaMemcpyAsync(cnt, d_cnt, n, cudaMemcpyDeviceToHost, c.stream));
-        CU_TRY(cudaMemcpyAsync(mult, d_mult, n * 8, cudaMemcpyDeviceToHost, c.stream));
-    }
-    cudaFreeAsync(d_q, c.stream); cudaFreeAsync(d_wl, c.stream); cudaFreeAsync(d_hq, c.stream); cudaFreeAsync(d_hw, c.stream);
-    cudaFreeAsync(d_cnt, c.stream); cudaFreeAsync(d_mult, c.stream); cudaFreeAsync(d_total, c.stream);
-    CU_TRY(cudaStreamSynchronize(c.stream));
-    *total = (size_t)tot;
-    if (tot > cap) return fail(BDG_ERR_CAPACITY, "%llu hits but room for %zu", tot, cap);
-    return BDG_OK;
+    bdg_kmer_index* ix = nullptr;
+    if (int rc = bdg_kmer_index_create(wl, W, &ix)) return rc;
+    const int rc = bdg_kmer_index_query(ix, q, Q, min_kmers, cap, hit_q, hit_w, cnt, mult, total);
+    bdg_kmer_index_free(ix);
+    return rc;
 }
 
 }  // extern "C"

@@ -207,6 +207,24 @@ BDG_HD bool quick_pass(uint32_t a, uint32_t b, int t)
     return u == 0;
 }
 
+// The same idea for any threshold (dense kernel, t >= 3): with <= t operations and a length difference <= 1 no
+// aligned column is more than k = (t+1)/2 bases off the main diagonal, so every column 0..14 of a is matched on one
+// of the diagonals -k..k or consumed by an operation: more than t columns that mismatch on ALL of them prove D > t.
+BDG_HD bool quick_pass_any(uint32_t a, uint32_t b, int t)
+{
+    const int k = (t + 1) / 2;
+    const uint32_t x0 = a ^ b;
+    uint32_t u = (x0 | (x0 << 1)) & QUICK_VALID;
+    for (int s = 1; s <= k && s < 16 && u; s++) {
+        const uint32_t xp = a ^ (b >> (2 * s));                 // a[i] vs b[i+s]: columns 16-s.. have no partner ...
+        const uint32_t xm = a ^ (b << (2 * s));                 // a[i] vs b[i-s]: columns ..s-1 have no partner
+        const uint32_t nop = ~(0xFFFFFFFFu >> (2 * s)), nom = ~(0xFFFFFFFFu << (2 * s));   // ... and count as mismatches there
+        u &= ((xp | (xp << 1)) | nop) & ((xm | (xm << 1)) | nom);
+    }
+    for (int i = 0; i < t && u; i++) u &= u - 1;
+    return u == 0;
+}
+
 constexpr int MAX_PASSES = 3;
 BDG_HD int n_passes(int t) { return t == 1 ? 2 : (t == 2 ? 3 : 0); }
 BDG_HD int pass_rot(int t, int p) { return t == 1 ? (p == 1 ? 16 : 0) : 10 * p; }

@@ -19,7 +19,7 @@
 //   * stage 2 is warp-cooperative: whenever the queue holds >= 32 candidates, each lane takes one, evaluates
 //     D and S exactly (bdg_core.cuh) and the warp appends the edges it found with one atomic.  The rare,
 //     expensive exact test therefore runs with 32 busy lanes instead of one.
-// MODE 1: t = 1.  MODE 2: t = 2.  MODE 3: any t, no prefilter (every pair goes through stage 2).
+// MODE 1: t = 1.  MODE 2: t = 2.  MODE 3: any t: the generic quick test (quick_pass_any) in front of the bit-vector distance.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -376,7 +376,7 @@ __global__ void __launch_bounds__(ENT, 3) edges_kernel(const EdgeWork w, const E
                         const uint32_t b = pick4(B, kk);
 #pragma unroll
                         for (int r = 0; r < RA; r++) {
-                            const bool hit = MODE == 1 ? prefilter_t1(a[r], b) : (MODE == 2 ? prefilter_t2(a[r], b) : true);
+                            const bool hit = MODE == 1 ? prefilter_t1(a[r], b) : (MODE == 2 ? prefilter_t2(a[r], b) : quick_pass_any(a[r], b, w.t));
                             h[0] |= (hit ? 1u : 0u) << (kk * 8 + r);
                         }
                     }

@@ -59,10 +59,10 @@ class QGramIndex:
             raise NotImplementedError("the B200 path indexes 16-bp barcodes by 6-mers only")
         if not self._packed:
             return []
-        if self._arr is None:
-            self._arr = np.asarray(self._packed, dtype=np.uint32)
+        if self._arr is None:                          # (re)build the device-resident index after add_to_index
+            self._arr = ops.KmerIndex(np.asarray(self._packed, dtype=np.uint32))
         q = np.asarray([rank(barcode, 16)], dtype=np.uint32)
-        _, hw, _, _ = ops.kmer_score(q, self._arr, min_kmers=self.threshold)
+        _, hw, _, _ = self._arr.query(q, min_kmers=self.threshold)
         out = {}
         for w in np.sort(hw).tolist():
             j = self._numbers[w]

@@ -51,10 +51,10 @@ class KmerIndexer:
         if not self.seq_list:
             return {}
         self._require_gpu_shape(sequence)
-        if self._packed is None:
-            self._packed = ops.pack16(self.seq_list)[0]
+        if self._packed is None:                      # (re)build the device-resident index after a change of the string list
+            self._packed = ops.KmerIndex(ops.pack16(self.seq_list)[0])
         q = ops.pack16([sequence])[0]
-        _, hw, cnt, mult = ops.kmer_score(q, self._packed, min_kmers=1)
+        _, hw, cnt, mult = self._packed.query(q, min_kmers=1)
         if hw.size == 0:
             return {}
         first_pos = np.argmax(mult > 0, axis=1)

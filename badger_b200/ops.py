@@ -161,19 +161,15 @@ def nearest_bounded(q: np.ndarray, targets_in_order: np.ndarray, max_d: int = 2)
     return am, dist
 
 
-def kmer_score(q: np.ndarray, wl: np.ndarray, min_kmers: int = 1, cap: int | None = None):
-    """kmer_indexer.py:49-61 counting step for packed 16-mers, k=6.
-    Returns (hit_q, hit_w, cnt, mult[hits,11]) for every pair with cnt >= min_kmers (order unspecified)."""
+def _kmer_query(call, q, n_known, min_kmers, cap):
     q = np.ascontiguousarray(q, dtype=np.uint32)
-    wl = np.ascontiguousarray(wl, dtype=np.uint32)
     if cap is None:
-        cap = max(1024, 4 * wl.size)
+        cap = max(1024, 4 * n_known)
     while True:
         hq = np.empty(cap, np.uint32); hw = np.empty(cap, np.uint32)
         cnt = np.empty(cap, np.uint8); mult = np.empty(cap, np.uint64)
         total = C.c_size_t(0)
-        rc = lib().bdg_kmer_score(ptr(q), q.size, ptr(wl), wl.size, int(min_kmers), cap,
-                                  ptr(hq), ptr(hw), ptr(cnt), ptr(mult), C.byref(total))
+        rc = call(ptr(q), q.size, int(min_kmers), cap, ptr(hq), ptr(hw), ptr(cnt), ptr(mult), C.byref(total))
         if rc == _lib.BDG_ERR_CAPACITY:
             cap = int(total.value)
             continue
@@ -182,3 +178,36 @@ def kmer_score(q: np.ndarray, wl: np.ndarray, min_kmers: int = 1, cap: int | Non
         m = mult[:n]
         nib = np.stack([(m >> np.uint64(4 * p)) & np.uint64(15) for p in range(11)], 1).astype(np.uint8) if n else np.zeros((0, 11), np.uint8)
         return hq[:n].copy(), hw[:n].copy(), cnt[:n].copy(), nib
+
+
+def kmer_score(q: np.ndarray, wl: np.ndarray, min_kmers: int = 1, cap: int | None = None):
+    """kmer_indexer.py:49-61 counting step for packed 16-mers, k=6.
+    Returns (hit_q, hit_w, cnt, mult[hits,11]) for every pair with cnt >= min_kmers (order unspecified)."""
+    wl = np.ascontiguousarray(wl, dtype=np.uint32)
+    L = lib()
+    return _kmer_query(lambda *a: L.bdg_kmer_score(a[0], a[1], ptr(wl), wl.size, *a[2:]), q, wl.size, min_kmers, cap)
+
+
+class KmerIndex:
+    """The known strings of a KmerIndexer / QGramIndex, uploaded once and kept on the device (bdg_kmer_index)."""
+
+    def __init__(self, known: np.ndarray):
+        known = np.ascontiguousarray(known, dtype=np.uint32)
+        self.size = int(known.size)
+        self._h = C.c_void_p()
+        check(lib().bdg_kmer_index_create(ptr(known), known.size, C.byref(self._h)))
+
+    def query(self, q: np.ndarray, min_kmers: int = 1, cap: int | None = None):
+        L = lib()
+        return _kmer_query(lambda *a: L.bdg_kmer_index_query(self._h, *a), q, self.size, min_kmers, cap)
+
+    def free(self):
+        if self._h is not None and self._h.value:
+            lib().bdg_kmer_index_free(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass

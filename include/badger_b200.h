@@ -114,6 +114,14 @@ int bdg_nearest_bounded(const uint32_t* q, size_t Q, const uint32_t* targets_in_
 int bdg_kmer_score(const uint32_t* q, size_t Q, const uint32_t* wl, size_t W, int min_kmers, size_t cap,
                    uint32_t* hit_q, uint32_t* hit_w, uint8_t* cnt, uint64_t* mult, size_t* total);
 
+/* The same with the known strings kept on the device between queries - the life cycle of the reference's index objects
+ * (KmerIndexer.__init__ / QGramIndex.add_to_index build once, get_occurrences / get_close query many times). */
+typedef struct bdg_kmer_index bdg_kmer_index;
+int bdg_kmer_index_create(const uint32_t* wl, size_t W, bdg_kmer_index** out);
+int bdg_kmer_index_query(bdg_kmer_index* ix, const uint32_t* q, size_t Q, int min_kmers, size_t cap, uint32_t* hit_q,
+                         uint32_t* hit_w, uint8_t* cnt, uint64_t* mult, size_t* total);
+void bdg_kmer_index_free(bdg_kmer_index* ix);
+
 /* ---- device-resident variants (bench.py "value" path; torch owns the memory and the stream) -------- */
 /* Edge construction over rows of part/nparts.  d_count (one uint64, device) is zeroed by the call and receives
  * the number of edges found, which may exceed cap (only the first cap are stored).  The current device must have

@@ -47,6 +47,10 @@ void shim_quick(int t, const uint32_t* a, const uint32_t* b, size_t n, uint8_t* 
 {
     for (size_t i = 0; i < n; i++) out[i] = bdg::quick_pass(a[i], b[i], t);
 }
+void shim_quick_any(int t, const uint32_t* a, const uint32_t* b, size_t n, uint8_t* out)
+{
+    for (size_t i = 0; i < n; i++) out[i] = bdg::quick_pass_any(a[i], b[i], t);
+}
 int shim_top_possible(int t, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi)
 {
     return t == 1 ? bdg::t1_top_possible(alo, ahi, blo, bhi) : bdg::t2_top_possible(alo, ahi, blo, bhi);

@@ -51,6 +51,18 @@ def kmer_score(q, wl, min_kmers=1, cap=None):
     return qi.astype(np.uint32), wi.astype(np.uint32), cnt[qi, wi], mult[qi, wi]
 
 
+class KmerIndex:
+    def __init__(self, known):
+        self.known = np.ascontiguousarray(known, dtype=np.uint32)
+        self.size = int(self.known.size)
+
+    def query(self, q, min_kmers=1, cap=None):
+        return kmer_score(q, self.known, min_kmers, cap)
+
+    def free(self):
+        pass
+
+
 def dedup_first_seen(ranks, want_map=False, want_sorted_pos=False):
     r, c = orc.dedup_count(np.ascontiguousarray(ranks, dtype=np.uint32))
     out = (r, c.astype(np.int64))
@@ -85,5 +97,5 @@ def cluster_levels(sorted_unique, ea, eb, centres, rounds=2):
 def install(monkeypatch):
     from badger_b200 import ops
     for name in ("pack16", "edges_build", "edges_build_part", "member_sorted", "nearest_bounded", "kmer_score", "dedup_first_seen",
-                 "cluster_levels"):
+                 "cluster_levels", "KmerIndex"):
         monkeypatch.setattr(ops, name, globals()[name])

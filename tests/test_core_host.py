@@ -33,6 +33,7 @@ def shim(tmp_path_factory):
     L.shim_pass_possible.argtypes = [C.c_int, C.c_int] + [C.c_uint32] * 4
     L.shim_pass_possible.restype = C.c_int
     L.shim_quick.argtypes = [C.c_int, u32p, u32p, C.c_size_t, u8p]
+    L.shim_quick_any.argtypes = [C.c_int, u32p, u32p, C.c_size_t, u8p]
     L.shim_top_possible.argtypes = [C.c_int] + [C.c_uint32] * 4
     L.shim_top_possible.restype = C.c_int
     return L
@@ -340,3 +341,28 @@ def test_quick_pass_sound(shim, t):
     out = np.zeros(ra.size, np.uint8)
     shim.shim_quick(t, ra, rb, ra.size, out)
     assert out.mean() < (0.004 if t == 1 else 0.03)
+
+
+@pytest.mark.parametrize("t", [1, 2, 3, 4, 5])
+def test_quick_pass_any_sound(shim, t):
+    """Generic quick test of the dense kernel (t >= 3): never rejects a pair with D <= t, in both frames."""
+    L = orc.lib()
+    a, b = make_pairs(30 + t, n_near=40000, n_rand=5000, n_low=15000)
+    rng = np.random.default_rng(t)
+    extra_a, extra_b = [], []
+    for _ in range(20000):                      # more operations than make_pairs uses, so that D = 3..5 is well covered
+        x = int(rng.integers(0, 1 << 32)); y = edit_ops(rng, x, int(rng.integers(3, 7)))
+        if x != y:
+            extra_a.append(x); extra_b.append(y)
+    a = np.concatenate([a, np.asarray(extra_a, np.uint32)]); b = np.concatenate([b, np.asarray(extra_b, np.uint32)])
+    D = np.fromiter((L.orc_D(int(x), int(y)) for x, y in zip(a, b)), np.int32, a.size)
+    for x, y in ((a, b), (b, a)):
+        out = np.zeros(x.size, np.uint8)
+        shim.shim_quick_any(t, x, y, x.size, out)
+        assert out[D <= t].all()
+    assert (D == t).sum() > 1000
+    ra = rng.integers(0, 1 << 32, 1 << 18, dtype=np.uint64).astype(np.uint32)
+    rb = rng.integers(0, 1 << 32, 1 << 18, dtype=np.uint64).astype(np.uint32)
+    out = np.zeros(ra.size, np.uint8)
+    shim.shim_quick_any(t, ra, rb, ra.size, out)
+    print("t", t, "random pass rate", out.mean())

@@ -437,6 +437,29 @@ def test_kmer_score_vs_oracle():
     assert hw.size >= 5
 
 
+def test_resident_kmer_index_many_queries():
+    """KmerIndexer / QGramIndex keep their strings on the device (ops.KmerIndex): repeated queries, growth after append."""
+    rng = np.random.default_rng(12)
+    wl = rng.integers(0, 1 << 32, 5000, dtype=np.uint64).astype(np.uint32)
+    ix = ops.KmerIndex(wl)
+    for _ in range(5):
+        q = wl[rng.integers(0, wl.size, 7)] ^ np.uint32(1 << int(rng.integers(0, 32)))
+        hq, hw, cnt, mult = ix.query(q, min_kmers=3)
+        wc, wm = orc.kmer_score(q, wl)
+        wq, ww = np.nonzero(wc >= 3)
+        o = np.lexsort((hw, hq))
+        assert np.array_equal(hq[o], wq) and np.array_equal(hw[o], ww) and np.array_equal(cnt[o], wc[wq, ww])
+    ix.free()
+    known = [orc.unrank(int(x)) for x in wl[:300].tolist()]
+    ki = KmerIndexer(known, 6)
+    before = ki.get_occurrences(known[5], min_kmers=2)
+    assert known[5] in before
+    extra = orc.unrank(int(wl[4000]))
+    ki.append(extra)
+    after = ki.get_occurrences(extra, min_kmers=2)
+    assert extra in after and after[extra][1] == 121 or after[extra][1] >= 11       # S(x,x) >= 11
+
+
 # ------------------------------------------------------------------------------------------ full size: properties
 def test_c2_full_size_properties(mode):
     """BASELINE config 2 at full size (1 M reads, t=1): sampled rows against the oracle's index walk, plus
