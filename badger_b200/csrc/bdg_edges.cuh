@@ -512,10 +512,11 @@ __device__ __forceinline__ void sparse_process(const SparseCtx& c, const EdgeOut
     uint32_t x = 0, y = 0;
     int d = 0;
     if (active && e.x < e.y && e.y < c.N) {             // each unordered pair once: row index < column index
-        x = rotr32(__ldg(&c.sorted[e.x]), c.rot);
-        y = rotr32(__ldg(&c.sorted[e.y]), c.rot);
+        const uint32_t xr = __ldg(&c.sorted[e.x]), yr = __ldg(&c.sorted[e.y]);
+        x = rotr32(xr, c.rot);
+        y = rotr32(yr, c.rot);
         if (x > y) { const uint32_t tmp = x; x = y; y = tmp; }
-        bool mine = pass_pred(T_, P_, x, y);            // found by this pass and by no earlier one
+        bool mine = pass_pred_rot(T_, P_, xr, yr);      // found by this pass (predicates are orientation-free) and by no earlier one
 #pragma unroll
         for (int q = 0; q < P_; q++) mine = mine && !pass_pred(T_, q, x, y);
         if (mine) {
@@ -596,7 +597,7 @@ __device__ __forceinline__ void sparse_push(uint32_t h, uint32_t row0, uint32_t 
 }
 
 template <int T_, int P_, bool BIP>
-__global__ void __launch_bounds__(ENT, 3) sparse_tile_kernel(const EdgeWork w, const EdgeOut out, const TileList list)
+__global__ void __launch_bounds__(ENT, 4) sparse_tile_kernel(const EdgeWork w, const EdgeOut out, const TileList list)
 {
     __shared__ __align__(16) uint32_t s_b[EW][3][SSB];   // unrotated b, b >> 2, b << 2 of the staged sub-tile
     __shared__ uint2 s_q[EW][SQCAP];

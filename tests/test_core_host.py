@@ -343,14 +343,14 @@ def test_quick_pass_sound(shim, t):
     assert out.mean() < (0.004 if t == 1 else 0.03)
 
 
-@pytest.mark.parametrize("t", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("t", [2, 3, 5])
 def test_quick_pass_any_sound(shim, t):
     """Generic quick test of the dense kernel (t >= 3): never rejects a pair with D <= t, in both frames."""
     L = orc.lib()
-    a, b = make_pairs(30 + t, n_near=40000, n_rand=5000, n_low=15000)
+    a, b = make_pairs(30 + t, n_near=25000, n_rand=3000, n_low=8000)
     rng = np.random.default_rng(t)
     extra_a, extra_b = [], []
-    for _ in range(20000):                      # more operations than make_pairs uses, so that D = 3..5 is well covered
+    for _ in range(12000):                      # more operations than make_pairs uses, so that D = 3..5 is well covered
         x = int(rng.integers(0, 1 << 32)); y = edit_ops(rng, x, int(rng.integers(3, 7)))
         if x != y:
             extra_a.append(x); extra_b.append(y)
