@@ -41,6 +41,9 @@ def lib():
     L.bdg_init.argtypes = [_vp, _i]
     L.bdg_device_count.restype = _i
     L.bdg_launch_count.restype = C.c_ulonglong
+    L.bdg_host_alloc.argtypes = [_sz, C.POINTER(_vp)]
+    L.bdg_host_free.argtypes = [_vp]
+    L.bdg_host_free.restype = None
     L.bdg_pack16.argtypes = [_vp, _sz, _vp, _vp]
     L.bdg_dedup_first_seen.argtypes = [_vp, _sz, _vp, _vp, _vp, _vp, C.POINTER(_sz)]
     L.bdg_edges_build.argtypes = [_vp, _sz, _i, C.POINTER(_vp)]
@@ -69,7 +72,7 @@ def lib():
     L.bdg_part_pairs.argtypes = [_sz, _i, _i]
     L.bdg_part_pairs.restype = C.c_ulonglong
     L.bdg_dev_pipe_probe.argtypes = [_i, _i, _i, _vp, C.POINTER(C.c_ulonglong), _vp]
-    for name in ("bdg_init", "bdg_pack16", "bdg_dedup_first_seen", "bdg_edges_build", "bdg_edges_build_part", "bdg_edges_copy", "bdg_cluster_levels", "bdg_cluster_levels_from_edges", "bdg_member_sorted",
+    for name in ("bdg_init", "bdg_host_alloc", "bdg_pack16", "bdg_dedup_first_seen", "bdg_edges_build", "bdg_edges_build_part", "bdg_edges_copy", "bdg_cluster_levels", "bdg_cluster_levels_from_edges", "bdg_member_sorted",
                  "bdg_nearest_bounded", "bdg_kmer_score", "bdg_kmer_index_create", "bdg_kmer_index_query", "bdg_dev_edges_build", "bdg_set_edge_mode", "bdg_dev_edges_stats", "bdg_dev_edges_balance", "bdg_dev_pack16", "bdg_dev_member_sorted",
                  "bdg_dev_nearest_bounded", "bdg_dev_pipe_probe"):
         getattr(L, name).restype = _i

@@ -498,6 +498,23 @@ int bdg_dev_edges_build(const uint32_t* d_sorted, size_t N, int t, int part, int
     return launch_edges(d_sorted, N, t, part, nparts, d_a, d_b, d_d, cap, d_count, (cudaStream_t)stream, c);
 }
 
+// Page-locked host memory for callers that want device-to-host copies at full PCIe speed (badger_b200.ops keeps a small
+// pool of such blocks behind the numpy arrays it returns).
+int bdg_host_alloc(size_t bytes, void** out)
+{
+    if (!out) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    *out = nullptr;
+    if (int rc = need_ctx()) return rc;
+    cudaError_t e = cudaHostAlloc(out, std::max<size_t>(bytes, 1), cudaHostAllocPortable);
+    if (e != cudaSuccess) { *out = nullptr; return fail(BDG_ERR_OOM, "cudaHostAlloc of %zu bytes: %s", bytes, cudaGetErrorString(e)); }
+    return BDG_OK;
+}
+
+void bdg_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
 int bdg_set_edge_mode(int mode)
 {
     if (mode < -1 || mode > 1) return fail(BDG_ERR_ARG, "edge mode must be -1 (default), 0 (dense) or 1 (sparse)");
@@ -716,8 +733,16 @@ static int edges_on_device(DevCtx& c, const uint32_t* sorted, size_t N, int t, i
     };
     CU_TRY(cudaSetDevice(c.dev));
     if (int e = ensure(c.sorted, std::max<size_t>(N, 1) * 4)) return e;
-    if (int e = ensure(c.count, sizeof(unsigned long long))) return e;
+    if (int e = ensure(c.count, 2 * sizeof(unsigned long long))) return e;      // [edge count | first unsorted index]
     CU_TRY(cudaMemcpyAsync(c.sorted.p, sorted, N * 4, cudaMemcpyHostToDevice, c.stream));
+    // the input must be strictly increasing: checked on the device, read back together with the edge count
+    unsigned long long* d_bad = (unsigned long long*)c.count.p + 1;
+    unsigned long long first_bad = ~0ull;
+    CU_TRY(cudaMemsetAsync(d_bad, 0xFF, 8, c.stream));
+    if (N > 1) {
+        bdg::sorted_check_kernel<<<(int)std::min<size_t>((N + 255) / 256, (size_t)c.sms * 8), 256, 0, c.stream>>>((const uint32_t*)c.sorted.p, (uint32_t)N, d_bad);
+        g_launches++;
+    }
     size_t cap = std::max(edge_cap_guess(N, t, nparts), c.ea.cap / 4);
     unsigned long long count = 0;
     bool done = false;
@@ -727,8 +752,12 @@ static int edges_on_device(DevCtx& c, const uint32_t* sorted, size_t N, int t, i
         if (int e = ensure(c.ed, cap)) return e;
         if (int e = launch_edges((const uint32_t*)c.sorted.p, N, t, part, nparts, (uint32_t*)c.ea.p, (uint32_t*)c.eb.p, (uint8_t*)c.ed.p, cap,
                                  (unsigned long long*)c.count.p, c.stream, &c)) return e;
-        CU_TRY(cudaMemcpyAsync(&count, c.count.p, sizeof(count), cudaMemcpyDeviceToHost, c.stream));
+        unsigned long long both[2] = {0, 0};
+        CU_TRY(cudaMemcpyAsync(both, c.count.p, sizeof(both), cudaMemcpyDeviceToHost, c.stream));
         CU_TRY(cudaStreamSynchronize(c.stream));
+        count = both[0];
+        first_bad = both[1];
+        if (first_bad != ~0ull) return fail(BDG_ERR_ARG, "input not strictly increasing at index %llu", first_bad);
         if (count >> 63) {                     // rare: a sparse pass listed more tiles than the list holds; grow it and run again
             unsigned long long hdr[(PLAN_HDR / 8) * bdg::MAX_PASSES];
             CU_TRY(cudaMemcpy(hdr, c.plan.p, sizeof(hdr), cudaMemcpyDeviceToHost));
@@ -792,8 +821,7 @@ int bdg_edges_build(const uint32_t* sorted_unique, size_t N, int t, bdg_edges** 
 {
     if (!out || (N && !sorted_unique)) return fail(BDG_ERR_ARG, "NULL pointer argument");
     *out = nullptr;
-    if (int rc = check_sorted(sorted_unique, N)) return rc;
-    if (int rc = need_ctx()) return rc;
+    if (int rc = need_ctx()) return rc;                    // (the strictly-increasing check runs on the device)
     bdg_edges* res = new (std::nothrow) bdg_edges();
     if (!res) return fail(BDG_ERR_OOM, "host allocation failed");
     std::vector<int> idx, parts;
@@ -813,7 +841,6 @@ int bdg_edges_build_part(const uint32_t* sorted_unique, size_t N, int t, int par
     if (!out || (N && !sorted_unique)) return fail(BDG_ERR_ARG, "NULL pointer argument");
     *out = nullptr;
     if (nparts < 1 || part < 0 || part >= nparts) return fail(BDG_ERR_ARG, "part %d of %d is not a valid part", part, nparts);
-    if (int rc = check_sorted(sorted_unique, N)) return rc;
     if (int rc = need_ctx()) return rc;
     bdg_edges* res = new (std::nothrow) bdg_edges();
     if (!res) return fail(BDG_ERR_OOM, "host allocation failed");
@@ -837,6 +864,7 @@ int bdg_edges_copy(const bdg_edges* e, uint32_t* a, uint32_t* b, uint8_t* d)
     if (!e) return fail(BDG_ERR_ARG, "NULL edge handle");
     const size_t n = bdg_edges_count(e);
     if (n && (!a || !b || !d)) return fail(BDG_ERR_ARG, "NULL output pointer");
+    const double tc0 = now_ms();
     size_t off = 0;
     for (size_t g = 0; g < e->ctx.size(); g++) {
         if (e->ctx[g] < 0 || (size_t)e->ctx[g] >= g_ctx.size() || g_ctx[e->ctx[g]].generation != e->gen[g])
@@ -854,6 +882,7 @@ int bdg_edges_copy(const bdg_edges* e, uint32_t* a, uint32_t* b, uint8_t* d)
     for (size_t g = 0; g < e->ctx.size(); g++)
         if (e->count[g]) { CU_TRY(cudaSetDevice(g_ctx[e->ctx[g]].dev)); CU_TRY(cudaStreamSynchronize(g_ctx[e->ctx[g]].stream)); }
     if (!g_ctx.empty()) cudaSetDevice(g_ctx[0].dev);
+    if (getenv("BDG_TRACE")) fprintf(stderr, "[bdg] edges_copy %zu edges %.3f ms\n", n, now_ms() - tc0);
     return BDG_OK;
 }
 

@@ -707,6 +707,15 @@ __global__ void __launch_bounds__(ENT, 4) sparse_tile_kernel(const EdgeWork w, c
     }
 }
 
+// first index i with v[i] <= v[i-1] (the edge construction needs a strictly increasing array); *first_bad primed with ~0
+__global__ void sorted_check_kernel(const uint32_t* __restrict__ v, uint32_t n, unsigned long long* __restrict__ first_bad)
+{
+    unsigned long long bad = ~0ull;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += gridDim.x * blockDim.x)
+        if (__ldg(&v[i]) <= __ldg(&v[i - 1])) { bad = i; break; }
+    if (bad != ~0ull) atomicMin(first_bad, bad);
+}
+
 // rotl(key, rot) and the identity payload for a whole array (input of the per-pass radix sort of the bipartite form)
 __global__ void rotate_keys_iota_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t* __restrict__ pay, uint32_t n, int rot)
 {

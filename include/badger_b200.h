@@ -53,6 +53,10 @@ int bdg_device_count(void);         /* devices held by this process after bdg_in
 const char* bdg_last_error(void);   /* thread-local; valid until the next call on this thread */
 const char* bdg_version(void);
 
+/* Page-locked host memory (cudaHostAlloc) for output buffers: device-to-host copies into it run at full PCIe speed. */
+int bdg_host_alloc(size_t bytes, void** out);
+void bdg_host_free(void* p);
+
 /* ---- a-1  rank(): common.py:21-25 (called per read at barcode_graph.py:198) ----------------------- */
 /* seqs: R records of exactly 16 bytes, no terminator.  valid[i] = 1 iff all 16 bytes are in "ACGT"
  * (the reference raises KeyError otherwise, common.py:24); out[i] is undefined when valid[i] == 0. */
