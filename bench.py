@@ -49,7 +49,7 @@ A_QUICK = {1: 14.5, 2: 16.5}       # 58 / 66 SASS instructions per 4 pairs
 A_LIGHT = {1: 1.25, 2: 6.0}
 A_EXACT = 110                      # loads, un-rotation, pass predicates, dist_small
 A_SCORE = 220                      # qgram_score, only for pairs with D <= t
-# DRAM traffic of one step's dominant kernels from the ncu --set full capture of this round (profiles/r1d_sparse_t*_ncu_full.txt:
+# DRAM traffic of one step's dominant kernels from the ncu --set full capture of this round (profiles/r1e_sparse_t*_ncu_full.txt:
 # dram__bytes_read.sum + dram__bytes_write.sum of the scan + tile kernels of all passes, C2, N = 492 093).  Writes stay in L2.
 NCU_TRAFFIC_BYTES = {1: 536064 + 2174976 + 535040 + 2056704, 2: 3 * 535808 + 2710528 + 2709760 + 2153728 + 1280}
 A_PAIR_SURVEY = {1: 15, 2: 25}   # SURVEY.md §8(d) nominal per-pair figure of a plain all-pairs kernel, reported alongside
