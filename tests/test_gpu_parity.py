@@ -142,6 +142,30 @@ def test_packed_pipeline_golden(gold_pipeline):
             assert (orc.unrank(int(c)) if c != pipeline.NONE else None) == want_hs.get(o), o
 
 
+def test_packed_pipeline_edge_cases_and_true_barcodes():
+    """assign_packed on empty / all-invalid input, and the --true_barcodes branch against the string mirror."""
+    from badger_b200 import pipeline
+    out, info = pipeline.assign_packed(np.empty(0, np.uint32), threshold=1, n_cells=10)
+    assert out.size == 0 and info["reads"] == 0
+    out, info = pipeline.assign_packed(np.arange(5, dtype=np.uint32), np.zeros(5, bool), threshold=1, n_cells=10)
+    assert (out == pipeline.NONE).all() and info["valid_reads"] == 0
+    rng = synth.rng_for(77)
+    cells = rng.integers(0, 1 << 32, 50, dtype=np.uint64).astype(np.uint32)
+    obs, valid = synth.simulate_reads(cells, 8000, 0.06, rng)
+    tb = cells[:40].tolist()
+    out, info = pipeline.assign_packed(obs, valid, threshold=2, n_cells=40, true_barcodes=tb, high_sens=True)
+    strs = [s.decode() for s in synth.unrank_many(obs[valid]).tolist()]
+    bg = BarcodeGraph(2)
+    bg.graph_construction(strs, 16, 1)
+    bg.cluster([orc.unrank(int(c)) for c in tb], None, 40, 16, 25)
+    assign = bg.assign_by_cluster(16)
+    used = sorted({orc.rank(v) for v in assign.values() if v not in ("", "*")})
+    assign = bg.postprocessing(assign, 16, _centre_order=[orc.unrank(u) for u in used])     # ascending order, as assign_packed's default
+    want = [assign[s_] if assign[s_] not in ("", "*") else None for s_ in strs]
+    got = [orc.unrank(int(c)) if c != pipeline.NONE else None for c in out[valid].tolist()]
+    assert got == want and sum(g is not None for g in got) > 6000
+
+
 def test_c1_golden(gold_c1):
     wl, cells, obs, valid, cfg = synth.make_dataset("C1")
     strs = [s.decode() for s in synth.unrank_many(obs[valid]).tolist()]
