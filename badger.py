@@ -11,6 +11,7 @@ import sys
 from io import StringIO
 from traceback import print_exc
 
+import numpy as np
 import pandas as pd
 
 from badger_b200 import BarcodeGraph, init
@@ -46,6 +47,9 @@ def parse_args(args):
     parser.add_argument("--threads", "-tr", dest="threads", default=1, type=int)
     parser.add_argument("--high_sens", "-hs", action='store_true', help="if set, Badger is run in high sensitivity mode. This increases recall but decreases precision", default=False)
     parser.add_argument("--devices", help="comma-separated CUDA device ids (default: all visible)", type=str, default=None)
+    parser.add_argument("--no_native_io", action='store_true', default=False,
+                        help="read and write the TSVs through pandas and the dict-shaped BarcodeGraph (the slower route the native "
+                             "reader falls back to by itself when it declines a file)")
     ns = parser.parse_args(args)
     if ns.reads is None:
         ns.reads = ns.bar_file
@@ -61,6 +65,48 @@ def set_logger(logger_instance):
     c_handler.setFormatter(logging.Formatter('%(asctime)s - %(levelname)s - %(message)s'))
     logger_instance.addHandler(c_handler)
     logger_instance.info("Starting")
+
+
+def run_native(args, bc_len, true_barcodes):
+    """The same run without per-read Python: extraction TSV and whitelist read by the native library (badger_b200.tsvio),
+    barcodes packed on the GPU, the array form of graph construction / clustering / assignment
+    (badger_b200.pipeline.assign_packed), output TSV written by the native library.  Same output file and same stdout as
+    the route below.  Returns False - nothing done yet - when the reader declines the file (anything pandas would treat
+    specially): the caller then goes through pandas like the reference."""
+    from badger_b200 import ops, pipeline, tsvio
+    from badger_b200.common import rank
+    try:
+        tsv = tsvio.ExtractionTsv(args.reads, bc_len)
+    except tsvio.Unsupported as e:
+        logger.info("%s - reading through pandas", e)
+        return False
+    with tsv:
+        logger.info("Imported barcodes from file")
+        init([int(x) for x in args.devices.split(",")] if args.devices else None)
+        logger.info("Initializing Graph")
+        print("k:", 6)                                          # index.py:21 (QGramIndex.__init__)
+        has = tsv.has_barcode
+        ranks = np.zeros(tsv.rows, np.uint32)
+        packed, ok = ops.pack16(tsv.seqs16[has].tobytes())
+        if not ok.all():                                        # common.py:24: rank() raises KeyError(letter)
+            bad = bytes(tsv.seqs16[has][int(np.argmin(ok))]).decode("ascii", "replace")
+            raise KeyError(next(c for c in bad if c not in "ACGT"))
+        ranks[has] = packed
+        whitelist = None
+        if args.barcode_list:                                   # badger.py:82-88
+            w, wok = ops.pack16(tsvio.whitelist_records(args.barcode_list).tobytes())
+            whitelist = np.unique(w[wok])
+        tb = [rank(bc, bc_len) for bc in true_barcodes] if true_barcodes else None
+        centre, info = pipeline.assign_packed(ranks, has, threshold=args.threshold, n_cells=args.n_cells, interval=args.interval,
+                                              whitelist_sorted=whitelist, true_barcodes=tb, high_sens=args.high_sens,
+                                              centre_order="set")
+        logger.info("Graph construction done")
+        print(1)                                                # barcode_graph.py:289 prints the round number
+        print(2)
+        logger.info("Clustering done")
+        tsv.write(args.output + "_output_file.tsv", centre)
+        print(info["disconnected"])                             # badger.py:131-132
+    return True
 
 
 def main(args):
@@ -79,13 +125,17 @@ def main(args):
                 true_barcodes[i] = true_barcodes[i][:-2]
         true_barcodes = set(true_barcodes)
 
+    out = args.output
+    if args.reads.endswith("tsv") and not args.stats and not args.no_native_io:
+        if run_native(args, bc_len, true_barcodes):
+            return
+
     if args.barcode_list:                                       # badger.py:82-88
         with open(args.barcode_list, "r") as list_file:
             barcode_list = set(list_file.read().split("\n"))
     else:
         barcode_list = None
 
-    out = args.output
     if not args.reads.endswith("tsv"):
         logger.error("FASTQ/FASTA/BAM input needs the barcode extraction step, which this drop-in does not replace; "
                      "run the reference's extract_raw_barcodes.py and pass its TSV")

@@ -13,7 +13,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libbadger_b200.so")
 
-BDG_OK, BDG_ERR_CUDA, BDG_ERR_OOM, BDG_ERR_ARG, BDG_ERR_NODEVICE, BDG_ERR_CAPACITY = 0, -1, -2, -3, -4, -5
+BDG_OK, BDG_ERR_CUDA, BDG_ERR_OOM, BDG_ERR_ARG, BDG_ERR_NODEVICE, BDG_ERR_CAPACITY, BDG_ERR_UNSUPPORTED, BDG_ERR_IO = 0, -1, -2, -3, -4, -5, -6, -7
 ROW_TILE = 2048  # BDG_ROW_TILE
 
 
@@ -72,9 +72,23 @@ def lib():
     L.bdg_part_pairs.argtypes = [_sz, _i, _i]
     L.bdg_part_pairs.restype = C.c_ulonglong
     L.bdg_dev_pipe_probe.argtypes = [_i, _i, _i, _vp, C.POINTER(C.c_ulonglong), _vp]
+    L.bdg_tsv_open.argtypes = [C.c_char_p, _i, _i, C.POINTER(_vp)]
+    L.bdg_tsv_rows.argtypes = [_vp]
+    L.bdg_tsv_rows.restype = _sz
+    L.bdg_tsv_barcodes.argtypes = [_vp, _vp, _vp]
+    L.bdg_tsv_write_assignments.argtypes = [_vp, C.c_char_p, _vp, _i]
+    L.bdg_tsv_close.argtypes = [_vp]
+    L.bdg_tsv_close.restype = None
+    L.bdg_lines16_open.argtypes = [C.c_char_p, C.POINTER(_vp)]
+    L.bdg_lines16_count.argtypes = [_vp]
+    L.bdg_lines16_count.restype = _sz
+    L.bdg_lines16_data.argtypes = [_vp]
+    L.bdg_lines16_data.restype = _vp
+    L.bdg_lines16_close.argtypes = [_vp]
+    L.bdg_lines16_close.restype = None
     for name in ("bdg_init", "bdg_host_alloc", "bdg_pack16", "bdg_dedup_first_seen", "bdg_edges_build", "bdg_edges_build_part", "bdg_edges_copy", "bdg_cluster_levels", "bdg_cluster_levels_from_edges", "bdg_member_sorted",
                  "bdg_nearest_bounded", "bdg_kmer_score", "bdg_kmer_index_create", "bdg_kmer_index_query", "bdg_dev_edges_build", "bdg_set_edge_mode", "bdg_dev_edges_stats", "bdg_dev_edges_balance", "bdg_dev_pack16", "bdg_dev_member_sorted",
-                 "bdg_dev_nearest_bounded", "bdg_dev_pipe_probe"):
+                 "bdg_dev_nearest_bounded", "bdg_dev_pipe_probe", "bdg_tsv_open", "bdg_tsv_barcodes", "bdg_tsv_write_assignments", "bdg_lines16_open"):
         getattr(L, name).restype = _i
     _lib = L
     return L

@@ -15,6 +15,7 @@
 
 #include "../../include/badger_b200.h"
 #include "bdg_kernels.cuh"
+#include "bdg_tsv.hpp"
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
@@ -915,7 +916,7 @@ static int cluster_on_device(DevCtx& c, const uint32_t* d_sorted, size_t N, uint
     if (C) bdg::cluster_seed_kernel<<<(int)std::min<size_t>((C + 255) / 256, (size_t)c.sms * 8), 256, 0, st>>>(d_sorted, (uint32_t)N, d_cen, (uint32_t)C, d_ci, d_lv);
     g_launches += 2;
     if (E) {
-        bdg::cluster_index_kernel<<<eb, 256, 0, st>>>(d_sorted, (uint32_t)N, d_ea, d_eb, E);
+        bdg::cluster_index_kernel<<<eb, 256, 0, st>>>(d_sorted, (uint32_t)N, d_ea, d_eb, E, d_lv);
         g_launches++;
         for (int r = 1; r <= rounds; r++) {
             bdg::cluster_claim_kernel<<<eb, 256, 0, st>>>(d_ea, d_eb, E, r, d_ci, d_lv, d_min, d_max);
@@ -935,7 +936,7 @@ int bdg_cluster_levels(const uint32_t* sorted_unique, size_t N, const uint32_t* 
 {
     if (N == 0) return BDG_OK;
     if (!sorted_unique || !centre_idx || !level || (E && (!ea || !eb)) || (C && !centres)) return fail(BDG_ERR_ARG, "NULL pointer argument");
-    if (N > 0x7FFFFFFFull || rounds < 0 || rounds > 254) return fail(BDG_ERR_ARG, "N must be < 2^31 and 0 <= rounds <= 254");
+    if (N > 0x7FFFFFFFull || rounds < 0 || rounds > 253) return fail(BDG_ERR_ARG, "N must be < 2^31 and 0 <= rounds <= 253");
     if (int rc = check_sorted(sorted_unique, N)) return rc;
     if (int rc = need_ctx()) return rc;
     DevCtx& c = g_ctx[0];
@@ -962,7 +963,7 @@ int bdg_cluster_levels_from_edges(bdg_edges* e, size_t N, const uint32_t* centre
     if (N == 0) return BDG_OK;
     if (!centre_idx || !level || (C && !centres)) return fail(BDG_ERR_ARG, "NULL pointer argument");
     if (e->ctx.size() != 1) return fail(BDG_ERR_ARG, "edge handle spans %zu devices; copy the edges out and use bdg_cluster_levels", e->ctx.size());
-    if (N > 0x7FFFFFFFull || rounds < 0 || rounds > 254) return fail(BDG_ERR_ARG, "N must be < 2^31 and 0 <= rounds <= 254");
+    if (N > 0x7FFFFFFFull || rounds < 0 || rounds > 253) return fail(BDG_ERR_ARG, "N must be < 2^31 and 0 <= rounds <= 253");
     DevCtx& c = g_ctx[e->ctx[0]];
     if (c.generation != e->gen[0]) return fail(BDG_ERR_ARG, "stale edge handle: a later edge build on the same device has reused its buffers");
     if (c.sorted.cap < N * 4) return fail(BDG_ERR_ARG, "N does not match the array the edges were built from");
@@ -1132,5 +1133,86 @@ int bdg_kmer_score(const uint32_t* q, size_t Q, const uint32_t* wl, size_t W, in
     bdg_kmer_index_free(ix);
     return rc;
 }
+
+// ---- f-2 / f-4  extraction TSV in, assignment TSV out, whitelist file (host only; bdg_tsv.hpp) -----------------
+struct bdg_tsv { tsvio::Tsv t; };
+struct bdg_lines16 { tsvio::Lines16 l; };
+
+int bdg_tsv_open(const char* path, int bc_len, int threads, bdg_tsv** out)
+{
+    if (!path || !out) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    *out = nullptr;
+    bdg_tsv* h = new (std::nothrow) bdg_tsv();
+    if (!h) return fail(BDG_ERR_OOM, "out of host memory");
+    bool io = false;
+    std::string why;
+    try {
+        why = tsvio::tsv_parse(h->t, path, bc_len, threads, &io);
+    } catch (const std::bad_alloc&) {
+        delete h;
+        return fail(BDG_ERR_OOM, "out of host memory while reading %s", path);
+    }
+    if (!why.empty()) {
+        delete h;
+        return fail(io ? BDG_ERR_IO : BDG_ERR_UNSUPPORTED, "%s%s", io ? "" : "native TSV reader refuses the file: ", why.c_str());
+    }
+    *out = h;
+    return BDG_OK;
+}
+
+size_t bdg_tsv_rows(const bdg_tsv* t) { return t ? t->t.rows : 0; }
+
+int bdg_tsv_barcodes(const bdg_tsv* t, char* seqs16, uint8_t* kind)
+{
+    if (!t) return fail(BDG_ERR_ARG, "NULL TSV handle");
+    if (t->t.rows && (!seqs16 || !kind)) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if (t->t.rows) {
+        memcpy(seqs16, t->t.seqs.data(), t->t.rows * 16);
+        memcpy(kind, t->t.kind.data(), t->t.rows);
+    }
+    return BDG_OK;
+}
+
+int bdg_tsv_write_assignments(const bdg_tsv* t, const char* out_path, const uint64_t* centre_per_row, int threads)
+{
+    if (!t || !out_path) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if (t->t.rows && !centre_per_row) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    std::string why;
+    try {
+        why = tsvio::tsv_write(t->t, out_path, centre_per_row, threads);
+    } catch (const std::bad_alloc&) {
+        return fail(BDG_ERR_OOM, "out of host memory while writing %s", out_path);
+    }
+    if (!why.empty()) return fail(BDG_ERR_IO, "%s", why.c_str());
+    return BDG_OK;
+}
+
+void bdg_tsv_close(bdg_tsv* t) { delete t; }
+
+int bdg_lines16_open(const char* path, bdg_lines16** out)
+{
+    if (!path || !out) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    *out = nullptr;
+    bdg_lines16* h = new (std::nothrow) bdg_lines16();
+    if (!h) return fail(BDG_ERR_OOM, "out of host memory");
+    bool io = false;
+    std::string why;
+    try {
+        why = tsvio::lines16_read(h->l, path, &io);
+    } catch (const std::bad_alloc&) {
+        delete h;
+        return fail(BDG_ERR_OOM, "out of host memory while reading %s", path);
+    }
+    if (!why.empty()) {
+        delete h;
+        return fail(BDG_ERR_IO, "%s", why.c_str());
+    }
+    *out = h;
+    return BDG_OK;
+}
+
+size_t bdg_lines16_count(const bdg_lines16* l) { return l ? l->l.count : 0; }
+const char* bdg_lines16_data(const bdg_lines16* l) { return l ? l->l.seqs.data() : nullptr; }
+void bdg_lines16_close(bdg_lines16* l) { delete l; }
 
 }  // extern "C"

@@ -337,11 +337,17 @@ __global__ void cluster_seed_kernel(const uint32_t* __restrict__ sorted, uint32_
 }
 
 // barcode values of the edge list -> node indices, in place
-__global__ void cluster_index_kernel(const uint32_t* __restrict__ sorted, uint32_t n, uint32_t* __restrict__ ea, uint32_t* __restrict__ eb, uint64_t n_edges)
+// and mark both ends "has an edge" (level 254; centres keep their 0, later rounds overwrite the mark of whoever they reach)
+constexpr uint8_t LEVEL_NONE = 255, LEVEL_HAS_EDGE = 254;
+__global__ void cluster_index_kernel(const uint32_t* __restrict__ sorted, uint32_t n, uint32_t* __restrict__ ea, uint32_t* __restrict__ eb, uint64_t n_edges,
+                                     uint8_t* __restrict__ level)
 {
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (uint64_t)gridDim.x * blockDim.x) {
-        ea[e] = lower_bound_u32(sorted, n, ea[e]);
-        eb[e] = lower_bound_u32(sorted, n, eb[e]);
+        const uint32_t ia = lower_bound_u32(sorted, n, ea[e]), ib = lower_bound_u32(sorted, n, eb[e]);
+        ea[e] = ia;
+        eb[e] = ib;
+        if (ia < n && level[ia] == LEVEL_NONE) level[ia] = LEVEL_HAS_EDGE;     // every writer stores the same value
+        if (ib < n && level[ib] == LEVEL_NONE) level[ib] = LEVEL_HAS_EDGE;
     }
 }
 
@@ -365,7 +371,7 @@ __global__ void cluster_resolve_kernel(int32_t* __restrict__ centre_idx, uint8_t
         if (lo != 0x7FFFFFFF) {
             const bool single = lo == cmax[i];
             centre_idx[i] = single ? lo : -1;
-            level[i] = single ? (uint8_t)round : (uint8_t)255;
+            level[i] = single ? (uint8_t)round : LEVEL_HAS_EDGE;             // evicted: still a node with edges
             cmin[i] = 0x7FFFFFFF; cmax[i] = -1;
         }
     }

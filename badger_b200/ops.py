@@ -125,13 +125,14 @@ class EdgeHandle:
         check(lib().bdg_edges_copy(self._h, ptr(a), ptr(b), ptr(d)))
         return a, b, d
 
-    def cluster_levels(self, centres: np.ndarray, rounds: int = 2):
-        """barcode_graph.py:279-301 straight from the device-resident edge list; CONSUMES the edges."""
+    def cluster_levels(self, centres: np.ndarray, rounds: int = 2, want_has_edge: bool = False):
+        """barcode_graph.py:279-301 straight from the device-resident edge list; CONSUMES the edges.
+        want_has_edge: also return the mask of the non-centre nodes with at least one edge (see ops.cluster_levels)."""
         cen = np.ascontiguousarray(centres, dtype=np.uint32)
         ci = np.full(self.n_nodes, -2, np.int32); lv = np.full(self.n_nodes, 255, np.uint8)
         if self.n_nodes:
             check(lib().bdg_cluster_levels_from_edges(self._h, self.n_nodes, ptr(cen), cen.size, int(rounds), ptr(ci), ptr(lv)))
-        return ci, lv
+        return _split_levels(ci, lv, want_has_edge)
 
     def free(self):
         if self._h is not None:
@@ -170,9 +171,24 @@ def edges_build_part(sorted_unique: np.ndarray, t: int, part: int, nparts: int):
     return _collect_edges(h)
 
 
-def cluster_levels(sorted_unique: np.ndarray, ea: np.ndarray, eb: np.ndarray, centres: np.ndarray, rounds: int = 2):
+LEVEL_NONE, LEVEL_HAS_EDGE = 255, 254
+
+
+def _split_levels(ci, lv, want_has_edge):
+    """The library marks nodes no round reached (and evicted ones) that have an edge with level 254; callers of the
+    (centre_idx, level) pair see the plain 255 = none."""
+    marked = lv == LEVEL_HAS_EDGE
+    has_edge = marked | ((lv != LEVEL_NONE) & (lv != 0)) if want_has_edge else None     # joined nodes were reached over an edge
+    lv[marked] = LEVEL_NONE
+    return (ci, lv, has_edge) if want_has_edge else (ci, lv)
+
+
+def cluster_levels(sorted_unique: np.ndarray, ea: np.ndarray, eb: np.ndarray, centres: np.ndarray, rounds: int = 2,
+                   want_has_edge: bool = False):
     """barcode_graph.py:279-301 on node positions of the sorted array: (centre_idx int32[N], level uint8[N]);
-    centre_idx -2 = untouched, -1 = evicted by a same-round conflict, level 255 = none."""
+    centre_idx -2 = untouched, -1 = evicted by a same-round conflict, level 255 = none.
+    want_has_edge adds the mask of the non-centre nodes with >= 1 edge (centre nodes, level 0, are never marked: the
+    reference touches `edges[centre]` whether or not the centre has an edge, barcode_graph.py:293)."""
     s = np.ascontiguousarray(sorted_unique, dtype=np.uint32)
     ea = np.ascontiguousarray(ea, dtype=np.uint32); eb = np.ascontiguousarray(eb, dtype=np.uint32)
     cen = np.ascontiguousarray(centres, dtype=np.uint32)
@@ -180,7 +196,7 @@ def cluster_levels(sorted_unique: np.ndarray, ea: np.ndarray, eb: np.ndarray, ce
     lv = np.full(s.size, 255, np.uint8)
     if s.size:
         check(lib().bdg_cluster_levels(ptr(s), s.size, ptr(ea), ptr(eb), ea.size, ptr(cen), cen.size, int(rounds), ptr(ci), ptr(lv)))
-    return ci, lv
+    return _split_levels(ci, lv, want_has_edge)
 
 
 def canonical(a, b, d):

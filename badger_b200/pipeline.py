@@ -19,7 +19,8 @@ import time
 import numpy as np
 
 from . import ops
-from .barcode_graph import BarcodeGraph
+from .barcode_graph import BarcodeGraph, _unrank_many
+from .common import rank
 
 NONE = np.uint64(1) << np.uint64(32)      # "no centre" marker in the uint64 result (every uint32 is a valid barcode)
 
@@ -37,7 +38,8 @@ def assign_packed(ranks, valid=None, *, threshold, n_cells, interval=25, whiteli
 
     ranks / valid: packed barcode and validity per read (valid=None: all valid); whitelist_sorted: ascending uint32 array
     or None; true_barcodes: iterable of packed centres or None (badger.py --true_barcodes); centre_order: order in which
-    --high_sens tries the centres (the reference iterates a Python set, barcode_graph.py:372; default: ascending)."""
+    --high_sens tries the centres (the reference iterates a Python set, barcode_graph.py:372; default: ascending; "set":
+    the iteration order of that very set of strings in this process, which is what badger_b200.BarcodeGraph meets too)."""
     T = timings if timings is not None else {}
 
     def tick(name, t0):
@@ -75,8 +77,10 @@ def assign_packed(ranks, valid=None, *, threshold, n_cells, interval=25, whiteli
     info["centres"] = int(centres.size)
 
     t0 = time.perf_counter()
-    ci, lv = handle.cluster_levels(centres, 2)            # consumes the handle's edges (no copy to the host)
+    ci, lv, has_edge = handle.cluster_levels(centres, 2, want_has_edge=True)   # consumes the handle's edges (no copy to the host)
     handle.free()
+    # badger.py:131 `len(counts) - len(edges.keys())`: the keys are the nodes with an edge plus every centre cluster() touched
+    info["disconnected"] = int(distinct.size) - (int(has_edge.sum()) + int(centres.size))
     centre_sorted = np.where(ci >= 0, s[np.maximum(ci, 0)].astype(np.uint64), NONE)
     centre_distinct = centre_sorted[spos]
     tick("cluster", t0)
@@ -85,7 +89,18 @@ def assign_packed(ranks, valid=None, *, threshold, n_cells, interval=25, whiteli
         t0 = time.perf_counter()
         todo = np.nonzero(centre_distinct == NONE)[0]
         used = np.unique(centre_distinct[centre_distinct != NONE]).astype(np.uint32)     # set(assignments.values())
-        targets = used if centre_order is None else np.asarray([c for c in centre_order if c in set(used.tolist())], np.uint32)
+        if centre_order is None:
+            targets = used
+        elif isinstance(centre_order, str) and centre_order == "set":
+            # the order the string route meets in this process: `set(assignments.values())` with the dict filled in
+            # first-seen order of the distinct barcodes (barcode_graph.py:322-329,372).  Re-adding a member leaves a set's
+            # table untouched, so the set of the first occurrences, added in that order, iterates identically.
+            vals = centre_distinct[centre_distinct != NONE]
+            u, first = np.unique(vals, return_index=True)
+            strs = _unrank_many(u[np.argsort(first, kind="stable")].astype(np.uint32))
+            targets = np.asarray([rank(c, 16) for c in set(strs)], np.uint32)
+        else:
+            targets = np.asarray([c for c in centre_order if c in set(used.tolist())], np.uint32)
         if todo.size and targets.size:
             am, _ = ops.nearest_bounded(distinct[todo], targets, 2)
             hit = am >= 0

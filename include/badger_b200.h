@@ -33,7 +33,9 @@ enum {
     BDG_ERR_OOM = -2,      /* host or device allocation failed */
     BDG_ERR_ARG = -3,      /* bad argument (NULL, unsorted input, size limit) */
     BDG_ERR_NODEVICE = -4, /* no CUDA device / library not initialised on one */
-    BDG_ERR_CAPACITY = -5  /* caller-provided output capacity too small; *total holds the need */
+    BDG_ERR_CAPACITY = -5, /* caller-provided output capacity too small; *total holds the need */
+    BDG_ERR_UNSUPPORTED = -6, /* bdg_tsv_open: the file uses a construct the native reader refuses (take the pandas route) */
+    BDG_ERR_IO = -7        /* a file could not be opened, mapped or written */
 };
 
 /* Rows of the sorted distinct-barcode array are dealt to parts (GPUs / ranks) in tiles of this many
@@ -90,7 +92,8 @@ void bdg_edges_free(bdg_edges* e);
 /* Nodes are positions in sorted_unique[N].  centres[C]: barcode values of the cluster centres (values that are not in
  * sorted_unique are ignored: a centre that was never observed has no node).  On return centre_idx[i] = position of the
  * centre node i joined, -1 if two centres claimed it in the same round (the reference's (-1,-1)), -2 if no round reached
- * it; level[i] = 0 for centres, the round number for joined nodes, 255 otherwise.  The reference runs rounds = 2.
+ * it; level[i] = 0 for centres, the round number for joined nodes, 254 for nodes no round reached that have at least one
+ * edge (what `len(graph.edges.keys())`, badger.py:131, needs), 255 otherwise.  The reference runs rounds = 2 (<= 253).
  * bdg_cluster_levels takes the edge list from host arrays (barcode values, each undirected edge once);
  * bdg_cluster_levels_from_edges takes it from a single-device edge handle without copying anything (N = the size of
  * the array the handle was built from) and CONSUMES the handle's edges: copy them out first if they are still needed. */
@@ -165,6 +168,35 @@ unsigned long long bdg_launch_count(void);
  * threads; the caller times it with CUDA events.  *ops_per_thread receives the instruction count. */
 int bdg_dev_pipe_probe(int kind, int blocks, int iters, uint32_t* d_sink, unsigned long long* ops_per_thread,
                        void* stream);
+
+/* ---- f-2 / f-4  the files either side of the path (host code, no device needed) --------------------------------
+ * bdg_tsv_open reads an extraction TSV the way badger.py:91-111 does through pandas.read_csv(sep="\t"): header line
+ * with `#read_id` and `barcode` columns, blank lines skipped, short rows padded with NaN, the NA strings of pandas ->
+ * no barcode, repeated header rows dropped, 17-character barcodes cut to 16 (barcode_graph.py:195-196, badger.py:107).
+ * Files with anything else pandas would treat specially (quotes, carriage returns, NUL / non-ASCII bytes, rows longer
+ * than the header, ids or barcodes that look like numbers / booleans) are refused with BDG_ERR_UNSUPPORTED and must be
+ * read through pandas.  Memory-mapped, `threads` parser threads (<= 0: all cores).
+ *   rows           data rows of the file (every non-blank line after the header)
+ *   barcodes       seqs16[rows*16]: the first 16 characters of the row's barcode ('A' x 16 when it has none);
+ *                  kind[rows]: bit 0 = the row's barcode goes into the graph (16/17 characters, not '*', not NaN, not a
+ *                  repeated header; LETTERS ARE NOT CHECKED HERE - bdg_pack16 does that on the GPU), bit 1 = the row is
+ *                  written to the output (badger.py:103-110)
+ *   write          barcode_graph.py:388-410 / to_csv(sep="\t", index=False): `readID\tbarcode`, then per written row its id
+ *                  and the unranked centre_per_row[row] (common.py:27-38), or `*` when that value is >= 2^32. */
+typedef struct bdg_tsv bdg_tsv;
+int bdg_tsv_open(const char* path, int bc_len, int threads, bdg_tsv** out);
+size_t bdg_tsv_rows(const bdg_tsv* t);
+int bdg_tsv_barcodes(const bdg_tsv* t, char* seqs16, uint8_t* kind);
+int bdg_tsv_write_assignments(const bdg_tsv* t, const char* out_path, const uint64_t* centre_per_row, int threads);
+void bdg_tsv_close(bdg_tsv* t);
+
+/* Whitelist file, badger.py:82-88 (`set(file.read().split("\n"))`): the entries of exactly 16 characters, 16 bytes each
+ * (no other entry can equal an unranked barcode, barcode_graph.py:264).  data stays valid until close. */
+typedef struct bdg_lines16 bdg_lines16;
+int bdg_lines16_open(const char* path, bdg_lines16** out);
+size_t bdg_lines16_count(const bdg_lines16* l);
+const char* bdg_lines16_data(const bdg_lines16* l);
+void bdg_lines16_close(bdg_lines16* l);
 
 #ifdef __cplusplus
 }

@@ -74,8 +74,15 @@ def dedup_first_seen(ranks, want_map=False, want_sorted_pos=False):
     return out
 
 
-def cluster_levels(sorted_unique, ea, eb, centres, rounds=2):
+def cluster_levels(sorted_unique, ea, eb, centres, rounds=2, want_has_edge=False):
     """Literal restatement of the reference's rounds (oracle.cluster) turned into the operator's array form."""
+    if want_has_edge:
+        ci, lv = cluster_levels(sorted_unique, ea, eb, centres, rounds)
+        s = np.ascontiguousarray(sorted_unique, dtype=np.uint32)
+        has = np.zeros(s.size, bool)
+        has[np.searchsorted(s, np.asarray(ea, np.uint32))] = True
+        has[np.searchsorted(s, np.asarray(eb, np.uint32))] = True
+        return ci, lv, has & (lv != 0)
     assert rounds == 2
     s = np.ascontiguousarray(sorted_unique, dtype=np.uint32)
     adj = {}
@@ -94,8 +101,30 @@ def cluster_levels(sorted_unique, ea, eb, centres, rounds=2):
     return ci, lv
 
 
+class EdgeHandle:
+    """Stand-in for ops.EdgeHandle (edges kept 'on the device')."""
+
+    def __init__(self, s, t):
+        self.s = s
+        self.a, self.b, self.d = edges_build(s, t)
+        self.count, self.n_nodes = int(self.a.size), int(s.size)
+
+    def copy(self):
+        return self.a, self.b, self.d
+
+    def cluster_levels(self, centres, rounds=2, want_has_edge=False):
+        return cluster_levels(self.s, self.a, self.b, centres, rounds, want_has_edge)
+
+    def free(self):
+        pass
+
+
+def edges_handle(sorted_unique, t):
+    return EdgeHandle(np.ascontiguousarray(sorted_unique, dtype=np.uint32), t)
+
+
 def install(monkeypatch):
     from badger_b200 import ops
     for name in ("pack16", "edges_build", "edges_build_part", "member_sorted", "nearest_bounded", "kmer_score", "dedup_first_seen",
-                 "cluster_levels", "KmerIndex"):
+                 "cluster_levels", "KmerIndex", "edges_handle"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -83,15 +83,30 @@ def test_pipeline_golden(gold_pipeline, tmp_path, capsys):
     cli = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(cli)
     g = gold_pipeline
-    out = str(tmp_path / "OUT")
-    cli.main(["-r", g["dir"] + "/reads.tsv", "-l", g["dir"] + "/whitelist.txt", "-d", "tenX_v3", "-t", str(g["t"]),
-              "--n_cells", str(g["n_cells"]), "-i", str(g["interval"]), "-o", out])
-    for h in list(logging.getLogger("BarcodeGraph").handlers):
-        logging.getLogger("BarcodeGraph").removeHandler(h)
-    with open(out + "_output_file.tsv", "rb") as fh, open(g["dir"] + "/expected_output_file.tsv", "rb") as ref:
-        assert fh.read() == ref.read()
-    tail = [ln for ln in capsys.readouterr().out.splitlines() if ln.strip().lstrip("-").isdigit()]
-    assert tail == g["stdout_tail"]
+    # both routes of the CLI: native reader / array pipeline / native writer (default) and pandas + dict-shaped BarcodeGraph
+    for k, route in enumerate(([], ["--no_native_io"])):
+        out = str(tmp_path / ("OUT%d" % k))
+        cli.main(["-r", g["dir"] + "/reads.tsv", "-l", g["dir"] + "/whitelist.txt", "-d", "tenX_v3", "-t", str(g["t"]),
+                  "--n_cells", str(g["n_cells"]), "-i", str(g["interval"]), "-o", out] + route)
+        for h in list(logging.getLogger("BarcodeGraph").handlers):
+            logging.getLogger("BarcodeGraph").removeHandler(h)
+        with open(out + "_output_file.tsv", "rb") as fh, open(g["dir"] + "/expected_output_file.tsv", "rb") as ref:
+            assert fh.read() == ref.read(), route
+        text = capsys.readouterr().out
+        assert "reading through pandas" not in text
+        tail = [ln for ln in text.splitlines() if ln.strip().lstrip("-").isdigit()]
+        assert tail == g["stdout_tail"], route
+    # --high_sens: the two routes meet the same set order inside one process
+    outs = []
+    for k, route in enumerate(([], ["--no_native_io"])):
+        out = str(tmp_path / ("HS%d" % k))
+        cli.main(["-r", g["dir"] + "/reads.tsv", "-l", g["dir"] + "/whitelist.txt", "-d", "10x", "-t", str(g["t"]), "-hs",
+                  "--n_cells", str(g["n_cells"]), "-i", str(g["interval"]), "-o", out] + route)
+        for h in list(logging.getLogger("BarcodeGraph").handlers):
+            logging.getLogger("BarcodeGraph").removeHandler(h)
+        outs.append((open(out + "_output_file.tsv", "rb").read(),
+                     [ln for ln in capsys.readouterr().out.splitlines() if ln.strip().lstrip("-").isdigit()]))
+    assert outs[0] == outs[1]
     # internals + --high_sens with the centre order the reference iterated
     import pandas as pd
     df = pd.read_csv(g["dir"] + "/reads.tsv", sep="\t")
@@ -394,6 +409,12 @@ def test_cluster_levels_vs_reference_rounds():
         for i in np.nonzero(ci != -2)[0].tolist():
             got[int(s[i])] = (int(s[ci[i]]), int(lv[i])) if ci[i] >= 0 else (-1, -1)
         assert got == {k: tuple(v) for k, v in want.items() if k in pos}
+        # the mask behind `len(graph.edges.keys())` (badger.py:131): non-centre nodes with at least one edge
+        ci2, lv2, has = ops.cluster_levels(s, ea, eb, cen, 2, want_has_edge=True)
+        assert np.array_equal(ci2, ci) and np.array_equal(lv2, lv)
+        deg = np.zeros(s.size, bool)
+        deg[np.searchsorted(s, ea)] = True; deg[np.searchsorted(s, eb)] = True
+        assert np.array_equal(has, deg & (lv != 0))
     assert any((ci == -1).any() for ci, _ in [ops.cluster_levels(*c, 2) for c in cases[:10]])      # conflicts were exercised
 
 
