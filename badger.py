@@ -95,7 +95,7 @@ def run_native(args, bc_len, true_barcodes):
         whitelist = None
         if args.barcode_list:                                   # badger.py:82-88
             w, wok = ops.pack16(tsvio.whitelist_records(args.barcode_list).tobytes())
-            whitelist = np.unique(w[wok])
+            whitelist = ops.sorted_unique(w[wok])
         tb = [rank(bc, bc_len) for bc in true_barcodes] if true_barcodes else None
         centre, info = pipeline.assign_packed(ranks, has, threshold=args.threshold, n_cells=args.n_cells, interval=args.interval,
                                               whitelist_sorted=whitelist, true_barcodes=tb, high_sens=args.high_sens,

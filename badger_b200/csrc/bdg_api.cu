@@ -87,6 +87,7 @@ struct DevCtx {
     uint64_t plan_key[4] = {0, 0, 0, 0};
     bool plan_valid = false;
     Buf cl[6];                                                // clustering: centres, centre index, level, claim min / max, index scratch
+    Buf gather_a, gather_b;                                   // edge ends of ALL devices of a multi-device handle, gathered here for cluster()
     Buf nn[9];                                                // sparse nearest: rotated keys + payload (in/out) of queries and targets, scratch
 };
 std::vector<DevCtx> g_ctx;
@@ -477,6 +478,7 @@ void bdg_shutdown(void)
         for (auto& b : c.dd) b.release();
         for (auto& b : c.nn) b.release();
         for (auto& b : c.cl) b.release();
+        c.gather_a.release(); c.gather_b.release();
         for (auto& b : c.rot_sorted) b.release();
     }
     g_ctx.clear();
@@ -962,12 +964,36 @@ int bdg_cluster_levels_from_edges(bdg_edges* e, size_t N, const uint32_t* centre
     if (!e) return fail(BDG_ERR_ARG, "NULL edge handle");
     if (N == 0) return BDG_OK;
     if (!centre_idx || !level || (C && !centres)) return fail(BDG_ERR_ARG, "NULL pointer argument");
-    if (e->ctx.size() != 1) return fail(BDG_ERR_ARG, "edge handle spans %zu devices; copy the edges out and use bdg_cluster_levels", e->ctx.size());
+    if (e->ctx.empty()) return fail(BDG_ERR_ARG, "empty edge handle");
     if (N > 0x7FFFFFFFull || rounds < 0 || rounds > 253) return fail(BDG_ERR_ARG, "N must be < 2^31 and 0 <= rounds <= 253");
+    for (size_t g = 0; g < e->ctx.size(); g++)
+        if (e->ctx[g] < 0 || (size_t)e->ctx[g] >= g_ctx.size() || g_ctx[e->ctx[g]].generation != e->gen[g])
+            return fail(BDG_ERR_ARG, "stale edge handle: a later edge build on the same device has reused its buffers");
     DevCtx& c = g_ctx[e->ctx[0]];
-    if (c.generation != e->gen[0]) return fail(BDG_ERR_ARG, "stale edge handle: a later edge build on the same device has reused its buffers");
     if (c.sorted.cap < N * 4) return fail(BDG_ERR_ARG, "N does not match the array the edges were built from");
     CU_TRY(cudaSetDevice(c.dev));
+    if (e->ctx.size() > 1) {
+        // Multi-device handle: the parts' edge lists are disjoint, so the clustering rounds need their plain
+        // concatenation.  It is gathered on the first device with peer copies (NVLink; every part's stream was synchronised
+        // by the build), into buffers of its own - the handle's edges stay intact on their devices.
+        size_t total = 0;
+        for (size_t k : e->count) total += k;
+        if (cudaError_t err = (cudaError_t)c.gather_a.ensure(std::max<size_t>(total, 1) * 4))
+            return fail(err == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "gather buffer of %zu edges: %s", total, cudaGetErrorString(err));
+        if (cudaError_t err = (cudaError_t)c.gather_b.ensure(std::max<size_t>(total, 1) * 4))
+            return fail(err == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "gather buffer of %zu edges: %s", total, cudaGetErrorString(err));
+        size_t off = 0;
+        for (size_t g = 0; g < e->ctx.size(); g++) {
+            const DevCtx& src = g_ctx[e->ctx[g]];
+            const size_t k = e->count[g];
+            if (k) {
+                CU_TRY(cudaMemcpyPeerAsync((uint32_t*)c.gather_a.p + off, c.dev, src.ea.p, src.dev, k * 4, c.stream));
+                CU_TRY(cudaMemcpyPeerAsync((uint32_t*)c.gather_b.p + off, c.dev, src.eb.p, src.dev, k * 4, c.stream));
+            }
+            off += k;
+        }
+        return cluster_on_device(c, (const uint32_t*)c.sorted.p, N, (uint32_t*)c.gather_a.p, (uint32_t*)c.gather_b.p, total, centres, C, rounds, centre_idx, level);
+    }
     // the handle's edge VALUES are turned into node indices in place: the handle is consumed (stale afterwards)
     c.generation++;
     return cluster_on_device(c, (const uint32_t*)c.sorted.p, N, (uint32_t*)c.ea.p, (uint32_t*)c.eb.p, e->count[0], centres, C, rounds, centre_idx, level);

@@ -334,15 +334,42 @@ inline std::string lines16_read(Lines16& L, const char* path, bool* io_error)
     if (!f.open_file(path, err)) { *io_error = true; return err; }
     const char* d = f.data;
     const size_t n = f.size;
-    L.seqs.reserve(n / 17 * 16 + 16);
-    size_t ls = 0;
-    for (size_t i = 0; i <= n; i++) {
-        if (i == n || d[i] == '\n' || d[i] == '\r') {
-            if (i - ls == 16) L.seqs.insert(L.seqs.end(), d + ls, d + i);
-            ls = i + 1;
-        }
+    const int T = pick_threads(0, n);
+    std::vector<size_t> cut(T + 1, n);
+    cut[0] = 0;
+    for (int k = 1; k < T; k++) {                           // slice borders moved to the next entry start
+        size_t c = std::max(cut[k - 1], n / T * k);
+        while (c < n && d[c] != '\n' && d[c] != '\r') c++;
+        cut[k] = c < n ? c + 1 : n;
     }
-    L.count = L.seqs.size() / 16;
+    // two sweeps per slice: count the 16-character entries, then copy them to their final place
+    std::vector<size_t> found(T + 1, 0);
+    auto sweep = [&](int k, char* dst) {
+        const size_t beg = cut[k], end = cut[k + 1];
+        size_t ls = beg, hits = 0;
+        // a slice ends right after a terminator, except the last one, whose final entry may end at the end of the file
+        for (size_t i = beg; i < end || (i == end && end == n && k == T - 1); i++) {
+            if (i == n || d[i] == '\n' || d[i] == '\r') {
+                if (i - ls == 16) {
+                    if (dst) memcpy(dst + hits * 16, d + ls, 16);
+                    hits++;
+                }
+                ls = i + 1;
+            }
+        }
+        if (!dst) found[k + 1] = hits;
+    };
+    auto run = [&](bool copy) {
+        std::vector<std::thread> pool;
+        for (int k = 1; k < T; k++) pool.emplace_back([&, k] { sweep(k, copy ? L.seqs.data() + found[k] * 16 : nullptr); });
+        sweep(0, copy ? L.seqs.data() : nullptr);
+        for (auto& th : pool) th.join();
+    };
+    run(false);
+    for (int k = 0; k < T; k++) found[k + 1] += found[k];
+    L.count = found[T];
+    L.seqs.resize(L.count * 16);
+    run(true);
     return "";
 }
 

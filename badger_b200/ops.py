@@ -10,6 +10,7 @@ import weakref
 import numpy as np
 
 from . import _lib
+from .common import sorted_unique  # noqa: F401  (re-exported)
 from ._lib import check, lib, ptr
 
 BC_LEN = 16
@@ -147,10 +148,11 @@ class EdgeHandle:
 
 
 def edges_handle(sorted_unique: np.ndarray, t: int) -> EdgeHandle:
-    """Edge construction on the FIRST claimed device, results left on it (single-device handle)."""
+    """Edge construction over all initialised GPUs (rows dealt to them, SURVEY.md 8e), every part left on its device;
+    EdgeHandle.cluster_levels gathers the parts on the first device over NVLink."""
     s = np.ascontiguousarray(sorted_unique, dtype=np.uint32)
     h = C.c_void_p()
-    check(lib().bdg_edges_build_part(ptr(s), s.size, int(t), 0, 1, C.byref(h)))
+    check(lib().bdg_edges_build(ptr(s), s.size, int(t), C.byref(h)))
     return EdgeHandle(h, s.size)
 
 

@@ -88,7 +88,7 @@ def assign_packed(ranks, valid=None, *, threshold, n_cells, interval=25, whiteli
     if high_sens:
         t0 = time.perf_counter()
         todo = np.nonzero(centre_distinct == NONE)[0]
-        used = np.unique(centre_distinct[centre_distinct != NONE]).astype(np.uint32)     # set(assignments.values())
+        used = ops.sorted_unique(centre_distinct[centre_distinct != NONE]).astype(np.uint32)     # set(assignments.values())
         if centre_order is None:
             targets = used
         elif isinstance(centre_order, str) and centre_order == "set":
@@ -96,8 +96,11 @@ def assign_packed(ranks, valid=None, *, threshold, n_cells, interval=25, whiteli
             # first-seen order of the distinct barcodes (barcode_graph.py:322-329,372).  Re-adding a member leaves a set's
             # table untouched, so the set of the first occurrences, added in that order, iterates identically.
             vals = centre_distinct[centre_distinct != NONE]
-            u, first = np.unique(vals, return_index=True)
-            strs = _unrank_many(u[np.argsort(first, kind="stable")].astype(np.uint32))
+            order = np.argsort(vals, kind="stable")                      # first occurrence of every value, in order of appearance
+            sv = vals[order]
+            head = np.ones(sv.size, bool)
+            head[1:] = sv[1:] != sv[:-1]
+            strs = _unrank_many(vals[np.sort(order[head])].astype(np.uint32))
             targets = np.asarray([rank(c, 16) for c in set(strs)], np.uint32)
         else:
             targets = np.asarray([c for c in centre_order if c in set(used.tolist())], np.uint32)

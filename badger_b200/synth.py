@@ -18,6 +18,8 @@ from __future__ import annotations
 
 import numpy as np
 
+from .common import sorted_unique
+
 BC_LEN = 16
 _ALPHABET = np.frombuffer(b"ACGT", dtype=np.uint8)
 
@@ -40,7 +42,7 @@ def make_whitelist(W: int, rng: np.random.Generator) -> np.ndarray:
     got = np.empty(0, dtype=np.uint32)
     while got.size < W:
         draw = rng.integers(0, 1 << 32, size=int((W - got.size) * 1.05) + 16, dtype=np.uint64).astype(np.uint32)
-        got = np.unique(np.concatenate([got, draw]))
+        got = sorted_unique(np.concatenate([got, draw]))
     got = got[rng.permutation(got.size)[:W]]
     return np.ascontiguousarray(got)
 
@@ -49,48 +51,68 @@ def pick_cells(whitelist: np.ndarray, n_cells: int, rng: np.random.Generator) ->
     return np.ascontiguousarray(whitelist[rng.permutation(whitelist.size)[:n_cells]])
 
 
+def _simulate_chunk(cells, n, perr, rng, star_frac, umi_len):
+    L = BC_LEN + umi_len
+    bc = cells[rng.integers(0, cells.size, size=n)]
+    src = np.empty((n, L), dtype=np.uint8)
+    for i in range(BC_LEN):
+        src[:, i] = (bc >> np.uint32(2 * i)) & np.uint32(3)
+    src[:, BC_LEN:] = rng.integers(0, 4, size=(n, umi_len), dtype=np.uint8)
+    u = rng.random((n, L), dtype=np.float32)
+    ev = np.zeros((n, L), dtype=np.uint8)           # 0 keep, 1 sub, 2 del, 3 ins(before base)
+    ev[u < perr] = 3
+    ev[u < perr * (2.0 / 3.0)] = 2
+    ev[u < perr * (1.0 / 3.0)] = 1
+    subst = (src + rng.integers(1, 4, size=(n, L), dtype=np.uint8)) & 3
+    insb = rng.integers(0, 4, size=(n, L), dtype=np.uint8)
+    cur = np.zeros(n, dtype=np.int64)
+    acc = np.zeros(n, dtype=np.uint64)
+    for j in range(L):
+        e = ev[:, j]
+        m = (e == 3) & (cur < BC_LEN)
+        sh = np.where(m, 2 * cur, 0).astype(np.uint64)
+        acc |= np.where(m, insb[:, j].astype(np.uint64) << sh, np.uint64(0))
+        cur += (e == 3)
+        m = (e != 2) & (cur < BC_LEN)
+        base = np.where(e == 1, subst[:, j], src[:, j]).astype(np.uint64)
+        sh = np.where(m, 2 * cur, 0).astype(np.uint64)
+        acc |= np.where(m, base << sh, np.uint64(0))
+        cur += (e != 2)
+    short = cur < BC_LEN                              # ≥13 deletions: pad with random bases
+    if short.any():
+        for idx in np.nonzero(short)[0]:
+            c = int(cur[idx])
+            while c < BC_LEN:
+                acc[idx] |= np.uint64(int(rng.integers(0, 4)) << (2 * c))
+                c += 1
+    return acc.astype(np.uint32), rng.random(n) >= star_frac
+
+
 def simulate_reads(cells: np.ndarray, R: int, perr: float, rng: np.random.Generator,
-                   star_frac: float = 0.03, umi_len: int = 12, chunk: int = 1 << 20):
-    """Return (observed uint32[R], valid bool[R]); ``valid[i]==False`` means the read got ``*``."""
+                   star_frac: float = 0.03, umi_len: int = 12, chunk: int = 1 << 20, workers: int = 1):
+    """Return (observed uint32[R], valid bool[R]); ``valid[i]==False`` means the read got ``*``.
+
+    workers > 1: the chunks are drawn from child generators of ``rng`` (``rng.spawn``) on a thread pool - deterministic
+    for a given seed, but a DIFFERENT stream than the serial form (used for the 10^8-read config, where the serial
+    synthesis takes two minutes)."""
     out = np.empty(R, dtype=np.uint32)
     valid = np.empty(R, dtype=bool)
-    L = BC_LEN + umi_len
-    for s in range(0, R, chunk):
+    starts = list(range(0, R, chunk))
+    if workers <= 1:
+        for s in starts:
+            n = min(chunk, R - s)
+            out[s:s + n], valid[s:s + n] = _simulate_chunk(cells, n, perr, rng, star_frac, umi_len)
+        return out, valid
+    from concurrent.futures import ThreadPoolExecutor
+    kids = rng.spawn(len(starts))
+
+    def work(k):
+        s = starts[k]
         n = min(chunk, R - s)
-        bc = cells[rng.integers(0, cells.size, size=n)]
-        src = np.empty((n, L), dtype=np.uint8)
-        for i in range(BC_LEN):
-            src[:, i] = (bc >> np.uint32(2 * i)) & np.uint32(3)
-        src[:, BC_LEN:] = rng.integers(0, 4, size=(n, umi_len), dtype=np.uint8)
-        u = rng.random((n, L), dtype=np.float32)
-        ev = np.zeros((n, L), dtype=np.uint8)           # 0 keep, 1 sub, 2 del, 3 ins(before base)
-        ev[u < perr] = 3
-        ev[u < perr * (2.0 / 3.0)] = 2
-        ev[u < perr * (1.0 / 3.0)] = 1
-        subst = (src + rng.integers(1, 4, size=(n, L), dtype=np.uint8)) & 3
-        insb = rng.integers(0, 4, size=(n, L), dtype=np.uint8)
-        cur = np.zeros(n, dtype=np.int64)
-        acc = np.zeros(n, dtype=np.uint64)
-        for j in range(L):
-            e = ev[:, j]
-            m = (e == 3) & (cur < BC_LEN)
-            sh = np.where(m, 2 * cur, 0).astype(np.uint64)
-            acc |= np.where(m, insb[:, j].astype(np.uint64) << sh, np.uint64(0))
-            cur += (e == 3)
-            m = (e != 2) & (cur < BC_LEN)
-            base = np.where(e == 1, subst[:, j], src[:, j]).astype(np.uint64)
-            sh = np.where(m, 2 * cur, 0).astype(np.uint64)
-            acc |= np.where(m, base << sh, np.uint64(0))
-            cur += (e != 2)
-        short = cur < BC_LEN                              # ≥13 deletions: pad with random bases
-        if short.any():
-            for idx in np.nonzero(short)[0]:
-                c = int(cur[idx])
-                while c < BC_LEN:
-                    acc[idx] |= np.uint64(int(rng.integers(0, 4)) << (2 * c))
-                    c += 1
-        out[s:s + n] = acc.astype(np.uint32)
-        valid[s:s + n] = rng.random(n) >= star_frac
+        out[s:s + n], valid[s:s + n] = _simulate_chunk(cells, n, perr, kids[k], star_frac, umi_len)
+
+    with ThreadPoolExecutor(max_workers=workers) as pool:
+        list(pool.map(work, range(len(starts))))
     return out, valid
 
 
@@ -118,8 +140,8 @@ def rank_many(strs) -> np.ndarray:
     return out
 
 
-def make_dataset(name_or_cfg, reads: int | None = None, seed: int | None = None):
-    """Generate (whitelist, cells, observed, valid) for a named config (optionally resized)."""
+def make_dataset(name_or_cfg, reads: int | None = None, seed: int | None = None, workers: int = 1):
+    """Generate (whitelist, cells, observed, valid) for a named config (optionally resized; workers: see simulate_reads)."""
     cfg = dict(CONFIGS[name_or_cfg]) if isinstance(name_or_cfg, str) else dict(name_or_cfg)
     if reads is not None:
         cfg["reads"] = reads
@@ -128,7 +150,7 @@ def make_dataset(name_or_cfg, reads: int | None = None, seed: int | None = None)
     rng = rng_for(cfg["seed"])
     wl = make_whitelist(cfg["whitelist"], rng)
     cells = pick_cells(wl, min(cfg["n_cells"], wl.size), rng)
-    obs, valid = simulate_reads(cells, cfg["reads"], cfg["perr"], rng)
+    obs, valid = simulate_reads(cells, cfg["reads"], cfg["perr"], rng, workers=workers)
     return wl, cells, obs, valid, cfg
 
 

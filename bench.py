@@ -85,7 +85,7 @@ def workload(args, world):
 
     def distinct_of(reads):
         wl, cells, obs, valid, _ = synth.make_dataset(cfg, reads=reads)
-        return np.unique(obs[valid]), (wl, obs, valid)
+        return synth.sorted_unique(obs[valid]), (wl, obs, valid)
 
     base_reads = args.reads if args.reads is not None else cfg["reads"]
     reads = base_reads
@@ -464,7 +464,7 @@ def other_stages(torch, dev, stream, L, s, args):
     dt = dev_time(lambda: chk(L.bdg_dev_pack16(seqs.data_ptr(), R, d_out.data_ptr(), d_ok.data_ptr(), stream.cuda_stream)))
     res["pack16"] = {"reads_per_s": R / dt, "GBps": 21 * R / dt / 1e9, "frac_of_hbm": 21 * R / dt / 1e9 / hbm, "n": R, "bytes_per_read": 21}
     # a-6 membership: 4 B in + 1 B out per query, 3 M-entry whitelist resident
-    wl = np.unique(rng.integers(0, 1 << 32, 3_000_000, dtype=np.uint64).astype(np.uint32))
+    wl = synth.sorted_unique(rng.integers(0, 1 << 32, 3_000_000, dtype=np.uint64).astype(np.uint32))
     Q = 8_000_000
     q = rng.integers(0, 1 << 32, Q, dtype=np.uint64).astype(np.uint32)
     q[::3] = wl[rng.integers(0, wl.size, q[::3].size)]

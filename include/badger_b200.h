@@ -95,8 +95,10 @@ void bdg_edges_free(bdg_edges* e);
  * it; level[i] = 0 for centres, the round number for joined nodes, 254 for nodes no round reached that have at least one
  * edge (what `len(graph.edges.keys())`, badger.py:131, needs), 255 otherwise.  The reference runs rounds = 2 (<= 253).
  * bdg_cluster_levels takes the edge list from host arrays (barcode values, each undirected edge once);
- * bdg_cluster_levels_from_edges takes it from a single-device edge handle without copying anything (N = the size of
- * the array the handle was built from) and CONSUMES the handle's edges: copy them out first if they are still needed. */
+ * bdg_cluster_levels_from_edges takes it from an edge handle without a trip through the host (N = the size of the array
+ * the handle was built from).  A single-device handle is used in place and CONSUMED: copy its edges out first if they are
+ * still needed.  The parts of a multi-device handle (bdg_edges_build on several GPUs) are gathered on the handle's first
+ * device with peer copies over NVLink - the only inter-GPU transfer of the whole path - and stay intact. */
 int bdg_cluster_levels(const uint32_t* sorted_unique, size_t N, const uint32_t* ea, const uint32_t* eb, size_t E,
                        const uint32_t* centres, size_t C, int rounds, int32_t* centre_idx, uint8_t* level);
 int bdg_cluster_levels_from_edges(bdg_edges* e, size_t N, const uint32_t* centres, size_t C, int rounds, int32_t* centre_idx,

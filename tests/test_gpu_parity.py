@@ -418,6 +418,41 @@ def test_cluster_levels_vs_reference_rounds():
     assert any((ci == -1).any() for ci, _ in [ops.cluster_levels(*c, 2) for c in cases[:10]])      # conflicts were exercised
 
 
+def test_packed_pipeline_on_all_devices_matches_one_device():
+    """rows dealt to the GPUs, per-GPU edge lists gathered on the first device for the clustering rounds
+    (bdg_cluster_levels_from_edges on a multi-device handle).  Needs >= 2 GPUs (gpurun --gpus 2)."""
+    from badger_b200 import pipeline
+    n_dev = badger_b200.init()
+    if n_dev < 2:
+        pytest.skip("one GPU visible")
+    rng = synth.rng_for(123)
+    wl = synth.make_whitelist(50000, rng)
+    cells = synth.pick_cells(wl, 1500, rng)
+    obs, valid = synth.simulate_reads(cells, 300000, 0.05, rng)
+    wls = np.sort(wl)
+    res = {}
+    try:
+        for devs in ([0], None):
+            badger_b200.init(devs)
+            for t in (1, 2):
+                out, info = pipeline.assign_packed(obs, valid, threshold=t, n_cells=1500, whitelist_sorted=wls, high_sens=(t == 2))
+                s = synth.sorted_unique(obs[valid])
+                h = ops.edges_handle(s, t)
+                e = ops.canonical(*h.copy())
+                ci, lv, has = h.cluster_levels(cells, 2, want_has_edge=True)
+                h.free()
+                res[(devs is None, t)] = (out, info, e, ci, lv, has)
+    finally:
+        badger_b200.init()
+    for t in (1, 2):
+        one, many = res[(False, t)], res[(True, t)]
+        assert np.array_equal(one[0], many[0]) and one[1] == many[1]
+        for x, y in zip(one[2], many[2]):
+            assert np.array_equal(x, y)
+        assert np.array_equal(one[3], many[3]) and np.array_equal(one[4], many[4]) and np.array_equal(one[5], many[5])
+        assert one[1]["edges"] > 1000
+
+
 def test_member_vs_oracle():
     rng = np.random.default_rng(8)
     for W in (0, 1, 5, 1000, 1024, 1025, 300000):

@@ -16,7 +16,7 @@ from badger_b200 import synth  # noqa: E402
 
 def dataset(reads):
     wl, cells, obs, valid, cfg = synth.make_dataset("C2", reads=reads)
-    return np.unique(obs[valid])
+    return synth.sorted_unique(obs[valid])
 
 
 def time_edges(s, t, reps=3):
