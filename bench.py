@@ -404,6 +404,7 @@ def run_b200(args):
     if rank == 0 and world == 1:
         out["stages"] = other_stages(torch, dev, stream, L, s, args)
         out["pipeline"] = whole_pipeline(t)
+        out["cli"] = cli_file_to_file(t)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"], _ = cpu_sample(s, t, args.cpu_seconds)
     if world > 1:
@@ -427,6 +428,56 @@ def whole_pipeline(t):
     dt = (time.perf_counter() - t0) / reps
     return {"reads_per_s": obs.size / dt, "ms": dt * 1e3, "stages_ms": {k: 1e3 * v / reps for k, v in T.items()}, **info,
             "api": "badger_b200.pipeline.assign_packed (packed barcodes per read in, centre per read out)"}
+
+
+def cli_file_to_file(t):
+    """reads/s of the drop-in command itself, file to file: `badger.py -r reads.tsv -l whitelist.txt -d 10x -t T --n_cells C
+    -o OUT` run in this process on the workload's reads written as an extraction TSV (wall clock; the files are written
+    before the clock starts and sit in the page cache).  Default route = native TSV reader -> GPU pack16 -> array pipeline
+    -> native TSV writer; `--no_native_io` = pandas + the dict-shaped BarcodeGraph, the reference's own host structure."""
+    import contextlib
+    import importlib.util
+    import io
+    import logging
+    import shutil
+    wl, obs, valid, cfg = workload.dataset
+    tmp = tempfile.mkdtemp(prefix="bdg_cli_")
+    try:
+        tsv, wlf = os.path.join(tmp, "reads.tsv"), os.path.join(tmp, "wl.txt")
+        synth.write_whitelist(wlf, wl)
+        synth.write_extraction_tsv(tsv, obs, valid, synth.rng_for(5))
+        spec = importlib.util.spec_from_file_location("badger_cli", os.path.join(ROOT, "badger.py"))
+        cli = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(cli)
+        cli.init = lambda *a, **k: 1                      # the bench already holds the device; keep its context
+        argv = ["-r", tsv, "-l", wlf, "-d", "10x", "-t", str(t), "--n_cells", str(cfg["n_cells"])]
+
+        def run(extra, out):
+            sink = io.StringIO()
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(sink):
+                cli.main(argv + ["-o", os.path.join(tmp, out)] + extra)
+            dt = time.perf_counter() - t0
+            for h in list(logging.getLogger("BarcodeGraph").handlers):
+                logging.getLogger("BarcodeGraph").removeHandler(h)
+            return dt, "reading through pandas" in sink.getvalue()
+
+        run([], "WARM")
+        reps = 3
+        dts = [run([], "NATIVE") for _ in range(reps)]
+        assert not any(fell_back for _, fell_back in dts), "the native TSV reader declined the bench's own file"
+        dt = sum(d for d, _ in dts) / reps
+        dt_pandas, _ = run(["--no_native_io"], "PANDAS")
+        with open(os.path.join(tmp, "NATIVE_output_file.tsv"), "rb") as a, open(os.path.join(tmp, "PANDAS_output_file.tsv"), "rb") as b:
+            same = a.read() == b.read()
+        assert same, "the two routes of badger.py wrote different output files"
+        return {"reads_per_s": obs.size / dt, "ms": dt * 1e3, "reads": int(obs.size),
+                "bytes_in": os.path.getsize(tsv) + os.path.getsize(wlf), "bytes_out": os.path.getsize(os.path.join(tmp, "NATIVE_output_file.tsv")),
+                "command": "badger.py -r reads.tsv -l whitelist.txt -d 10x -t %d --n_cells %d -o OUT (in-process, files in the page cache)" % (t, cfg["n_cells"]),
+                "pandas_route": {"reads_per_s": obs.size / dt_pandas, "ms": dt_pandas * 1e3, "flag": "--no_native_io"},
+                "outputs_identical": same}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def other_stages(torch, dev, stream, L, s, args):
