@@ -19,6 +19,7 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <thrust/iterator/transform_iterator.h>
 
 namespace {
 
@@ -87,6 +88,10 @@ struct DevCtx {
     uint64_t plan_key[4] = {0, 0, 0, 0};
     bool plan_valid = false;
     Buf cl[6];                                                // clustering: centres, centre index, level, claim min / max, index scratch
+    Buf as[8];                                                // masked dedup + per-read gather: all ranks, valid bytes, their scan, scratch, centre idx / value, result, counter
+    unsigned long long map_token = 0, map_serial = 0;         // read map left on the device by bdg_dedup_reads (0: none)
+    size_t map_rows = 0, map_reads = 0, map_distinct = 0;
+    bool map_masked = false;
     Buf gather_a, gather_b;                                   // edge ends of ALL devices of a multi-device handle, gathered here for cluster()
     Buf nn[9];                                                // sparse nearest: rotated keys + payload (in/out) of queries and targets, scratch
 };
@@ -460,7 +465,16 @@ int bdg_init(const int* device_ids, int n_devices)
         }
         g_ctx.push_back(c);
     }
+    // direct NVLink copies into the first device (bdg_cluster_levels_from_edges gathers the other devices' edge lists there);
+    // without peer access cudaMemcpyPeerAsync stages through host memory
     CU_TRY(cudaSetDevice(g_ctx[0].dev));
+    for (size_t g = 1; g < g_ctx.size(); g++) {
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, g_ctx[0].dev, g_ctx[g].dev) == cudaSuccess && can) {
+            const cudaError_t pe = cudaDeviceEnablePeerAccess(g_ctx[g].dev, 0);
+            if (pe != cudaSuccess) (void)cudaGetLastError();      // already enabled (e.g. by the caller's framework): fine
+        }
+    }
     return BDG_OK;
 }
 
@@ -479,6 +493,7 @@ void bdg_shutdown(void)
         for (auto& b : c.nn) b.release();
         for (auto& b : c.cl) b.release();
         c.gather_a.release(); c.gather_b.release();
+        for (auto& b : c.as) b.release();
         for (auto& b : c.rot_sorted) b.release();
     }
     g_ctx.clear();
@@ -643,26 +658,20 @@ int bdg_dev_pipe_probe(int kind, int blocks, int iters, uint32_t* d_sink, unsign
 
 // ---------------------------------------------------------------- host-buffer entry points
 // ---- a-2  dedup + count in first-seen order (barcode_graph.py:192-204) ------------------------------------
-int bdg_dedup_first_seen(const uint32_t* ranks, size_t R, uint32_t* distinct, uint32_t* counts, uint32_t* read_to_distinct,
-                         uint32_t* sorted_pos, size_t* n_distinct)
+// The keys of the n reads sit in dd[0] on entry (put there by the caller).  keep_map: compute the read -> first-seen
+// position map and leave it in dd[7] (download it too when read_to_distinct != NULL).
+static int dedup_core(DevCtx& c, uint32_t n, uint32_t* distinct, uint32_t* counts, uint32_t* read_to_distinct, uint32_t* sorted_pos,
+                      bool keep_map, size_t* n_distinct)
 {
-    if (!n_distinct) return fail(BDG_ERR_ARG, "NULL n_distinct pointer");
-    *n_distinct = 0;
-    if (R == 0) return BDG_OK;
-    if (!ranks || !distinct || !counts) return fail(BDG_ERR_ARG, "NULL pointer argument");
-    if (R > 0x7FFFFFFFull) return fail(BDG_ERR_ARG, "more than 2^31 reads in one call");
-    if (int rc = need_ctx()) return rc;
-    DevCtx& c = g_ctx[0];
-    CU_TRY(cudaSetDevice(c.dev));
     cudaStream_t st = c.stream;
-    const uint32_t n = (uint32_t)R;
     auto ensure = [&](Buf& b, size_t bytes) -> int {
         if (cudaError_t e = (cudaError_t)b.ensure(bytes))
             return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation of %zu bytes: %s", bytes, cudaGetErrorString(e));
         return BDG_OK;
     };
+    const size_t R = n;
     // dd[0] keys, [1] idx, [2] sorted keys, [3] sorted idx, [4] heads, [5] inclusive scan, [6] run key, [7] run first, [8] run start, [9] scratch
-    for (int k = 0; k < 9; k++) if (int e = ensure(c.dd[k], R * 4)) return e;
+    for (int k = 1; k < 9; k++) if (int e = ensure(c.dd[k], R * 4)) return e;
     uint32_t *d_k = (uint32_t*)c.dd[0].p, *d_i = (uint32_t*)c.dd[1].p, *d_sk = (uint32_t*)c.dd[2].p, *d_si = (uint32_t*)c.dd[3].p;
     uint32_t *d_head = (uint32_t*)c.dd[4].p, *d_scan = (uint32_t*)c.dd[5].p, *d_rk = (uint32_t*)c.dd[6].p, *d_rf = (uint32_t*)c.dd[7].p, *d_rs = (uint32_t*)c.dd[8].p;
     size_t tmp1 = 0, tmp2 = 0;
@@ -670,7 +679,6 @@ int bdg_dedup_first_seen(const uint32_t* ranks, size_t R, uint32_t* distinct, ui
     CU_TRY(cub::DeviceScan::InclusiveSum(nullptr, tmp2, d_head, d_scan, (int)n, st));
     if (int e = ensure(c.dd[9], std::max(tmp1, tmp2))) return e;
     const int blocks = (int)std::min<size_t>((R + 255) / 256, (size_t)c.sms * 8);
-    CU_TRY(cudaMemcpyAsync(d_k, ranks, R * 4, cudaMemcpyHostToDevice, st));
     bdg::iota_kernel<<<blocks, 256, 0, st>>>(d_i, n);
     CU_TRY(cub::DeviceRadixSort::SortPairs(c.dd[9].p, tmp1, d_k, d_sk, d_i, d_si, (int)n, 0, 32, st));
     bdg::dedup_heads_kernel<<<blocks, 256, 0, st>>>(d_sk, n, d_head);
@@ -690,14 +698,132 @@ int bdg_dedup_first_seen(const uint32_t* ranks, size_t R, uint32_t* distinct, ui
     CU_TRY(cudaMemcpyAsync(distinct, d_distinct, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(counts, d_counts, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st));
     if (sorted_pos) CU_TRY(cudaMemcpyAsync(sorted_pos, d_i, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st));   // order[pos] = run = ascending position
-    if (read_to_distinct) {
+    if (keep_map || read_to_distinct) {
         bdg::dedup_scatter_kernel<<<blocks, 256, 0, st>>>(d_si, d_scan, d_pos, n, d_rf);   // d_rf is free after the run sort
         g_launches++;
-        CU_TRY(cudaMemcpyAsync(read_to_distinct, d_rf, R * 4, cudaMemcpyDeviceToHost, st));
+        if (read_to_distinct) CU_TRY(cudaMemcpyAsync(read_to_distinct, d_rf, R * 4, cudaMemcpyDeviceToHost, st));
     }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(st));
     *n_distinct = n_runs;
+    return BDG_OK;
+}
+
+int bdg_dedup_first_seen(const uint32_t* ranks, size_t R, uint32_t* distinct, uint32_t* counts, uint32_t* read_to_distinct,
+                         uint32_t* sorted_pos, size_t* n_distinct)
+{
+    if (!n_distinct) return fail(BDG_ERR_ARG, "NULL n_distinct pointer");
+    *n_distinct = 0;
+    if (R == 0) return BDG_OK;
+    if (!ranks || !distinct || !counts) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if (R > 0x7FFFFFFFull) return fail(BDG_ERR_ARG, "more than 2^31 reads in one call");
+    if (int rc = need_ctx()) return rc;
+    DevCtx& c = g_ctx[0];
+    CU_TRY(cudaSetDevice(c.dev));
+    c.map_token = 0;                                  // the workspaces are about to be reused: an older read map dies here
+    if (cudaError_t e = (cudaError_t)c.dd[0].ensure(R * 4))
+        return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation of %zu bytes: %s", R * 4, cudaGetErrorString(e));
+    CU_TRY(cudaMemcpyAsync(c.dd[0].p, ranks, R * 4, cudaMemcpyHostToDevice, c.stream));
+    return dedup_core(c, (uint32_t)R, distinct, counts, read_to_distinct, sorted_pos, false, n_distinct);
+}
+
+// ---- f-1 + f-2 on the device: masked dedup that keeps the read map resident, and the per-read gather that uses it ------
+int bdg_dedup_reads(const uint32_t* ranks, const uint8_t* valid, size_t R_all, uint32_t* distinct, uint32_t* counts, uint32_t* sorted_pos,
+                    size_t* n_distinct, size_t* n_valid, unsigned long long* token)
+{
+    if (!n_distinct || !n_valid || !token) return fail(BDG_ERR_ARG, "NULL result pointer");
+    *n_distinct = 0; *n_valid = 0; *token = 0;
+    if (R_all == 0) return BDG_OK;
+    if (!ranks || !distinct || !counts) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if (R_all > 0x7FFFFFFFull) return fail(BDG_ERR_ARG, "more than 2^31 reads in one call");
+    if (int rc = need_ctx()) return rc;
+    DevCtx& c = g_ctx[0];
+    CU_TRY(cudaSetDevice(c.dev));
+    cudaStream_t st = c.stream;
+    c.map_token = 0;
+    auto ensure = [&](Buf& b, size_t bytes) -> int {
+        if (cudaError_t e = (cudaError_t)b.ensure(bytes))
+            return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation of %zu bytes: %s", bytes, cudaGetErrorString(e));
+        return BDG_OK;
+    };
+    if (int e = ensure(c.dd[0], R_all * 4)) return e;
+    size_t n_reads = R_all;
+    c.map_masked = valid != nullptr;
+    if (valid) {
+        // as[0] all ranks, as[1] valid bytes, as[2] exclusive scan of valid (the index of a valid row among the valid rows), as[3] scratch
+        if (int e = ensure(c.as[0], R_all * 4)) return e;
+        if (int e = ensure(c.as[1], R_all)) return e;
+        if (int e = ensure(c.as[2], (R_all + 1) * 4)) return e;
+        const uint8_t* d_valid = (const uint8_t*)c.as[1].p;
+        uint32_t* d_excl = (uint32_t*)c.as[2].p;
+        auto flags = thrust::make_transform_iterator(d_valid, bdg::NonZero());
+        size_t tmp = 0;
+        CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp, flags, d_excl, (int)R_all, st));
+        if (int e = ensure(c.as[3], tmp)) return e;
+        CU_TRY(cudaMemcpyAsync(c.as[0].p, ranks, R_all * 4, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(c.as[1].p, valid, R_all, cudaMemcpyHostToDevice, st));
+        CU_TRY(cub::DeviceScan::ExclusiveSum(c.as[3].p, tmp, flags, d_excl, (int)R_all, st));
+        const int blocks = (int)std::min<size_t>((R_all + 255) / 256, (size_t)c.sms * 8);
+        bdg::compact_valid_kernel<<<blocks, 256, 0, st>>>((const uint32_t*)c.as[0].p, d_valid, d_excl, (uint32_t)R_all, (uint32_t*)c.dd[0].p);
+        g_launches++;
+        uint32_t last_excl = 0;
+        uint8_t last_valid = 0;
+        CU_TRY(cudaMemcpyAsync(&last_excl, d_excl + (R_all - 1), 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(&last_valid, d_valid + (R_all - 1), 1, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        n_reads = (size_t)last_excl + (last_valid ? 1 : 0);
+    } else {
+        CU_TRY(cudaMemcpyAsync(c.dd[0].p, ranks, R_all * 4, cudaMemcpyHostToDevice, st));
+    }
+    *n_valid = n_reads;
+    c.map_rows = R_all; c.map_reads = n_reads; c.map_distinct = 0;
+    if (n_reads == 0) return BDG_OK;
+    if (int rc = dedup_core(c, (uint32_t)n_reads, distinct, counts, nullptr, sorted_pos, true, n_distinct)) return rc;
+    c.map_distinct = *n_distinct;
+    c.map_token = ++c.map_serial;
+    *token = c.map_token;
+    return BDG_OK;
+}
+
+int bdg_assign_reads(unsigned long long token, const int32_t* centre_idx, size_t N, uint64_t* centre_per_row, size_t R_all, size_t* n_assigned)
+{
+    if (n_assigned) *n_assigned = 0;
+    if (R_all == 0) return BDG_OK;
+    if (!centre_per_row || (N && !centre_idx)) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if (int rc = need_ctx()) return rc;
+    DevCtx& c = g_ctx[0];
+    if (token == 0 || token != c.map_token) return fail(BDG_ERR_ARG, "stale read-map token: a later dedup call has reused the workspaces");
+    if (N != c.map_distinct || R_all != c.map_rows) return fail(BDG_ERR_ARG, "sizes do not match the dedup call the token came from");
+    CU_TRY(cudaSetDevice(c.dev));
+    cudaStream_t st = c.stream;
+    auto ensure = [&](Buf& b, size_t bytes) -> int {
+        if (cudaError_t e = (cudaError_t)b.ensure(bytes))
+            return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation of %zu bytes: %s", bytes, cudaGetErrorString(e));
+        return BDG_OK;
+    };
+    // as[4] centre index per node (upload), as[5] centre value per distinct barcode in first-seen order, as[6] result per row, as[7] counter
+    if (int e = ensure(c.as[4], std::max<size_t>(N, 1) * 4)) return e;
+    if (int e = ensure(c.as[5], std::max<size_t>(N, 1) * 8)) return e;
+    if (int e = ensure(c.as[6], R_all * 8)) return e;
+    if (int e = ensure(c.as[7], 8)) return e;
+    CU_TRY(cudaMemcpyAsync(c.as[4].p, centre_idx, N * 4, cudaMemcpyHostToDevice, st));
+    CU_TRY(cudaMemsetAsync(c.as[7].p, 0, 8, st));
+    if (N) {
+        const int nb = (int)std::min<size_t>((N + 255) / 256, (size_t)c.sms * 8);
+        bdg::centre_of_distinct_kernel<<<nb, 256, 0, st>>>((const int32_t*)c.as[4].p, (const uint32_t*)c.dd[1].p /* first-seen -> node */,
+                                                           (const uint32_t*)c.dd[6].p /* node -> barcode */, (uint32_t)N, (uint64_t*)c.as[5].p);
+    }
+    const int rb = (int)std::min<size_t>((R_all + 255) / 256, (size_t)c.sms * 8);
+    bdg::assign_reads_kernel<<<rb, 256, 0, st>>>((const uint64_t*)c.as[5].p, (const uint32_t*)c.dd[7].p, c.map_masked ? (const uint8_t*)c.as[1].p : nullptr,
+                                                 c.map_masked ? (const uint32_t*)c.as[2].p : nullptr, (uint32_t)R_all, (uint64_t*)c.as[6].p,
+                                                 (unsigned long long*)c.as[7].p);
+    g_launches += 2;
+    CU_TRY(cudaGetLastError());
+    unsigned long long cnt = 0;
+    CU_TRY(cudaMemcpyAsync(centre_per_row, c.as[6].p, R_all * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(&cnt, c.as[7].p, 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (n_assigned) *n_assigned = (size_t)cnt;
     return BDG_OK;
 }
 
@@ -913,6 +1039,9 @@ static int cluster_on_device(DevCtx& c, const uint32_t* d_sorted, size_t N, uint
     uint8_t* d_lv = (uint8_t*)c.cl[2].p;
     const int nb = (int)std::min<size_t>((N + 255) / 256, (size_t)c.sms * 8);
     const int eb = (int)std::min<size_t>((E + 255) / 256, (size_t)c.sms * 16);
+    const bool trace = getenv("BDG_TRACE") != nullptr;
+    double tr0 = 0, tr1 = 0, tr2 = 0;
+    if (trace) { cudaStreamSynchronize(st); tr0 = now_ms(); }
     CU_TRY(cudaMemcpyAsync(d_cen, centres, C * 4, cudaMemcpyHostToDevice, st));
     bdg::cluster_init_kernel<<<nb, 256, 0, st>>>(d_ci, d_lv, d_min, d_max, (uint32_t)N);
     if (C) bdg::cluster_seed_kernel<<<(int)std::min<size_t>((C + 255) / 256, (size_t)c.sms * 8), 256, 0, st>>>(d_sorted, (uint32_t)N, d_cen, (uint32_t)C, d_ci, d_lv);
@@ -920,6 +1049,7 @@ static int cluster_on_device(DevCtx& c, const uint32_t* d_sorted, size_t N, uint
     if (E) {
         bdg::cluster_index_kernel<<<eb, 256, 0, st>>>(d_sorted, (uint32_t)N, d_ea, d_eb, E, d_lv);
         g_launches++;
+        if (trace) { cudaStreamSynchronize(st); tr1 = now_ms(); }
         for (int r = 1; r <= rounds; r++) {
             bdg::cluster_claim_kernel<<<eb, 256, 0, st>>>(d_ea, d_eb, E, r, d_ci, d_lv, d_min, d_max);
             bdg::cluster_resolve_kernel<<<nb, 256, 0, st>>>(d_ci, d_lv, d_min, d_max, (uint32_t)N, r);
@@ -927,9 +1057,13 @@ static int cluster_on_device(DevCtx& c, const uint32_t* d_sorted, size_t N, uint
         }
     }
     CU_TRY(cudaGetLastError());
+    if (trace) { cudaStreamSynchronize(st); tr2 = now_ms(); }
     CU_TRY(cudaMemcpyAsync(centre_idx, d_ci, N * 4, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(level, d_lv, N, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
+    if (trace)
+        fprintf(stderr, "[bdg] cluster N=%zu E=%zu: (gather +) seed + index %.2f ms, %d rounds %.2f ms, read-back %.2f ms\n", N, E, tr1 - tr0, rounds,
+                tr2 - tr1, now_ms() - tr2);
     return BDG_OK;
 }
 

@@ -55,6 +55,44 @@ def dedup_first_seen(ranks: np.ndarray, want_map: bool = False, want_sorted_pos:
     return out
 
 
+class ReadMap:
+    """Result of dedup_reads: distinct barcodes in first-seen order, their counts and ascending positions on the host; the
+    read -> barcode map stays on the device under `token` until the next dedup call."""
+
+    def __init__(self, distinct, counts, sorted_pos, n_valid, rows, token):
+        self.distinct, self.counts, self.sorted_pos = distinct, counts, sorted_pos
+        self.n_valid, self.rows, self.token = n_valid, rows, token
+
+
+def dedup_reads(ranks: np.ndarray, valid=None) -> ReadMap:
+    """barcode_graph.py:192-204 over the rows with valid[i] (None: all), compacted on the device; the per-read map is
+    kept there for assign_reads (include/badger_b200.h bdg_dedup_reads)."""
+    r = np.ascontiguousarray(ranks, dtype=np.uint32)
+    v = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8 if valid.dtype != bool else bool).view(np.uint8)
+    cap = r.size
+    distinct = np.empty(cap, np.uint32); counts = np.empty(cap, np.uint32); spos = np.empty(cap, np.uint32)
+    n, nv, tok = C.c_size_t(0), C.c_size_t(0), C.c_ulonglong(0)
+    if r.size:
+        check(lib().bdg_dedup_reads(ptr(r), ptr(v) if v is not None else None, r.size, ptr(distinct), ptr(counts), ptr(spos),
+                                    C.byref(n), C.byref(nv), C.byref(tok)))
+    k = int(n.value)
+    return ReadMap(distinct[:k].copy(), counts[:k].astype(np.int64), spos[:k].copy(), int(nv.value), int(r.size), int(tok.value))
+
+
+def assign_reads(rmap: ReadMap, centre_idx: np.ndarray):
+    """barcode_graph.py:322-329 + 395-404 on the device: centre barcode of every input row of the dedup call (uint64, 2^32 =
+    none) from the clustering result on node positions; returns (centre_per_row, rows with a centre)."""
+    ci = np.ascontiguousarray(centre_idx, dtype=np.int32)
+    out = np.empty(rmap.rows, np.uint64)
+    n = C.c_size_t(0)
+    if rmap.rows:
+        if rmap.token == 0:                                   # no valid row at all: nothing was deduplicated
+            out[:] = np.uint64(1) << np.uint64(32)
+        else:
+            check(lib().bdg_assign_reads(rmap.token, ptr(ci), ci.size, ptr(out), out.size, C.byref(n)))
+    return out, int(n.value)
+
+
 class _PinnedPool:
     """Page-locked blocks behind the (large) edge arrays the operators return: a device-to-host copy into pinned memory
     runs at full PCIe speed, into pageable memory at about a third of it.  A block goes back to the pool when the last

@@ -49,15 +49,18 @@ def assign_packed(ranks, valid=None, *, threshold, n_cells, interval=25, whiteli
     R = ranks.size
     if valid is not None:
         valid = np.ascontiguousarray(valid, dtype=bool)
-    reads = ranks if valid is None else ranks[valid]
-    out = np.full(R, NONE, dtype=np.uint64)
-    info = {"reads": int(R), "valid_reads": int(reads.size)}
-    if reads.size == 0:
-        return out, info
+    info = {"reads": int(R)}
+    if R == 0:
+        info["valid_reads"] = 0
+        return np.full(0, NONE, dtype=np.uint64), info
 
     t0 = time.perf_counter()
-    distinct, counts, rmap, spos = ops.dedup_first_seen(reads, want_map=True, want_sorted_pos=True)
+    rm = ops.dedup_reads(ranks, valid)                    # valid rows compacted on the device, read map stays there
+    distinct, counts, spos = rm.distinct, rm.counts, rm.sorted_pos
     tick("dedup_first_seen", t0)
+    info["valid_reads"] = int(rm.n_valid)
+    if rm.n_valid == 0:
+        return np.full(R, NONE, dtype=np.uint64), info
     t0 = time.perf_counter()
     s = np.empty_like(distinct)
     s[spos] = distinct                                    # ascending order, no host sort
@@ -81,40 +84,38 @@ def assign_packed(ranks, valid=None, *, threshold, n_cells, interval=25, whiteli
     handle.free()
     # badger.py:131 `len(counts) - len(edges.keys())`: the keys are the nodes with an edge plus every centre cluster() touched
     info["disconnected"] = int(distinct.size) - (int(has_edge.sum()) + int(centres.size))
-    centre_sorted = np.where(ci >= 0, s[np.maximum(ci, 0)].astype(np.uint64), NONE)
-    centre_distinct = centre_sorted[spos]
     tick("cluster", t0)
 
     if high_sens:
+        # barcode_graph.py:370-385 on node positions: every node without a centre looks for the nearest used centre
         t0 = time.perf_counter()
-        todo = np.nonzero(centre_distinct == NONE)[0]
-        used = ops.sorted_unique(centre_distinct[centre_distinct != NONE]).astype(np.uint32)     # set(assignments.values())
+        todo = np.nonzero(ci < 0)[0]
+        used_nodes = ops.sorted_unique(ci[ci >= 0])                              # set(assignments.values()), as nodes (ascending = by value)
         if centre_order is None:
-            targets = used
+            targets = s[used_nodes]
         elif isinstance(centre_order, str) and centre_order == "set":
             # the order the string route meets in this process: `set(assignments.values())` with the dict filled in
             # first-seen order of the distinct barcodes (barcode_graph.py:322-329,372).  Re-adding a member leaves a set's
             # table untouched, so the set of the first occurrences, added in that order, iterates identically.
-            vals = centre_distinct[centre_distinct != NONE]
-            order = np.argsort(vals, kind="stable")                      # first occurrence of every value, in order of appearance
+            cfs = ci[spos]                                                       # centre node per distinct barcode, first-seen order
+            vals = cfs[cfs >= 0]
+            order = np.argsort(vals, kind="stable")                              # first occurrence of every value, in order of appearance
             sv = vals[order]
             head = np.ones(sv.size, bool)
             head[1:] = sv[1:] != sv[:-1]
-            strs = _unrank_many(vals[np.sort(order[head])].astype(np.uint32))
+            strs = _unrank_many(s[vals[np.sort(order[head])]])
             targets = np.asarray([rank(c, 16) for c in set(strs)], np.uint32)
         else:
-            targets = np.asarray([c for c in centre_order if c in set(used.tolist())], np.uint32)
+            used = set(s[used_nodes].tolist())
+            targets = np.asarray([c for c in centre_order if c in used], np.uint32)
         if todo.size and targets.size:
-            am, _ = ops.nearest_bounded(distinct[todo], targets, 2)
+            am, _ = ops.nearest_bounded(s[todo], targets, 2)
             hit = am >= 0
-            centre_distinct[todo[hit]] = targets[am[hit]].astype(np.uint64)
+            ci[todo[hit]] = np.searchsorted(s, targets[am[hit]]).astype(np.int32)
         tick("high_sens", t0)
 
     t0 = time.perf_counter()
-    if valid is None:
-        out[:] = centre_distinct[rmap]
-    else:
-        out[valid] = centre_distinct[rmap]
+    out, n_assigned = ops.assign_reads(rm, ci)            # per-read gather on the device
     tick("gather", t0)
-    info["assigned_reads"] = int((out != NONE).sum())
+    info["assigned_reads"] = int(n_assigned)
     return out, info

@@ -74,6 +74,19 @@ int bdg_pack16(const char* seqs, size_t R, uint32_t* out, uint8_t* valid);
 int bdg_dedup_first_seen(const uint32_t* ranks, size_t R, uint32_t* distinct, uint32_t* counts, uint32_t* read_to_distinct,
                          uint32_t* sorted_pos, size_t* n_distinct);
 
+/* ---- f-1 / f-2 with the per-read arrays resident on the device -------------------------------------------------- */
+/* bdg_dedup_reads = bdg_dedup_first_seen over the rows with valid[i] != 0 (valid == NULL: all rows), compacted on the
+ * device; the read -> barcode map is NOT copied out but kept on the first device, and *token names it.
+ * bdg_assign_reads is the per-read half of assign_by_cluster + output_file (barcode_graph.py:322-329, 395-404):
+ * centre_idx[N] is the clustering result on node positions of the ascending array (bdg_cluster_levels*, possibly patched
+ * by the caller, e.g. for --high_sens); centre_per_row[R_all] receives, for every input row of the dedup call, the
+ * barcode of the centre its barcode was assigned to, or 2^32 (rows with valid == 0, unassigned / evicted barcodes:
+ * the reference writes '*').  *n_assigned = rows with a centre.  The token dies with the next dedup call. */
+int bdg_dedup_reads(const uint32_t* ranks, const uint8_t* valid, size_t R_all, uint32_t* distinct, uint32_t* counts,
+                    uint32_t* sorted_pos, size_t* n_distinct, size_t* n_valid, unsigned long long* token);
+int bdg_assign_reads(unsigned long long token, const int32_t* centre_idx, size_t N, uint64_t* centre_per_row, size_t R_all,
+                     size_t* n_assigned);
+
 /* ---- a-3 + a-4  QGramIndex.get_close + verify/emit: index.py:77-93, barcode_graph.py:224-249 ------ */
 /* Edge set {(a,b,D): a<b, S(a,b) >= T(t), D(a,b) <= t} over a STRICTLY INCREASING array of distinct
  * barcodes (checked).  bdg_edges_build uses every initialised device (rows dealt per BDG_ROW_TILE) and

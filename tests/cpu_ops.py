@@ -74,6 +74,32 @@ def dedup_first_seen(ranks, want_map=False, want_sorted_pos=False):
     return out
 
 
+def dedup_reads(ranks, valid=None):
+    from badger_b200 import ops
+    r = np.ascontiguousarray(ranks, dtype=np.uint32)
+    v = np.ones(r.size, bool) if valid is None else np.asarray(valid, bool)
+    if not v.any():
+        return ops.ReadMap(np.empty(0, np.uint32), np.empty(0, np.int64), np.empty(0, np.uint32), 0, int(r.size), 0)
+    d, c, rmap, spos = dedup_first_seen(r[v], want_map=True, want_sorted_pos=True)
+    rm = ops.ReadMap(d, c, spos, int(v.sum()), int(r.size), 1)
+    rm._cpu = (v, rmap)
+    return rm
+
+
+def assign_reads(rm, centre_idx):
+    none = np.uint64(1) << np.uint64(32)
+    out = np.full(rm.rows, none, np.uint64)
+    if rm.token == 0:
+        return out, 0
+    v, rmap = rm._cpu
+    s = np.empty_like(rm.distinct)
+    s[rm.sorted_pos] = rm.distinct
+    ci = np.asarray(centre_idx, np.int32)[rm.sorted_pos]
+    cd = np.where(ci >= 0, s[np.maximum(ci, 0)].astype(np.uint64), none)
+    out[v] = cd[rmap]
+    return out, int((out != none).sum())
+
+
 def cluster_levels(sorted_unique, ea, eb, centres, rounds=2, want_has_edge=False):
     """Literal restatement of the reference's rounds (oracle.cluster) turned into the operator's array form."""
     if want_has_edge:
@@ -126,5 +152,5 @@ def edges_handle(sorted_unique, t):
 def install(monkeypatch):
     from badger_b200 import ops
     for name in ("pack16", "edges_build", "edges_build_part", "member_sorted", "nearest_bounded", "kmer_score", "dedup_first_seen",
-                 "cluster_levels", "KmerIndex", "edges_handle"):
+                 "cluster_levels", "KmerIndex", "edges_handle", "dedup_reads", "assign_reads"):
         monkeypatch.setattr(ops, name, globals()[name])

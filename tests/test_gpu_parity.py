@@ -418,6 +418,43 @@ def test_cluster_levels_vs_reference_rounds():
     assert any((ci == -1).any() for ci, _ in [ops.cluster_levels(*c, 2) for c in cases[:10]])      # conflicts were exercised
 
 
+def test_dedup_reads_and_assign_reads_vs_numpy():
+    """Rows f-1 / f-2 with the per-read arrays resident on the device (bdg_dedup_reads + bdg_assign_reads) against the
+    host-array operators and a numpy restatement: masks of every kind, the token life cycle, bad sizes."""
+    rng = np.random.default_rng(17)
+    none = np.uint64(1) << np.uint64(32)
+    for R, pool, pv in ((1, 1, 1.0), (5, 3, 0.5), (1000, 40, 0.9), (200000, 30000, 0.97), (200000, 5, 0.0), (77777, 70000, 1.0), (300001, 1000, 0.3)):
+        keys = rng.integers(0, 1 << 32, pool, dtype=np.uint64).astype(np.uint32)
+        ranks = keys[rng.integers(0, pool, R)]
+        for valid in (None, rng.random(R) < pv):
+            rm = ops.dedup_reads(ranks, valid)
+            v = np.ones(R, bool) if valid is None else valid
+            assert rm.n_valid == int(v.sum()) and rm.rows == R
+            if rm.n_valid == 0:
+                out, n = ops.assign_reads(rm, np.empty(0, np.int32))
+                assert (out == none).all() and n == 0
+                continue
+            d, c, rmap, spos = ops.dedup_first_seen(ranks[v], want_map=True, want_sorted_pos=True)       # kills the token ...
+            with pytest.raises(badger_b200.BadgerB200Error):
+                ops.assign_reads(rm, np.zeros(d.size, np.int32))
+            rm = ops.dedup_reads(ranks, valid)                                                            # ... so take a new one
+            assert np.array_equal(rm.distinct, d) and np.array_equal(rm.counts, c) and np.array_equal(rm.sorted_pos, spos)
+            N = d.size
+            s = np.sort(d)
+            ci = rng.integers(-2, N, N).astype(np.int32)
+            out, n = ops.assign_reads(rm, ci)
+            cd = np.where(ci[spos] >= 0, s[np.maximum(ci[spos], 0)].astype(np.uint64), none)
+            want = np.full(R, none, np.uint64)
+            want[v] = cd[rmap]
+            assert np.array_equal(out, want) and n == int((want != none).sum())
+            out2, _ = ops.assign_reads(rm, ci)                                                            # the token survives its use
+            assert np.array_equal(out2, want)
+            with pytest.raises(badger_b200.BadgerB200Error):
+                ops.assign_reads(rm, ci[:-1] if N > 1 else np.zeros(2, np.int32))
+    rm = ops.dedup_reads(np.empty(0, np.uint32))
+    assert rm.rows == 0 and ops.assign_reads(rm, np.empty(0, np.int32))[0].size == 0
+
+
 def test_packed_pipeline_on_all_devices_matches_one_device():
     """rows dealt to the GPUs, per-GPU edge lists gathered on the first device for the clustering rounds
     (bdg_cluster_levels_from_edges on a multi-device handle).  Needs >= 2 GPUs (gpurun --gpus 2)."""
