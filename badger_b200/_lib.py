@@ -46,7 +46,7 @@ def lib():
     L.bdg_host_free.restype = None
     L.bdg_pack16.argtypes = [_vp, _sz, _vp, _vp]
     L.bdg_dedup_first_seen.argtypes = [_vp, _sz, _vp, _vp, _vp, _vp, C.POINTER(_sz)]
-    L.bdg_dedup_reads.argtypes = [_vp, _vp, _sz, _vp, _vp, _vp, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(C.c_ulonglong)]
+    L.bdg_dedup_reads.argtypes = [_vp, _vp, _sz, _vp, _vp, _vp, _vp, C.POINTER(_sz), C.POINTER(_sz), C.POINTER(C.c_ulonglong)]
     L.bdg_assign_reads.argtypes = [C.c_ulonglong, _vp, _sz, _vp, _sz, C.POINTER(_sz)]
     L.bdg_edges_build.argtypes = [_vp, _sz, _i, C.POINTER(_vp)]
     L.bdg_edges_build_part.argtypes = [_vp, _sz, _i, _i, _i, C.POINTER(_vp)]

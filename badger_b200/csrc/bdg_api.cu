@@ -661,7 +661,7 @@ int bdg_dev_pipe_probe(int kind, int blocks, int iters, uint32_t* d_sink, unsign
 // The keys of the n reads sit in dd[0] on entry (put there by the caller).  keep_map: compute the read -> first-seen
 // position map and leave it in dd[7] (download it too when read_to_distinct != NULL).
 static int dedup_core(DevCtx& c, uint32_t n, uint32_t* distinct, uint32_t* counts, uint32_t* read_to_distinct, uint32_t* sorted_pos,
-                      bool keep_map, size_t* n_distinct)
+                      bool keep_map, size_t* n_distinct, uint32_t* sorted_distinct = nullptr)
 {
     cudaStream_t st = c.stream;
     auto ensure = [&](Buf& b, size_t bytes) -> int {
@@ -698,6 +698,7 @@ static int dedup_core(DevCtx& c, uint32_t n, uint32_t* distinct, uint32_t* count
     CU_TRY(cudaMemcpyAsync(distinct, d_distinct, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(counts, d_counts, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st));
     if (sorted_pos) CU_TRY(cudaMemcpyAsync(sorted_pos, d_i, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st));   // order[pos] = run = ascending position
+    if (sorted_distinct) CU_TRY(cudaMemcpyAsync(sorted_distinct, d_rk, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st));   // runs are numbered in key order
     if (keep_map || read_to_distinct) {
         bdg::dedup_scatter_kernel<<<blocks, 256, 0, st>>>(d_si, d_scan, d_pos, n, d_rf);   // d_rf is free after the run sort
         g_launches++;
@@ -729,7 +730,7 @@ int bdg_dedup_first_seen(const uint32_t* ranks, size_t R, uint32_t* distinct, ui
 
 // ---- f-1 + f-2 on the device: masked dedup that keeps the read map resident, and the per-read gather that uses it ------
 int bdg_dedup_reads(const uint32_t* ranks, const uint8_t* valid, size_t R_all, uint32_t* distinct, uint32_t* counts, uint32_t* sorted_pos,
-                    size_t* n_distinct, size_t* n_valid, unsigned long long* token)
+                    uint32_t* sorted_distinct, size_t* n_distinct, size_t* n_valid, unsigned long long* token)
 {
     if (!n_distinct || !n_valid || !token) return fail(BDG_ERR_ARG, "NULL result pointer");
     *n_distinct = 0; *n_valid = 0; *token = 0;
@@ -778,7 +779,7 @@ int bdg_dedup_reads(const uint32_t* ranks, const uint8_t* valid, size_t R_all, u
     *n_valid = n_reads;
     c.map_rows = R_all; c.map_reads = n_reads; c.map_distinct = 0;
     if (n_reads == 0) return BDG_OK;
-    if (int rc = dedup_core(c, (uint32_t)n_reads, distinct, counts, nullptr, sorted_pos, true, n_distinct)) return rc;
+    if (int rc = dedup_core(c, (uint32_t)n_reads, distinct, counts, nullptr, sorted_pos, true, n_distinct, sorted_distinct)) return rc;
     c.map_distinct = *n_distinct;
     c.map_token = ++c.map_serial;
     *token = c.map_token;
@@ -921,8 +922,11 @@ static int edges_on_devices(const uint32_t* sorted, size_t N, int t, const std::
     std::vector<int> rcs(G, BDG_OK);
     std::vector<std::string> errs(G);
     std::vector<size_t> counts(G, 0);
+    std::vector<double> took(G, 0.0);
     auto work = [&](size_t g) {
+        const double w0 = now_ms();
         rcs[g] = edges_on_device(g_ctx[ctx_idx[g]], sorted, N, t, parts[g], nparts, &counts[g]);
+        took[g] = now_ms() - w0;
         if (rcs[g]) errs[g] = g_err;       // g_err is thread-local
     };
     if (G == 1) work(0);
@@ -941,8 +945,11 @@ static int edges_on_devices(const uint32_t* sorted, size_t N, int t, const std::
         res->gen.push_back(g_ctx[ctx_idx[g]].generation);
         total += counts[g];
     }
-    if (getenv("BDG_TRACE"))
-        fprintf(stderr, "[bdg] edges N=%zu t=%d devices=%zu: upload + kernels %.2f ms, edges %zu\n", N, t, G, now_ms() - t0, total);
+    if (getenv("BDG_TRACE")) {
+        fprintf(stderr, "[bdg] edges N=%zu t=%d devices=%zu: upload + kernels %.2f ms, edges %zu; per device (ms / edges):", N, t, G, now_ms() - t0, total);
+        for (size_t g = 0; g < G; g++) fprintf(stderr, " %.1f/%zu", took[g], counts[g]);
+        fprintf(stderr, "\n");
+    }
     return BDG_OK;
 }
 

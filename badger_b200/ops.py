@@ -59,9 +59,13 @@ class ReadMap:
     """Result of dedup_reads: distinct barcodes in first-seen order, their counts and ascending positions on the host; the
     read -> barcode map stays on the device under `token` until the next dedup call."""
 
-    def __init__(self, distinct, counts, sorted_pos, n_valid, rows, token):
+    def __init__(self, distinct, counts, sorted_pos, n_valid, rows, token, sorted_distinct=None):
         self.distinct, self.counts, self.sorted_pos = distinct, counts, sorted_pos
         self.n_valid, self.rows, self.token = n_valid, rows, token
+        if sorted_distinct is None:                           # ascending order without a host sort
+            sorted_distinct = np.empty_like(distinct)
+            sorted_distinct[sorted_pos] = distinct
+        self.sorted_distinct = sorted_distinct
 
 
 def dedup_reads(ranks: np.ndarray, valid=None) -> ReadMap:
@@ -70,13 +74,13 @@ def dedup_reads(ranks: np.ndarray, valid=None) -> ReadMap:
     r = np.ascontiguousarray(ranks, dtype=np.uint32)
     v = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8 if valid.dtype != bool else bool).view(np.uint8)
     cap = r.size
-    distinct = np.empty(cap, np.uint32); counts = np.empty(cap, np.uint32); spos = np.empty(cap, np.uint32)
+    distinct = np.empty(cap, np.uint32); counts = np.empty(cap, np.uint32); spos = np.empty(cap, np.uint32); sd = np.empty(cap, np.uint32)
     n, nv, tok = C.c_size_t(0), C.c_size_t(0), C.c_ulonglong(0)
     if r.size:
-        check(lib().bdg_dedup_reads(ptr(r), ptr(v) if v is not None else None, r.size, ptr(distinct), ptr(counts), ptr(spos),
+        check(lib().bdg_dedup_reads(ptr(r), ptr(v) if v is not None else None, r.size, ptr(distinct), ptr(counts), ptr(spos), ptr(sd),
                                     C.byref(n), C.byref(nv), C.byref(tok)))
     k = int(n.value)
-    return ReadMap(distinct[:k].copy(), counts[:k].astype(np.int64), spos[:k].copy(), int(nv.value), int(r.size), int(tok.value))
+    return ReadMap(distinct[:k].copy(), counts[:k].astype(np.int64), spos[:k].copy(), int(nv.value), int(r.size), int(tok.value), sd[:k].copy())
 
 
 def assign_reads(rmap: ReadMap, centre_idx: np.ndarray):

@@ -1,13 +1,14 @@
 """Array form of the correction step (reference badger.py:120-129 with barcode_graph.py:192-410 behind it): packed
 barcodes per read in, cluster-centre barcode per read out, every stage on the GPU operators, no per-read Python.
 
-    read barcodes (uint32 per read + valid mask)
-      -> ops.dedup_first_seen            barcode_graph.py:192-204   distinct barcodes in first-seen order, counts, read map
-      -> ops.edges_handle                index.py:77-93 + barcode_graph.py:224-249   (edges stay on the device)
+    read barcodes (uint32 per row + valid mask)
+      -> ops.dedup_reads                 barcode_graph.py:192-204   valid rows compacted on the device; distinct barcodes in
+                                                                    first-seen order, counts; the read map STAYS on the device
+      -> ops.edges_handle                index.py:77-93 + barcode_graph.py:224-249   every claimed GPU builds its part; edges stay there
       -> BarcodeGraph.get_cluster_centers   barcode_graph.py:252-277   (count-sorted scan, whitelist membership on the GPU)
-      -> EdgeHandle.cluster_levels       barcode_graph.py:279-301   two rounds, same-round conflicts evict
-      -> ops.nearest_bounded             barcode_graph.py:370-385   only with high_sens
-      -> gather                          barcode_graph.py:322-329,395-404   centre of every read
+      -> EdgeHandle.cluster_levels       barcode_graph.py:279-301   two rounds, same-round conflicts evict (parts gathered over NVLink)
+      -> ops.nearest_bounded             barcode_graph.py:370-385   only with high_sens; patches the node -> centre array
+      -> ops.assign_reads                barcode_graph.py:322-329,395-404   centre of every row: gather kernel over the resident read map
 
 The string-based mirror (``BarcodeGraph`` + ``badger.py``) gives the same assignments; this module exists for callers
 that already hold packed barcodes and for the reads/s figure of ``bench.py``.
@@ -62,8 +63,7 @@ def assign_packed(ranks, valid=None, *, threshold, n_cells, interval=25, whiteli
     if rm.n_valid == 0:
         return np.full(R, NONE, dtype=np.uint64), info
     t0 = time.perf_counter()
-    s = np.empty_like(distinct)
-    s[spos] = distinct                                    # ascending order, no host sort
+    s = rm.sorted_distinct                                # ascending order straight from the dedup's sort
     handle = ops.edges_handle(s, threshold)
     tick("edges", t0)
     info.update(distinct=int(distinct.size), edges=int(handle.count))

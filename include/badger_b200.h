@@ -83,7 +83,8 @@ int bdg_dedup_first_seen(const uint32_t* ranks, size_t R, uint32_t* distinct, ui
  * barcode of the centre its barcode was assigned to, or 2^32 (rows with valid == 0, unassigned / evicted barcodes:
  * the reference writes '*').  *n_assigned = rows with a centre.  The token dies with the next dedup call. */
 int bdg_dedup_reads(const uint32_t* ranks, const uint8_t* valid, size_t R_all, uint32_t* distinct, uint32_t* counts,
-                    uint32_t* sorted_pos, size_t* n_distinct, size_t* n_valid, unsigned long long* token);
+                    uint32_t* sorted_pos, uint32_t* sorted_distinct /* optional: the distinct barcodes ascending */,
+                    size_t* n_distinct, size_t* n_valid, unsigned long long* token);
 int bdg_assign_reads(unsigned long long token, const int32_t* centre_idx, size_t N, uint64_t* centre_per_row, size_t R_all,
                      size_t* n_assigned);
 

@@ -439,6 +439,7 @@ def test_dedup_reads_and_assign_reads_vs_numpy():
                 ops.assign_reads(rm, np.zeros(d.size, np.int32))
             rm = ops.dedup_reads(ranks, valid)                                                            # ... so take a new one
             assert np.array_equal(rm.distinct, d) and np.array_equal(rm.counts, c) and np.array_equal(rm.sorted_pos, spos)
+            assert np.array_equal(rm.sorted_distinct, np.sort(d))
             N = d.size
             s = np.sort(d)
             ci = rng.integers(-2, N, N).astype(np.int32)
