@@ -87,14 +87,14 @@ def run_native(args, bc_len, true_barcodes):
         print("k:", 6)                                          # index.py:21 (QGramIndex.__init__)
         has = tsv.has_barcode
         ranks = np.zeros(tsv.rows, np.uint32)
-        packed, ok = ops.pack16(tsv.seqs16[has].tobytes())
+        packed, ok = ops.pack16(tsv.seqs16[has])
         if not ok.all():                                        # common.py:24: rank() raises KeyError(letter)
             bad = bytes(tsv.seqs16[has][int(np.argmin(ok))]).decode("ascii", "replace")
             raise KeyError(next(c for c in bad if c not in "ACGT"))
         ranks[has] = packed
         whitelist = None
         if args.barcode_list:                                   # badger.py:82-88
-            w, wok = ops.pack16(tsvio.whitelist_records(args.barcode_list).tobytes())
+            w, wok = ops.pack16(tsvio.whitelist_records(args.barcode_list))
             whitelist = ops.sorted_unique(w[wok])
         tb = [rank(bc, bc_len) for bc in true_barcodes] if true_barcodes else None
         centre, info = pipeline.assign_packed(ranks, has, threshold=args.threshold, n_cells=args.n_cells, interval=args.interval,

@@ -17,8 +17,18 @@ BC_LEN = 16
 
 
 def pack16(seqs) -> tuple[np.ndarray, np.ndarray]:
-    """common.py:21-25 `rank` for many 16-mers at once.  seqs: list of str/bytes (each exactly 16 long) or one
-    bytes object of R*16 characters.  Returns (ranks uint32[R], valid bool[R])."""
+    """common.py:21-25 `rank` for many 16-mers at once.  seqs: list of str/bytes (each exactly 16 long), one bytes object
+    of R*16 characters, or a uint8 array of R*16 characters.  Returns (ranks uint32[R], valid bool[R])."""
+    if isinstance(seqs, np.ndarray):                         # uint8[R, 16] (badger_b200.tsvio records): no copy
+        arr = np.ascontiguousarray(seqs, dtype=np.uint8)
+        if arr.size % BC_LEN:
+            raise ValueError("pack16 needs records of exactly 16 characters")
+        R = arr.size // BC_LEN
+        out = np.empty(R, np.uint32)
+        valid = np.empty(R, np.uint8)
+        if R:
+            check(lib().bdg_pack16(ptr(arr), R, ptr(out), ptr(valid)))
+        return out, valid.astype(bool)
     if isinstance(seqs, (bytes, bytearray, memoryview)):
         buf = bytes(seqs)
     else:
@@ -72,7 +82,7 @@ def dedup_reads(ranks: np.ndarray, valid=None) -> ReadMap:
     """barcode_graph.py:192-204 over the rows with valid[i] (None: all), compacted on the device; the per-read map is
     kept there for assign_reads (include/badger_b200.h bdg_dedup_reads)."""
     r = np.ascontiguousarray(ranks, dtype=np.uint32)
-    v = None if valid is None else np.ascontiguousarray(valid, dtype=np.uint8 if valid.dtype != bool else bool).view(np.uint8)
+    v = None if valid is None else np.ascontiguousarray(np.asarray(valid) != 0).view(np.uint8)
     cap = r.size
     distinct = np.empty(cap, np.uint32); counts = np.empty(cap, np.uint32); spos = np.empty(cap, np.uint32); sd = np.empty(cap, np.uint32)
     n, nv, tok = C.c_size_t(0), C.c_size_t(0), C.c_ulonglong(0)

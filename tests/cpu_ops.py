@@ -7,6 +7,8 @@ from oracle import oracle as orc
 
 
 def pack16(seqs):
+    if isinstance(seqs, np.ndarray):
+        seqs = np.ascontiguousarray(seqs, dtype=np.uint8).tobytes()
     if isinstance(seqs, (bytes, bytearray)):
         seqs = [bytes(seqs[i:i + 16]) for i in range(0, len(seqs), 16)]
     out = np.zeros(len(seqs), np.uint32); valid = np.ones(len(seqs), bool)

@@ -54,6 +54,11 @@ def test_pack16_and_pairs(gold_pairs):
     assert r.tolist() == [p["ra"] for p in gold_pairs["pairs"]] + [p["rb"] for p in gold_pairs["pairs"]]
     r2, v2 = ops.pack16(["ACGTACGTACGTACGN", "acgtacgtacgtacgt", "ACGTACGTACGTACGT", "ACGTACGTACGTAC\nT"])
     assert v2.tolist() == [False, False, True, False] and int(r2[2]) == 3840206052
+    arr = np.frombuffer("".join(strs).encode(), np.uint8).reshape(-1, 16)         # the record matrix of badger_b200.tsvio
+    r3, v3 = ops.pack16(arr)
+    assert np.array_equal(r3, r) and v3.all()
+    r4, v4 = ops.pack16(arr[::2])                                                   # a strided view is made contiguous first
+    assert np.array_equal(r4, r[::2]) and v4.all()
     # every golden pair as a two-node graph: edge iff S >= T(t) and D <= t, stored distance D
     for t in (0, 1, 2, 3, 4):
         for p in gold_pairs["pairs"][::3]:

@@ -82,12 +82,12 @@ def native_route(tsv, wlf, cfg, tmp, R, high_sens, other_output):
         t0 = time.perf_counter()
         has = t.has_barcode
         ranks = np.zeros(t.rows, np.uint32)
-        packed, ok = ops.pack16(t.seqs16[has].tobytes())
+        packed, ok = ops.pack16(t.seqs16[has])
         assert ok.all()
         ranks[has] = packed
         T["pack16 of the reads (GPU)"] = time.perf_counter() - t0
         t0 = time.perf_counter()
-        w, wok = ops.pack16(tsvio.whitelist_records(wlf).tobytes())
+        w, wok = ops.pack16(tsvio.whitelist_records(wlf))
         whitelist = ops.sorted_unique(w[wok])
         T["whitelist file -> sorted uint32 (native + GPU)"] = time.perf_counter() - t0
         t0 = time.perf_counter()
