@@ -157,7 +157,32 @@ def gold_kmer():
     return cases
 
 
-def gold_pipeline(name, reads, n_cells, W, perr, t, seed, interval=25, extra17=0.1):
+def make_tricky(path, rng):
+    """Rewrite an extraction TSV with everything pandas.read_csv treats specially that such files can plausibly hold:
+    blank lines, lines of spaces, repeated header lines, short rows, empty / NA-string / '*' barcodes, barcodes of other
+    lengths, read ids with spaces and '#', no newline at the end of the file (badger.py:91-111 is the code under test)."""
+    with open(path) as fh:
+        lines = fh.read().split("\n")
+    header, rows = lines[0], [ln for ln in lines[1:] if ln]
+    out = [header]
+    for i, ln in enumerate(rows):
+        f = ln.split("\t")
+        r = rng.random()
+        if r < 0.03: f[1] = ""
+        elif r < 0.06: f[1] = str(rng.choice(["NA", "nan", "NULL", "N/A", "None", "<NA>", "n/a", "#N/A"]))
+        elif r < 0.08: f[1] = f[1][:int(rng.integers(1, 16))]
+        elif r < 0.10 and f[1] != "*": f[1] = f[1] + "ACGTA"[:int(rng.integers(2, 5))]
+        elif r < 0.11: f[1] = "barcode"
+        r = rng.random()
+        if r < 0.02: f[0] = str(rng.choice(["#read_id", " lead_%d" % i, "trail_%d " % i, "a b_%d" % i, "x#y_%d" % i, "0a1f-%d" % i]))
+        if rng.random() < 0.03: f = f[:int(rng.integers(1, 8))]
+        out.append("\t".join(f))
+        if rng.random() < 0.02: out.append(str(rng.choice(["", "   ", header])))
+    with open(path, "w") as fh:
+        fh.write("\n".join(out))                        # no trailing newline
+
+
+def gold_pipeline(name, reads, n_cells, W, perr, t, seed, interval=25, extra17=0.1, tricky=False):
     """Full badger.py run on files (badger.py:62-175) + graph internals, with and without --high_sens."""
     rng = synth.rng_for(seed)
     wl = synth.make_whitelist(W, rng)
@@ -167,6 +192,8 @@ def gold_pipeline(name, reads, n_cells, W, perr, t, seed, interval=25, extra17=0
     os.makedirs(d, exist_ok=True)
     tsv, wlf = os.path.join(d, "reads.tsv"), os.path.join(d, "whitelist.txt")
     synth.write_extraction_tsv(tsv, obs, valid, rng, extra17_frac=extra17)
+    if tricky:
+        make_tricky(tsv, rng)
     synth.write_whitelist(wlf, wl)
     meta = dict(name=name, t=t, n_cells=n_cells, interval=interval)
     with tempfile.TemporaryDirectory() as tmp:
@@ -221,6 +248,9 @@ def gold_c1():
 
 def main():
     os.makedirs(GOLD, exist_ok=True)
+    if sys.argv[1:] == ["tricky"]:                      # only the fixture added later (the others stay as committed)
+        gold_pipeline("pipeline_tricky", reads=3000, n_cells=150, W=3000, perr=0.05, t=1, seed=23, tricky=True)
+        return
     with open(os.path.join(GOLD, "pairs.json"), "w") as fh:
         json.dump(gold_pairs(), fh)
     with open(os.path.join(GOLD, "graphs.json"), "w") as fh:
@@ -229,6 +259,7 @@ def main():
         json.dump(gold_kmer(), fh)
     gold_pipeline("pipeline_t1", reads=3000, n_cells=200, W=4000, perr=0.05, t=1, seed=21)
     gold_pipeline("pipeline_t2", reads=2500, n_cells=120, W=3000, perr=0.07, t=2, seed=22)
+    gold_pipeline("pipeline_tricky", reads=3000, n_cells=150, W=3000, perr=0.05, t=1, seed=23, tricky=True)
     with open(os.path.join(GOLD, "c1.json"), "w") as fh:
         json.dump(gold_c1(), fh)
     print("golden fixtures written to", GOLD)

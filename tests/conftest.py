@@ -39,7 +39,7 @@ def gold_c1():
     return load_golden("c1.json")
 
 
-@pytest.fixture(scope="session", params=["pipeline_t1", "pipeline_t2"])
+@pytest.fixture(scope="session", params=["pipeline_t1", "pipeline_t2", "pipeline_tricky"])
 def gold_pipeline(request):
     d = os.path.join(GOLD, request.param)
     with open(os.path.join(d, "golden.json")) as fh:

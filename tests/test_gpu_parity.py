@@ -140,6 +140,7 @@ def test_packed_pipeline_golden(gold_pipeline):
     g = gold_pipeline
     df = pd.read_csv(g["dir"] + "/reads.tsv", sep="\t")
     obs = df["barcode"].fillna("*").tolist()
+    emitted = [i != "#read_id" and o != "barcode" for i, o in zip(df["#read_id"].tolist(), obs)]     # badger.py:103-110
     keep = [o[:-1] if len(o) == 17 else o for o in obs]
     valid = np.asarray([len(o) == 16 and not (set(o) - set("ACGT")) for o in keep])
     ranks = np.zeros(len(keep), np.uint32)
@@ -149,7 +150,7 @@ def test_packed_pipeline_golden(gold_pipeline):
     out, info = pipeline.assign_packed(ranks, valid, threshold=g["t"], n_cells=g["n_cells"], interval=g["interval"],
                                        whitelist_sorted=np.sort(synth.rank_many(wl)))
     want = pd.read_csv(g["dir"] + "/expected_output_file.tsv", sep="\t")["barcode"].tolist()
-    got = ["*" if c == pipeline.NONE else orc.unrank(int(c)) for c in out.tolist()]
+    got = ["*" if c == pipeline.NONE else orc.unrank(int(c)) for c, e in zip(out.tolist(), emitted) if e]
     assert got == want
     assert info["edges"] == len(g["edges"]) and info["centres"] == len(g["centres"])
     # --high_sens with the centre order the reference iterated

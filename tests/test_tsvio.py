@@ -79,8 +79,8 @@ def test_reader_matches_pandas_on_golden(gold_pipeline):
     path = gold_pipeline["dir"] + "/reads.tsv"
     graph, ra = reference_ingest(path)
     ngraph, nra, rows = native_ingest(path)
-    assert ngraph == graph and len(nra) == len(ra) == rows
-    assert [o if o is not None else "*" for _, o in nra] == [o if len(o) == 16 else "*" for _, o in ra]
+    assert ngraph == graph and len(nra) == len(ra) <= rows
+    assert [o for _, o in nra] == [o if len(o) == 16 and o != "barcode" else None for _, o in ra]
 
 
 @pytest.mark.parametrize("seed", range(6))
