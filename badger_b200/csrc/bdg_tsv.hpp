@@ -16,9 +16,12 @@
 #include <unistd.h>
 
 #include <algorithm>
+#include <cerrno>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <new>
+#include <stdexcept>
 #include <string>
 #include <thread>
 #include <vector>
@@ -229,14 +232,19 @@ inline std::string tsv_parse(Tsv& t, const char* path, int bc_len, int threads, 
     }
     std::vector<RowBlock> blocks(T);
     {
+        // an exception must not leave a worker thread (std::terminate): a failed allocation becomes the slice's verdict
+        auto guarded = [&](int k) {
+            try { parse_slice(d, cut[k], cut[k + 1], ncols, id_col, bc_col, bc_len, blocks[k]); }
+            catch (const std::exception&) { blocks[k].why = "\x01out of host memory"; }
+        };
         std::vector<std::thread> pool;
-        for (int k = 1; k < T; k++)
-            pool.emplace_back([&, k] { parse_slice(d, cut[k], cut[k + 1], ncols, id_col, bc_col, bc_len, blocks[k]); });
-        parse_slice(d, cut[0], cut[1], ncols, id_col, bc_col, bc_len, blocks[0]);
+        for (int k = 1; k < T; k++) pool.emplace_back(guarded, k);
+        guarded(0);
         for (auto& th : pool) th.join();
     }
     size_t rows = 0;
     for (auto& b : blocks) {
+        if (!b.why.empty() && b.why[0] == '\x01') throw std::bad_alloc();     // reported as BDG_ERR_OOM by the caller
         if (!b.why.empty()) return b.why;
         rows += b.kind.size();
     }
