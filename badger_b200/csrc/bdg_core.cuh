@@ -405,6 +405,68 @@ BDG_HD int qgram_score(uint32_t a, uint32_t b, uint64_t* mult = nullptr)
     return s;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two-block seeds for t = 2 (groundwork for the next form of the sparse passes; no kernel uses it yet - DESIGN.md 8).
+// The single-block passes above leave 11 * N^2 / 2048 pairs to score one by one, which is what the step costs at
+// N > 10^6.  Cutting a[0:15] into FOUR blocks (4, 4, 4, 3 bases = bits 0-7, 8-15, 16-23, 24-29) leaves at least TWO
+// blocks untouched by <= 2 operations, and the diagonals of two untouched blocks are tied together:
+//   * two adjacent untouched blocks sit on the same diagonal d in {-1, 0, +1} (block 0 only on 0);
+//   * two untouched blocks with touched ones between / before them: every touched block holds exactly one
+//     operation (two touched blocks, two operations), so the diagonal moves by at most one per touched block
+//     and ends within +-1 of the start.
+// That gives 20 conditions "two fields of a equal two fields of b" on 14 or 16 bits each (a random pair meets one with
+// probability 69 / 65536 ~ 1 / 950, against 1 / 93 for the single blocks), each a plain key equality, i.e. a sort-merge
+// join of seed2_key_a over the rows with seed2_key_b over the columns.  Necessary for D <= 2 under EITHER labelling of
+// the pair, so a join may fix a = min(x, y); tests/test_core_host.py checks that on the oracle's distances (random near
+// pairs, low-complexity seeds, exhaustive two-operation neighbourhoods).
+// ---------------------------------------------------------------------------------------------
+constexpr int SEED2_N = 20;
+struct Seed2 { int8_t blk0, d0, blk1, d1; };     // a[block blk0] == b[the same columns + d0]  and  a[block blk1] == b[... + d1]
+
+BDG_HD Seed2 seed2_cond(int c)
+{
+    // 0: blocks 0,1 | 1-3: blocks 1,2 | 4-6: blocks 2,3 | 7-9: blocks 0,2 | 10-12: blocks 0,3 | 13-19: blocks 1,3
+    if (c == 0) return Seed2{0, 0, 1, 0};
+    if (c <= 3) return Seed2{1, (int8_t)(c - 2), 2, (int8_t)(c - 2)};
+    if (c <= 6) return Seed2{2, (int8_t)(c - 5), 3, (int8_t)(c - 5)};
+    if (c <= 9) return Seed2{0, 0, 2, (int8_t)(c - 8)};
+    if (c <= 12) return Seed2{0, 0, 3, (int8_t)(c - 11)};
+    // (d of block 1, d of block 3) with |d3 - d1| <= 1: (-1,-1) (-1,0) (0,-1) (0,0) (0,1) (1,0) (1,1)
+    const int k = c - 13;
+    const int d1 = k < 2 ? -1 : (k < 5 ? 0 : 1);
+    const int d3 = k == 0 ? -1 : k == 1 ? 0 : k == 2 ? -1 : k == 3 ? 0 : k == 4 ? 1 : k == 5 ? 0 : 1;
+    return Seed2{1, (int8_t)d1, 3, (int8_t)d3};
+}
+
+BDG_HD int seed2_block_lo(int blk) { return 8 * blk; }                       // first bit of block blk
+BDG_HD int seed2_block_bits(int blk) { return blk == 3 ? 6 : 8; }
+
+BDG_HD uint32_t seed2_field(uint32_t v, int blk, int d)                     // block blk of v, columns moved by d bases
+{
+    return (v >> (seed2_block_lo(blk) + 2 * d)) & ((1u << seed2_block_bits(blk)) - 1u);
+}
+
+// the join keys of condition c: rows are keyed by the two blocks of a, columns by the matching stretches of b
+BDG_HD uint32_t seed2_key_a(int c, uint32_t a)
+{
+    const Seed2 s = seed2_cond(c);
+    return seed2_field(a, s.blk0, 0) | (seed2_field(a, s.blk1, 0) << seed2_block_bits(s.blk0));
+}
+BDG_HD uint32_t seed2_key_b(int c, uint32_t b)
+{
+    const Seed2 s = seed2_cond(c);
+    return seed2_field(b, s.blk0, s.d0) | (seed2_field(b, s.blk1, s.d1) << seed2_block_bits(s.blk0));
+}
+BDG_HD bool seed2_pred(int c, uint32_t a, uint32_t b) { return seed2_key_a(c, a) == seed2_key_b(c, b); }
+
+// first condition the pair meets (the pass that would emit it), -1 if none: D(a,b) <= 2 implies >= 0
+BDG_HD int seed2_first(uint32_t a, uint32_t b)
+{
+    for (int c = 0; c < SEED2_N; c++)
+        if (seed2_pred(c, a, b)) return c;
+    return -1;
+}
+
 // Full predicate of barcode_graph.py:233-249 for a != b: returns D when (a,b) is an edge at threshold t,
 // else 0.  t <= 2 uses the case analysis, larger t the generic bit-vector pass.
 BDG_HD int edge_dist(uint32_t a, uint32_t b, int t)

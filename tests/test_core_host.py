@@ -36,6 +36,9 @@ def shim(tmp_path_factory):
     L.shim_quick_any.argtypes = [C.c_int, u32p, u32p, C.c_size_t, u8p]
     L.shim_top_possible.argtypes = [C.c_int] + [C.c_uint32] * 4
     L.shim_top_possible.restype = C.c_int
+    L.shim_seed2_first.argtypes = [u32p, u32p, C.c_size_t, np.ctypeslib.ndpointer(np.int8, flags="C")]
+    L.shim_seed2_keys.argtypes = [C.c_int, u32p, u32p, C.c_size_t, u32p, u32p]
+    L.shim_seed2_count.restype = C.c_int
     return L
 
 
@@ -366,3 +369,103 @@ def test_quick_pass_any_sound(shim, t):
     out = np.zeros(ra.size, np.uint8)
     shim.shim_quick_any(t, ra, rb, ra.size, out)
     print("t", t, "random pass rate", out.mean())
+
+
+# ------------------------------------------------------------------------------------------ two-block seeds (t = 2)
+def seed2_first(shim, a, b):
+    out = np.zeros(a.size, np.int8)
+    shim.shim_seed2_first(np.ascontiguousarray(a), np.ascontiguousarray(b), a.size, out)
+    return out
+
+
+def two_op_neighbourhood(x):
+    """Every 16-mer reachable from x by at most two edit operations (all paddings of the shortened ones)."""
+    def one(seq):
+        out = []
+        for pos in range(len(seq)):
+            for c in range(4):
+                if c != seq[pos]:
+                    out.append(seq[:pos] + [c] + seq[pos + 1:])
+            out.append(seq[:pos] + seq[pos + 1:])
+        for pos in range(len(seq) + 1):
+            for c in range(4):
+                out.append(seq[:pos] + [c] + seq[pos:])
+        return out
+
+    s = [(x >> (2 * i)) & 3 for i in range(16)]
+    lvl1 = one(s)
+    neigh = set()
+    for seq in lvl1 + [y for z in lvl1 for y in one(z)]:
+        if len(seq) >= 16:
+            neigh.add(sum(c << (2 * i) for i, c in enumerate(seq[:16])))
+        else:
+            for p1 in range(4):
+                for p2 in range(4):
+                    neigh.add(sum(c << (2 * i) for i, c in enumerate((seq + [p1, p2])[:16])))
+    neigh.discard(x)
+    return np.fromiter(neigh, dtype=np.uint32)
+
+
+def test_seed2_conditions_are_necessary_for_d2(shim):
+    """bdg_core.cuh two-block seeds: D(a,b) <= 2 implies that one of the 20 key equalities holds, under either labelling
+    of the pair (so a join may fix a = min); checked on random near pairs, low-complexity and shifted pairs, and on the
+    complete two-operation neighbourhoods of random and repetitive seeds."""
+    L = orc.lib()
+    assert shim.shim_seed2_count() == 20
+    tot = 0
+    for seed in (5, 8):
+        a, b = make_pairs(seed)
+        D = np.fromiter((L.orc_D(int(x), int(y)) for x, y in zip(a, b)), np.int32, a.size)
+        near = D <= 2
+        assert (seed2_first(shim, a, b)[near] >= 0).all()
+        assert (seed2_first(shim, b, a)[near] >= 0).all()
+        assert (seed2_first(shim, np.minimum(a, b), np.maximum(a, b))[near] >= 0).all()
+        tot += int(near.sum())
+    assert tot > 50000
+    rng = np.random.default_rng(9)
+    seeds = [int(rng.integers(0, 1 << 32)) for _ in range(3)] + [0, 0x44444444] + \
+        [int(v) for v in synth.rank_many(["ACACACACACACACAC", "AAAAAAAACCCCCCCC", "ACGACGACGACGACGA", "TTTTGTTTTGTTTTGT"])]
+    for x in seeds:
+        b = two_op_neighbourhood(x)
+        a = np.full(b.size, x, dtype=np.uint32)
+        D = np.fromiter((L.orc_D(x, int(y)) for y in b), np.int32, b.size)
+        near = D <= 2
+        assert near.sum() > 1000
+        assert (seed2_first(shim, a, b)[near] >= 0).all() and (seed2_first(shim, b, a)[near] >= 0).all()
+
+
+def test_seed2_keys_and_selectivity(shim):
+    """The join keys are what the predicate compares (14 or 16 bits), every condition fires on its own construction, and a
+    random pair meets some condition with probability ~ 69 / 65536 (an order of magnitude below the single-block passes)."""
+    rng = np.random.default_rng(4)
+    n = 1 << 21
+    ra = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    rb = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    first = seed2_first(shim, ra, rb)
+    rate = (first >= 0).mean()
+    assert 0.5 * 69 / 65536 < rate < 1.2 * 69 / 65536
+    ka = np.zeros(n, np.uint32); kb = np.zeros(n, np.uint32)
+    fired = np.zeros(n, bool)
+    for c in range(20):
+        shim.shim_seed2_keys(c, ra, rb, n, ka, kb)
+        bits = 14 if (4 <= c <= 6 or c >= 10) else 16
+        assert int(ka.max()) < (1 << bits) and int(kb.max()) < (1 << bits)
+        eq = ka == kb
+        assert np.array_equal(first == c, eq & ~fired)        # `first` is the lowest condition whose keys agree
+        fired |= eq
+        # construct a partner that meets condition c and nothing else is required: copy a's two blocks into b at the shifted place
+        blocks = {0: [(0, 0), (1, 0)]}
+        for k in range(1, 4): blocks[k] = [(1, k - 2), (2, k - 2)]
+        for k in range(4, 7): blocks[k] = [(2, k - 5), (3, k - 5)]
+        for k in range(7, 10): blocks[k] = [(0, 0), (2, k - 8)]
+        for k in range(10, 13): blocks[k] = [(0, 0), (3, k - 11)]
+        for k, (d1, d3) in enumerate([(-1, -1), (-1, 0), (0, -1), (0, 0), (0, 1), (1, 0), (1, 1)]):
+            blocks[13 + k] = [(1, d1), (3, d3)]
+        y = rb[:4096].astype(np.uint64)
+        x = ra[:4096].astype(np.uint64)
+        for blk, d in blocks[c]:
+            lo, nb = 8 * blk, (6 if blk == 3 else 8)
+            mask = np.uint64(((1 << nb) - 1) << (lo + 2 * d))
+            y = (y & ~mask) | (((x >> np.uint64(lo)) & np.uint64((1 << nb) - 1)) << np.uint64(lo + 2 * d))
+        shim.shim_seed2_keys(c, ra[:4096].copy(), y.astype(np.uint32), 4096, ka[:4096], kb[:4096])
+        assert np.array_equal(ka[:4096], kb[:4096]), c
