@@ -110,6 +110,47 @@ def test_reader_matches_pandas_on_tricky_files(tmp_path, seed):
     assert open(out, "rb").read() == open(str(tmp_path / "pandas.tsv"), "rb").read()
 
 
+def test_reader_fuzz_accepts_only_what_it_reads_like_pandas(tmp_path):
+    """Small hostile files (random fields, stray tabs, numbers, NA strings, spaces, '#'): the native reader either declines
+    or agrees with pandas on the graph's barcodes, on the written rows and - through the writer - on the ids byte for byte."""
+    import warnings
+    rng = np.random.default_rng(2)
+    alph = list("ACGTN*ab1.e-   #/_\t\n") + ["NA", "nan", "barcode", "#read_id", "read_", "ACGTACGTACGTACGT", "ACGTACGTACGTACGTA", "True", "12", ""]
+    path, out_n, out_p = str(tmp_path / "f.tsv"), str(tmp_path / "n.tsv"), str(tmp_path / "p.tsv")
+    accepted = 0
+    for trial in range(1200):
+        cols = ["#read_id", "barcode", "UMI"]
+        if rng.random() < 0.2:
+            rng.shuffle(cols)
+        lines = ["\t".join(cols)]
+        for r in range(int(rng.integers(1, 8))):
+            if rng.random() < 0.6:
+                rid = "r%d" % r if rng.random() < 0.8 else "".join(rng.choice(alph, int(rng.integers(0, 4))))
+                bc = str(rng.choice(["ACGTACGTACGTACGT", "ACGTACGTACGTACGTA", "*", "", "NA", "ACGT", "barcode", "TTTTACGTACGTACGT "])) \
+                    if rng.random() < 0.8 else "".join(rng.choice(alph, int(rng.integers(0, 4))))
+                f = [rid, bc, "x"]
+                lines.append("\t".join(f[:int(rng.integers(1, 4))] if rng.random() < 0.2 else f))
+            else:
+                lines.append("".join(rng.choice(alph, int(rng.integers(0, 6)))))
+        with open(path, "w") as fh:
+            fh.write("\n".join(lines) + ("\n" if rng.random() < 0.5 else ""))
+        try:
+            ngraph, nra, _ = native_ingest(path)
+        except tsvio.Unsupported:
+            continue
+        accepted += 1
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            graph, ra = reference_ingest(path)                 # must not raise on a file the native reader accepted
+        assert ngraph == graph, lines
+        assert [o for _, o in nra] == [o if isinstance(o, str) and len(o) == 16 and o != "barcode" else None for _, o in ra], lines
+        with tsvio.ExtractionTsv(path) as t:
+            t.write(out_n, np.full(t.rows, tsvio.NONE, np.uint64))
+        pd.DataFrame({"readID": [r[0] for r in ra], "barcode": ["*"] * len(ra)}).to_csv(out_p, sep="\t", index=False)
+        assert open(out_n, "rb").read() == open(out_p, "rb").read(), lines
+    assert accepted > 150
+
+
 @pytest.mark.parametrize("body,why", [
     ('r1\t"ACGTACGTACGTACGT"\tx\n', "quote"),
     ("r1\tACGTACGTACGTACGT\tx\r\n", "carriage"),
