@@ -467,6 +467,56 @@ BDG_HD int seed2_first(uint32_t a, uint32_t b)
     return -1;
 }
 
+// Sort form of a condition: a bijection of the 32-bit word that puts the join key (field 0 in the low part, field 1 above
+// it) into the TOP n0 + n1 bits and the remaining bits, in their order, below.  Rows are permuted with seed2_perm_a(c),
+// columns with seed2_perm_b(c); after a plain radix sort of the permuted words equal keys are adjacent on both sides,
+// a tile's key range is its first and last word >> (32 - n0 - n1), and seed_unpermute gives the barcode back.
+struct SeedPerm { uint8_t lo0, n0, lo1, n1; };   // the two fields inside the word: bits [lo0, lo0+n0) and [lo1, lo1+n1), lo0 + n0 <= lo1
+
+BDG_HD SeedPerm seed2_perm_a(int c)
+{
+    const Seed2 s = seed2_cond(c);
+    return SeedPerm{(uint8_t)seed2_block_lo(s.blk0), (uint8_t)seed2_block_bits(s.blk0), (uint8_t)seed2_block_lo(s.blk1), (uint8_t)seed2_block_bits(s.blk1)};
+}
+BDG_HD SeedPerm seed2_perm_b(int c)
+{
+    const Seed2 s = seed2_cond(c);
+    return SeedPerm{(uint8_t)(seed2_block_lo(s.blk0) + 2 * s.d0), (uint8_t)seed2_block_bits(s.blk0), (uint8_t)(seed2_block_lo(s.blk1) + 2 * s.d1),
+                    (uint8_t)seed2_block_bits(s.blk1)};
+}
+BDG_HD int seed_key_bits(SeedPerm p) { return p.n0 + p.n1; }
+BDG_HD uint32_t low_mask(int n) { return n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u); }
+
+BDG_HD uint32_t seed_permute(uint32_t v, SeedPerm p)
+{
+    const int e0 = p.lo0 + p.n0, e1 = p.lo1 + p.n1;                 // ends of the fields
+    const uint32_t key = ((v >> p.lo0) & low_mask(p.n0)) | (((v >> p.lo1) & low_mask(p.n1)) << p.n0);
+    const uint32_t seg0 = v & low_mask(p.lo0);                      // below field 0
+    const uint32_t seg1 = (v >> e0) & low_mask(p.lo1 - e0);         // between the fields
+    const uint32_t seg2 = e1 >= 32 ? 0u : (v >> e1);                // above field 1
+    const uint32_t rest = seg0 | (seg1 << p.lo0) | (e1 >= 32 ? 0u : (seg2 << (p.lo0 + p.lo1 - e0)));
+    const int kb = p.n0 + p.n1;
+    return (key << (32 - kb)) | rest;
+}
+BDG_HD uint32_t seed_unpermute(uint32_t w, SeedPerm p)
+{
+    const int e0 = p.lo0 + p.n0, e1 = p.lo1 + p.n1, kb = p.n0 + p.n1;
+    const uint32_t key = w >> (32 - kb), rest = w & low_mask(32 - kb);
+    const int l1 = p.lo1 - e0;                                       // length of the middle segment
+    uint32_t v = rest & low_mask(p.lo0);
+    v |= (key & low_mask(p.n0)) << p.lo0;
+    v |= ((rest >> p.lo0) & low_mask(l1)) << e0;
+    v |= (key >> p.n0) << p.lo1;
+    if (e1 < 32) v |= (rest >> (p.lo0 + l1)) << e1;
+    return v;
+}
+// can a row tile [alo, ahi] and a column tile [blo, bhi] (permuted, sorted words) hold two equal keys?
+BDG_HD bool seed_tiles_meet(uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, int key_bits)
+{
+    const int s = 32 - key_bits;
+    return (alo >> s) <= (bhi >> s) && (blo >> s) <= (ahi >> s);
+}
+
 // Full predicate of barcode_graph.py:233-249 for a != b: returns D when (a,b) is an edge at threshold t,
 // else 0.  t <= 2 uses the case analysis, larger t the generic bit-vector pass.
 BDG_HD int edge_dist(uint32_t a, uint32_t b, int t)

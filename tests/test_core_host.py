@@ -39,6 +39,8 @@ def shim(tmp_path_factory):
     L.shim_seed2_first.argtypes = [u32p, u32p, C.c_size_t, np.ctypeslib.ndpointer(np.int8, flags="C")]
     L.shim_seed2_keys.argtypes = [C.c_int, u32p, u32p, C.c_size_t, u32p, u32p]
     L.shim_seed2_count.restype = C.c_int
+    L.shim_seed2_permute.argtypes = [C.c_int, u32p, u32p, C.c_size_t, u32p, u32p, u32p, u32p]
+    L.shim_seed_tiles_meet.argtypes = [C.c_uint32] * 4 + [C.c_int]
     return L
 
 
@@ -469,3 +471,32 @@ def test_seed2_keys_and_selectivity(shim):
             y = (y & ~mask) | (((x >> np.uint64(lo)) & np.uint64((1 << nb) - 1)) << np.uint64(lo + 2 * d))
         shim.shim_seed2_keys(c, ra[:4096].copy(), y.astype(np.uint32), 4096, ka[:4096], kb[:4096])
         assert np.array_equal(ka[:4096], kb[:4096]), c
+
+
+def test_seed2_sort_form(shim):
+    """The permuted words of a condition: a bijection (unpermute gives the barcode back), the join key on top (equal top
+    bits <=> the condition holds), order of the words = order of (key, remaining bits), and the tile test is conservative."""
+    rng = np.random.default_rng(6)
+    n = 1 << 18
+    a = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    b = a.copy()
+    flip = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32) & rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32) \
+        & rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    b ^= flip                                                   # ~1/8 of the bits differ: many key hits, many misses
+    pa, pb, ua, ub, ka, kb_ = (np.zeros(n, np.uint32) for _ in range(6))
+    for c in range(20):
+        shim.shim_seed2_permute(c, a, b, n, pa, pb, ua, ub)
+        assert np.array_equal(ua, a) and np.array_equal(ub, b), c
+        bits = shim.shim_seed2_key_bits(c)
+        shim.shim_seed2_keys(c, a, b, n, ka, kb_)
+        assert np.array_equal(pa >> np.uint32(32 - bits), ka) and np.array_equal(pb >> np.uint32(32 - bits), kb_), c
+        assert np.unique(pa).size == np.unique(a).size               # injective
+        # tiles of the two sorted sides: whenever a tile pair holds an equal key, the tile test says so
+        sa, sb = np.sort(pa), np.sort(pb)
+        for _ in range(300):
+            i = int(rng.integers(0, n - 64)); j = int(np.searchsorted(sb >> np.uint32(32 - bits), sa[i] >> np.uint32(32 - bits)))
+            j = min(max(j + int(rng.integers(-200, 200)), 0), n - 64)
+            A, B = sa[i:i + 64], sb[j:j + 64]
+            hit = np.intersect1d(A >> np.uint32(32 - bits), B >> np.uint32(32 - bits)).size > 0
+            poss = bool(shim.shim_seed_tiles_meet(int(A[0]), int(A[-1]), int(B[0]), int(B[-1]), bits))
+            assert poss or not hit
