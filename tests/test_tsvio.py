@@ -251,6 +251,38 @@ def test_cli_native_route_golden(gold_pipeline, monkeypatch, tmp_path, capsys):
         assert tail_a == tail_b, extra
 
 
+@pytest.mark.parametrize("seed", range(4))
+def test_cli_routes_agree_on_random_inputs(seed, monkeypatch, tmp_path, capsys):
+    """Array route (native reader, assign_packed with --high_sens resolved on node positions, native writer) against the
+    pandas + dict route on fresh random inputs: thresholds 1 and 2, with / without whitelist, --high_sens, --true_barcodes,
+    17-mers in the file, dense clusters that produce same-round conflicts (evictions)."""
+    from badger_b200 import synth
+    cpu_ops.install(monkeypatch)
+    cli = _cli()
+    monkeypatch.setattr(cli, "init", lambda *a, **k: 1)
+    rng = synth.rng_for(500 + seed)
+    wl = synth.make_whitelist(800, rng)
+    cells = synth.pick_cells(wl, 40, rng)
+    if seed % 2:                                            # near-identical cells: nodes claimed by two centres in one round
+        cells[1::2] = cells[::2] ^ np.uint32(1 << int(rng.integers(0, 32)))
+    obs, valid = synth.simulate_reads(cells, 1500, 0.07, rng)
+    tsv, wlf, tb = str(tmp_path / "r.tsv"), str(tmp_path / "wl.txt"), str(tmp_path / "tb.tsv")
+    synth.write_extraction_tsv(tsv, obs, valid, rng, extra17_frac=0.2)
+    synth.write_whitelist(wlf, wl)
+    with open(tb, "w") as fh:
+        for c in cells[:25].tolist():
+            fh.write(orc.unrank(int(c)) + "-1\n")
+    t = 1 + seed % 2
+    base = ["-r", tsv, "-d", "10x", "-t", str(t), "--n_cells", "40"]
+    for extra in (["-l", wlf], ["-l", wlf, "-hs"], ["--true_barcodes", tb, "-hs"], ["-hs"]):
+        a, b = str(tmp_path / "A"), str(tmp_path / "B")
+        tail_a, text = _run(cli, base + extra + ["-o", a], capsys)
+        assert "reading through pandas" not in text
+        tail_b, _ = _run(cli, base + extra + ["-o", b, "--no_native_io"], capsys)
+        assert open(a + "_output_file.tsv", "rb").read() == open(b + "_output_file.tsv", "rb").read(), extra
+        assert tail_a == tail_b, extra
+
+
 def test_cli_falls_back_to_pandas_when_the_reader_declines(gold_pipeline, monkeypatch, tmp_path, capsys):
     cpu_ops.install(monkeypatch)
     cli = _cli()
