@@ -500,3 +500,40 @@ def test_seed2_sort_form(shim):
             hit = np.intersect1d(A >> np.uint32(32 - bits), B >> np.uint32(32 - bits)).size > 0
             poss = bool(shim.shim_seed_tiles_meet(int(A[0]), int(A[-1]), int(B[0]), int(B[-1]), bits))
             assert poss or not hit
+
+
+def test_seed2_join_passes_reproduce_the_oracle_edge_set(shim):
+    """The planned join passes, emulated in numpy: for every condition both sides are permuted and sorted, equal-key buckets
+    are paired, a pair is kept under the labelling a = min by the FIRST condition it meets, then the exact D and S decide.
+    The union over the 20 passes must be the oracle's edge set at t = 2, every edge exactly once."""
+    L = orc.lib()
+    rng = synth.rng_for(91)
+    cells = rng.integers(0, 1 << 32, 120, dtype=np.uint64).astype(np.uint32)
+    obs, _ = synth.simulate_reads(cells, 9000, 0.06, rng)
+    s = np.unique(obs)
+    n = s.size
+    wa, wb, wd, _ = orc.Index(s).edges(2)
+    want = sorted(zip(wa.tolist(), wb.tolist(), wd.tolist()))
+    got = []
+    pa, pb, ua, ub = (np.zeros(n, np.uint32) for _ in range(4))
+    n_cand = 0
+    for c in range(20):
+        shim.shim_seed2_permute(c, s, s, n, pa, pb, ua, ub)
+        bits = shim.shim_seed2_key_bits(c)
+        oa, ob = np.argsort(pa, kind="stable"), np.argsort(pb, kind="stable")          # sorted sides; the barcode rides along
+        ka, kb = pa[oa] >> np.uint32(32 - bits), pb[ob] >> np.uint32(32 - bits)
+        lo, hi = np.searchsorted(kb, ka, "left"), np.searchsorted(kb, ka, "right")
+        rows = np.repeat(np.arange(n), hi - lo)
+        cols = np.concatenate([np.arange(l, h) for l, h in zip(lo.tolist(), hi.tolist())]) if rows.size else np.empty(0, np.int64)
+        x, y = s[oa[rows]], s[ob[cols]]
+        keep = x < y
+        x, y = np.ascontiguousarray(x[keep]), np.ascontiguousarray(y[keep])
+        n_cand += x.size
+        first = seed2_first(shim, x, y)
+        for xv, yv in zip(x[first == c].tolist(), y[first == c].tolist()):
+            d = L.orc_D(xv, yv)
+            if d <= 2 and L.orc_S(xv, yv) >= 4:
+                got.append((xv, yv, d))
+    assert len(got) == len(set(got))                        # no pair twice
+    assert sorted(got) == want and len(want) > 5000
+    assert n_cand < 0.02 * n * (n - 1) / 2                  # the seeds leave a small share of the pairs (clustered data)
