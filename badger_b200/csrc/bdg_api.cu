@@ -15,6 +15,7 @@
 
 #include "../../include/badger_b200.h"
 #include "bdg_kernels.cuh"
+#include "bdg_join.cuh"
 #include "bdg_tsv.hpp"
 
 #include <cub/device/device_radix_sort.cuh>
@@ -94,6 +95,10 @@ struct DevCtx {
     bool map_masked = false;
     Buf gather_a, gather_b;                                   // edge ends of ALL devices of a multi-device handle, gathered here for cluster()
     Buf nn[9];                                                // sparse nearest: rotated keys + payload (in/out) of queries and targets, scratch
+    // join form of the t = 2 edge construction (bdg_join.cuh): barcodes in the key order of every condition's row side / column
+    // side, first column of every key, scratch keys (in / sorted) and radix-sort scratch, units per slab and their prefix sums
+    Buf jn_rows[bdg::SEED_MAX_CONDS], jn_cols[bdg::SEED_MAX_CONDS], jn_tab[bdg::SEED_MAX_CONDS], jn_key_in, jn_key_out, jn_cub, jn_counts, jn_offs, jn_lut;
+    int scheme_serial = 0;                                    // which scheme sits in this device's constant memory (0: none)
 };
 std::vector<DevCtx> g_ctx;
 
@@ -150,14 +155,51 @@ void build_plan(size_t N, int part, int nparts, int workers, Plan& p, uint64_t c
 
 constexpr size_t PLAN_HDR = 128;  // per launch: [work cursor u64 | tile-list count u64 | 8 x u64 statistics | pad]
 constexpr size_t HDR_LIST = 8, HDR_STATS = 16;
-int g_edge_mode = -1;             // -1: BDG_EDGE_MODE or default (sparse); 0 dense; 1 sparse
+int g_edge_mode = -1;             // -1: BDG_EDGE_MODE or default (by threshold and size); 0 dense; 1 sparse; 2 join
 
-bool sparse_mode(int t)
+// 0 dense, 1 sparse, 2 join.  The join form exists for t = 2 only and pays off once the key buckets fill.
+int edge_mode_for(int t, size_t N)
 {
-    if (t != 1 && t != 2) return false;
+    if (t != 1 && t != 2) return 0;
     int m = g_edge_mode;
-    if (m < 0) { const char* e = getenv("BDG_EDGE_MODE"); m = (e && !strcmp(e, "dense")) ? 0 : 1; }
-    return m == 1;
+    if (m < 0) {
+        const char* e = getenv("BDG_EDGE_MODE");
+        if (e && !strcmp(e, "dense")) m = 0;
+        else if (e && !strcmp(e, "sparse")) m = 1;
+        else if (e && !strcmp(e, "join")) m = 2;
+        else {
+            size_t min_n = 150000;
+            if (const char* j = getenv("BDG_JOIN_MIN_N")) min_n = (size_t)std::max(0ll, atoll(j));
+            m = (t == 2 && N >= min_n) ? 2 : 1;
+        }
+    }
+    if (m == 2 && (t != 2 || N >= (1ull << 28))) m = 1;
+    return m;
+}
+
+// ---- the seed scheme of the join form: built once on the host (bdg_seed.cuh), copied to every device that uses it ----
+bdg::SeedScheme g_scheme;
+std::vector<uint8_t> g_scheme_lut;
+int g_scheme_serial = 0;
+
+int scheme_ready()
+{
+    if (g_scheme_serial) return BDG_OK;
+    int bases[bdg::SEED_MAX_BLOCKS] = {3, 3, 3, 3, 3};
+    int nb = 5;
+    if (const char* e = getenv("BDG_JOIN_BLOCKS")) {          // e.g. "4,4,4,3": development aid
+        nb = 0;
+        for (const char* p = e; *p && nb < bdg::SEED_MAX_BLOCKS;) {
+            bases[nb++] = atoi(p);
+            while (*p && *p != ',') p++;
+            if (*p == ',') p++;
+        }
+    }
+    if (!bdg::seed_scheme_build(g_scheme, bases, nb)) return fail(BDG_ERR_ARG, "BDG_JOIN_BLOCKS is not a usable block layout (3..6 blocks, 15 bases in all)");
+    g_scheme_lut.assign((size_t)1 << g_scheme.nflags, 0);
+    bdg::seed_lut_build(g_scheme, g_scheme_lut.data());
+    g_scheme_serial = 1;
+    return BDG_OK;
 }
 
 template <int T_, int P_>
@@ -188,6 +230,98 @@ void launch_tiles_bip(int blocks, cudaStream_t st, const bdg::EdgeWork& w, const
         else FN<2, 2>(__VA_ARGS__);                                                   \
     } while (0)
 
+// Join form (t = 2): per condition of the seed scheme sort the barcodes by the row-side / column-side key, list the first
+// column of every key, count the work units per slab of rows, and run ONE persistent kernel over all units (bdg_join.cuh).
+// Every part sorts the whole array (replicated, a few % of the step) and takes every nparts-th batch of units.
+int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, uint32_t* d_a, uint32_t* d_b, uint8_t* d_d, size_t cap,
+                      unsigned long long* d_count, cudaStream_t st, DevCtx* ws)
+{
+    if (int rc = scheme_ready()) return rc;
+    const bdg::SeedScheme& S = g_scheme;
+    auto ensure = [&](Buf& b, size_t bytes) -> int {
+        if (cudaError_t e = (cudaError_t)b.ensure(bytes))
+            return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "workspace of %zu bytes: %s", bytes, cudaGetErrorString(e));
+        return BDG_OK;
+    };
+    if (ws->scheme_serial != g_scheme_serial) {
+        if (int e = ensure(ws->jn_lut, g_scheme_lut.size())) return e;
+        CU_TRY(cudaMemcpyToSymbolAsync(bdg::c_scheme, &g_scheme, sizeof(g_scheme), 0, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(ws->jn_lut.p, g_scheme_lut.data(), g_scheme_lut.size(), cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaStreamSynchronize(st));                  // the host copies above are read asynchronously
+        ws->scheme_serial = g_scheme_serial;
+    }
+    // rows per slab: 8 when the key buckets are short (a slab then spans few foreign buckets), else 32
+    int rs = (N >> S.ka[0].key_bits) < 48 ? 8 : 32;
+    if (const char* e = getenv("BDG_JOIN_RS")) rs = atoi(e) == 8 ? 8 : 32;
+    const uint32_t n_slabs = (uint32_t)((N + rs - 1) / rs);
+    const uint64_t total_slabs = (uint64_t)S.nconds * n_slabs;
+    if (int e = ensure(ws->plan, PLAN_HDR * bdg::MAX_PASSES)) return e;
+    if (int e = ensure(ws->jn_key_in, N * 4)) return e;
+    if (int e = ensure(ws->jn_key_out, N * 4)) return e;
+    if (int e = ensure(ws->jn_counts, (total_slabs + 1) * 4)) return e;
+    if (int e = ensure(ws->jn_offs, (total_slabs + 1) * 4)) return e;
+    size_t tmp_sort = 0, tmp_scan = 0;
+    CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)N, 0, 20, st));
+    CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)(total_slabs + 1), st));
+    if (int e = ensure(ws->jn_cub, std::max(tmp_sort, tmp_scan))) return e;
+    char* d_plan = (char*)ws->plan.p;
+    CU_TRY(cudaMemsetAsync(d_plan, 0, PLAN_HDR * bdg::MAX_PASSES, st));
+    for (int p = 0; p < bdg::MAX_PASSES; p++) ws->host_stats[p][0] = ws->host_stats[p][1] = 0;
+
+    bdg::JoinArgs A{};
+    const int gb = (int)std::min<size_t>((N + 255) / 256, (size_t)ws->sms * 8);
+    uint32_t* key_in = (uint32_t*)ws->jn_key_in.p;
+    uint32_t* key_out = (uint32_t*)ws->jn_key_out.p;
+    auto sort_side = [&](const bdg::SeedKey& k, Buf& dst) -> int {
+        if (int e = ensure(dst, N * 4)) return e;
+        bdg::join_keys_kernel<<<gb, 256, 0, st>>>(d_sorted, key_in, (uint32_t)N, k);
+        g_launches++;
+        size_t bytes = ws->jn_cub.cap;
+        CU_TRY(cub::DeviceRadixSort::SortPairs(ws->jn_cub.p, bytes, (const uint32_t*)key_in, key_out, d_sorted, (uint32_t*)dst.p, (int)N, 0, (int)k.key_bits, st));
+        return BDG_OK;
+    };
+    for (int c = 0; c < S.nconds; c++) {
+        const int rsrt = S.cond[c].row_sort;
+        if (rsrt == c) { if (int e = sort_side(S.ka[c], ws->jn_rows[c])) return e; }
+        A.rows[c] = (const uint32_t*)ws->jn_rows[rsrt].p;
+        if (S.cond[c].self) A.cols[c] = A.rows[c];
+        else {
+            if (int e = sort_side(S.kb[c], ws->jn_cols[c])) return e;
+            A.cols[c] = (const uint32_t*)ws->jn_cols[c].p;
+        }
+        const uint32_t nkeys = 1u << S.kb[c].key_bits;
+        if (int e = ensure(ws->jn_tab[c], ((size_t)nkeys + 1) * 4)) return e;
+        bdg::join_colstart_kernel<<<gb, 256, 0, st>>>(A.cols[c], (uint32_t)N, S.kb[c], nkeys, (uint32_t*)ws->jn_tab[c].p);
+        g_launches++;
+        A.colstart[c] = (const uint32_t*)ws->jn_tab[c].p;
+    }
+    A.offs = (const uint32_t*)ws->jn_offs.p;
+    A.lut = (const uint8_t*)ws->jn_lut.p;
+    A.cursor = (unsigned long long*)d_plan;
+    A.stats = (unsigned long long*)(d_plan + HDR_STATS);
+    A.N = (uint32_t)N;
+    A.n_slabs = n_slabs;
+    A.nconds = S.nconds;
+    A.part = part;
+    A.nparts = nparts;
+    A.T = bdg::qgram_threshold(2);
+    A.one = 1u;
+    A.mone = 0xFFFFFFFFu;
+    const int bb = (int)std::min<uint64_t>((total_slabs + 256) / 256, (uint64_t)ws->sms * 16);
+    bdg::join_band_kernel<<<bb, 256, 0, st>>>(A, rs, (uint32_t*)ws->jn_counts.p);
+    g_launches++;
+    size_t bytes = ws->jn_cub.cap;
+    CU_TRY(cub::DeviceScan::ExclusiveSum(ws->jn_cub.p, bytes, (const uint32_t*)ws->jn_counts.p, (uint32_t*)ws->jn_offs.p, (int)(total_slabs + 1), st));
+    bdg::EdgeOut o{d_a, d_b, d_d, d_count, (unsigned long long)cap};
+    int grid = 0;
+    if (int rc = grid_for(rs == 8 ? (const void*)bdg::join_kernel<8> : (const void*)bdg::join_kernel<32>, &grid, bdg::ENT)) return rc;
+    if (rs == 8) bdg::join_kernel<8><<<grid, bdg::ENT, 0, st>>>(A, o);
+    else bdg::join_kernel<32><<<grid, bdg::ENT, 0, st>>>(A, o);
+    g_launches++;
+    CU_TRY(cudaGetLastError());
+    return BDG_OK;
+}
+
 // Launch the edge construction of one part on the current device / stream.  d_count is zeroed on the stream.
 // ws: the device's grow-only workspaces (plan, rotated keys, sort scratch); one in-flight call per device.
 int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts, uint32_t* d_a, uint32_t* d_b,
@@ -198,7 +332,9 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
     if (!ws) return fail(BDG_ERR_NODEVICE, "bdg_init has not claimed the current CUDA device");
     CU_TRY(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
     if (t <= 0 || N < 2) return BDG_OK;   // D >= 1 for distinct barcodes: no edges (barcode_graph.py:245)
-    const bool sparse = sparse_mode(t);
+    const int mode = edge_mode_for(t, N);
+    if (mode == 2) return launch_edges_join(d_sorted, N, part, nparts, d_a, d_b, d_d, cap, d_count, st, ws);
+    const bool sparse = mode == 1;
     const int passes = sparse ? bdg::n_passes(t) : 1;
     const void* kern = sparse ? (t == 1 ? (const void*)bdg::sparse_tile_kernel<1, 0, false> : (const void*)bdg::sparse_tile_kernel<2, 0, false>)
                               : (t == 1 ? (const void*)bdg::edges_kernel<1> : t == 2 ? (const void*)bdg::edges_kernel<2>
@@ -495,6 +631,10 @@ void bdg_shutdown(void)
         c.gather_a.release(); c.gather_b.release();
         for (auto& b : c.as) b.release();
         for (auto& b : c.rot_sorted) b.release();
+        for (auto& b : c.jn_rows) b.release();
+        for (auto& b : c.jn_cols) b.release();
+        for (auto& b : c.jn_tab) b.release();
+        c.jn_key_in.release(); c.jn_key_out.release(); c.jn_cub.release(); c.jn_counts.release(); c.jn_offs.release(); c.jn_lut.release();
     }
     g_ctx.clear();
 }
@@ -535,7 +675,7 @@ void bdg_host_free(void* p)
 
 int bdg_set_edge_mode(int mode)
 {
-    if (mode < -1 || mode > 1) return fail(BDG_ERR_ARG, "edge mode must be -1 (default), 0 (dense) or 1 (sparse)");
+    if (mode < -1 || mode > 2) return fail(BDG_ERR_ARG, "edge mode must be -1 (default), 0 (dense), 1 (sparse) or 2 (join)");
     g_edge_mode = mode;
     return BDG_OK;
 }
@@ -554,6 +694,25 @@ int bdg_dev_edges_stats(unsigned long long* out5, void* stream)
             out5[k] += v[(PLAN_HDR / 8) * p + HDR_STATS / 8 + slot];
             if (k == 0) out5[k] += c->host_stats[p][0];                       // interval tests of the sparse scans (counted on the host)
             if (k == 1) out5[k] += v[(PLAN_HDR / 8) * p + HDR_LIST / 8];      // tiles the scans listed
+        }
+    }
+    return BDG_OK;
+}
+
+// The kernels' eight raw counters summed over the passes (join form: [0] work units, [2] pairs tested, [3] candidates,
+// [6] candidates with D <= 2, [7] pairs whose 6-mer score was computed; [4] / [5] sum / max of the warps' busy time in ns).
+int bdg_dev_edges_stats_raw(unsigned long long* out8, void* stream)
+{
+    DevCtx* c = ctx_of_current_device();
+    if (!c || !c->plan.p || !out8) return fail(BDG_ERR_ARG, "no edge launch on this device yet");
+    unsigned long long v[(PLAN_HDR / 8) * bdg::MAX_PASSES];
+    CU_TRY(cudaMemcpyAsync(v, c->plan.p, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    CU_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+    for (int k = 0; k < 8; k++) {
+        out8[k] = 0;
+        for (int p = 0; p < bdg::MAX_PASSES; p++) {
+            const unsigned long long x = v[(PLAN_HDR / 8) * p + HDR_STATS / 8 + k];
+            out8[k] = k == 5 ? std::max(out8[k], x) : out8[k] + x;
         }
     }
     return BDG_OK;

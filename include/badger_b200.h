@@ -154,10 +154,13 @@ void bdg_kmer_index_free(bdg_kmer_index* ix);
 int bdg_dev_edges_build(const uint32_t* d_sorted, size_t N, int t, int part, int nparts, uint32_t* d_a,
                         uint32_t* d_b, uint8_t* d_d, size_t cap, unsigned long long* d_count, void* stream);
 /* How the edge set is searched for t = 1, 2 (results are identical; DESIGN.md "edge construction"):
- *   1 sparse (default): one pass per prefilter block over the array sorted by a rotated key, pairs are decided
+ *   2 join (t = 2 only): sort-merge joins on multi-block seeds - per seed condition the array is sorted by the condition's
+ *     key, equal-key buckets are paired and only those pairs are tested (bdg_join.cuh); the default for t = 2 from
+ *     BDG_JOIN_MIN_N (150 000) distinct barcodes upwards;
+ *   1 sparse (default otherwise): one pass per prefilter block over the array sorted by a rotated key, pairs are decided
  *     tile by tile from key intervals and scored only inside the tiles that can hold a candidate;
  *   0 dense: one pass, the low-block conditions are scored for every pair (the all-pairs kernel);
- *  -1 back to the default / BDG_EDGE_MODE=dense|sparse.  t >= 3 always runs dense without a prefilter. */
+ *  -1 back to the default / BDG_EDGE_MODE=dense|sparse|join.  t >= 3 always runs dense without a block prefilter. */
 int bdg_set_edge_mode(int mode);
 /* Work statistics of the last bdg_dev_edges_build / bdg_edges_build* launch on the current device, summed over
  * its passes: out5[0] column sub-tiles whose key interval was tested, out5[1] sub-tiles that could hold a
@@ -165,6 +168,10 @@ int bdg_set_edge_mode(int mode);
  * out5[3] candidates handed to the exact stage, out5[4] pairs with D <= t whose 6-mer score S was computed (sparse
  * mode only).  Synchronises the stream.  (bench.py's roofline numerator.) */
 int bdg_dev_edges_stats(unsigned long long* out5, void* stream);
+/* The kernels' eight raw counters of the last edge launch on the current device, summed over its passes.  Join form: [0] work
+ * units, [2] pairs tested, [3] candidates handed to the exact stage, [6] candidates with D <= 2, [7] pairs whose 6-mer score was
+ * computed; [4] / [5] sum / max over the warps of their busy time in ns.  Synchronises the stream. */
+int bdg_dev_edges_stats_raw(unsigned long long* out8, void* stream);
 /* Development aid: out[2p], out[2p+1] = sum and max over the warps of pass p of (warp exit - first warp start), ns. */
 int bdg_dev_edges_balance(unsigned long long* out6, void* stream);
 int bdg_dev_pack16(const char* d_seqs, size_t R, uint32_t* d_out, uint8_t* d_valid, void* stream);

@@ -192,7 +192,14 @@ void orc_index_free(orc_index *ix)
 
 /* get_close for one query row (index.py:77-93).  acc is a zeroed n-byte scratch, touched an n-entry
  * scratch; returns the number of candidates written to cand (indices into ranks). */
+static size_t get_close_row_dir(const orc_index *ix, size_t row, int T, uint8_t *acc, uint32_t *touched, uint32_t *cand, int smaller);
 static size_t get_close_row(const orc_index *ix, size_t row, int T, uint8_t *acc, uint32_t *touched, uint32_t *cand)
+{
+    return get_close_row_dir(ix, row, T, acc, touched, cand, 0);
+}
+/* smaller = 0: index.py:77-93 as written (candidates with rank > number).  smaller = 1: the candidates with rank < number,
+ * i.e. the queries whose own get_close returns this row - S is symmetric, so walking the row's buckets finds them. */
+static size_t get_close_row_dir(const orc_index *ix, size_t row, int T, uint8_t *acc, uint32_t *touched, uint32_t *cand, int smaller)
 {
     uint32_t number = ix->ranks[row];
     size_t nt = 0, nc = 0;
@@ -200,7 +207,7 @@ static size_t get_close_row(const orc_index *ix, size_t row, int T, uint8_t *acc
         uint32_t k = kmer_at(number, p);
         for (uint64_t e = ix->start[k]; e < ix->start[k + 1]; e++) {
             uint32_t j = ix->ids[e];
-            if (ix->ranks[j] > number) { /* index.py:87 */
+            if (smaller ? ix->ranks[j] < number : ix->ranks[j] > number) { /* index.py:87 */
                 if (!acc[j]) touched[nt++] = j;
                 acc[j] += ix->mult[e];
             }
@@ -265,6 +272,46 @@ int64_t orc_edges_index(const orc_index *ix, int t, const uint32_t *rows, size_t
         free(acc); free(touched); free(cand);
     }
     if (verified) *verified = ver;
+    return cnt;
+}
+
+/* Every edge that has one of `rows` as an END POINT (smaller or larger barcode): what graph_construction leaves in
+ * edges[rows[x]] (barcode_graph.py:245-249 appends both directions).  Used for sampled-row parity at sizes where the whole
+ * index walk is out of reach.  An edge between two sampled rows is reported from both of them. */
+int64_t orc_edges_rows_both(const orc_index *ix, int t, const uint32_t *rows, size_t nrows, int threads,
+                            uint32_t *oa, uint32_t *ob, uint8_t *od, size_t cap)
+{
+    size_t n = ix->n;
+    int T = orc_T(t);
+    int64_t cnt = 0;
+#ifdef _OPENMP
+    if (threads > 0) omp_set_num_threads(threads);
+#endif
+#pragma omp parallel
+    {
+        uint8_t *acc = (uint8_t *)calloc(n ? n : 1, 1);
+        uint32_t *touched = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
+        uint32_t *cand = (uint32_t *)malloc(sizeof(uint32_t) * (n ? n : 1));
+#pragma omp for schedule(dynamic, 16)
+        for (size_t x = 0; x < nrows; x++) {
+            uint32_t a = ix->ranks[rows[x]];
+            for (int dir = 0; dir < 2; dir++) {
+                size_t nc = get_close_row_dir(ix, rows[x], T, acc, touched, cand, dir);
+                for (size_t c = 0; c < nc; c++) {
+                    uint32_t b = ix->ranks[cand[c]];
+                    if (b == a) continue;
+                    int d = orc_D(a, b);
+                    if (d <= t) {
+                        int64_t slot;
+#pragma omp atomic capture
+                        slot = cnt++;
+                        if (oa && (size_t)slot < cap) { oa[slot] = a < b ? a : b; ob[slot] = a < b ? b : a; od[slot] = (uint8_t)d; }
+                    }
+                }
+            }
+        }
+        free(acc); free(touched); free(cand);
+    }
     return cnt;
 }
 

@@ -59,6 +59,8 @@ def lib():
         L.orc_edges_index.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
         L.orc_edges_index.restype = C.c_int64
+        L.orc_edges_rows_both.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.orc_edges_rows_both.restype = C.c_int64
         L.orc_dedup_count.argtypes = [u32p, C.c_void_p, C.c_size_t, u32p, u32p]
         L.orc_dedup_count.restype = C.c_size_t
         L.orc_member.argtypes = [u32p, C.c_size_t, u32p, C.c_size_t, u8p]
@@ -152,6 +154,19 @@ class Index:
         n = min(n, cap)
         a, b, d = _canon(a[:n], b[:n], d[:n])
         return a, b, d, ver.value
+
+
+def edges_touching(ix: "Index", t: int, rows, threads: int = 0):
+    """Every edge with one of `rows` (indices into ix.ranks) as its smaller OR larger end point, each once, canonical order:
+    the adjacency lists graph_construction leaves for those rows (barcode_graph.py:245-249)."""
+    rows = np.ascontiguousarray(rows, dtype=np.uint32)
+    cap = lib().orc_edges_rows_both(ix._h, t, rows.ctypes.data, rows.size, threads, None, None, None, 0)
+    a = np.empty(cap, np.uint32); b = np.empty(cap, np.uint32); d = np.empty(cap, np.uint8)
+    n = lib().orc_edges_rows_both(ix._h, t, rows.ctypes.data, rows.size, threads, a.ctypes.data, b.ctypes.data, d.ctypes.data, cap)
+    assert n == cap
+    key = (a.astype(np.uint64) << np.uint64(32)) | b.astype(np.uint64)
+    _, first = np.unique(key, return_index=True)            # an edge between two sampled rows was found from both
+    return _canon(a[first], b[first], d[first])
 
 
 def dedup_count(reads: np.ndarray, valid: np.ndarray | None = None):

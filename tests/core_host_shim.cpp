@@ -1,7 +1,9 @@
 // Host build of badger_b200/csrc/bdg_core.cuh for the CPU-side unit tests (tests/test_core_host.py).
 // Test infrastructure: lets the per-pair device arithmetic be checked against the oracle without a GPU.
-#include "../badger_b200/csrc/bdg_core.cuh"
+#include "../badger_b200/csrc/bdg_seed.cuh"
 #include <stddef.h>
+#include <algorithm>
+#include <vector>
 
 extern "C" {
 void shim_pairs(const uint32_t* a, const uint32_t* b, size_t n, uint8_t* pre1, uint8_t* pre2, uint8_t* dsmall,
@@ -74,5 +76,77 @@ int shim_seed_tiles_meet(uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
 int shim_top_possible(int t, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi)
 {
     return t == 1 ? bdg::t1_top_possible(alo, ahi, blo, bhi) : bdg::t2_top_possible(alo, ahi, blo, bhi);
+}
+
+// ---- multi-block seeds (bdg_seed.cuh): scheme tables, hand-over table, sort forms, and the join passes emulated on the host
+static bdg::SeedScheme g_scheme;
+static std::vector<uint8_t> g_lut;
+int shim_scheme(const int* bases, int nblocks)          // returns the number of conditions, -1 if the layout is refused
+{
+    if (!bdg::seed_scheme_build(g_scheme, bases, nblocks)) return -1;
+    g_lut.assign((size_t)1 << g_scheme.nflags, 0);
+    bdg::seed_lut_build(g_scheme, g_lut.data());
+    return g_scheme.nconds;
+}
+int shim_scheme_nself(void) { return g_scheme.nself; }
+int shim_scheme_key_bits(int c) { return g_scheme.ka[c].key_bits; }
+int shim_scheme_row_sort(int c) { return g_scheme.cond[c].row_sort; }
+// first (condition, orientation) by the definition and by the table over the block-match flags
+void shim_scheme_first(const uint32_t* a, const uint32_t* b, size_t n, uint8_t* slow, uint8_t* fast)
+{
+    for (size_t i = 0; i < n; i++) {
+        slow[i] = (uint8_t)bdg::seed_first_slow(g_scheme, a[i], b[i]);
+        fast[i] = g_lut[bdg::seed_flags(g_scheme, a[i], b[i])];
+    }
+}
+void shim_scheme_keys(int c, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* ka, uint32_t* kb, uint8_t* pred)
+{
+    for (size_t i = 0; i < n; i++) {
+        ka[i] = bdg::seed_key(a[i], g_scheme.ka[c]); kb[i] = bdg::seed_key(b[i], g_scheme.kb[c]);
+        pred[i] = bdg::seed_pred(g_scheme, c, a[i], b[i]);
+    }
+}
+// The join passes emulated: per condition both sides are sorted by their join key, equal-key buckets are paired, and a candidate
+// goes through the very checks of the kernel (quick test, dist_small, hand-over table, qgram_score).  Returns the number of
+// edges (first `cap` stored).  stats[5 * (c + 1) + k], summed over the conditions in stats[k]: k = 0 pairs of the buckets
+// (quick tests), 1 pairs that pass the quick test, 2 of those with D <= 2, 3 of those handed to this pass, 4 edges.
+size_t shim_join_emulate(const uint32_t* s, size_t n, uint32_t* oa, uint32_t* ob, uint8_t* od, size_t cap, unsigned long long* stats)
+{
+    const bdg::SeedScheme& S = g_scheme;
+    size_t cnt = 0;
+    for (int k = 0; k < 5 * (S.nconds + 1); k++) stats[k] = 0;
+    std::vector<uint32_t> rows(s, s + n), cols(s, s + n);
+    for (int c = 0; c < S.nconds; c++) {
+        unsigned long long* st = stats + 5 * (c + 1);
+        const bdg::SeedKey A = S.ka[c], B = S.kb[c];
+        std::stable_sort(rows.begin(), rows.end(), [&](uint32_t p, uint32_t q) { return bdg::seed_key(p, A) < bdg::seed_key(q, A); });
+        std::stable_sort(cols.begin(), cols.end(), [&](uint32_t p, uint32_t q) { return bdg::seed_key(p, B) < bdg::seed_key(q, B); });
+        size_t lo = 0, hi = 0;
+        for (size_t r = 0; r < n; r++) {
+            const uint32_t x = rows[r], ka = bdg::seed_key(x, A);
+            while (lo < n && bdg::seed_key(cols[lo], B) < ka) lo++;
+            if (hi < lo) hi = lo;
+            while (hi < n && bdg::seed_key(cols[hi], B) <= ka) hi++;
+            for (size_t j = lo; j < hi; j++) {
+                const uint32_t y = cols[j];
+                if (S.cond[c].self && !(x < y)) continue;          // a symmetric condition pairs each couple once
+                st[0]++;
+                if (x == y || !bdg::quick_pass(x, y, 2)) continue;
+                st[1]++;
+                const uint32_t a = x < y ? x : y, b = x < y ? y : x;
+                const int d = bdg::dist_small(a, b);
+                if (d > 2) continue;
+                st[2]++;
+                if (g_lut[bdg::seed_flags(S, a, b)] != 2 * c + (x < y ? 0 : 1)) continue;
+                st[3]++;
+                if (bdg::qgram_score(a, b) < bdg::qgram_threshold(2)) continue;
+                st[4]++;
+                if (cnt < cap) { oa[cnt] = a; ob[cnt] = b; od[cnt] = (uint8_t)d; }
+                cnt++;
+            }
+        }
+        for (int k = 0; k < 5; k++) stats[k] += st[k];
+    }
+    return cnt;
 }
 }

@@ -24,14 +24,22 @@ def _init():
     yield
 
 
-@pytest.fixture(params=["sparse", "dense"])
+MODES = {"dense": 0, "sparse": 1, "join": 2}
+
+
+@pytest.fixture(params=["sparse", "dense", "join"])
 def mode(request):
-    """Both search strategies of the edge construction (include/badger_b200.h bdg_set_edge_mode) must give the
-    reference's edge set."""
+    """Every search strategy of the edge construction (include/badger_b200.h bdg_set_edge_mode) must give the
+    reference's edge set.  The join form exists for t = 2 only (other thresholds take the sparse / dense route)."""
     L = badger_b200.lib()
-    badger_b200._lib.check(L.bdg_set_edge_mode(1 if request.param == "sparse" else 0))
+    badger_b200._lib.check(L.bdg_set_edge_mode(MODES[request.param]))
     yield request.param
     badger_b200._lib.check(L.bdg_set_edge_mode(-1))
+
+
+def skip_join_unless_t2(mode, t):
+    if mode == "join" and t != 2:
+        pytest.skip("the join form is the t = 2 route; other thresholds run the sparse / dense kernels tested beside it")
 
 
 def edge_rows(a, b, d):
@@ -220,6 +228,7 @@ def test_kmer_indexer_golden(gold_kmer):
 # ------------------------------------------------------------------------------------------ oracle, seeded inputs
 @pytest.mark.parametrize("t", [1, 2, 3])
 def test_edges_vs_oracle_clustered(t, mode):
+    skip_join_unless_t2(mode, t)
     s = clustered_set(40 + t, 300, 30000 if t < 3 else 6000, 0.06)
     a, b, d = ops.edges_build(s, t)
     ix = orc.Index(s)
@@ -231,6 +240,7 @@ def test_edges_vs_oracle_clustered(t, mode):
 @pytest.mark.parametrize("t", [1, 2])
 def test_edges_dense_neighbourhoods(t, mode):
     """Consecutive integers and low-complexity families: every sub-tile next to the diagonal is dense."""
+    skip_join_unless_t2(mode, t)
     rng = np.random.default_rng(5)
     base = int(rng.integers(0, 1 << 31))
     s = np.unique(np.concatenate([np.arange(base, base + 3000, dtype=np.uint64),
@@ -277,6 +287,7 @@ def _structured_set(rng, kind, n):
 @pytest.mark.parametrize("t", [1, 2])
 def test_edges_many_small_structured_sets(t, mode):
     """Every pair decided by brute force (oracle predicate on all pairs) on many small sets of each structure."""
+    skip_join_unless_t2(mode, t)
     rng = np.random.default_rng(100 + t)
     total = 0
     for trial in range(36):
@@ -588,6 +599,7 @@ def test_resident_kmer_index_many_queries():
 def test_c2_full_size_properties(mode):
     """BASELINE config 2 at full size (1 M reads, t=1): sampled rows against the oracle's index walk, plus
     structural properties that do not depend on the size."""
+    skip_join_unless_t2(mode, 1)
     wl, cells, obs, valid, cfg = synth.make_dataset("C2")
     s = np.unique(obs[valid])
     a, b, d = ops.edges_build(s, cfg["threshold"])
@@ -617,7 +629,36 @@ def test_t2_large_sampled_rows(mode):
     s = np.unique(obs[valid])
     a, b, d = ops.edges_build(s, 2)
     rows = np.sort(rng.choice(s.size, 1500, replace=False)).astype(np.uint32)
-    wa, wb, wd, _ = orc.Index(s).edges(2, rows=rows)
-    sel = np.isin(a, s[rows])
-    assert np.array_equal(edge_rows(a[sel], b[sel], d[sel]), np.stack([wa, wb, wd], 1).astype(np.int64))
+    assert_sampled_rows(s, a, b, d, rows, 2)
     assert (d == 2).sum() > 1000 and (d == 1).sum() > 1000
+
+
+def assert_sampled_rows(s, a, b, d, rows, t):
+    """The edges that touch the sampled rows - as the smaller OR the larger barcode - against the oracle's index walk
+    (index.py:77-93 + barcode_graph.py:233-249) over the full array: SURVEY.md 0.6(ii)."""
+    wa, wb, wd = orc.edges_touching(orc.Index(s), t, rows)
+    picked = np.zeros(s.size, bool)
+    picked[rows] = True
+    sel = picked[np.searchsorted(s, a)] | picked[np.searchsorted(s, b)]
+    assert np.array_equal(edge_rows(a[sel], b[sel], d[sel]), np.stack([wa, wb, wd], 1).astype(np.int64))
+    assert wa.size > rows.size
+
+
+@pytest.mark.parametrize("name", ["C4", "C5"])
+def test_full_size_t2_sampled_rows(name):
+    """BASELINE configs 4 and 5 (as synthesised: 2e7 / 1e8 reads, t = 2) at FULL size on the default route (join form):
+    1 500 sampled rows as either end point against the oracle, plus the size-independent properties."""
+    import os
+    workers = min(32, len(os.sched_getaffinity(0)))
+    wl, cells, obs, valid, cfg = synth.make_dataset(name, workers=workers)
+    s = synth.sorted_unique(obs[valid])
+    del obs, valid
+    a, b, d = ops.edges_build(s, cfg["threshold"])
+    assert a.size > 20 * s.size
+    assert (a < b).all() and ((d >= 1) & (d <= 2)).all()
+    rows = np.sort(np.random.default_rng(12).choice(s.size, 1500, replace=False)).astype(np.uint32)
+    assert_sampled_rows(s, a, b, d, rows, cfg["threshold"])
+    # no edge twice: the (a, b) keys of a 1/64 slice of the key space are distinct
+    part = (a & np.uint32(63)) == 7
+    key = (a[part].astype(np.uint64) << np.uint64(32)) | b[part].astype(np.uint64)
+    assert np.unique(key).size == key.size

@@ -15,7 +15,7 @@ from badger_b200 import synth  # noqa: E402
 
 
 def dataset(reads):
-    wl, cells, obs, valid, cfg = synth.make_dataset("C2", reads=reads)
+    wl, cells, obs, valid, cfg = synth.make_dataset("C2", reads=reads, workers=min(32, len(os.sched_getaffinity(0))))
     return synth.sorted_unique(obs[valid])
 
 
@@ -42,6 +42,10 @@ def time_edges(s, t, reps=3):
     import ctypes as C
     v = (C.c_ulonglong * 5)()
     L.bdg_dev_edges_stats(v, st.cuda_stream)
+    raw = (C.c_ulonglong * 8)()
+    L.bdg_dev_edges_stats_raw(raw, st.cuda_stream)
+    global RAW
+    RAW = list(raw)
     bal = (C.c_ulonglong * 6)()
     L.bdg_dev_edges_balance(bal, st.cuda_stream)
     nw = 148 * 3 * 8
@@ -54,7 +58,7 @@ def main():
     badger_b200.init([0])
     sizes = [int(x) for x in os.environ.get("SWEEP_READS", "400000,1000000").split(",")]
     ts = [int(x) for x in os.environ.get("SWEEP_T", "1,2").split(",")]
-    knobs = {k: os.environ.get("SWEEP_" + k, d).split(",") for k, d in (("ITEMS", "16"), ("MODE", "1,0"))}
+    knobs = {k: os.environ.get("SWEEP_" + k, d).split(",") for k, d in (("ITEMS", "16"), ("MODE", "2,1"))}
     data = {r: dataset(r) for r in sizes}
     for r, t in itertools.product(sizes, ts):
         s = data[r]
@@ -64,8 +68,11 @@ def main():
             badger_b200.lib().bdg_set_edge_mode(int(mode))
             ms, edges, (subs, fulls, scored, cand, nS) = time_edges(s, t)
             print("reads=%8d N=%8d t=%d items=%-3s mode=%s  %9.3f ms  %.3e pairs/s  edges=%d  sub-tiles=%d full=%.2f%% scored=%.3e cand=%.3e" % (
-                r, n, t, items, "sparse" if mode == "1" else "dense ", ms, n * (n - 1) / 2 / (ms * 1e-3), edges, subs, 100.0 * fulls / max(subs, 1), scored, cand), flush=True)
+                r, n, t, items, {"0": "dense ", "1": "sparse", "2": "join  "}[mode], ms, n * (n - 1) / 2 / (ms * 1e-3), edges, subs, 100.0 * fulls / max(subs, 1), scored, cand), flush=True)
             print("      balance (warp exit times): " + BALANCE, flush=True)
+            if mode == "2" and t == 2:
+                print("      join: units=%d pairs tested=%.3e candidates=%.3e D<=2=%.3e scored=%.3e warp busy mean %.0f us max %.0f us" % (
+                    RAW[0], RAW[2], RAW[3], RAW[6], RAW[7], RAW[4] / (148 * 5 * 8) / 1e3, RAW[5] / 1e3), flush=True)
 
 
 if __name__ == "__main__":
