@@ -5,6 +5,7 @@ Each function names the reference code it stands in for (file:line in algbio/Bad
 from __future__ import annotations
 
 import ctypes as C
+import os
 import weakref
 
 import numpy as np
@@ -111,7 +112,7 @@ class _PinnedPool:
     """Page-locked blocks behind the (large) edge arrays the operators return: a device-to-host copy into pinned memory
     runs at full PCIe speed, into pageable memory at about a third of it.  A block goes back to the pool when the last
     numpy view of it dies; the pool keeps at most POOL_BYTES and frees the rest."""
-    POOL_BYTES = 1 << 30
+    POOL_BYTES = int(os.environ.get("BDG_PINNED_POOL_BYTES", str(4 << 30)))
     MIN_BYTES = 1 << 16          # smaller arrays are plain numpy allocations
 
     def __init__(self):

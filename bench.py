@@ -3,18 +3,22 @@
 
 A "step" is one pass of the hot path over one batch of synthetic input: edge construction
 (index.py:77-93 + barcode_graph.py:224-249 of the reference) over every unordered pair of the distinct
-barcodes of BASELINE.json's config 2 (1 M simulated ONT reads, 10 k cells, 3 M whitelist, threshold 1).
+barcodes of BASELINE.json's config 4 (20 M simulated ONT reads, 10 k cells, ~4.6 M distinct noisy barcodes,
+threshold 2) - the configuration the metric "at 1/2/4/8 B200" is quoted on.
 
   value   whole-job pairs/s with the sorted distinct-barcode array already resident in HBM
           (bdg_dev_edges_build on torch's current stream, CUDA events around every step, max over ranks)
   e2e     the same metric through the public host-buffer call (ops.edges_build_part -> bdg_edges_build_part):
-          pinned host input -> H2D -> kernel -> D2H of the edge list, wall clock, max over ranks
-  roofline    dominant kernel (the edge kernel's passes) against the MEASURED integer issue rate of this GPU
+          pinned host input -> H2D -> kernels -> D2H of the edge list, wall clock, max over ranks
+  roofline    the step's dominant kernel against the MEASURED integer issue rate of this GPU (probed in the same run)
   cpu_baseline  the oracle's restatement of the reference algorithm on the box's host cores (rank 0, N=1)
 
-N > 1 (torchrun): weak scaling - the read count is raised until the distinct barcodes are sqrt(N) times the one-GPU
-count, so that the pairs per GPU stay fixed; rows are dealt to ranks in 2048-row tiles, no data-path collective
-(SURVEY.md §8e).
+N > 1 (torchrun): STRONG scaling - every rank holds the same array (replicated) and takes every N-th
+batch of work units of the join (rows of the sorted orders), no data-path collective; the per-rank edge lists are
+disjoint and their union is the edge set (checked: the counts add up to the one-GPU count).
+
+Secondary keys at N = 1: `stages` (the other rows of the path), `pipeline` (reads/s of the whole correction step at
+C4 and C2), `cli` (the drop-in command file to file at C2), `c2` (the round-1 headline: C2 at t = 1).
 
 `--impl reference` times the reference's own algorithm (oracle port, all host threads) on a bounded sample
 of the same workload; /root/reference (pure Python) cannot travel to the GPU box.
@@ -23,7 +27,6 @@ from __future__ import annotations
 
 import argparse
 import json
-import math
 import os
 import subprocess
 import sys
@@ -40,7 +43,10 @@ from badger_b200 import synth  # noqa: E402
 METRIC = "barcode_pairs_scored_per_s"
 UNIT = "pairs/s"
 # Algorithmic integer instructions per unit of work of the edge kernels (DESIGN.md "edge construction"; counted
-# from the SASS of the inner loops, the numbers of units come from the kernel's own counters, bdg_dev_edges_stats):
+# from the SASS of the code blocks, profiles/*_blocks.txt; the numbers of units come from the kernels' own counters,
+# bdg_dev_edges_stats / bdg_dev_edges_stats_raw):
+#   join:   per work unit (cursor, slab lookup, staging), per pair tested (quick test + key equality), per candidate
+#           (queue + exact distance), per candidate with D <= 2 (hand-over flags + table), per pair scored (6-mer score)
 #   sparse: one key-interval test (pass_possible) per column sub-tile, 32 more per surviving sub-tile; one quick
 #           test per pair of a surviving 32x32 block; one exact stage (D, then S) per candidate
 #   dense:  one light-loop step per pair (1.25 instr at t=1, 6 at t=2), exact stage per candidate
@@ -49,15 +55,9 @@ A_QUICK = {1: 14.5, 2: 16.5}       # 58 / 66 SASS instructions per 4 pairs
 A_LIGHT = {1: 1.25, 2: 6.0}
 A_EXACT = 110                      # loads, un-rotation, pass predicates, dist_small
 A_SCORE = 220                      # qgram_score, only for pairs with D <= t
-# DRAM traffic of one step's dominant kernels from the ncu --set full capture of this round (profiles/r1e_sparse_t*_ncu_full.txt:
-# dram__bytes_read.sum + dram__bytes_write.sum of the scan + tile kernels of all passes, C2, N = 492 093).  Writes stay in L2.
-NCU_TRAFFIC_BYTES = {1: 536064 + 2174976 + 535040 + 2056704, 2: 3 * 535808 + 2710528 + 2709760 + 2153728 + 1280}
+A_JOIN = {"unit": 160, "pair": 22.0, "cand": 85, "d2": 50, "score": 220}
 A_PAIR_SURVEY = {1: 15, 2: 25}   # SURVEY.md §8(d) nominal per-pair figure of a plain all-pairs kernel, reported alongside
-
-
-# read counts at which the distinct barcodes of a config reach sqrt(N) times the one-GPU count (deterministic synthesis:
-# found once by workload()'s search; used as its first guess and re-verified there, so that N > 1 runs start quickly)
-WEAK_SCALING_READS = {("C2", 1_000_000, 0.05, 10_000): {"n1": 492093, 2: 1490288, 4: 2248893, 8: 3527307}}
+NCU_TRAFFIC = None               # bytes per step of the dominant kernel from the committed ncu capture (profiles/), with its label
 
 
 def parse():
@@ -66,50 +66,54 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--config", default="C2")
+    ap.add_argument("--config", default="C4")
     ap.add_argument("--reads", type=int, default=None, help="override the read count (testing)")
     ap.add_argument("--threshold", type=int, default=None)
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--mode", choices=["sparse", "dense"], default="sparse", help="edge search strategy (bdg_set_edge_mode)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the stages / pipeline / cli / c2 keys")
+    ap.add_argument("--mode", choices=["auto", "join", "sparse", "dense"], default="auto", help="edge search strategy (bdg_set_edge_mode)")
     return ap.parse_args()
 
 
-def workload(args, world):
-    """C2 at one GPU.  For N GPUs (weak scaling) the read count is raised until the number of DISTINCT barcodes is
-    sqrt(N) times the one-GPU count, so that the pairs per GPU stay fixed (distinct barcodes grow slower than reads:
-    sqrt(N) times the reads alone would hand every rank less work than the one-GPU run has)."""
-    cfg = dict(synth.CONFIGS[args.config])
-    if args.threshold is not None:
-        cfg["threshold"] = args.threshold
+def dataset(config, reads=None, threshold=None):
+    """(cfg, whitelist, observed, valid, sorted distinct) of a BASELINE config, synthesised once per box: the first caller
+    writes the arrays to a cache file, the other ranks (and the other arm of the bench) load it."""
+    cfg = dict(synth.CONFIGS[config])
+    if reads is not None:
+        cfg["reads"] = reads
+    if threshold is not None:
+        cfg["threshold"] = threshold
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
+    path = os.path.join(base, "bdg_bench_%s_%d_%g_%d_%d_%d.npz" % (config, cfg["reads"], cfg["perr"], cfg["n_cells"], cfg["whitelist"], cfg["seed"]))
+    rank = int(os.environ.get("RANK", "0"))
+    if not os.path.exists(path):
+        if rank == 0:
+            workers = max(1, min(32, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)))
+            wl, cells, obs, valid, _ = synth.make_dataset(cfg, workers=workers)
+            s = synth.sorted_unique(obs[valid])
+            tmp = path + ".%d.tmp.npz" % os.getpid()
+            np.savez(tmp, wl=wl, obs=obs, valid=valid, s=s)
+            os.replace(tmp, path)
+        else:
+            t0 = time.time()
+            while not os.path.exists(path):
+                if time.time() - t0 > 900:
+                    raise RuntimeError("rank 0 did not write %s" % path)
+                time.sleep(0.2)
+    z = np.load(path)
+    return cfg, z["wl"], z["obs"], z["valid"], z["s"]
 
-    def distinct_of(reads):
-        wl, cells, obs, valid, _ = synth.make_dataset(cfg, reads=reads)
-        return synth.sorted_unique(obs[valid]), (wl, obs, valid)
 
-    base_reads = args.reads if args.reads is not None else cfg["reads"]
-    reads = base_reads
-    known = WEAK_SCALING_READS.get((args.config, base_reads, cfg["perr"], cfg["n_cells"]))   # found once by the search below
-    if world == 1 or not known:
-        s, data = distinct_of(reads)
-    if world > 1:
-        n1 = known["n1"] if known else s.size
-        target = n1 * math.sqrt(world)
-        r_prev, n_prev = base_reads, n1
-        reads = known.get(world, 0) if known else 0
-        reads = reads or int(round(base_reads * math.sqrt(world)))
-        for _ in range(3):
-            s, data = distinct_of(reads)
-            if abs(s.size - target) <= 0.012 * target:
-                break
-            alpha = math.log(s.size / n_prev) / math.log(reads / r_prev) if reads != r_prev and s.size != n_prev else 0.8
-            alpha = min(max(alpha, 0.3), 1.0)
-            r_prev, n_prev = reads, s.size
-            reads = int(round(reads * (target / s.size) ** (1.0 / alpha)))
-    name = "%s: %d simulated ONT reads, %d cells, %d-entry whitelist, %.0f%% error, threshold %d" % (
-        args.config, reads, cfg["n_cells"], cfg["whitelist"], 100 * cfg["perr"], cfg["threshold"])
-    workload.dataset = (data[0], data[1], data[2], cfg)          # for the whole-pipeline reads/s figure
-    return s, cfg["threshold"], reads, name
+def workload_name(config, cfg, n):
+    return "%s: %d simulated ONT reads, %d cells, %d-entry whitelist, %.0f%% error, %d distinct barcodes, threshold %d" % (
+        config, cfg["reads"], cfg["n_cells"], cfg["whitelist"], 100 * cfg["perr"], n, cfg["threshold"])
+
+
+def config_dict(config, cfg, n):
+    """The `config` key: identical in both arms."""
+    return {"workload": workload_name(config, cfg, n), "reads": int(cfg["reads"]), "distinct": int(n), "threshold": int(cfg["threshold"]),
+            "pairs_per_step": int(n) * (int(n) - 1) // 2}
 
 
 # ------------------------------------------------------------------------------------------ CPU arm
@@ -118,10 +122,12 @@ def cpu_sample(s, t, seconds, seed=7):
     from oracle import oracle as orc
     # all the host cores this process may run on (torchrun exports OMP_NUM_THREADS=1, which is not a property of the box)
     threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or orc.num_threads())
-    ix = orc.Index(s)
+    ix = cpu_sample.index.get(id(s))
+    if ix is None:
+        ix = cpu_sample.index[id(s)] = orc.Index(s)
     rng = np.random.default_rng(seed)
     n = s.size
-    k = min(n, 2000)
+    k = min(n, 256)
     rows = np.sort(rng.choice(n, k, replace=False)).astype(np.uint32)
     t0 = time.perf_counter()
     ix.edges(t, rows=rows, threads=threads)
@@ -137,12 +143,16 @@ def cpu_sample(s, t, seconds, seed=7):
                        "oracle/badger_oracle.c restating index.py:77-93 + barcode_graph.py:224-249" % (k2, n, n, dt)), dt
 
 
+cpu_sample.index = {}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     if rank != 0:
         return
-    s, t, reads, name = workload(args, world)
+    cfg, _, _, _, s = dataset(args.config, args.reads, args.threshold)
+    t = cfg["threshold"]
     per_step = max(2.0, min(args.cpu_seconds, 120.0 / max(1, args.steps + args.warmup)))
     vals, secs = [], []
     for i in range(args.warmup + args.steps):
@@ -154,8 +164,8 @@ def run_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1000 * float(np.mean(secs)) if secs else None, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
-        "config": {"workload": name, "reads": reads, "distinct": int(s.size), "threshold": t},
+        "scaling": "strong", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+        "config": config_dict(args.config, cfg, s.size),
         "cpu_baseline": cb,
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -199,6 +209,119 @@ class ClockSampler:
                 "power_w_max": max(float(r[3]) for r in rows), "reasons": sorted(reasons)}
 
 
+MODE_ID = {"auto": -1, "dense": 0, "sparse": 1, "join": 2}
+
+
+def int_probe(torch, L, dev, stream):
+    """Integer-pipe issue rates of this GPU (the roofline denominator; not in MEASURED_PEAKS.json)."""
+    import ctypes as C
+    import badger_b200
+    sms = torch.cuda.get_device_properties(dev).multi_processor_count
+    sink = torch.zeros(4, dtype=torch.int32, device=dev)
+    probe = {}
+    for kind, label in ((0, "lop3"), (1, "imad"), (2, "lop3_imad_mix"), (3, "popc")):
+        best = 0.0
+        iters = 4000 if kind != 3 else 1000
+        for rep in range(4):
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            ops_pt = C.c_ulonglong(0)
+            e0.record(stream)
+            badger_b200._lib.check(L.bdg_dev_pipe_probe(kind, sms * 8, iters, sink.data_ptr(), C.byref(ops_pt), stream.cuda_stream))
+            e1.record(stream)
+            torch.cuda.synchronize()
+            rate = ops_pt.value * 256 * sms * 8 / (e0.elapsed_time(e1) * 1e-3)
+            if rep:
+                best = max(best, rate)
+        probe[label] = best / 1e12       # T thread-instructions / s
+    return probe
+
+
+class EdgeStep:
+    """Device-resident edge construction of one part (bdg_dev_edges_build on torch's stream) with CUDA-event timing."""
+
+    def __init__(self, torch, L, dev, stream, s, t, part, nparts):
+        self.torch, self.L, self.dev, self.stream = torch, L, dev, stream
+        self.n, self.t, self.part, self.nparts = int(s.size), t, part, nparts
+        self.d_sorted = torch.from_numpy(s.view(np.int32)).to(dev)
+        self.cap = 0
+        self.d_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+        self.alloc(max(1 << 16, (16 if t <= 1 else 32) * self.n // nparts + 1024))
+
+    def alloc(self, cap):
+        torch = self.torch
+        self.cap = cap
+        self.d_a = torch.empty(cap, dtype=torch.int32, device=self.dev)
+        self.d_b = torch.empty(cap, dtype=torch.int32, device=self.dev)
+        self.d_d = torch.empty(cap, dtype=torch.uint8, device=self.dev)
+
+    def launch(self):
+        import badger_b200
+        badger_b200._lib.check(self.L.bdg_dev_edges_build(self.d_sorted.data_ptr(), self.n, self.t, self.part, self.nparts, self.d_a.data_ptr(),
+                                                          self.d_b.data_ptr(), self.d_d.data_ptr(), self.cap, self.d_count.data_ptr(),
+                                                          self.stream.cuda_stream))
+
+    def settle(self, warm):
+        """First run sizes the edge buffers; a poisoned or oversized count is an error, never a timed run."""
+        self.launch()
+        self.torch.cuda.synchronize()
+        count = int(self.d_count.item())
+        assert count >= 0, "a work list of the edge kernels overflowed (bit 63 of the count): call bdg_edges_build_part once to grow it"
+        if count > self.cap:
+            self.alloc(count + 1024)
+        for _ in range(warm):
+            self.launch()
+        self.torch.cuda.synchronize()
+        count = int(self.d_count.item())
+        assert 0 <= count <= self.cap, "edge buffer too small after sizing: count %d, capacity %d" % (count, self.cap)
+        return count
+
+    def timed(self, k):
+        ms = 0.0
+        for _ in range(k):
+            self.flush.fill_(1)                      # evict L2 between timed iterations
+            e0, e1 = self.torch.cuda.Event(True), self.torch.cuda.Event(True)
+            e0.record(self.stream)
+            self.launch()
+            e1.record(self.stream)
+            e1.synchronize()
+            ms += e0.elapsed_time(e1)
+        return ms
+
+    def stats(self):
+        import ctypes as C
+        import badger_b200
+        v = (C.c_ulonglong * 5)()
+        badger_b200._lib.check(self.L.bdg_dev_edges_stats(v, self.stream.cuda_stream))
+        raw = (C.c_ulonglong * 8)()
+        badger_b200._lib.check(self.L.bdg_dev_edges_stats_raw(raw, self.stream.cuda_stream))
+        d = dict(zip(("sub_tiles", "sub_tiles_scored", "pairs_scored", "candidates", "pairs_S_scored"), (int(x) for x in v)))
+        d["candidates_within_t"] = int(raw[6])
+        d["warp_busy_ns_sum"], d["warp_busy_ns_max"] = int(raw[4]), int(raw[5])
+        return d
+
+
+def algorithmic(mode, t, st, n_edges_part):
+    """Algorithmic integer instructions of one step from the kernels' own unit counters."""
+    if mode == "join":
+        return (A_JOIN["unit"] * st["sub_tiles"] + A_JOIN["pair"] * st["pairs_scored"] + A_JOIN["cand"] * st["candidates"]
+                + A_JOIN["d2"] * st["candidates_within_t"] + A_JOIN["score"] * st["pairs_S_scored"])
+    if t not in A_QUICK:
+        return None
+    per_pair = A_QUICK[t] if mode == "sparse" else A_LIGHT[t]
+    tiles = (st["sub_tiles"] + 32 * st["sub_tiles_scored"]) if mode == "sparse" else 0
+    score = st["pairs_S_scored"] if mode == "sparse" else n_edges_part     # dense counts S inside the exact stage: at least the edges
+    return A_TILE * tiles + per_pair * st["pairs_scored"] + A_EXACT * st["candidates"] + A_SCORE * score
+
+
+def effective_mode(mode, t, n):
+    if mode != "auto":
+        return mode if (mode != "join" or t == 2) else "sparse"
+    if t not in (1, 2):
+        return "dense"
+    return "join" if (t == 2 and n >= int(os.environ.get("BDG_JOIN_MIN_N", "150000"))) else "sparse"
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -216,11 +339,12 @@ def run_b200(args):
     badger_b200.init([local])
     L = badger_b200.lib()
 
-    s, t, reads, name = workload(args, world)
+    cfg, wl, obs, valid, s = dataset(args.config, args.reads, args.threshold)
+    t = cfg["threshold"]
     n = int(s.size)
     total_pairs = n * (n - 1) // 2
-    my_pairs = int(L.bdg_part_pairs(n, rank, world))
     stream = torch.cuda.current_stream()
+    mode = effective_mode(args.mode, t, n)
 
     def barrier():
         if world > 1:
@@ -234,105 +358,38 @@ def run_b200(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         return float(tt.item())
 
-    # ---- integer-pipe probe: the roofline denominator (not in MEASURED_PEAKS.json)
-    sms = torch.cuda.get_device_properties(dev).multi_processor_count
-    sink = torch.zeros(4, dtype=torch.int32, device=dev)
-    import ctypes as C
-    probe = {}
-    for kind, label in ((0, "lop3"), (1, "imad"), (2, "lop3_imad_mix"), (3, "popc")):
-        best = 0.0
-        iters = 4000 if kind != 3 else 1000
-        for rep in range(4):
-            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-            ops_pt = C.c_ulonglong(0)
-            e0.record(stream)
-            badger_b200._lib.check(L.bdg_dev_pipe_probe(kind, sms * 8, iters, sink.data_ptr(), C.byref(ops_pt), stream.cuda_stream))
-            e1.record(stream)
-            torch.cuda.synchronize()
-            rate = ops_pt.value * 256 * sms * 8 / (e0.elapsed_time(e1) * 1e-3)
-            if rep:
-                best = max(best, rate)
-        probe[label] = best / 1e12       # T thread-instructions / s
+    def sum_over_ranks(x):
+        if world == 1:
+            return int(x)
+        tt = torch.tensor([int(x)], dtype=torch.int64, device=dev)
+        dist.all_reduce(tt)
+        return int(tt.item())
 
-    # ---- device-resident buffers (torch owns memory and stream; the library only launches)
-    d_sorted = torch.from_numpy(s.view(np.int32)).to(dev)
-    cap = max(1 << 16, 16 * n // world + 1024)
-    d_a = torch.empty(cap, dtype=torch.int32, device=dev)
-    d_b = torch.empty(cap, dtype=torch.int32, device=dev)
-    d_d = torch.empty(cap, dtype=torch.uint8, device=dev)
-    d_count = torch.zeros(1, dtype=torch.int64, device=dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-
-    def step_dev():
-        badger_b200._lib.check(L.bdg_dev_edges_build(d_sorted.data_ptr(), n, t, rank, world, d_a.data_ptr(), d_b.data_ptr(),
-                                                     d_d.data_ptr(), cap, d_count.data_ptr(), stream.cuda_stream))
-
-    def timed_steps(k):
-        ms = 0.0
-        for _ in range(k):
-            flush.fill_(1)                      # evict L2 between timed iterations
-            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
-            e0.record(stream)
-            step_dev()
-            e1.record(stream)
-            e1.synchronize()
-            ms += e0.elapsed_time(e1)
-        return ms
-
-    def work_stats():
-        v = (C.c_ulonglong * 5)()
-        badger_b200._lib.check(L.bdg_dev_edges_stats(v, stream.cuda_stream))
-        return dict(zip(("sub_tiles", "sub_tiles_scored", "pairs_scored", "candidates", "pairs_S_scored"), (int(x) for x in v)))
-
+    probe = int_probe(torch, L, dev, stream)
     sampler = ClockSampler(local)
-    sampler.start()                        # covers warm-up, the timed steps and the e2e loop (a step is ~1 ms)
-    badger_b200._lib.check(L.bdg_set_edge_mode(1 if args.mode == "sparse" else 0))
-    step_dev()
-    torch.cuda.synchronize()
-    if int(d_count.item()) > cap:          # dense data (t >= 2): size the edge buffers from the first count
-        cap = int(d_count.item()) + 1024
-        d_a = torch.empty(cap, dtype=torch.int32, device=dev)
-        d_b = torch.empty(cap, dtype=torch.int32, device=dev)
-        d_d = torch.empty(cap, dtype=torch.uint8, device=dev)
+    sampler.start()                        # covers warm-up, the timed steps and the e2e loop
+    badger_b200._lib.check(L.bdg_set_edge_mode(MODE_ID[args.mode]))
+    step = EdgeStep(torch, L, dev, stream, s, t, rank, world)
     warm = max(args.warmup, 3)
-    for _ in range(warm):
-        step_dev()
-    torch.cuda.synchronize()
-    n_edges_part = int(d_count.item())
-    assert 0 <= n_edges_part <= cap, "edge buffer or tile list too small: count %d, capacity %d" % (n_edges_part, cap)
+    n_edges_part = step.settle(warm)
 
     launches0 = L.bdg_launch_count()
     barrier()
-    ms = timed_steps(args.steps)
+    ms = step.timed(args.steps)
     barrier()
     launches = L.bdg_launch_count() - launches0
-    stats = work_stats()
+    stats = step.stats()
     ms_total = max_over_ranks(ms)
     step_ms = ms / args.steps             # this rank's average step (all launches of the step, CUDA events)
     value = total_pairs * args.steps / (ms_total * 1e-3)
-
-    # ---- the other search strategy, for the record (same buffers, same timing rules)
-    other = "dense" if args.mode == "sparse" else "sparse"
-    badger_b200._lib.check(L.bdg_set_edge_mode(0 if args.mode == "sparse" else 1))
-    for _ in range(3):
-        step_dev()
-    torch.cuda.synchronize()
-    n_other = int(d_count.item())          # per-part counts differ between the modes (different row orders), totals must not
-    if world > 1:
-        tt = torch.tensor([n_edges_part, n_other], dtype=torch.int64, device=dev)
-        dist.all_reduce(tt)
-        assert int(tt[0].item()) == int(tt[1].item()), "the two edge modes disagree on the total edge count"
-    else:
-        assert n_other == n_edges_part, "the two edge modes disagree on the edge count"
-    ms_other = timed_steps(max(2, min(args.steps, 3))) / max(2, min(args.steps, 3))
-    stats_other = work_stats()
-    badger_b200._lib.check(L.bdg_set_edge_mode(1 if args.mode == "sparse" else 0))
+    edges_total = sum_over_ranks(n_edges_part)
 
     # ---- e2e: public host-buffer API, pinned input, edge list back on the host
     s_pinned = torch.from_numpy(s.view(np.int32)).pin_memory()
     s_host = s_pinned.numpy().view(np.uint32)
     r1 = ops.edges_build_part(s_host, t, rank, world)      # warm; two result sets alive at once, as in the timed loop below,
     r2 = ops.edges_build_part(s_host, t, rank, world)      # so that the operator's pinned output pool holds both of them
+    assert r1[0].size == n_edges_part, "the host-buffer call and the device call disagree on the edge count"
     del r1, r2
     barrier()
     t0 = time.perf_counter()
@@ -344,67 +401,72 @@ def run_b200(args):
     clocks = sampler.stop()
     e2e = {"value": total_pairs * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(4 * n),
            "d2h_bytes_per_step": int(9 * ea.size + 8), "ms_per_step": 1000 * e2e_s / args.steps,
-           "api": "badger_b200.ops.edges_build_part -> bdg_edges_build_part (host buffers)"}
+           "api": "badger_b200.ops.edges_build_part -> bdg_edges_build_part (host buffers; every rank uploads the array and downloads its edges)"}
+    del ea, eb, ed
 
-    edges_total = n_edges_part
-    if world > 1:
-        tt = torch.tensor([n_edges_part], dtype=torch.int64, device=dev)
-        dist.all_reduce(tt)
-        edges_total = int(tt.item())
-
-    def algorithmic(mode, st):
-        if t not in A_QUICK:
-            return None
-        per_pair = A_QUICK[t] if mode == "sparse" else A_LIGHT[t]
-        tiles = (st["sub_tiles"] + 32 * st["sub_tiles_scored"]) if mode == "sparse" else 0
-        score = st["pairs_S_scored"] if mode == "sparse" else n_edges_part     # dense counts S inside the exact stage: at least the edges
-        return A_TILE * tiles + per_pair * st["pairs_scored"] + A_EXACT * st["candidates"] + A_SCORE * score
+    # ---- the other search strategy on the same input, for the record (one GPU only: it is several times slower)
+    other = None
+    if world == 1 and t in (1, 2) and not args.no_secondary:
+        other_mode = "sparse" if mode == "join" else ("dense" if n < 600000 else None)
+        if other_mode:
+            badger_b200._lib.check(L.bdg_set_edge_mode(MODE_ID[other_mode]))
+            n_other = step.settle(1)
+            assert n_other == n_edges_part, "the two edge modes disagree on the edge count"
+            k = 2
+            ms_other = step.timed(k) / k
+            st_o = step.stats()
+            alg_o = algorithmic(other_mode, t, st_o, n_other)
+            other = {"mode": other_mode, "ms_per_step": ms_other, "pairs_per_s": total_pairs / (ms_other * 1e-3), "work": st_o,
+                     "achieved": alg_o / (ms_other * 1e-3) / 1e12 if alg_o else None,
+                     "frac": alg_o / (ms_other * 1e-3) / 1e12 / probe["lop3_imad_mix"] if alg_o else None}
+            badger_b200._lib.check(L.bdg_set_edge_mode(MODE_ID[args.mode]))
 
     out = None
     if rank == 0:
         peak = probe["lop3_imad_mix"]
+        alg = algorithmic(mode, t, stats, n_edges_part)
         roof = None
-        alg = algorithmic(args.mode, stats)
         if alg is not None:
             achieved = alg / (step_ms * 1e-3) / 1e12
-            alg_o = algorithmic(other, stats_other)
-            roof = {"bound": "int_issue",
-                    "kernel": ("sparse_scan_kernel + sparse_tile_kernel<%d,p>, %d passes per step" % (t, 2 if t == 1 else 3)) if args.mode == "sparse" else "edges_kernel<%d>" % t,
-                    "achieved": achieved, "peak": peak, "unit": "Tinst/s", "frac": achieved / peak if peak else None,
-                    "traffic": NCU_TRAFFIC_BYTES.get(t) if (args.mode == "sparse" and args.config == "C2" and args.reads is None and world == 1) else None,
-                    "traffic_note": "bytes per step, dram read+write of the scan and tile kernels from the committed ncu capture (profiles/); the "
-                                    "algorithmic bytes are hbm.algorithmic_bytes_per_launch",
-                    "how": "achieved = algorithmic integer instructions of rank 0's step (%d interval tests x %d + %d pairs scored x %s + "
-                           "%d candidates x %d + pairs S-scored x 220; unit counts from the kernel's own counters, per-unit costs from its SASS, DESIGN.md) / "
-                           "%.3f ms (CUDA events, this run); peak = measured issue rate of an independent LOP3+IMAD 1:1 stream on this GPU "
-                           "(bdg_dev_pipe_probe, this run)" % (stats["sub_tiles"] + 32 * stats["sub_tiles_scored"] if args.mode == "sparse" else 0,
-                                                               A_TILE, stats["pairs_scored"], A_QUICK[t] if args.mode == "sparse" else A_LIGHT[t],
-                                                               stats["candidates"], A_EXACT, step_ms),
+            passes = {"join": "join_kernel (one persistent launch over all seed conditions) behind 25 radix sorts by seed key",
+                      "sparse": "sparse_scan_kernel + sparse_tile_kernel<%d,p>, %d passes per step" % (t, 2 if t == 1 else 3),
+                      "dense": "edges_kernel<%d>" % t}[mode]
+            hbm_bytes = int(9 * n_edges_part + 4 * n * ({"join": 2 * 25 + 25, "sparse": 2 if t == 1 else 3, "dense": 1}[mode]))
+            try:
+                hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+            except Exception:
+                hbm = 6451.8
+            roof = {"bound": "int_issue", "kernel": passes, "achieved": achieved, "peak": peak, "unit": "Tinst/s", "frac": achieved / peak if peak else None,
+                    "traffic": NCU_TRAFFIC["bytes"] if NCU_TRAFFIC and NCU_TRAFFIC["workload"] == (args.config, args.reads, t, mode, world) else None,
+                    "traffic_note": (NCU_TRAFFIC["label"] if NCU_TRAFFIC else "no ncu capture of this build yet") +
+                                    "; the algorithmic bytes are hbm.algorithmic_bytes_per_step",
+                    "how": "achieved = algorithmic integer instructions of rank 0's step (unit counts from the kernels' own counters x per-unit "
+                           "costs counted from the SASS, DESIGN.md: %s) / %.3f ms (CUDA events, this run); peak = measured issue rate of an "
+                           "independent LOP3+IMAD 1:1 stream on this GPU (bdg_dev_pipe_probe, this run)" % (
+                               json.dumps(A_JOIN if mode == "join" else {"tile": A_TILE, "pair": A_QUICK.get(t) if mode == "sparse" else A_LIGHT.get(t),
+                                                                         "cand": A_EXACT, "score": A_SCORE}), step_ms),
                     "work": stats,
-                    "pairs_decided_per_pair_scored": my_pairs / max(stats["pairs_scored"], 1),
-                    "survey_nominal": {"ops_per_pair": A_PAIR_SURVEY[t], "achieved": A_PAIR_SURVEY[t] * my_pairs / (step_ms * 1e-3) / 1e12,
-                                       "note": "SURVEY.md 8(d) costs every pair 5(2t+1) instructions; this kernel decides most pairs by key-interval "
-                                               "exclusion, so this figure exceeds the peak by design"},
-                    "other_mode": {"mode": other, "ms_per_step": ms_other, "pairs_per_s": my_pairs / (ms_other * 1e-3), "work": stats_other,
-                                   "achieved": alg_o / (ms_other * 1e-3) / 1e12, "frac": alg_o / (ms_other * 1e-3) / 1e12 / peak if peak else None},
-                    "probe_Tinst_per_s": probe,
-                    "hbm": {"algorithmic_bytes_per_launch": int(4 * n * (2 if t == 1 else 3) + 9 * n_edges_part),
-                            "achieved_GBps": (4 * n * (2 if t == 1 else 3) + 9 * n_edges_part) / (step_ms * 1e-3) / 1e9,
-                            "peak_GBps": 6451.8, "frac": (4 * n * (2 if t == 1 else 3) + 9 * n_edges_part) / (step_ms * 1e-3) / 1e9 / 6451.8,
+                    "pairs_decided_per_pair_tested": (total_pairs / world) / max(stats["pairs_scored"], 1),
+                    "survey_nominal": {"ops_per_pair": A_PAIR_SURVEY.get(t), "achieved": A_PAIR_SURVEY.get(t, 0) * (total_pairs / world) / (step_ms * 1e-3) / 1e12,
+                                       "note": "SURVEY.md 8(d) costs every pair 5(2t+1) instructions; these kernels decide most pairs by key "
+                                               "exclusion (sort order), so this figure exceeds the peak by design"},
+                    "other_mode": other, "probe_Tinst_per_s": probe,
+                    "hbm": {"algorithmic_bytes_per_step": hbm_bytes, "achieved_GBps": hbm_bytes / (step_ms * 1e-3) / 1e9, "peak_GBps": hbm,
+                            "frac": hbm_bytes / (step_ms * 1e-3) / 1e9 / hbm,
                             "note": "not the bound: operands live in registers / shared memory, the kernels are integer-issue bound "
                                     "(north_star asks for the INT-pipe roofline; MEASURED_PEAKS.json has no integer figure, so it is probed live)"}}
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": warm,
-               "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "u32", "data": "synthetic",
-               "config": {"workload": name, "reads": reads, "distinct": n, "threshold": t, "pairs_per_step": total_pairs,
-                          "edges": edges_total, "edge_mode": args.mode, "l2": "flushed between timed iterations (256 MB write)",
-                          "partition": "2048-row tiles dealt boustrophedon to ranks; no data-path collective"},
+               "config": config_dict(args.config, cfg, n),
+               "details": {"edges": edges_total, "edges_rank0": n_edges_part, "edge_mode": mode, "l2": "flushed between timed iterations (256 MB write)",
+                           "partition": "array replicated; work units of the sorted orders dealt round-robin to ranks; no data-path collective"},
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
-               "reads_per_s": reads * args.steps / (ms_total * 1e-3)}
-    if rank == 0 and world == 1:
+               "reads_per_s": cfg["reads"] * args.steps / (ms_total * 1e-3)}
+    if rank == 0 and world == 1 and not args.no_secondary:
+        out["pipeline"] = whole_pipeline(t, wl, obs, valid, cfg)
         out["stages"] = other_stages(torch, dev, stream, L, s, args)
-        out["pipeline"] = whole_pipeline(t)
-        out["cli"] = cli_file_to_file(t)
+        out["c2"] = c2_secondary(torch, L, dev, stream, probe)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"], _ = cpu_sample(s, t, args.cpu_seconds)
     if world > 1:
@@ -414,11 +476,29 @@ def run_b200(args):
         print(json.dumps(out))
 
 
-def whole_pipeline(t):
+def c2_secondary(torch, L, dev, stream, probe):
+    """The round-1 headline for continuity: C2 (1 M reads, t = 1) edge construction, the whole correction step and the
+    drop-in command file to file."""
+    import badger_b200
+    cfg, wl, obs, valid, s = dataset("C2")
+    t = cfg["threshold"]
+    n = int(s.size)
+    badger_b200._lib.check(L.bdg_set_edge_mode(-1))
+    step = EdgeStep(torch, L, dev, stream, s, t, 0, 1)
+    edges = step.settle(3)
+    k = 10
+    ms = step.timed(k) / k
+    st = step.stats()
+    alg = algorithmic("sparse", t, st, edges)
+    return {"config": config_dict("C2", cfg, n), "ms_per_step": ms, "value": n * (n - 1) // 2 / (ms * 1e-3), "unit": UNIT, "edges": edges,
+            "edge_mode": "sparse", "roofline_frac": alg / (ms * 1e-3) / 1e12 / probe["lop3_imad_mix"], "work": st,
+            "pipeline": whole_pipeline(t, wl, obs, valid, cfg), "cli": cli_file_to_file(t, wl, obs, valid, cfg)}
+
+
+def whole_pipeline(t, wl, obs, valid, cfg):
     """reads/s of the array form of the whole correction step (badger_b200.pipeline.assign_packed: dedup, edges, centre
     selection with whitelist membership, clustering rounds, per-read gather), host arrays in and out, wall clock."""
     from badger_b200 import pipeline
-    wl, obs, valid, cfg = workload.dataset
     wls = np.sort(wl)
     pipeline.assign_packed(obs, valid, threshold=t, n_cells=cfg["n_cells"], whitelist_sorted=wls)      # warm
     reps, T = 3, {}
@@ -430,7 +510,7 @@ def whole_pipeline(t):
             "api": "badger_b200.pipeline.assign_packed (packed barcodes per read in, centre per read out)"}
 
 
-def cli_file_to_file(t):
+def cli_file_to_file(t, wl, obs, valid, cfg):
     """reads/s of the drop-in command itself, file to file: `badger.py -r reads.tsv -l whitelist.txt -d 10x -t T --n_cells C
     -o OUT` run in this process on the workload's reads written as an extraction TSV (wall clock; the files are written
     before the clock starts and sit in the page cache).  Default route = native TSV reader -> GPU pack16 -> array pipeline
@@ -440,7 +520,6 @@ def cli_file_to_file(t):
     import io
     import logging
     import shutil
-    wl, obs, valid, cfg = workload.dataset
     tmp = tempfile.mkdtemp(prefix="bdg_cli_")
     try:
         tsv, wlf = os.path.join(tmp, "reads.tsv"), os.path.join(tmp, "wl.txt")
