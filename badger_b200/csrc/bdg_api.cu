@@ -97,7 +97,8 @@ struct DevCtx {
     Buf nn[9];                                                // sparse nearest: rotated keys + payload (in/out) of queries and targets, scratch
     // join form of the t = 2 edge construction (bdg_join.cuh): barcodes in the key order of every condition's row side / column
     // side, first column of every key, scratch keys (in / sorted) and radix-sort scratch, units per slab and their prefix sums
-    Buf jn_rows[bdg::SEED_MAX_CONDS], jn_cols[bdg::SEED_MAX_CONDS], jn_tab[bdg::SEED_MAX_CONDS], jn_key_in, jn_key_out, jn_cub, jn_counts, jn_offs, jn_lut;
+    // (one set per stream: the conditions of a block set run back to back on one stream)
+    Buf jn_rows[2], jn_cols[2], jn_tab[2], jn_key_in[2], jn_key_out[2], jn_cub[2], jn_counts[2], jn_offs[2], jn_lut;
     int scheme_serial = 0;                                    // which scheme sits in this device's constant memory (0: none)
 };
 std::vector<DevCtx> g_ctx;
@@ -230,11 +231,14 @@ void launch_tiles_bip(int blocks, cudaStream_t st, const bdg::EdgeWork& w, const
         else FN<2, 2>(__VA_ARGS__);                                                   \
     } while (0)
 
-// Join form (t = 2): per condition of the seed scheme sort the barcodes by the row-side / column-side key, list the first
-// column of every key, count the work units per slab of rows, and run ONE persistent kernel over all units (bdg_join.cuh).
-// Every part sorts the whole array (replicated, a few % of the step) and takes every nparts-th batch of units.
+// Join form (t = 2), bdg_join.cuh.  The seed conditions are laid on a line by weight (a symmetric condition pairs each couple
+// once: weight 1; a shifted one pairs both value orders: weight 2) and the line is cut into nparts equal pieces: a part sorts and
+// joins only the conditions its piece touches, a condition on a cut is shared by unit range.  Per condition: keys -> radix sort
+// (rows once per block set, columns for the shifted conditions) -> first column of every key -> units per slab -> prefix sums ->
+// one persistent join launch.  The conditions of a block set follow one another and share the row order.  Consecutive block sets alternate between the caller's stream and an auxiliary one, so that one
+// condition's sorts and the tail of its join overlap the neighbour's join.
 int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, uint32_t* d_a, uint32_t* d_b, uint8_t* d_d, size_t cap,
-                      unsigned long long* d_count, cudaStream_t st, DevCtx* ws)
+                      unsigned long long* d_count, cudaStream_t caller, DevCtx* ws)
 {
     if (int rc = scheme_ready()) return rc;
     const bdg::SeedScheme& S = g_scheme;
@@ -245,80 +249,102 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
     };
     if (ws->scheme_serial != g_scheme_serial) {
         if (int e = ensure(ws->jn_lut, g_scheme_lut.size())) return e;
-        CU_TRY(cudaMemcpyToSymbolAsync(bdg::c_scheme, &g_scheme, sizeof(g_scheme), 0, cudaMemcpyHostToDevice, st));
-        CU_TRY(cudaMemcpyAsync(ws->jn_lut.p, g_scheme_lut.data(), g_scheme_lut.size(), cudaMemcpyHostToDevice, st));
-        CU_TRY(cudaStreamSynchronize(st));                  // the host copies above are read asynchronously
+        CU_TRY(cudaMemcpyToSymbolAsync(bdg::c_scheme, &g_scheme, sizeof(g_scheme), 0, cudaMemcpyHostToDevice, caller));
+        CU_TRY(cudaMemcpyAsync(ws->jn_lut.p, g_scheme_lut.data(), g_scheme_lut.size(), cudaMemcpyHostToDevice, caller));
+        CU_TRY(cudaStreamSynchronize(caller));              // the host copies above are read asynchronously
         ws->scheme_serial = g_scheme_serial;
     }
-    // rows per slab: 8 when the key buckets are short (a slab then spans few foreign buckets), else 32
+    // rows per sub-slab: 8 when the key buckets are short (fewer rows then span fewer foreign buckets), else 32
     int rs = (N >> S.ka[0].key_bits) < 48 ? 8 : 32;
     if (const char* e = getenv("BDG_JOIN_RS")) rs = atoi(e) == 8 ? 8 : 32;
-    const uint32_t n_slabs = (uint32_t)((N + rs - 1) / rs);
-    const uint64_t total_slabs = (uint64_t)S.nconds * n_slabs;
-    if (int e = ensure(ws->plan, PLAN_HDR * bdg::MAX_PASSES)) return e;
-    if (int e = ensure(ws->jn_key_in, N * 4)) return e;
-    if (int e = ensure(ws->jn_key_out, N * 4)) return e;
-    if (int e = ensure(ws->jn_counts, (total_slabs + 1) * 4)) return e;
-    if (int e = ensure(ws->jn_offs, (total_slabs + 1) * 4)) return e;
-    size_t tmp_sort = 0, tmp_scan = 0;
-    CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)N, 0, 20, st));
-    CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)(total_slabs + 1), st));
-    if (int e = ensure(ws->jn_cub, std::max(tmp_sort, tmp_scan))) return e;
+    const uint32_t n_slabs = (uint32_t)((N + bdg::JROWS - 1) / bdg::JROWS);
+    // the part's piece of the weight line, in units of 1 / nparts
+    int W = 0;
+    for (int c = 0; c < S.nconds; c++) W += S.cond[c].self ? 1 : 2;
+    const long long piece_lo = (long long)part * W, piece_hi = (long long)(part + 1) * W;      // cond c covers [start_c * nparts, (start_c + w_c) * nparts)
+    if (int e = ensure(ws->plan, PLAN_HDR * bdg::MAX_PASSES + 8 * bdg::SEED_MAX_CONDS)) return e;
     char* d_plan = (char*)ws->plan.p;
-    CU_TRY(cudaMemsetAsync(d_plan, 0, PLAN_HDR * bdg::MAX_PASSES, st));
+    CU_TRY(cudaMemsetAsync(d_plan, 0, PLAN_HDR * bdg::MAX_PASSES + 8 * bdg::SEED_MAX_CONDS, caller));
     for (int p = 0; p < bdg::MAX_PASSES; p++) ws->host_stats[p][0] = ws->host_stats[p][1] = 0;
-
-    bdg::JoinArgs A{};
-    const int gb = (int)std::min<size_t>((N + 255) / 256, (size_t)ws->sms * 8);
-    uint32_t* key_in = (uint32_t*)ws->jn_key_in.p;
-    uint32_t* key_out = (uint32_t*)ws->jn_key_out.p;
-    auto sort_side = [&](const bdg::SeedKey& k, Buf& dst) -> int {
-        if (int e = ensure(dst, N * 4)) return e;
-        bdg::join_keys_kernel<<<gb, 256, 0, st>>>(d_sorted, key_in, (uint32_t)N, k);
-        g_launches++;
-        size_t bytes = ws->jn_cub.cap;
-        CU_TRY(cub::DeviceRadixSort::SortPairs(ws->jn_cub.p, bytes, (const uint32_t*)key_in, key_out, d_sorted, (uint32_t*)dst.p, (int)N, 0, (int)k.key_bits, st));
-        return BDG_OK;
-    };
-    for (int c = 0; c < S.nconds; c++) {
-        const int rsrt = S.cond[c].row_sort;
-        if (rsrt == c) { if (int e = sort_side(S.ka[c], ws->jn_rows[c])) return e; }
-        A.rows[c] = (const uint32_t*)ws->jn_rows[rsrt].p;
-        if (S.cond[c].self) A.cols[c] = A.rows[c];
-        else {
-            if (int e = sort_side(S.kb[c], ws->jn_cols[c])) return e;
-            A.cols[c] = (const uint32_t*)ws->jn_cols[c].p;
-        }
-        const uint32_t nkeys = 1u << S.kb[c].key_bits;
-        if (int e = ensure(ws->jn_tab[c], ((size_t)nkeys + 1) * 4)) return e;
-        bdg::join_colstart_kernel<<<gb, 256, 0, st>>>(A.cols[c], (uint32_t)N, S.kb[c], nkeys, (uint32_t*)ws->jn_tab[c].p);
-        g_launches++;
-        A.colstart[c] = (const uint32_t*)ws->jn_tab[c].p;
+    unsigned long long* d_cursors = (unsigned long long*)(d_plan + PLAN_HDR * bdg::MAX_PASSES);
+    size_t tmp_sort = 0, tmp_scan = 0;
+    CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)N, 0, 24, caller));
+    CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)(n_slabs + 1), caller));
+    const size_t tmp_bytes = std::max(tmp_sort, tmp_scan);
+    for (int k = 0; k < 2; k++) {                           // one scratch set per stream
+        if (int e = ensure(ws->jn_key_in[k], N * 4)) return e;
+        if (int e = ensure(ws->jn_key_out[k], N * 4)) return e;
+        if (int e = ensure(ws->jn_cub[k], tmp_bytes)) return e;
+        if (int e = ensure(ws->jn_counts[k], ((size_t)n_slabs + 1) * 4)) return e;
+        if (int e = ensure(ws->jn_offs[k], ((size_t)n_slabs + 1) * 4)) return e;
     }
-    A.offs = (const uint32_t*)ws->jn_offs.p;
-    A.lut = (const uint8_t*)ws->jn_lut.p;
-    A.cursor = (unsigned long long*)d_plan;
-    A.stats = (unsigned long long*)(d_plan + HDR_STATS);
-    A.N = (uint32_t)N;
-    A.n_slabs = n_slabs;
-    A.nconds = S.nconds;
-    A.part = part;
-    A.nparts = nparts;
-    A.T = bdg::qgram_threshold(2);
-    A.one = 1u;
-    A.mone = 0xFFFFFFFFu;
-    const int bb = (int)std::min<uint64_t>((total_slabs + 256) / 256, (uint64_t)ws->sms * 16);
-    bdg::join_band_kernel<<<bb, 256, 0, st>>>(A, rs, (uint32_t*)ws->jn_counts.p);
-    g_launches++;
-    size_t bytes = ws->jn_cub.cap;
-    CU_TRY(cub::DeviceScan::ExclusiveSum(ws->jn_cub.p, bytes, (const uint32_t*)ws->jn_counts.p, (uint32_t*)ws->jn_offs.p, (int)(total_slabs + 1), st));
-    bdg::EdgeOut o{d_a, d_b, d_d, d_count, (unsigned long long)cap};
     int grid = 0;
     if (int rc = grid_for(rs == 8 ? (const void*)bdg::join_kernel<8> : (const void*)bdg::join_kernel<32>, &grid, bdg::ENT)) return rc;
-    if (rs == 8) bdg::join_kernel<8><<<grid, bdg::ENT, 0, st>>>(A, o);
-    else bdg::join_kernel<32><<<grid, bdg::ENT, 0, st>>>(A, o);
-    g_launches++;
-    CU_TRY(cudaGetLastError());
+    const int gb = (int)std::min<size_t>((N + 255) / 256, (size_t)ws->sms * 8);
+    const int bb = (int)std::min<size_t>(((size_t)n_slabs + 256) / 256, (size_t)ws->sms * 8);
+    const bool fork = !getenv("BDG_EDGE_SERIAL");
+    if (fork) CU_TRY(cudaEventRecord(ws->ev_start, caller));
+    bool aux_used = false;
+    bdg::EdgeOut o{d_a, d_b, d_d, d_count, (unsigned long long)cap};
+    long long start = 0;
+    int cur_set = -1, k = 1;                                 // k: scratch set / stream of the current block set
+    for (int c = 0; c < S.nconds; c++) {
+        const int w = S.cond[c].self ? 1 : 2;
+        const long long c_lo = start * nparts, c_hi = (start + w) * nparts;
+        start += w;
+        const long long lo = std::max(c_lo, piece_lo), hi = std::min(c_hi, piece_hi);
+        if (lo >= hi) continue;
+        const int set = S.cond[c].row_sort;
+        const bool new_set = set != cur_set;
+        if (new_set) { cur_set = set; k ^= 1; }
+        cudaStream_t st = (fork && k == 1) ? ws->aux[1] : caller;
+        if (fork && k == 1 && !aux_used) { CU_TRY(cudaStreamWaitEvent(st, ws->ev_start, 0)); aux_used = true; }
+        uint32_t* key_in = (uint32_t*)ws->jn_key_in[k].p;
+        uint32_t* key_out = (uint32_t*)ws->jn_key_out[k].p;
+        auto sort_side = [&](const bdg::SeedKey& key, Buf& dst) -> int {
+            if (int e = ensure(dst, N * 4)) return e;
+            bdg::join_keys_kernel<<<gb, 256, 0, st>>>(d_sorted, key_in, (uint32_t)N, key);
+            g_launches++;
+            size_t bytes = ws->jn_cub[k].cap;
+            CU_TRY(cub::DeviceRadixSort::SortPairs(ws->jn_cub[k].p, bytes, (const uint32_t*)key_in, key_out, d_sorted, (uint32_t*)dst.p, (int)N, 0, (int)key.key_bits, st));
+            return BDG_OK;
+        };
+        if (new_set) { if (int e = sort_side(S.ka[c], ws->jn_rows[k])) return e; }      // the stream's row order: this block set
+        bdg::JoinArgs A{};
+        A.rows = (const uint32_t*)ws->jn_rows[k].p;
+        if (S.cond[c].self) A.cols = A.rows;
+        else {
+            if (int e = sort_side(S.kb[c], ws->jn_cols[k])) return e;
+            A.cols = (const uint32_t*)ws->jn_cols[k].p;
+        }
+        const uint32_t nkeys = 1u << S.kb[c].key_bits;
+        if (int e = ensure(ws->jn_tab[k], ((size_t)nkeys + 1) * 4)) return e;
+        bdg::join_colstart_kernel<<<gb, 256, 0, st>>>(A.cols, (uint32_t)N, S.kb[c], nkeys, (uint32_t*)ws->jn_tab[k].p);
+        A.colstart = (const uint32_t*)ws->jn_tab[k].p;
+        A.offs = (const uint32_t*)ws->jn_offs[k].p;
+        A.lut = (const uint8_t*)ws->jn_lut.p;
+        A.cursor = d_cursors + c;
+        A.stats = (unsigned long long*)(d_plan + HDR_STATS);
+        A.N = (uint32_t)N;
+        A.n_slabs = n_slabs;
+        A.cond = c;
+        A.self = S.cond[c].self;
+        A.f0 = (uint32_t)(lo - c_lo); A.f1 = (uint32_t)(hi - c_lo); A.fden = (uint32_t)(c_hi - c_lo);
+        A.T = bdg::qgram_threshold(2);
+        A.one = 1u;
+        A.mone = 0xFFFFFFFFu;
+        bdg::join_band_kernel<<<bb, 256, 0, st>>>(A, (uint32_t*)ws->jn_counts[k].p);
+        size_t bytes = ws->jn_cub[k].cap;
+        CU_TRY(cub::DeviceScan::ExclusiveSum(ws->jn_cub[k].p, bytes, (const uint32_t*)ws->jn_counts[k].p, (uint32_t*)ws->jn_offs[k].p, (int)(n_slabs + 1), st));
+        if (rs == 8) bdg::join_kernel<8><<<grid, bdg::ENT, 0, st>>>(A, o);
+        else bdg::join_kernel<32><<<grid, bdg::ENT, 0, st>>>(A, o);
+        g_launches += 3;
+        CU_TRY(cudaGetLastError());
+    }
+    if (aux_used) {
+        CU_TRY(cudaEventRecord(ws->ev_done[1], ws->aux[1]));
+        CU_TRY(cudaStreamWaitEvent(caller, ws->ev_done[1], 0));
+    }
     return BDG_OK;
 }
 
@@ -631,10 +657,11 @@ void bdg_shutdown(void)
         c.gather_a.release(); c.gather_b.release();
         for (auto& b : c.as) b.release();
         for (auto& b : c.rot_sorted) b.release();
-        for (auto& b : c.jn_rows) b.release();
-        for (auto& b : c.jn_cols) b.release();
-        for (auto& b : c.jn_tab) b.release();
-        c.jn_key_in.release(); c.jn_key_out.release(); c.jn_cub.release(); c.jn_counts.release(); c.jn_offs.release(); c.jn_lut.release();
+        for (int k = 0; k < 2; k++) {
+            c.jn_rows[k].release(); c.jn_cols[k].release(); c.jn_tab[k].release(); c.jn_key_in[k].release(); c.jn_key_out[k].release();
+            c.jn_cub[k].release(); c.jn_counts[k].release(); c.jn_offs[k].release();
+        }
+        c.jn_lut.release();
     }
     g_ctx.clear();
 }

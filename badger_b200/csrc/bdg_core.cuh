@@ -405,6 +405,19 @@ BDG_HD int qgram_score(uint32_t a, uint32_t b, uint64_t* mult = nullptr)
     return s;
 }
 
+// The same score as a compact loop (one diagonal pair per trip, nothing unrolled): the join kernel keeps its whole hot path
+// inside the instruction cache, and 21 unrolled diagonals are a third of it.
+BDG_HD int qgram_score_compact(uint32_t a, uint32_t b)
+{
+    int s = popc(run6(~mism(a, b) & EVEN));
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int k = 1; k <= 10; k++)
+        s += popc(run6(~mism(a, b >> (2 * k)) & (EVEN >> (2 * k)))) + popc(run6(~mism(a, b << (2 * k)) & (EVEN << (2 * k))));
+    return s;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Two-block seeds for t = 2 (groundwork for the next form of the sparse passes; no kernel uses it yet - DESIGN.md 8).
 // The single-block passes above leave 11 * N^2 / 2048 pairs to score one by one, which is what the step costs at

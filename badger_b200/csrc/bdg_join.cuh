@@ -8,16 +8,17 @@
 //   join_keys_kernel       barcode -> join key of one side of one condition
 //   (cub::DeviceRadixSort::SortPairs on the key bits)
 //   join_colstart_kernel   first column of every key value (lower bounds of all 2^key_bits keys in one streaming pass)
-//   join_band_kernel       per slab of RS consecutive rows: number of work units (runs of <= JUNIT columns) it needs
+//   join_band_kernel       per slab of 32 consecutive rows: number of work units (runs of <= JUNIT columns) it needs
 //   (cub::DeviceScan::ExclusiveSum: unit index -> slab)
-//   join_kernel<RS>        ONE persistent launch over the units of ALL conditions: warps pull batches of units from an atomic
-//                          cursor (batches are dealt round-robin to the parts = GPUs / ranks), stage the unit's columns in
-//                          their own slice of shared memory (y, y >> 2, y << 2, key) and test every
-//                          (row, column) pair: quick test of bdg_core.cuh + key equality, one hit bit per pair; hits go
+//   join_kernel<RS>        one persistent launch per condition: warps pull batches of units from an atomic cursor, stage the
+//                          unit's columns in their own slice of shared memory (y, y >> 2, y << 2, key) and test
+//                          (row, column) pairs: quick test of bdg_core.cuh + key equality, one hit bit per pair; hits go
 //                          through the warp's queue to the exact stage on full warps (dist_small, hand-over table, then
 //                          the 6-mer score in a second queue), edges are appended with one atomic per warp.
-// A warp works on RS rows x 32/RS column phases: RS = 32 when the key buckets are long, RS = 8 when they are short (a slab of
-// fewer rows spans fewer foreign buckets).  No block-level barrier anywhere.
+// A unit's 32 rows are worked through as 32/RS sub-slabs of RS rows x 32/RS column phases, each against its own column run:
+// RS = 32 when the key buckets are long, RS = 8 when they are short (fewer rows span fewer foreign buckets).
+// The conditions are dealt to the parts (GPUs / ranks) by weight, a condition on a part boundary is split by unit range,
+// so a part sorts only the conditions it works on.  No block-level barrier anywhere.
 #pragma once
 #include "bdg_edges.cuh"
 #include "bdg_seed.cuh"
@@ -25,24 +26,28 @@
 namespace bdg {
 
 constexpr int JCH = 128;           // columns staged at a time
+constexpr int JPAD = 32;           // slack behind the staged columns (steps may start up to one step early)
 constexpr int JUNIT = 2048;        // columns per work unit
 constexpr int JBATCH = 4;          // units per cursor fetch
 constexpr int JQCAP = 160;         // candidate queue entries per warp
 constexpr int JQ2CAP = 64;         // entries of the scoring queue
+constexpr int JROWS = 32;          // rows per slab
 
 __constant__ SeedScheme c_scheme;
 
 struct JoinArgs {
-    const uint32_t* rows[SEED_MAX_CONDS];       // barcodes in the order of the row-side key
-    const uint32_t* cols[SEED_MAX_CONDS];       // ... of the column-side key (== rows for the symmetric conditions)
-    const uint32_t* colstart[SEED_MAX_CONDS];   // (1 << key_bits) + 1 lower bounds into cols
-    const uint32_t* offs;                       // exclusive prefix sums of the units per slab: nconds * n_slabs + 1 entries
-    const uint8_t* lut;                         // hand-over table over seed_flags
-    unsigned long long* cursor;                 // batches handed out on this device
-    unsigned long long* stats;                  // [0] units, [2] pairs tested, [3] candidates, [6] pairs with D <= 2, [7] pairs scored, [4]/[5] warp times
+    const uint32_t* rows;          // barcodes in the order of the row-side key of the condition
+    const uint32_t* cols;          // ... of the column-side key (== rows for a symmetric condition)
+    const uint32_t* colstart;      // (1 << key_bits) + 1 lower bounds into cols
+    const uint32_t* offs;          // exclusive prefix sums of the units per slab: n_slabs + 1 entries
+    const uint8_t* lut;            // hand-over table over seed_flags
+    unsigned long long* cursor;    // batches handed out by this launch
+    unsigned long long* stats;     // [0] units, [2] pairs tested, [3] candidates, [6] pairs with D <= 2, [7] pairs scored, [4]/[5] warp times
     uint32_t N, n_slabs;
-    int nconds, part, nparts, T;
-    uint32_t one, mone;                         // runtime 1 / -1: u * one + mone is u - 1 on the FMA pipe
+    int cond, self;
+    uint32_t f0, f1, fden;         // this part works on the units [total * f0 / fden, total * f1 / fden) of the condition
+    int T;
+    uint32_t one, mone;            // runtime 1 / -1: u * one + mone is u - 1 on the FMA pipe
 };
 
 __global__ void join_keys_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, SeedKey k)
@@ -60,30 +65,21 @@ __global__ void join_colstart_kernel(const uint32_t* __restrict__ cols, uint32_t
     }
 }
 
-// column run of the slab [i0, i0 + rs) of condition c: the buckets of its first .. last key; a symmetric condition pairs
-// each couple once (column index > row index), so its run starts behind the slab's first row
-__device__ __forceinline__ void join_slab_run(const uint32_t* rows, const uint32_t* colstart, uint32_t N, uint32_t i0, int rs, const SeedKey& ka, bool self,
-                                              uint32_t& lo, uint32_t& hi)
+// units of every slab of 32 rows: its column run (first key's bucket .. last key's bucket; a symmetric condition pairs
+// each couple once - column index > row index - so its run starts behind the slab's first row) in pieces of JUNIT columns
+__global__ void join_band_kernel(const JoinArgs A, uint32_t* __restrict__ counts)
 {
-    const uint32_t i1 = min(N, i0 + (uint32_t)rs) - 1u;
-    lo = __ldg(&colstart[seed_key(__ldg(&rows[i0]), ka)]);
-    hi = __ldg(&colstart[seed_key(__ldg(&rows[i1]), ka) + 1u]);
-    if (self) lo = max(lo, i0 + 1u);
-}
-
-__global__ void join_band_kernel(const JoinArgs A, int rs, uint32_t* __restrict__ counts)
-{
-    const uint64_t total = (uint64_t)A.nconds * A.n_slabs;
-    for (uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; g <= total; g += (uint64_t)gridDim.x * blockDim.x) {
+    const SeedKey& ka = c_scheme.ka[A.cond];
+    for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s <= A.n_slabs; s += gridDim.x * blockDim.x) {
         uint32_t cnt = 0;
-        if (g < total) {
-            const int c = (int)(g / A.n_slabs);
-            const uint32_t s = (uint32_t)(g - (uint64_t)c * A.n_slabs);
-            uint32_t lo, hi;
-            join_slab_run(A.rows[c], A.colstart[c], A.N, s * (uint32_t)rs, rs, c_scheme.ka[c], c_scheme.cond[c].self != 0, lo, hi);
+        if (s < A.n_slabs) {
+            const uint32_t i0 = s * JROWS, i1 = min(A.N, i0 + JROWS) - 1u;
+            uint32_t lo = __ldg(&A.colstart[seed_key(__ldg(&A.rows[i0]), ka)]);
+            const uint32_t hi = __ldg(&A.colstart[seed_key(__ldg(&A.rows[i1]), ka) + 1u]);
+            if (A.self) lo = max(lo, i0 + 1u);
             cnt = hi > lo ? (hi - lo + JUNIT - 1) / JUNIT : 0u;
         }
-        counts[g] = cnt;
+        counts[s] = cnt;
     }
 }
 
@@ -96,8 +92,10 @@ struct JoinCtx {
     unsigned long long n_d2, n_score;
 };
 
-// exact stage on a batch of candidates of condition c.cond (one per lane)
-__device__ __forceinline__ void join_process(JoinCtx& c, const EdgeOut& out, uint2 e, bool active, int& q2n)
+// exact stage on a batch of candidates of condition c.cond (one per lane).  A real call, not inlined: one copy of the exact
+// distance and of the score loop keeps the kernel's hot code inside the instruction cache (ncu: the fully inlined form
+// spent most of its issue slots waiting for instructions).
+__device__ __noinline__ void join_process(JoinCtx& c, const EdgeOut& out, uint2 e, bool active, int& q2n)
 {
     const uint32_t a = min(e.x, e.y), b = max(e.x, e.y);
     bool ok = active && a != b;
@@ -119,7 +117,7 @@ __device__ __forceinline__ void join_process(JoinCtx& c, const EdgeOut& out, uin
         q2n -= 32;
         const uint2 mv = c.q2[q2n + c.lane];
         const uint8_t md = c.q2d[q2n + c.lane];
-        const bool good = qgram_score(mv.x, mv.y) >= c.T;
+        const bool good = qgram_score_compact(mv.x, mv.y) >= c.T;
         emit_warp(good, mv.x, mv.y, md, out);
         __syncwarp();
     }
@@ -179,7 +177,7 @@ __global__ void __launch_bounds__(ENT, 5) join_kernel(const JoinArgs A, const Ed
 {
     constexpr int PH = 32 / RS;                          // column phases of a warp
     constexpr int STEP = 4 * PH;                         // columns per inner step
-    __shared__ __align__(16) uint32_t s_b[EW][4][JCH];   // y, y >> 2, y << 2, key of the staged columns
+    __shared__ __align__(16) uint32_t s_b[EW][4][JCH + JPAD];   // y, y >> 2, y << 2, key of the staged columns
     __shared__ uint2 s_q[EW][JQCAP];
     __shared__ uint2 s_q2[EW][JQ2CAP];
     __shared__ uint8_t s_q2d[EW][JQ2CAP];
@@ -190,95 +188,105 @@ __global__ void __launch_bounds__(ENT, 5) join_kernel(const JoinArgs A, const Ed
     uint32_t* const sbM = s_b[wid][2];
     uint32_t* const sbK = s_b[wid][3];
     JoinCtx c;
-    c.q = s_q[wid]; c.q2 = s_q2[wid]; c.q2d = s_q2d[wid]; c.lut = A.lut; c.lane = lane; c.T = A.T; c.cond = -1; c.n_d2 = 0; c.n_score = 0;
+    c.q = s_q[wid]; c.q2 = s_q2[wid]; c.q2d = s_q2d[wid]; c.lut = A.lut; c.lane = lane; c.T = A.T; c.cond = A.cond; c.n_d2 = 0; c.n_score = 0;
     int qn = 0, q2n = 0;
     const uint32_t mone = A.mone;
     const unsigned long long t_start = global_ns();
-    unsigned long long n_units = 0, n_cols = 0, n_cand = 0;
-    const uint64_t total_slabs = (uint64_t)A.nconds * A.n_slabs;
-    const uint64_t total_units = __ldg(&A.offs[total_slabs]);
-    const uint64_t total_batches = (total_units + JBATCH - 1) / JBATCH;
-    bool self = false;
+    unsigned long long n_units = 0, n_pairs = 0, n_cand = 0;
+    const SeedKey& ka = c_scheme.ka[A.cond];
+    const SeedKey& kb = c_scheme.kb[A.cond];
+    const bool self = A.self != 0;
+    const uint64_t total_units = __ldg(&A.offs[A.n_slabs]);
+    const uint32_t u_lo = (uint32_t)(total_units * A.f0 / A.fden), u_hi = (uint32_t)(total_units * A.f1 / A.fden);
+    const uint64_t n_batches = ((uint64_t)(u_hi - u_lo) + JBATCH - 1) / JBATCH;
 
     for (;;) {
         unsigned long long bi = 0;
         if (lane == 0) bi = atomicAdd(A.cursor, 1ull);
-        bi = __shfl_sync(FULL, bi, 0) * (unsigned long long)A.nparts + (unsigned long long)A.part;
-        if (bi >= total_batches) break;
-        const uint32_t u0 = (uint32_t)(bi * JBATCH), u1 = (uint32_t)min((uint64_t)total_units, (uint64_t)u0 + JBATCH);
+        bi = __shfl_sync(FULL, bi, 0);
+        if (bi >= n_batches) break;
+        const uint32_t u0 = u_lo + (uint32_t)bi * JBATCH, u1 = (uint32_t)min((uint64_t)u_hi, (uint64_t)u0 + JBATCH);
         // slab of the first unit: offs[lo] <= u0 < offs[hi] by a 32-ary search (offs is non-decreasing)
-        uint64_t lo = 0, hi = total_slabs;
+        uint32_t lo = 0, hi = A.n_slabs;
         while (hi - lo > 1) {
-            const uint64_t step = (hi - lo + 32) / 33;
-            const uint64_t pos = lo + (uint64_t)(lane + 1) * step;
+            const uint32_t step = (hi - lo + 32) / 33;
+            const uint32_t pos = lo + (uint32_t)(lane + 1) * step;
             const bool le = pos < hi && __ldg(&A.offs[pos]) <= u0;
             const uint32_t k = (uint32_t)__popc(__ballot_sync(FULL, le));
-            hi = min(hi, lo + (uint64_t)(k + 1) * step);
-            lo = lo + (uint64_t)k * step;
+            hi = min(hi, lo + (k + 1) * step);
+            lo = lo + k * step;
         }
-        uint64_t sl = lo;
+        uint32_t sl = lo;
         for (uint32_t u = u0; u < u1; u++) {
             for (;;) {                                   // skip slabs without units: first sl with offs[sl + 1] > u
-                const uint32_t v = __ldg(&A.offs[min(sl + 1 + (uint64_t)lane, total_slabs)]);
+                const uint32_t v = __ldg(&A.offs[min(sl + 1u + (uint32_t)lane, A.n_slabs)]);
                 const unsigned m = __ballot_sync(FULL, v > u);
-                if (m) { sl += (uint64_t)(__ffs(m) - 1); break; }
+                if (m) { sl += (uint32_t)(__ffs(m) - 1); break; }
                 sl += 32;
             }
             const uint32_t chunk = u - __ldg(&A.offs[sl]);
-            const int cond = (int)(sl / A.n_slabs);
-            const uint32_t s = (uint32_t)(sl - (uint64_t)cond * A.n_slabs);
-            if (cond != c.cond) {                        // the queue holds candidates of ONE condition (the hand-over needs it)
-                join_drain(c, out, qn, q2n, true);
-                c.cond = cond;
-                self = c_scheme.cond[cond].self != 0;
-            }
-            const uint32_t* const rows = A.rows[cond];
-            const uint32_t* const cols = A.cols[cond];
-            const uint32_t i0 = s * (uint32_t)RS, i = i0 + (uint32_t)r;
-            const uint32_t x = i < A.N ? __ldg(&rows[i]) : 0u;
-            const uint32_t ka = i < A.N ? seed_key(x, c_scheme.ka[cond]) : 0xFFFFFFFFu;    // a pad row matches no column
-            uint32_t run_lo, run_hi;
-            join_slab_run(rows, A.colstart[cond], A.N, i0, RS, c_scheme.ka[cond], self, run_lo, run_hi);
+            const uint32_t i0 = sl * JROWS, i = i0 + (uint32_t)lane;
+            const int last = (int)min(A.N - i0, (uint32_t)JROWS) - 1;            // last real row of the slab
+            const uint32_t x = i < A.N ? __ldg(&A.rows[i]) : 0u;
+            const uint32_t k = i < A.N ? seed_key(x, ka) : 0xFFFFFFFFu;         // a pad row matches no column
+            const uint32_t my_lo = i < A.N ? __ldg(&A.colstart[k]) : 0u;        // this row's bucket on the column side
+            const uint32_t my_hi = i < A.N ? __ldg(&A.colstart[k + 1u]) : 0u;
+            uint32_t run_lo = __shfl_sync(FULL, my_lo, 0);
+            const uint32_t run_hi = __shfl_sync(FULL, my_hi, last);
+            if (self) run_lo = max(run_lo, i0 + 1u);
             const uint32_t c0 = run_lo + chunk * (uint32_t)JUNIT, c1 = min(run_hi, c0 + (uint32_t)JUNIT);
             n_units++;
-            n_cols += c1 - c0;
             for (uint32_t base = c0; base < c1; base += JCH) {
                 const int ncols = (int)min((uint32_t)JCH, c1 - base);
                 __syncwarp();                            // every lane is done with the previous sub-tile
-                for (int t = 0; t * 32 < ncols; t++) {
+                for (int t = 0; t * 32 < ncols + JPAD; t++) {
                     const uint32_t j = base + (uint32_t)(t * 32 + lane);
-                    const uint32_t y = j < c1 ? __ldg(&cols[j]) : 0u;
+                    const bool real = t * 32 + lane < ncols;
+                    const uint32_t y = real ? __ldg(&A.cols[j]) : 0u;
                     sb0[t * 32 + lane] = y;
                     sbP[t * 32 + lane] = y >> 2;
                     sbM[t * 32 + lane] = y << 2;
-                    sbK[t * 32 + lane] = j < c1 ? seed_key(y, c_scheme.kb[cond]) : 0xFFFFFFFEu;   // a pad column matches no row
+                    sbK[t * 32 + lane] = real ? seed_key(y, kb) : 0xFFFFFFFEu;   // a pad column matches no row
                 }
                 __syncwarp();
 #pragma unroll 1
-                for (int g0 = 0; g0 < ncols; g0 += 8 * STEP) {
-                    uint32_t h = 0;
+                for (int q = 0; q * RS <= last; q++) {   // sub-slab q = rows q * RS .. + RS - 1 against their own column run
+                    uint32_t s_lo = __shfl_sync(FULL, my_lo, q * RS);
+                    const uint32_t s_hi = __shfl_sync(FULL, my_hi, min(q * RS + RS - 1, last));
+                    const uint32_t xq = __shfl_sync(FULL, x, q * RS + r);
+                    const uint32_t kq = __shfl_sync(FULL, k, q * RS + r);
+                    const uint32_t iq = i0 + (uint32_t)(q * RS + r);
+                    if (self) s_lo = max(s_lo, i0 + (uint32_t)(q * RS) + 1u);
+                    const uint32_t g_lo = max(s_lo, base), g_hi = min(s_hi, base + (uint32_t)ncols);
+                    if (g_lo >= g_hi) continue;
+                    const int gb = (int)(g_lo - base) & ~3, ge = (int)(g_hi - base);      // 16-byte aligned start
+                    n_pairs += (unsigned long long)(ge - gb);
+#pragma unroll 1
+                    for (int g0 = gb; g0 < ge; g0 += 8 * STEP) {
+                        uint32_t h = 0;
+#pragma unroll 2
+                        for (int st = 0; st < 8; st++) {
+                            if (g0 + st * STEP < ge) {   // uniform across the warp
+                                const int off = g0 + st * STEP + 4 * ph;
+                                const uint4 B0 = *reinterpret_cast<const uint4*>(&sb0[off]);
+                                const uint4 BP = *reinterpret_cast<const uint4*>(&sbP[off]);
+                                const uint4 BM = *reinterpret_cast<const uint4*>(&sbM[off]);
+                                const uint4 BK = *reinterpret_cast<const uint4*>(&sbK[off]);
 #pragma unroll
-                    for (int st = 0; st < 8; st++) {
-                        if (g0 + st * STEP < ncols) {    // uniform across the warp
-                            const int off = g0 + st * STEP + 4 * ph;
-                            const uint4 B0 = *reinterpret_cast<const uint4*>(&sb0[off]);
-                            const uint4 BP = *reinterpret_cast<const uint4*>(&sbP[off]);
-                            const uint4 BM = *reinterpret_cast<const uint4*>(&sbM[off]);
-                            const uint4 BK = *reinterpret_cast<const uint4*>(&sbK[off]);
-#pragma unroll
-                            for (int kk = 0; kk < 4; kk++) {
-                                uint32_t u = quick_marks(x, pick4(B0, kk), pick4(BP, kk), pick4(BM, kk));
-                                u &= u * A.one + mone;   // drop the two lowest marks (IMAD keeps the -1 off the ALU pipe)
-                                u &= u * A.one + mone;
-                                bool hit = u == 0 && pick4(BK, kk) == ka;
-                                if (self) hit = hit && base + (uint32_t)(off + kk) > i;
-                                h |= (hit ? 1u : 0u) << (st * 4 + kk);
+                                for (int kk = 0; kk < 4; kk++) {
+                                    uint32_t w = quick_marks(xq, pick4(B0, kk), pick4(BP, kk), pick4(BM, kk));
+                                    w &= w * A.one + mone;   // drop the two lowest marks (IMAD keeps the -1 off the ALU pipe)
+                                    w &= w * A.one + mone;
+                                    bool hit = w == 0 && pick4(BK, kk) == kq;
+                                    if (self) hit = hit && base + (uint32_t)(off + kk) > iq;
+                                    h |= (hit ? 1u : 0u) << (st * 4 + kk);
+                                }
                             }
                         }
-                    }
-                    if (__any_sync(FULL, h != 0)) {
-                        n_cand += __popc(h);
-                        join_push<STEP>(h, x, sb0, g0 + 4 * ph, qn, q2n, c, out);
+                        if (__any_sync(FULL, h != 0)) {
+                            n_cand += __popc(h);
+                            join_push<STEP>(h, xq, sb0, g0 + 4 * ph, qn, q2n, c, out);
+                        }
                     }
                 }
             }
@@ -292,14 +300,14 @@ __global__ void __launch_bounds__(ENT, 5) join_kernel(const JoinArgs A, const Ed
         if (lane < q2n) {
             const uint2 e = c.q2[lane];
             a = e.x; b = e.y; d = c.q2d[lane];
-            ok = qgram_score(a, b) >= A.T;
+            ok = qgram_score_compact(a, b) >= A.T;
         }
         emit_warp(ok, a, b, d, out);
     }
     if (A.stats) {
         for (int o = 16; o; o >>= 1) n_cand += __shfl_down_sync(FULL, n_cand, o);           // per-lane counts
         if (lane == 0) {                                                                  // the others are uniform per warp
-            atomicAdd(&A.stats[0], n_units); atomicAdd(&A.stats[2], n_cols * (unsigned long long)RS); atomicAdd(&A.stats[3], n_cand);
+            atomicAdd(&A.stats[0], n_units); atomicAdd(&A.stats[2], n_pairs * (unsigned long long)RS); atomicAdd(&A.stats[3], n_cand);
             atomicAdd(&A.stats[6], c.n_d2); atomicAdd(&A.stats[7], c.n_score);
             warp_exit_stats(A.stats, t_start);
         }

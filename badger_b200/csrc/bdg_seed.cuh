@@ -28,23 +28,24 @@ namespace bdg {
 constexpr int SEED_MAX_BLOCKS = 6;
 constexpr int SEED_MAX_FIELDS = 4;
 constexpr int SEED_MAX_CONDS = 48;
-constexpr int SEED_MAX_FLAGS = 3 * SEED_MAX_BLOCKS - 2;
+constexpr int SEED_MAX_FLAGS = 3 * SEED_MAX_BLOCKS;
 constexpr uint8_t SEED_NONE = 255;
 
-// How one side of a condition reads its join key off a barcode: field f = bits [lo[f], lo[f] + n[f]), field 0 lowest.
+// How one side of a condition reads its join key off a barcode: field f = (v >> lo[f]) & mask[f], placed at bit at[f] of the key
+// (field 0 lowest).  Unused fields have mask 0, so the extraction is four branch-free shift-and-mask steps.
 struct SeedKey {
     uint8_t nf, key_bits;
-    uint8_t lo[SEED_MAX_FIELDS], n[SEED_MAX_FIELDS];
+    uint8_t lo[SEED_MAX_FIELDS], n[SEED_MAX_FIELDS], at[SEED_MAX_FIELDS];
+    uint32_t mask[SEED_MAX_FIELDS];
 };
 
 BDG_HD uint32_t seed_key(uint32_t v, const SeedKey& k)
 {
     uint32_t r = 0;
-    int at = 0;
-    for (int f = 0; f < k.nf; f++) {
-        r |= ((v >> k.lo[f]) & low_mask(k.n[f])) << at;
-        at += k.n[f];
-    }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int f = 0; f < SEED_MAX_FIELDS; f++) r |= ((v >> k.lo[f]) & k.mask[f]) << k.at[f];
     return r;
 }
 
@@ -53,16 +54,17 @@ struct SeedCond {
     uint8_t blk[SEED_MAX_FIELDS];     // ascending
     uint8_t d[SEED_MAX_FIELDS];       // diagonal of each block: 0 or 1 (x[block] == y[block columns + d])
     uint8_t self;                     // all diagonals 0
-    uint8_t row_sort;                 // first condition with the same blocks (its row order serves this one too)
+    uint8_t row_sort;                 // first condition with the same blocks (they follow one another and share the row order)
 };
 
 struct SeedScheme {
     int nblocks;
     uint8_t blo[SEED_MAX_BLOCKS], bn[SEED_MAX_BLOCKS];     // first bit / number of bits of every block
-    int nconds, nself;                                     // conditions 0..nself-1 are the symmetric ones
+    int nconds, nself;                                     // nself of the conditions are symmetric (the first of every block set)
     SeedCond cond[SEED_MAX_CONDS];
     SeedKey ka[SEED_MAX_CONDS], kb[SEED_MAX_CONDS];        // join key of the row side (fields of x) / column side (fields of y)
-    int nflags;                                            // bits of seed_flags
+    int nflags;                                            // bits of seed_flags: 3 per block
+    uint32_t hi_mask, lo_mask;                             // top bit of every block / the other bits of the blocks
 };
 
 // x[fields of condition c] == y[the same fields moved by their diagonals]
@@ -79,21 +81,31 @@ BDG_HD int seed_first_slow(const SeedScheme& s, uint32_t a, uint32_t b)
     return SEED_NONE;
 }
 
-// Block-match flags of a pair: bit k: a[block k] == b[block k] (k = 0..B-1); bit B + k - 1: a[block k] == b[block k + 1 column]
-// (k = 1..B-1); bit 2B - 1 + k - 1: b[block k] == a[block k + 1 column].  first_lut[flags] = seed_first_slow.
+// Block-match flags of a pair, three bits per block k at bit 3k: a[block k] == b[block k] | a[block k] == b[block k moved one
+// column up] << 1 | b[block k] == a[block k moved one column up] << 2.  first_lut[flags] = seed_first_slow.
+// seed_flags_slow is the definition; seed_flags finds the zero fields of the three difference words at once (a field x is
+// non-zero iff ((x_low + low_ones) | x) has its top bit set, exact per field and free of carries across fields).
+BDG_HD uint32_t seed_flags_slow(const SeedScheme& s, uint32_t a, uint32_t b)
+{
+    const uint32_t x0 = a ^ b, xa = a ^ (b >> 2), xb = b ^ (a >> 2);
+    uint32_t f = 0;
+    for (int k = 0; k < s.nblocks; k++) {
+        const uint32_t m = low_mask(s.bn[k]) << s.blo[k];
+        f |= (((x0 & m) == 0 ? 1u : 0u) | ((xa & m) == 0 ? 2u : 0u) | ((xb & m) == 0 ? 4u : 0u)) << (3 * k);
+    }
+    return f;
+}
+
 BDG_HD uint32_t seed_flags(const SeedScheme& s, uint32_t a, uint32_t b)
 {
     const uint32_t x0 = a ^ b, xa = a ^ (b >> 2), xb = b ^ (a >> 2);
-    const int B = s.nblocks;
+    const uint32_t HI = s.hi_mask, LM = s.lo_mask;
+    const uint32_t z0 = ~(((x0 & LM) + LM) | x0) & HI;        // top bit of every block whose field of x0 is zero
+    const uint32_t za = ~(((xa & LM) + LM) | xa) & HI;
+    const uint32_t zb = ~(((xb & LM) + LM) | xb) & HI;
+    const uint32_t z = (z0 >> 2) | (za >> 1) | zb;             // three flags below / at the top bit of every block (blocks have >= 4 bits)
     uint32_t f = 0;
-    for (int k = 0; k < B; k++) {
-        const uint32_t m = low_mask(s.bn[k]) << s.blo[k];
-        f |= ((x0 & m) == 0 ? 1u : 0u) << k;
-        if (k) {
-            f |= ((xa & m) == 0 ? 1u : 0u) << (B + k - 1);
-            f |= ((xb & m) == 0 ? 1u : 0u) << (2 * B - 1 + k - 1);
-        }
-    }
+    for (int k = 0; k < s.nblocks; k++) f |= ((z >> (s.blo[k] + s.bn[k] - 3)) & 7u) << (3 * k);
     return f;
 }
 
@@ -107,15 +119,19 @@ inline bool seed_scheme_build(SeedScheme& s, const int* bases, int nblocks)
     for (int k = 0; k < nblocks; k++) { s.blo[k] = (uint8_t)(2 * col); s.bn[k] = (uint8_t)(2 * bases[k]); col += bases[k]; }
     if (col != 15) return false;
     s.nblocks = nblocks;
-    s.nflags = 3 * nblocks - 2;
+    s.nflags = 3 * nblocks;
+    for (int k = 0; k < nblocks; k++) {
+        if (bases[k] < 2) return false;                    // the flag extraction wants >= 4 bits per block
+        s.hi_mask |= 1u << (s.blo[k] + s.bn[k] - 1);
+        s.lo_mask |= low_mask(s.bn[k] - 1) << s.blo[k];
+    }
     const int nf = nblocks - 2;
-    for (int pass = 0; pass < 2; pass++) {                 // symmetric conditions first, then the shifted ones
+    {                                                      // block set by block set: its symmetric condition, then the shifted ones
         for (uint32_t sub = 0; sub < (1u << nblocks); sub++) {
             if (popc(sub) != nf) continue;
             int blk[SEED_MAX_FIELDS], q = 0;
             for (int k = 0; k < nblocks; k++) if (sub & (1u << k)) blk[q++] = k;
             for (uint32_t dm = 0; dm < (1u << nf); dm++) {      // bit f: diagonal of field f
-                if ((dm == 0) != (pass == 0)) continue;
                 bool ok = true;
                 if (blk[0] == 0 && (dm & 1u)) ok = false;                                     // block 0 sits on diagonal 0
                 for (int f = 0; f + 1 < nf && ok; f++)
@@ -134,6 +150,8 @@ inline bool seed_scheme_build(SeedScheme& s, const int* bases, int nblocks)
                     c.d[f] = (uint8_t)((dm >> f) & 1u);
                     ka.lo[f] = s.blo[blk[f]]; kb.lo[f] = (uint8_t)(s.blo[blk[f]] + 2 * c.d[f]);
                     ka.n[f] = kb.n[f] = s.bn[blk[f]];
+                    ka.at[f] = kb.at[f] = (uint8_t)bits;
+                    ka.mask[f] = kb.mask[f] = low_mask(s.bn[blk[f]]);
                     bits += s.bn[blk[f]];
                 }
                 ka.key_bits = kb.key_bits = (uint8_t)bits;
@@ -146,15 +164,14 @@ inline bool seed_scheme_build(SeedScheme& s, const int* bases, int nblocks)
                 s.nconds++;
             }
         }
-        if (pass == 0) s.nself = s.nconds;
     }
+    for (int c = 0; c < s.nconds; c++) s.nself += s.cond[c].self;
     return true;
 }
 
 // lut: 1 << s.nflags entries
 inline void seed_lut_build(const SeedScheme& s, uint8_t* lut)
 {
-    const int B = s.nblocks;
     for (uint32_t f = 0; f < (1u << s.nflags); f++) {
         uint8_t first = SEED_NONE;
         for (int c = 0; c < s.nconds && first == SEED_NONE; c++) {
@@ -162,7 +179,7 @@ inline void seed_lut_build(const SeedScheme& s, uint8_t* lut)
                 bool all = true;
                 for (int k = 0; k < s.cond[c].nf; k++) {
                     const int b = s.cond[c].blk[k];
-                    const int bit = s.cond[c].d[k] == 0 ? b : (o == 0 ? B + b - 1 : 2 * B - 1 + b - 1);
+                    const int bit = 3 * b + (s.cond[c].d[k] == 0 ? 0 : (o == 0 ? 1 : 2));
                     all = all && ((f >> bit) & 1u);
                 }
                 if (all) first = (uint8_t)(2 * c + o);

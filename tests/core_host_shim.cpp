@@ -97,7 +97,12 @@ void shim_scheme_first(const uint32_t* a, const uint32_t* b, size_t n, uint8_t* 
     for (size_t i = 0; i < n; i++) {
         slow[i] = (uint8_t)bdg::seed_first_slow(g_scheme, a[i], b[i]);
         fast[i] = g_lut[bdg::seed_flags(g_scheme, a[i], b[i])];
+        if (bdg::seed_flags(g_scheme, a[i], b[i]) != bdg::seed_flags_slow(g_scheme, a[i], b[i])) fast[i] = 254;   // must agree
     }
+}
+void shim_qgram_compact(const uint32_t* a, const uint32_t* b, size_t n, uint8_t* full, uint8_t* compact)
+{
+    for (size_t i = 0; i < n; i++) { full[i] = (uint8_t)bdg::qgram_score(a[i], b[i]); compact[i] = (uint8_t)bdg::qgram_score_compact(a[i], b[i]); }
 }
 void shim_scheme_keys(int c, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* ka, uint32_t* kb, uint8_t* pred)
 {
