@@ -629,14 +629,19 @@ int bdg_init(const int* device_ids, int n_devices)
     }
     // direct NVLink copies into the first device (bdg_cluster_levels_from_edges gathers the other devices' edge lists there);
     // without peer access cudaMemcpyPeerAsync stages through host memory
-    CU_TRY(cudaSetDevice(g_ctx[0].dev));
+    // (both directions: the edge lists travel to the first device, the distinct-barcode array fans out from it)
     for (size_t g = 1; g < g_ctx.size(); g++) {
-        int can = 0;
-        if (cudaDeviceCanAccessPeer(&can, g_ctx[0].dev, g_ctx[g].dev) == cudaSuccess && can) {
-            const cudaError_t pe = cudaDeviceEnablePeerAccess(g_ctx[g].dev, 0);
-            if (pe != cudaSuccess) (void)cudaGetLastError();      // already enabled (e.g. by the caller's framework): fine
+        for (int dir = 0; dir < 2; dir++) {
+            const int from = dir ? g_ctx[g].dev : g_ctx[0].dev, to = dir ? g_ctx[0].dev : g_ctx[g].dev;
+            int can = 0;
+            CU_TRY(cudaSetDevice(from));
+            if (cudaDeviceCanAccessPeer(&can, from, to) == cudaSuccess && can) {
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(to, 0);
+                if (pe != cudaSuccess) (void)cudaGetLastError();      // already enabled (e.g. by the caller's framework): fine
+            }
         }
     }
+    CU_TRY(cudaSetDevice(g_ctx[0].dev));
     return BDG_OK;
 }
 
@@ -1040,7 +1045,9 @@ int bdg_pack16(const char* seqs, size_t R, uint32_t* out, uint8_t* valid)
 // One device's share of a host-buffer edge build: upload, launch, read the count back (re-run once with the exact
 // size when the guess was too small).  Runs on its own host thread when several devices take part, because the
 // sparse passes read a tile count back between their kernels.
-static int edges_on_device(DevCtx& c, const uint32_t* sorted, size_t N, int t, int part, int nparts, size_t* n_out)
+// src_dev < 0: `sorted` is a host array; else it lives on device src_dev (peer copy over NVLink, or nothing to copy at all
+// when that is this device's own workspace).
+static int edges_on_device(DevCtx& c, const uint32_t* sorted, size_t N, int t, int part, int nparts, size_t* n_out, int src_dev = -1)
 {
     auto ensure = [&](Buf& b, size_t bytes) -> int {
         if (cudaError_t e = (cudaError_t)b.ensure(bytes))
@@ -1050,7 +1057,9 @@ static int edges_on_device(DevCtx& c, const uint32_t* sorted, size_t N, int t, i
     CU_TRY(cudaSetDevice(c.dev));
     if (int e = ensure(c.sorted, std::max<size_t>(N, 1) * 4)) return e;
     if (int e = ensure(c.count, 2 * sizeof(unsigned long long))) return e;      // [edge count | first unsorted index]
-    CU_TRY(cudaMemcpyAsync(c.sorted.p, sorted, N * 4, cudaMemcpyHostToDevice, c.stream));
+    if (src_dev < 0) CU_TRY(cudaMemcpyAsync(c.sorted.p, sorted, N * 4, cudaMemcpyHostToDevice, c.stream));
+    else if (src_dev == c.dev) CU_TRY(cudaMemcpyAsync(c.sorted.p, sorted, N * 4, cudaMemcpyDeviceToDevice, c.stream));
+    else CU_TRY(cudaMemcpyPeerAsync(c.sorted.p, c.dev, sorted, src_dev, N * 4, c.stream));
     // the input must be strictly increasing: checked on the device, read back together with the edge count
     unsigned long long* d_bad = (unsigned long long*)c.count.p + 1;
     unsigned long long first_bad = ~0ull;
@@ -1101,7 +1110,7 @@ static double now_ms()
 }
 
 static int edges_on_devices(const uint32_t* sorted, size_t N, int t, const std::vector<int>& ctx_idx,
-                            const std::vector<int>& parts, int nparts, bdg_edges* res)
+                            const std::vector<int>& parts, int nparts, bdg_edges* res, int src_dev = -1)
 {
     const double t0 = now_ms();
     const size_t G = ctx_idx.size();
@@ -1111,7 +1120,7 @@ static int edges_on_devices(const uint32_t* sorted, size_t N, int t, const std::
     std::vector<double> took(G, 0.0);
     auto work = [&](size_t g) {
         const double w0 = now_ms();
-        rcs[g] = edges_on_device(g_ctx[ctx_idx[g]], sorted, N, t, parts[g], nparts, &counts[g]);
+        rcs[g] = edges_on_device(g_ctx[ctx_idx[g]], sorted, N, t, parts[g], nparts, &counts[g], src_dev);
         took[g] = now_ms() - w0;
         if (rcs[g]) errs[g] = g_err;       // g_err is thread-local
     };
@@ -1151,6 +1160,29 @@ int bdg_edges_build(const uint32_t* sorted_unique, size_t N, int t, bdg_edges** 
     for (int g = 0; g < G; g++) { idx.push_back(g); parts.push_back(g); }
     int rc = BDG_OK;
     try { rc = edges_on_devices(sorted_unique, N, t, idx, parts, G, res); }
+    catch (const std::bad_alloc&) { rc = fail(BDG_ERR_OOM, "host allocation failed"); }
+    catch (const std::exception& e) { rc = fail(BDG_ERR_CUDA, "host thread failure: %s", e.what()); }
+    if (rc) { delete res; return rc; }
+    *out = res;
+    return BDG_OK;
+}
+
+// The same over the ascending distinct barcodes a bdg_dedup_reads call left on the first device: nothing is uploaded, the other
+// devices fetch the array with peer copies.
+int bdg_edges_build_resident(unsigned long long token, int t, bdg_edges** out)
+{
+    if (!out) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    *out = nullptr;
+    if (int rc = need_ctx()) return rc;
+    DevCtx& c0 = g_ctx[0];
+    if (token == 0 || token != c0.map_token) return fail(BDG_ERR_ARG, "stale read-map token: a later dedup call has reused the workspaces");
+    bdg_edges* res = new (std::nothrow) bdg_edges();
+    if (!res) return fail(BDG_ERR_OOM, "host allocation failed");
+    std::vector<int> idx, parts;
+    const int G = (int)g_ctx.size();
+    for (int g = 0; g < G; g++) { idx.push_back(g); parts.push_back(g); }
+    int rc = BDG_OK;
+    try { rc = edges_on_devices((const uint32_t*)c0.dd[6].p, c0.map_distinct, t, idx, parts, G, res, c0.dev); }
     catch (const std::bad_alloc&) { rc = fail(BDG_ERR_OOM, "host allocation failed"); }
     catch (const std::exception& e) { rc = fail(BDG_ERR_CUDA, "host thread failure: %s", e.what()); }
     if (rc) { delete res; return rc; }

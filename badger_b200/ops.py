@@ -209,6 +209,13 @@ def edges_handle(sorted_unique: np.ndarray, t: int) -> EdgeHandle:
     return EdgeHandle(h, s.size)
 
 
+def edges_handle_resident(rmap: "ReadMap", t: int) -> EdgeHandle:
+    """edges_handle over the ascending distinct barcodes the dedup_reads call left on the first device (no upload)."""
+    h = C.c_void_p()
+    check(lib().bdg_edges_build_resident(rmap.token, int(t), C.byref(h)))
+    return EdgeHandle(h, int(rmap.distinct.size))
+
+
 def edges_build(sorted_unique: np.ndarray, t: int):
     """index.py:77-93 + barcode_graph.py:224-249 over all initialised GPUs.
     Returns (a, b, d): every undirected edge once with a < b; order unspecified."""

@@ -64,7 +64,7 @@ def assign_packed(ranks, valid=None, *, threshold, n_cells, interval=25, whiteli
         return np.full(R, NONE, dtype=np.uint64), info
     t0 = time.perf_counter()
     s = rm.sorted_distinct                                # ascending order straight from the dedup's sort
-    handle = ops.edges_handle(s, threshold)
+    handle = ops.edges_handle_resident(rm, threshold)     # the array is already on the device: no upload, peer copies to the other GPUs
     tick("edges", t0)
     info.update(distinct=int(distinct.size), edges=int(handle.count))
 

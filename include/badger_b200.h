@@ -98,6 +98,9 @@ int bdg_assign_reads(unsigned long long token, const int32_t* centre_idx, size_t
 typedef struct bdg_edges bdg_edges;
 int bdg_edges_build(const uint32_t* sorted_unique, size_t N, int t, bdg_edges** out);
 int bdg_edges_build_part(const uint32_t* sorted_unique, size_t N, int t, int part, int nparts, bdg_edges** out);
+/* The same over the ascending distinct barcodes that the bdg_dedup_reads call named by `token` left on the first device: no
+ * upload; with several devices the array fans out over NVLink peer copies. */
+int bdg_edges_build_resident(unsigned long long token, int t, bdg_edges** out);
 size_t bdg_edges_count(const bdg_edges* e);
 int bdg_edges_copy(const bdg_edges* e, uint32_t* a, uint32_t* b, uint8_t* d); /* caller-allocated, length = count */
 void bdg_edges_free(bdg_edges* e);
