@@ -26,11 +26,13 @@ def parse_args(args):
     parser = argparse.ArgumentParser(formatter_class=argparse.RawDescriptionHelpFormatter)
     parser.add_argument("--barcodes", "-b", help="(README spelling) tsv file containing the observed cell barcodes; "
                         "same as --reads", type=str, dest="bar_file", default=None)
-    parser.add_argument("--threshold", "-t", help="Maximal accepted difference between barcodes",
+    parser.add_argument("--threshold", "-t", help="Maximal accepted difference between barcodes "
+                        "(1 and 2 run the sorted / joined searches; >= 3 runs the dense all-pairs kernel, meant for small inputs)",
                         type=int, dest="threshold", default=1)
     parser.add_argument("--reads", "-r", help="TSV from barcode extraction",
                         type=str, dest="reads", default=None)
-    parser.add_argument("--ground_truth", help="File connecting each observed barcode to its read ID containing true barcode, only used for statistics",
+    parser.add_argument("--ground_truth", help="File connecting each observed barcode to its read ID containing true barcode, only used for statistics "
+                        "(accepted for compatibility; the statistics it feeds are outside this drop-in: a warning is logged and the file is not read)",
                         type=str, default=None)
     parser.add_argument("--barcode_list", "-l", help="List of all possible barcodes for the used method, helps identify correct barcodes",
                         type=str, dest="barcode_list", default=None)
@@ -45,7 +47,9 @@ def parse_args(args):
     parser.add_argument("--interval", "-i", help="Percentage by which the number of cells is allowed to differ from estimated cell number, default 25%%", default=25, type=int)
     parser.add_argument("--stats", "-s", action='store_true', help="(not provided by the B200 path)", default=False)
     parser.add_argument("--threads", "-tr", dest="threads", default=1, type=int)
-    parser.add_argument("--high_sens", "-hs", action='store_true', help="if set, Badger is run in high sensitivity mode. This increases recall but decreases precision", default=False)
+    parser.add_argument("--high_sens", "-hs", action='store_true', help="if set, Badger is run in high sensitivity mode. This increases recall but decreases precision. "
+                        "Ties between equally near centres are broken by the iteration order of a Python set of strings, in the reference and here alike: "
+                        "the result is reproducible only under a fixed PYTHONHASHSEED", default=False)
     parser.add_argument("--devices", help="comma-separated CUDA device ids (default: all visible)", type=str, default=None)
     parser.add_argument("--no_native_io", action='store_true', default=False,
                         help="read and write the TSVs through pandas and the dict-shaped BarcodeGraph (the slower route the native "
@@ -116,6 +120,8 @@ def main(args):
         logger.error("Please specify the type of single cell data used. Options are tenX_v2, tenX_v3 (aliases 10x, visium).")
         exit(-3)
     bc_len = BARCODE_CALLING_MODES[args.data_type]
+    if args.ground_truth:
+        logger.warning("--ground_truth only feeds the reference's accuracy statistics (badger.py:146-174), which this drop-in does not compute: ignored")
     true_barcodes = args.true_barcodes
     if true_barcodes:                                           # badger.py:74-80
         true_barcodes = pd.read_csv(true_barcodes, sep="\t", header=None)
@@ -176,9 +182,11 @@ def main(args):
         exit(-3)
 
 
-if __name__ == "__main__":
+def cli(argv=None):
+    """The command's top level (reference badger.py:177-196): any failure is logged as 'Barcode Graph failed' and exits with -1.
+    badger.py and its README alias barcodes.py both enter here."""
     try:
-        main(sys.argv[1:])
+        main(sys.argv[1:] if argv is None else argv)
     except SystemExit:
         raise
     except KeyboardInterrupt:
@@ -196,3 +204,7 @@ if __name__ == "__main__":
             sys.stderr.write("Barcode Graph failed")
             print_exc()
         sys.exit(-1)
+
+
+if __name__ == "__main__":
+    cli()

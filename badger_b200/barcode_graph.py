@@ -2,8 +2,9 @@
 B200 kernels.  Same method names, arguments, attributes and results; the O(N^2) candidate search and the
 edit-distance verification (barcode_graph.py:224-249, index.py:77-93) run in ``libbadger_b200.so``.
 
-What stays on the host (numpy): first-seen-order dedup/count, centre selection bookkeeping, the two BFS
-rounds of ``cluster`` (vectorised, order-free restatement), dict-shaped views for downstream readers.
+Dedup / count in first-seen order, whitelist membership, the two rounds of ``cluster`` and ``--high_sens`` scoring run on
+the device as well (``ops.dedup_first_seen``, ``ops.member_sorted``, ``ops.cluster_levels``, ``ops.nearest_bounded``); the host
+keeps the centre-selection walk over the count-sorted barcodes and the dict-shaped views downstream readers expect.
 """
 from __future__ import annotations
 

@@ -85,15 +85,13 @@ struct DevCtx {
     unsigned long long host_stats[bdg::MAX_PASSES][2] = {};   // interval tests done / tiles listed per pass of the last launch
     unsigned long long generation = 0;                        // bumped by every host-buffer edge build on this device
     Buf dd[10];                                               // dedup: keys, idx, sorted keys/idx, heads, scan, run arrays, cub scratch
-    Plan plan_host;                                           // cached work plan (host copy; the device copy lives in `plan`)
-    uint64_t plan_key[4] = {0, 0, 0, 0};
-    bool plan_valid = false;
     Buf cl[6];                                                // clustering: centres, centre index, level, claim min / max, index scratch
     Buf as[8];                                                // masked dedup + per-read gather: all ranks, valid bytes, their scan, scratch, centre idx / value, result, counter
     unsigned long long map_token = 0, map_serial = 0;         // read map left on the device by bdg_dedup_reads (0: none)
     size_t map_rows = 0, map_reads = 0, map_distinct = 0;
     bool map_masked = false;
     Buf gather_a, gather_b;                                   // edge ends of ALL devices of a multi-device handle, gathered here for cluster()
+    Buf io[4];                                                // host-buffer calls of pack16 / membership: inputs, outputs, check flag
     Buf nn[9];                                                // sparse nearest: rotated keys + payload (in/out) of queries and targets, scratch
     // join form of the t = 2 edge construction (bdg_join.cuh): barcodes in the key order of every condition's row side / column
     // side, first column of every key, scratch keys (in / sorted) and radix-sort scratch, units per slab and their prefix sums
@@ -658,6 +656,7 @@ void bdg_shutdown(void)
         if (c.ev_start) cudaEventDestroy(c.ev_start);
         for (auto& b : c.dd) b.release();
         for (auto& b : c.nn) b.release();
+        for (auto& b : c.io) b.release();
         for (auto& b : c.cl) b.release();
         c.gather_a.release(); c.gather_b.release();
         for (auto& b : c.as) b.release();
@@ -801,6 +800,7 @@ int bdg_dev_nearest_bounded(const uint32_t* d_q, size_t Q, const uint32_t* d_t, 
     if (Q == 0) return BDG_OK;
     if (!d_q || !d_keys || !d_argmin || !d_dist || (W && !d_t)) return fail(BDG_ERR_ARG, "NULL pointer argument");
     if (W >= (1ull << bdg::NEAR_IDX_BITS) || Q > 0xFFFFFFFFull) return fail(BDG_ERR_ARG, "W must be < 2^28 and Q < 2^32");
+    if (max_d > 15) return fail(BDG_ERR_ARG, "max_d must be <= 15 (a distance of 16 does not fit the packed (distance, index) key)");
     cudaStream_t st = (cudaStream_t)stream;
     CU_TRY(cudaMemsetAsync(d_keys, 0xFF, Q * sizeof(uint32_t), st));
     DevCtx* ws = ctx_of_current_device();
@@ -1026,19 +1026,16 @@ int bdg_pack16(const char* seqs, size_t R, uint32_t* out, uint8_t* valid)
     if (int rc = need_ctx()) return rc;
     DevCtx& c = g_ctx[0];
     CU_TRY(cudaSetDevice(c.dev));
-    char* d_in = nullptr; uint32_t* d_out = nullptr; uint8_t* d_valid = nullptr;
-    CU_TRY(cudaMallocAsync((void**)&d_in, R * 16, c.stream));
-    CU_TRY(cudaMallocAsync((void**)&d_out, R * 4, c.stream));
-    CU_TRY(cudaMallocAsync((void**)&d_valid, R, c.stream));
-    CU_TRY(cudaMemcpyAsync(d_in, seqs, R * 16, cudaMemcpyHostToDevice, c.stream));
-    int rc = bdg_dev_pack16(d_in, R, d_out, d_valid, c.stream);
-    if (rc == BDG_OK) {
-        CU_TRY(cudaMemcpyAsync(out, d_out, R * 4, cudaMemcpyDeviceToHost, c.stream));
-        CU_TRY(cudaMemcpyAsync(valid, d_valid, R, cudaMemcpyDeviceToHost, c.stream));
-    }
-    cudaFreeAsync(d_in, c.stream); cudaFreeAsync(d_out, c.stream); cudaFreeAsync(d_valid, c.stream);
+    const size_t sizes[3] = {R * 16, R * 4, R};               // grow-only workspaces: letters, ranks, validity
+    for (int k = 0; k < 3; k++)
+        if (cudaError_t e = (cudaError_t)c.io[k].ensure(sizes[k]))
+            return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation of %zu bytes: %s", sizes[k], cudaGetErrorString(e));
+    CU_TRY(cudaMemcpyAsync(c.io[0].p, seqs, R * 16, cudaMemcpyHostToDevice, c.stream));
+    if (int rc = bdg_dev_pack16((const char*)c.io[0].p, R, (uint32_t*)c.io[1].p, (uint8_t*)c.io[2].p, c.stream)) return rc;
+    CU_TRY(cudaMemcpyAsync(out, c.io[1].p, R * 4, cudaMemcpyDeviceToHost, c.stream));
+    CU_TRY(cudaMemcpyAsync(valid, c.io[2].p, R, cudaMemcpyDeviceToHost, c.stream));
     CU_TRY(cudaStreamSynchronize(c.stream));
-    return rc;
+    return BDG_OK;
 }
 
 
@@ -1065,7 +1062,7 @@ static int edges_on_device(DevCtx& c, const uint32_t* sorted, size_t N, int t, i
     unsigned long long first_bad = ~0ull;
     CU_TRY(cudaMemsetAsync(d_bad, 0xFF, 8, c.stream));
     if (N > 1) {
-        bdg::sorted_check_kernel<<<(int)std::min<size_t>((N + 255) / 256, (size_t)c.sms * 8), 256, 0, c.stream>>>((const uint32_t*)c.sorted.p, (uint32_t)N, d_bad);
+        bdg::sorted_check_kernel<true><<<(int)std::min<size_t>((N + 255) / 256, (size_t)c.sms * 8), 256, 0, c.stream>>>((const uint32_t*)c.sorted.p, (uint32_t)N, d_bad);
         g_launches++;
     }
     size_t cap = std::max(edge_cap_guess(N, t, nparts), c.ea.cap / 4);
@@ -1259,6 +1256,9 @@ static int cluster_on_device(DevCtx& c, const uint32_t* d_sorted, size_t N, uint
     if (int e = ensure(c.cl[2], N)) return e;
     if (int e = ensure(c.cl[3], N * 4)) return e;
     if (int e = ensure(c.cl[4], N * 4)) return e;
+    if (int e = ensure(c.cl[5], 4)) return e;
+    unsigned int* d_bad = (unsigned int*)c.cl[5].p;
+    CU_TRY(cudaMemsetAsync(d_bad, 0, 4, c.stream));
     uint32_t* d_cen = (uint32_t*)c.cl[0].p;
     int32_t *d_ci = (int32_t*)c.cl[1].p, *d_min = (int32_t*)c.cl[3].p, *d_max = (int32_t*)c.cl[4].p;
     uint8_t* d_lv = (uint8_t*)c.cl[2].p;
@@ -1272,7 +1272,7 @@ static int cluster_on_device(DevCtx& c, const uint32_t* d_sorted, size_t N, uint
     if (C) bdg::cluster_seed_kernel<<<(int)std::min<size_t>((C + 255) / 256, (size_t)c.sms * 8), 256, 0, st>>>(d_sorted, (uint32_t)N, d_cen, (uint32_t)C, d_ci, d_lv);
     g_launches += 2;
     if (E) {
-        bdg::cluster_index_kernel<<<eb, 256, 0, st>>>(d_sorted, (uint32_t)N, d_ea, d_eb, E, d_lv);
+        bdg::cluster_index_kernel<<<eb, 256, 0, st>>>(d_sorted, (uint32_t)N, d_ea, d_eb, E, d_lv, d_bad);
         g_launches++;
         if (trace) { cudaStreamSynchronize(st); tr1 = now_ms(); }
         for (int r = 1; r <= rounds; r++) {
@@ -1285,7 +1285,10 @@ static int cluster_on_device(DevCtx& c, const uint32_t* d_sorted, size_t N, uint
     if (trace) { cudaStreamSynchronize(st); tr2 = now_ms(); }
     CU_TRY(cudaMemcpyAsync(centre_idx, d_ci, N * 4, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(level, d_lv, N, cudaMemcpyDeviceToHost, st));
+    unsigned int bad = 0;
+    CU_TRY(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
+    if (bad) return fail(BDG_ERR_ARG, "an edge end point is not in the barcode array");
     if (trace)
         fprintf(stderr, "[bdg] cluster N=%zu E=%zu: (gather +) seed + index %.2f ms, %d rounds %.2f ms, read-back %.2f ms\n", N, E, tr1 - tr0, rounds,
                 tr2 - tr1, now_ms() - tr2);
@@ -1362,22 +1365,31 @@ int bdg_member_sorted(const uint32_t* sorted_wl, size_t W, const uint32_t* q, si
 {
     if (Q == 0) return BDG_OK;
     if (!q || !hit || (W && !sorted_wl)) return fail(BDG_ERR_ARG, "NULL pointer argument");
-    for (size_t i = 1; i < W; i++)
-        if (sorted_wl[i] < sorted_wl[i - 1]) return fail(BDG_ERR_ARG, "whitelist not sorted at index %zu", i);
+    if (W > 0xFFFFFFFFull || Q > 0xFFFFFFFFull) return fail(BDG_ERR_ARG, "size exceeds 2^32");
     if (int rc = need_ctx()) return rc;
     DevCtx& c = g_ctx[0];
     CU_TRY(cudaSetDevice(c.dev));
-    uint32_t *d_wl = nullptr, *d_q = nullptr; uint8_t* d_hit = nullptr;
-    CU_TRY(cudaMallocAsync((void**)&d_wl, std::max<size_t>(W, 1) * 4, c.stream));
-    CU_TRY(cudaMallocAsync((void**)&d_q, Q * 4, c.stream));
-    CU_TRY(cudaMallocAsync((void**)&d_hit, Q, c.stream));
+    const size_t sizes[4] = {std::max<size_t>(W, 1) * 4, Q * 4, Q, 8};       // grow-only workspaces: whitelist, queries, hits, check flag
+    for (int k = 0; k < 4; k++)
+        if (cudaError_t e = (cudaError_t)c.io[k].ensure(sizes[k]))
+            return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation of %zu bytes: %s", sizes[k], cudaGetErrorString(e));
+    uint32_t *d_wl = (uint32_t*)c.io[0].p, *d_q = (uint32_t*)c.io[1].p;
+    uint8_t* d_hit = (uint8_t*)c.io[2].p;
+    unsigned long long* d_bad = (unsigned long long*)c.io[3].p;
     CU_TRY(cudaMemcpyAsync(d_wl, sorted_wl, W * 4, cudaMemcpyHostToDevice, c.stream));
     CU_TRY(cudaMemcpyAsync(d_q, q, Q * 4, cudaMemcpyHostToDevice, c.stream));
-    int rc = bdg_dev_member_sorted(d_wl, W, d_q, Q, d_hit, c.stream);
-    if (rc == BDG_OK) CU_TRY(cudaMemcpyAsync(hit, d_hit, Q, cudaMemcpyDeviceToHost, c.stream));
-    cudaFreeAsync(d_wl, c.stream); cudaFreeAsync(d_q, c.stream); cudaFreeAsync(d_hit, c.stream);
+    CU_TRY(cudaMemsetAsync(d_bad, 0xFF, 8, c.stream));
+    if (W > 1) {                                            // the whitelist must be sorted: checked on the device, read back with the hits
+        bdg::sorted_check_kernel<false><<<(int)std::min<size_t>((W + 255) / 256, (size_t)c.sms * 8), 256, 0, c.stream>>>(d_wl, (uint32_t)W, d_bad);
+        g_launches++;
+    }
+    if (int rc = bdg_dev_member_sorted(d_wl, W, d_q, Q, d_hit, c.stream)) return rc;
+    unsigned long long first_bad = ~0ull;
+    CU_TRY(cudaMemcpyAsync(hit, d_hit, Q, cudaMemcpyDeviceToHost, c.stream));
+    CU_TRY(cudaMemcpyAsync(&first_bad, d_bad, 8, cudaMemcpyDeviceToHost, c.stream));
     CU_TRY(cudaStreamSynchronize(c.stream));
-    return rc;
+    if (first_bad != ~0ull) return fail(BDG_ERR_ARG, "whitelist not sorted at index %llu", first_bad);
+    return BDG_OK;
 }
 
 int bdg_nearest_bounded(const uint32_t* q, size_t Q, const uint32_t* targets, size_t W, int max_d, int32_t* argmin, uint8_t* dist)

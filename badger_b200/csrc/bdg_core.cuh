@@ -418,117 +418,7 @@ BDG_HD int qgram_score_compact(uint32_t a, uint32_t b)
     return s;
 }
 
-// ---------------------------------------------------------------------------------------------
-// Two-block seeds for t = 2 (groundwork for the next form of the sparse passes; no kernel uses it yet - DESIGN.md 8).
-// The single-block passes above leave 11 * N^2 / 2048 pairs to score one by one, which is what the step costs at
-// N > 10^6.  Cutting a[0:15] into FOUR blocks (4, 4, 4, 3 bases = bits 0-7, 8-15, 16-23, 24-29) leaves at least TWO
-// blocks untouched by <= 2 operations, and the diagonals of two untouched blocks are tied together:
-//   * two adjacent untouched blocks sit on the same diagonal d in {-1, 0, +1} (block 0 only on 0);
-//   * two untouched blocks with touched ones between / before them: every touched block holds exactly one
-//     operation (two touched blocks, two operations), so the diagonal moves by at most one per touched block
-//     and ends within +-1 of the start.
-// That gives 20 conditions "two fields of a equal two fields of b" on 14 or 16 bits each (a random pair meets one with
-// probability 69 / 65536 ~ 1 / 950, against 1 / 93 for the single blocks), each a plain key equality, i.e. a sort-merge
-// join of seed2_key_a over the rows with seed2_key_b over the columns.  Necessary for D <= 2 under EITHER labelling of
-// the pair, so a join may fix a = min(x, y); tests/test_core_host.py checks that on the oracle's distances (random near
-// pairs, low-complexity seeds, exhaustive two-operation neighbourhoods).
-// ---------------------------------------------------------------------------------------------
-constexpr int SEED2_N = 20;
-struct Seed2 { int8_t blk0, d0, blk1, d1; };     // a[block blk0] == b[the same columns + d0]  and  a[block blk1] == b[... + d1]
-
-BDG_HD Seed2 seed2_cond(int c)
-{
-    // 0: blocks 0,1 | 1-3: blocks 1,2 | 4-6: blocks 2,3 | 7-9: blocks 0,2 | 10-12: blocks 0,3 | 13-19: blocks 1,3
-    if (c == 0) return Seed2{0, 0, 1, 0};
-    if (c <= 3) return Seed2{1, (int8_t)(c - 2), 2, (int8_t)(c - 2)};
-    if (c <= 6) return Seed2{2, (int8_t)(c - 5), 3, (int8_t)(c - 5)};
-    if (c <= 9) return Seed2{0, 0, 2, (int8_t)(c - 8)};
-    if (c <= 12) return Seed2{0, 0, 3, (int8_t)(c - 11)};
-    // (d of block 1, d of block 3) with |d3 - d1| <= 1: (-1,-1) (-1,0) (0,-1) (0,0) (0,1) (1,0) (1,1)
-    const int k = c - 13;
-    const int d1 = k < 2 ? -1 : (k < 5 ? 0 : 1);
-    const int d3 = k == 0 ? -1 : k == 1 ? 0 : k == 2 ? -1 : k == 3 ? 0 : k == 4 ? 1 : k == 5 ? 0 : 1;
-    return Seed2{1, (int8_t)d1, 3, (int8_t)d3};
-}
-
-BDG_HD int seed2_block_lo(int blk) { return 8 * blk; }                       // first bit of block blk
-BDG_HD int seed2_block_bits(int blk) { return blk == 3 ? 6 : 8; }
-
-BDG_HD uint32_t seed2_field(uint32_t v, int blk, int d)                     // block blk of v, columns moved by d bases
-{
-    return (v >> (seed2_block_lo(blk) + 2 * d)) & ((1u << seed2_block_bits(blk)) - 1u);
-}
-
-// the join keys of condition c: rows are keyed by the two blocks of a, columns by the matching stretches of b
-BDG_HD uint32_t seed2_key_a(int c, uint32_t a)
-{
-    const Seed2 s = seed2_cond(c);
-    return seed2_field(a, s.blk0, 0) | (seed2_field(a, s.blk1, 0) << seed2_block_bits(s.blk0));
-}
-BDG_HD uint32_t seed2_key_b(int c, uint32_t b)
-{
-    const Seed2 s = seed2_cond(c);
-    return seed2_field(b, s.blk0, s.d0) | (seed2_field(b, s.blk1, s.d1) << seed2_block_bits(s.blk0));
-}
-BDG_HD bool seed2_pred(int c, uint32_t a, uint32_t b) { return seed2_key_a(c, a) == seed2_key_b(c, b); }
-
-// first condition the pair meets (the pass that would emit it), -1 if none: D(a,b) <= 2 implies >= 0
-BDG_HD int seed2_first(uint32_t a, uint32_t b)
-{
-    for (int c = 0; c < SEED2_N; c++)
-        if (seed2_pred(c, a, b)) return c;
-    return -1;
-}
-
-// Sort form of a condition: a bijection of the 32-bit word that puts the join key (field 0 in the low part, field 1 above
-// it) into the TOP n0 + n1 bits and the remaining bits, in their order, below.  Rows are permuted with seed2_perm_a(c),
-// columns with seed2_perm_b(c); after a plain radix sort of the permuted words equal keys are adjacent on both sides,
-// a tile's key range is its first and last word >> (32 - n0 - n1), and seed_unpermute gives the barcode back.
-struct SeedPerm { uint8_t lo0, n0, lo1, n1; };   // the two fields inside the word: bits [lo0, lo0+n0) and [lo1, lo1+n1), lo0 + n0 <= lo1
-
-BDG_HD SeedPerm seed2_perm_a(int c)
-{
-    const Seed2 s = seed2_cond(c);
-    return SeedPerm{(uint8_t)seed2_block_lo(s.blk0), (uint8_t)seed2_block_bits(s.blk0), (uint8_t)seed2_block_lo(s.blk1), (uint8_t)seed2_block_bits(s.blk1)};
-}
-BDG_HD SeedPerm seed2_perm_b(int c)
-{
-    const Seed2 s = seed2_cond(c);
-    return SeedPerm{(uint8_t)(seed2_block_lo(s.blk0) + 2 * s.d0), (uint8_t)seed2_block_bits(s.blk0), (uint8_t)(seed2_block_lo(s.blk1) + 2 * s.d1),
-                    (uint8_t)seed2_block_bits(s.blk1)};
-}
-BDG_HD int seed_key_bits(SeedPerm p) { return p.n0 + p.n1; }
 BDG_HD uint32_t low_mask(int n) { return n >= 32 ? 0xFFFFFFFFu : ((1u << n) - 1u); }
-
-BDG_HD uint32_t seed_permute(uint32_t v, SeedPerm p)
-{
-    const int e0 = p.lo0 + p.n0, e1 = p.lo1 + p.n1;                 // ends of the fields
-    const uint32_t key = ((v >> p.lo0) & low_mask(p.n0)) | (((v >> p.lo1) & low_mask(p.n1)) << p.n0);
-    const uint32_t seg0 = v & low_mask(p.lo0);                      // below field 0
-    const uint32_t seg1 = (v >> e0) & low_mask(p.lo1 - e0);         // between the fields
-    const uint32_t seg2 = e1 >= 32 ? 0u : (v >> e1);                // above field 1
-    const uint32_t rest = seg0 | (seg1 << p.lo0) | (e1 >= 32 ? 0u : (seg2 << (p.lo0 + p.lo1 - e0)));
-    const int kb = p.n0 + p.n1;
-    return (key << (32 - kb)) | rest;
-}
-BDG_HD uint32_t seed_unpermute(uint32_t w, SeedPerm p)
-{
-    const int e0 = p.lo0 + p.n0, e1 = p.lo1 + p.n1, kb = p.n0 + p.n1;
-    const uint32_t key = w >> (32 - kb), rest = w & low_mask(32 - kb);
-    const int l1 = p.lo1 - e0;                                       // length of the middle segment
-    uint32_t v = rest & low_mask(p.lo0);
-    v |= (key & low_mask(p.n0)) << p.lo0;
-    v |= ((rest >> p.lo0) & low_mask(l1)) << e0;
-    v |= (key >> p.n0) << p.lo1;
-    if (e1 < 32) v |= (rest >> (p.lo0 + l1)) << e1;
-    return v;
-}
-// can a row tile [alo, ahi] and a column tile [blo, bhi] (permuted, sorted words) hold two equal keys?
-BDG_HD bool seed_tiles_meet(uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, int key_bits)
-{
-    const int s = 32 - key_bits;
-    return (alo >> s) <= (bhi >> s) && (blo >> s) <= (ahi >> s);
-}
 
 // Full predicate of barcode_graph.py:233-249 for a != b: returns D when (a,b) is an edge at threshold t,
 // else 0.  t <= 2 uses the case analysis, larger t the generic bit-vector pass.

@@ -707,12 +707,16 @@ __global__ void __launch_bounds__(ENT, 4) sparse_tile_kernel(const EdgeWork w, c
     }
 }
 
-// first index i with v[i] <= v[i-1] (the edge construction needs a strictly increasing array); *first_bad primed with ~0
+// first index i with v[i] <= v[i-1] (STRICT: the edge construction needs a strictly increasing array) or v[i] < v[i-1] (the
+// whitelist only has to be sorted); *first_bad primed with ~0
+template <bool STRICT>
 __global__ void sorted_check_kernel(const uint32_t* __restrict__ v, uint32_t n, unsigned long long* __restrict__ first_bad)
 {
     unsigned long long bad = ~0ull;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += gridDim.x * blockDim.x)
-        if (__ldg(&v[i]) <= __ldg(&v[i - 1])) { bad = i; break; }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t cur = __ldg(&v[i]), prev = __ldg(&v[i - 1]);
+        if (STRICT ? cur <= prev : cur < prev) { bad = i; break; }
+    }
     if (bad != ~0ull) atomicMin(first_bad, bad);
 }
 

@@ -383,15 +383,20 @@ __global__ void cluster_seed_kernel(const uint32_t* __restrict__ sorted, uint32_
 // barcode values of the edge list -> node indices, in place
 // and mark both ends "has an edge" (level 254; centres keep their 0, later rounds overwrite the mark of whoever they reach)
 constexpr uint8_t LEVEL_NONE = 255, LEVEL_HAS_EDGE = 254;
+// An end point that is not a node (a value absent from `sorted`) raises *bad and the edge is dropped (both ends 0xFFFFFFFF).
+constexpr uint32_t NO_NODE = 0xFFFFFFFFu;
 __global__ void cluster_index_kernel(const uint32_t* __restrict__ sorted, uint32_t n, uint32_t* __restrict__ ea, uint32_t* __restrict__ eb, uint64_t n_edges,
-                                     uint8_t* __restrict__ level)
+                                     uint8_t* __restrict__ level, unsigned int* __restrict__ bad)
 {
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t ia = lower_bound_u32(sorted, n, ea[e]), ib = lower_bound_u32(sorted, n, eb[e]);
+        const uint32_t va = ea[e], vb = eb[e];
+        uint32_t ia = lower_bound_u32(sorted, n, va), ib = lower_bound_u32(sorted, n, vb);
+        if (ia >= n || ib >= n || __ldg(&sorted[ia]) != va || __ldg(&sorted[ib]) != vb) { *bad = 1u; ia = ib = NO_NODE; }
         ea[e] = ia;
         eb[e] = ib;
-        if (ia < n && level[ia] == LEVEL_NONE) level[ia] = LEVEL_HAS_EDGE;     // every writer stores the same value
-        if (ib < n && level[ib] == LEVEL_NONE) level[ib] = LEVEL_HAS_EDGE;
+        if (ia == NO_NODE) continue;
+        if (level[ia] == LEVEL_NONE) level[ia] = LEVEL_HAS_EDGE;               // every writer stores the same value
+        if (level[ib] == LEVEL_NONE) level[ib] = LEVEL_HAS_EDGE;
     }
 }
 
@@ -401,6 +406,7 @@ __global__ void cluster_claim_kernel(const uint32_t* __restrict__ ia, const uint
 {
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (uint64_t)gridDim.x * blockDim.x) {
         const uint32_t u = __ldg(&ia[e]), v = __ldg(&ib[e]);
+        if (u == NO_NODE) continue;
         const int32_t cu = centre_idx[u], cv = centre_idx[v];
         if (cu >= 0 && cv == -2 && level[u] == round - 1) { atomicMin(&cmin[v], cu); atomicMax(&cmax[v], cu); }
         if (cv >= 0 && cu == -2 && level[v] == round - 1) { atomicMin(&cmin[u], cv); atomicMax(&cmax[u], cv); }

@@ -53,26 +53,6 @@ void shim_quick_any(int t, const uint32_t* a, const uint32_t* b, size_t n, uint8
 {
     for (size_t i = 0; i < n; i++) out[i] = bdg::quick_pass_any(a[i], b[i], t);
 }
-// two-block seeds (t = 2): first condition met by (a, b), -1 if none; and the two join keys of condition c
-void shim_seed2_first(const uint32_t* a, const uint32_t* b, size_t n, int8_t* out)
-{
-    for (size_t i = 0; i < n; i++) out[i] = (int8_t)bdg::seed2_first(a[i], b[i]);
-}
-void shim_seed2_keys(int c, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* ka, uint32_t* kb)
-{
-    for (size_t i = 0; i < n; i++) { ka[i] = bdg::seed2_key_a(c, a[i]); kb[i] = bdg::seed2_key_b(c, b[i]); }
-}
-int shim_seed2_count(void) { return bdg::SEED2_N; }
-void shim_seed2_permute(int c, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* pa, uint32_t* pb, uint32_t* ua, uint32_t* ub)
-{
-    const bdg::SeedPerm A = bdg::seed2_perm_a(c), B = bdg::seed2_perm_b(c);
-    for (size_t i = 0; i < n; i++) {
-        pa[i] = bdg::seed_permute(a[i], A); pb[i] = bdg::seed_permute(b[i], B);
-        ua[i] = bdg::seed_unpermute(pa[i], A); ub[i] = bdg::seed_unpermute(pb[i], B);
-    }
-}
-int shim_seed2_key_bits(int c) { return bdg::seed_key_bits(bdg::seed2_perm_a(c)); }
-int shim_seed_tiles_meet(uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi, int kb) { return bdg::seed_tiles_meet(alo, ahi, blo, bhi, kb); }
 int shim_top_possible(int t, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi)
 {
     return t == 1 ? bdg::t1_top_possible(alo, ahi, blo, bhi) : bdg::t2_top_possible(alo, ahi, blo, bhi);

@@ -36,11 +36,12 @@ def shim(tmp_path_factory):
     L.shim_quick_any.argtypes = [C.c_int, u32p, u32p, C.c_size_t, u8p]
     L.shim_top_possible.argtypes = [C.c_int] + [C.c_uint32] * 4
     L.shim_top_possible.restype = C.c_int
-    L.shim_seed2_first.argtypes = [u32p, u32p, C.c_size_t, np.ctypeslib.ndpointer(np.int8, flags="C")]
-    L.shim_seed2_keys.argtypes = [C.c_int, u32p, u32p, C.c_size_t, u32p, u32p]
-    L.shim_seed2_count.restype = C.c_int
-    L.shim_seed2_permute.argtypes = [C.c_int, u32p, u32p, C.c_size_t, u32p, u32p, u32p, u32p]
-    L.shim_seed_tiles_meet.argtypes = [C.c_uint32] * 4 + [C.c_int]
+    L.shim_scheme.argtypes = [C.c_void_p, C.c_int]
+    L.shim_scheme_first.argtypes = [u32p, u32p, C.c_size_t, u8p, u8p]
+    L.shim_scheme_keys.argtypes = [C.c_int, u32p, u32p, C.c_size_t, u32p, u32p, u8p]
+    L.shim_join_emulate.argtypes = [u32p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    L.shim_join_emulate.restype = C.c_size_t
+    L.shim_qgram_compact.argtypes = [u32p, u32p, C.c_size_t, u8p, u8p]
     return L
 
 
@@ -374,12 +375,6 @@ def test_quick_pass_any_sound(shim, t):
 
 
 # ------------------------------------------------------------------------------------------ two-block seeds (t = 2)
-def seed2_first(shim, a, b):
-    out = np.zeros(a.size, np.int8)
-    shim.shim_seed2_first(np.ascontiguousarray(a), np.ascontiguousarray(b), a.size, out)
-    return out
-
-
 def two_op_neighbourhood(x):
     """Every 16-mer reachable from x by at most two edit operations (all paddings of the shortened ones)."""
     def one(seq):
@@ -408,20 +403,62 @@ def two_op_neighbourhood(x):
     return np.fromiter(neigh, dtype=np.uint32)
 
 
-def test_seed2_conditions_are_necessary_for_d2(shim):
-    """bdg_core.cuh two-block seeds: D(a,b) <= 2 implies that one of the 20 key equalities holds, under either labelling
-    of the pair (so a join may fix a = min); checked on random near pairs, low-complexity and shifted pairs, and on the
-    complete two-operation neighbourhoods of random and repetitive seeds."""
+SCHEMES = {"4": [4, 4, 4, 3], "5": [3, 3, 3, 3, 3], "6": [3, 3, 3, 2, 2, 2]}
+
+
+def set_scheme(shim, name):
+    bases = SCHEMES[name]
+    n = shim.shim_scheme((C.c_int * len(bases))(*bases), len(bases))
+    assert n > 0
+    return n
+
+
+def scheme_first(shim, a, b):
+    """First (condition, orientation) a pair meets: by the definition and through the flag table; they must agree."""
+    slow = np.zeros(a.size, np.uint8); fast = np.zeros(a.size, np.uint8)
+    shim.shim_scheme_first(np.ascontiguousarray(a), np.ascontiguousarray(b), a.size, slow, fast)
+    assert np.array_equal(slow, fast)
+    return slow
+
+
+def test_seed_scheme_tables(shim):
+    """bdg_seed.cuh: number of conditions per block layout, symmetric ones first in every block set, keys of both sides."""
+    assert set_scheme(shim, "4") == 13 and shim.shim_scheme_nself() == 6
+    assert set_scheme(shim, "5") == 25 and shim.shim_scheme_nself() == 10
+    assert set_scheme(shim, "6") == 41 and shim.shim_scheme_nself() == 15
+    assert shim.shim_scheme((C.c_int * 3)(5, 5, 4), 3) == -1              # not 15 bases
+    rng = np.random.default_rng(4)
+    n = 1 << 18
+    a = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+    b = a ^ (rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32) & rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
+             & rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32))      # ~1/8 of the bits differ: many key hits, many misses
+    for name in SCHEMES:
+        nc = set_scheme(shim, name)
+        ka = np.zeros(n, np.uint32); kb = np.zeros(n, np.uint32); pred = np.zeros(n, np.uint8)
+        fired = np.zeros(n, bool)
+        first = scheme_first(shim, np.minimum(a, b), np.maximum(a, b))
+        for c in range(nc):
+            shim.shim_scheme_keys(c, np.minimum(a, b), np.maximum(a, b), n, ka, kb, pred)
+            bits = shim.shim_scheme_key_bits(c)
+            assert int(ka.max()) < (1 << bits) and int(kb.max()) < (1 << bits)
+            assert np.array_equal(pred.astype(bool), ka == kb)
+            assert shim.shim_scheme_row_sort(c) <= c
+            fired |= pred.astype(bool) & (first == 2 * c)
+        assert fired.sum() > 1000
+
+
+@pytest.mark.parametrize("name", ["4", "5", "6"])
+def test_seed_conditions_are_necessary_for_d2(shim, name):
+    """D(a,b) <= 2 implies that some condition holds for (min, max) or for (max, min): checked on random near pairs,
+    low-complexity and shifted pairs, and on the complete two-operation neighbourhoods of random and repetitive seeds."""
     L = orc.lib()
-    assert shim.shim_seed2_count() == 20
+    set_scheme(shim, name)
     tot = 0
     for seed in (5, 8):
         a, b = make_pairs(seed)
         D = np.fromiter((L.orc_D(int(x), int(y)) for x, y in zip(a, b)), np.int32, a.size)
         near = D <= 2
-        assert (seed2_first(shim, a, b)[near] >= 0).all()
-        assert (seed2_first(shim, b, a)[near] >= 0).all()
-        assert (seed2_first(shim, np.minimum(a, b), np.maximum(a, b))[near] >= 0).all()
+        assert (scheme_first(shim, np.minimum(a, b), np.maximum(a, b))[near] != 255).all()
         tot += int(near.sum())
     assert tot > 50000
     rng = np.random.default_rng(9)
@@ -433,107 +470,40 @@ def test_seed2_conditions_are_necessary_for_d2(shim):
         D = np.fromiter((L.orc_D(x, int(y)) for y in b), np.int32, b.size)
         near = D <= 2
         assert near.sum() > 1000
-        assert (seed2_first(shim, a, b)[near] >= 0).all() and (seed2_first(shim, b, a)[near] >= 0).all()
+        assert (scheme_first(shim, np.minimum(a, b), np.maximum(a, b))[near] != 255).all()
+    # and the seeds do select: a random pair meets a condition far less often than a single 5-base block (11 / 1024)
+    ra = rng.integers(0, 1 << 32, 1 << 20, dtype=np.uint64).astype(np.uint32)
+    rb = rng.integers(0, 1 << 32, 1 << 20, dtype=np.uint64).astype(np.uint32)
+    rate = (scheme_first(shim, np.minimum(ra, rb), np.maximum(ra, rb)) != 255).mean()
+    assert rate < {"4": 1.3e-3, "5": 2.5e-4, "6": 1.2e-4}[name]
 
 
-def test_seed2_keys_and_selectivity(shim):
-    """The join keys are what the predicate compares (14 or 16 bits), every condition fires on its own construction, and a
-    random pair meets some condition with probability ~ 69 / 65536 (an order of magnitude below the single-block passes)."""
-    rng = np.random.default_rng(4)
-    n = 1 << 21
-    ra = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
-    rb = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
-    first = seed2_first(shim, ra, rb)
-    rate = (first >= 0).mean()
-    assert 0.5 * 69 / 65536 < rate < 1.2 * 69 / 65536
-    ka = np.zeros(n, np.uint32); kb = np.zeros(n, np.uint32)
-    fired = np.zeros(n, bool)
-    for c in range(20):
-        shim.shim_seed2_keys(c, ra, rb, n, ka, kb)
-        bits = 14 if (4 <= c <= 6 or c >= 10) else 16
-        assert int(ka.max()) < (1 << bits) and int(kb.max()) < (1 << bits)
-        eq = ka == kb
-        assert np.array_equal(first == c, eq & ~fired)        # `first` is the lowest condition whose keys agree
-        fired |= eq
-        # construct a partner that meets condition c and nothing else is required: copy a's two blocks into b at the shifted place
-        blocks = {0: [(0, 0), (1, 0)]}
-        for k in range(1, 4): blocks[k] = [(1, k - 2), (2, k - 2)]
-        for k in range(4, 7): blocks[k] = [(2, k - 5), (3, k - 5)]
-        for k in range(7, 10): blocks[k] = [(0, 0), (2, k - 8)]
-        for k in range(10, 13): blocks[k] = [(0, 0), (3, k - 11)]
-        for k, (d1, d3) in enumerate([(-1, -1), (-1, 0), (0, -1), (0, 0), (0, 1), (1, 0), (1, 1)]):
-            blocks[13 + k] = [(1, d1), (3, d3)]
-        y = rb[:4096].astype(np.uint64)
-        x = ra[:4096].astype(np.uint64)
-        for blk, d in blocks[c]:
-            lo, nb = 8 * blk, (6 if blk == 3 else 8)
-            mask = np.uint64(((1 << nb) - 1) << (lo + 2 * d))
-            y = (y & ~mask) | (((x >> np.uint64(lo)) & np.uint64((1 << nb) - 1)) << np.uint64(lo + 2 * d))
-        shim.shim_seed2_keys(c, ra[:4096].copy(), y.astype(np.uint32), 4096, ka[:4096], kb[:4096])
-        assert np.array_equal(ka[:4096], kb[:4096]), c
-
-
-def test_seed2_sort_form(shim):
-    """The permuted words of a condition: a bijection (unpermute gives the barcode back), the join key on top (equal top
-    bits <=> the condition holds), order of the words = order of (key, remaining bits), and the tile test is conservative."""
-    rng = np.random.default_rng(6)
-    n = 1 << 18
-    a = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
-    b = a.copy()
-    flip = rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32) & rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32) \
-        & rng.integers(0, 1 << 32, n, dtype=np.uint64).astype(np.uint32)
-    b ^= flip                                                   # ~1/8 of the bits differ: many key hits, many misses
-    pa, pb, ua, ub, ka, kb_ = (np.zeros(n, np.uint32) for _ in range(6))
-    for c in range(20):
-        shim.shim_seed2_permute(c, a, b, n, pa, pb, ua, ub)
-        assert np.array_equal(ua, a) and np.array_equal(ub, b), c
-        bits = shim.shim_seed2_key_bits(c)
-        shim.shim_seed2_keys(c, a, b, n, ka, kb_)
-        assert np.array_equal(pa >> np.uint32(32 - bits), ka) and np.array_equal(pb >> np.uint32(32 - bits), kb_), c
-        assert np.unique(pa).size == np.unique(a).size               # injective
-        # tiles of the two sorted sides: whenever a tile pair holds an equal key, the tile test says so
-        sa, sb = np.sort(pa), np.sort(pb)
-        for _ in range(300):
-            i = int(rng.integers(0, n - 64)); j = int(np.searchsorted(sb >> np.uint32(32 - bits), sa[i] >> np.uint32(32 - bits)))
-            j = min(max(j + int(rng.integers(-200, 200)), 0), n - 64)
-            A, B = sa[i:i + 64], sb[j:j + 64]
-            hit = np.intersect1d(A >> np.uint32(32 - bits), B >> np.uint32(32 - bits)).size > 0
-            poss = bool(shim.shim_seed_tiles_meet(int(A[0]), int(A[-1]), int(B[0]), int(B[-1]), bits))
-            assert poss or not hit
-
-
-def test_seed2_join_passes_reproduce_the_oracle_edge_set(shim):
-    """The planned join passes, emulated in numpy: for every condition both sides are permuted and sorted, equal-key buckets
-    are paired, a pair is kept under the labelling a = min by the FIRST condition it meets, then the exact D and S decide.
-    The union over the 20 passes must be the oracle's edge set at t = 2, every edge exactly once."""
-    L = orc.lib()
+@pytest.mark.parametrize("name", ["4", "5"])
+def test_join_passes_reproduce_the_oracle_edge_set(shim, name):
+    """The passes of bdg_join.cuh emulated on the host with the kernel's own per-pair functions (sort by key, pair equal-key
+    buckets, quick test, dist_small, hand-over table, score): the union over the conditions must be the oracle's edge set at
+    t = 2, every edge exactly once."""
+    nc = set_scheme(shim, name)
     rng = synth.rng_for(91)
     cells = rng.integers(0, 1 << 32, 120, dtype=np.uint64).astype(np.uint32)
     obs, _ = synth.simulate_reads(cells, 9000, 0.06, rng)
     s = np.unique(obs)
     n = s.size
     wa, wb, wd, _ = orc.Index(s).edges(2)
-    want = sorted(zip(wa.tolist(), wb.tolist(), wd.tolist()))
-    got = []
-    pa, pb, ua, ub = (np.zeros(n, np.uint32) for _ in range(4))
-    n_cand = 0
-    for c in range(20):
-        shim.shim_seed2_permute(c, s, s, n, pa, pb, ua, ub)
-        bits = shim.shim_seed2_key_bits(c)
-        oa, ob = np.argsort(pa, kind="stable"), np.argsort(pb, kind="stable")          # sorted sides; the barcode rides along
-        ka, kb = pa[oa] >> np.uint32(32 - bits), pb[ob] >> np.uint32(32 - bits)
-        lo, hi = np.searchsorted(kb, ka, "left"), np.searchsorted(kb, ka, "right")
-        rows = np.repeat(np.arange(n), hi - lo)
-        cols = np.concatenate([np.arange(l, h) for l, h in zip(lo.tolist(), hi.tolist())]) if rows.size else np.empty(0, np.int64)
-        x, y = s[oa[rows]], s[ob[cols]]
-        keep = x < y
-        x, y = np.ascontiguousarray(x[keep]), np.ascontiguousarray(y[keep])
-        n_cand += x.size
-        first = seed2_first(shim, x, y)
-        for xv, yv in zip(x[first == c].tolist(), y[first == c].tolist()):
-            d = L.orc_D(xv, yv)
-            if d <= 2 and L.orc_S(xv, yv) >= 4:
-                got.append((xv, yv, d))
-    assert len(got) == len(set(got))                        # no pair twice
-    assert sorted(got) == want and len(want) > 5000
-    assert n_cand < 0.02 * n * (n - 1) / 2                  # the seeds leave a small share of the pairs (clustered data)
+    cap = 64 * n
+    a = np.empty(cap, np.uint32); b = np.empty(cap, np.uint32); d = np.empty(cap, np.uint8)
+    st = np.zeros(5 * (nc + 1), np.uint64)
+    k = shim.shim_join_emulate(s, n, a.ctypes.data, b.ctypes.data, d.ctypes.data, cap, st.ctypes.data)
+    assert k == wa.size and k > 5000
+    o = np.lexsort((b[:k], a[:k]))
+    assert np.array_equal(a[:k][o], wa) and np.array_equal(b[:k][o], wb) and np.array_equal(d[:k][o], wd)
+    tested, passed, near, mine, edges = (int(x) for x in st[:5])
+    assert edges == k and mine >= edges and near >= mine and passed >= near and tested >= passed
+    assert tested < 0.03 * n * (n - 1) / 2                  # the seeds leave a small share of the pairs (clustered data)
+
+
+def test_compact_score_equals_the_unrolled_one(shim):
+    a, b = make_pairs(11, n_near=30000, n_rand=10000, n_low=20000)
+    full = np.zeros(a.size, np.uint8); compact = np.zeros(a.size, np.uint8)
+    shim.shim_qgram_compact(a, b, a.size, full, compact)
+    assert np.array_equal(full, compact) and full.max() > 50
