@@ -151,8 +151,12 @@ def edges_handle(sorted_unique, t):
     return EdgeHandle(np.ascontiguousarray(sorted_unique, dtype=np.uint32), t)
 
 
+def edges_handle_resident(rm, t):
+    return EdgeHandle(np.ascontiguousarray(rm.sorted_distinct, dtype=np.uint32), t)
+
+
 def install(monkeypatch):
     from badger_b200 import ops
     for name in ("pack16", "edges_build", "edges_build_part", "member_sorted", "nearest_bounded", "kmer_score", "dedup_first_seen",
-                 "cluster_levels", "KmerIndex", "edges_handle", "dedup_reads", "assign_reads"):
+                 "cluster_levels", "KmerIndex", "edges_handle", "edges_handle_resident", "dedup_reads", "assign_reads"):
         monkeypatch.setattr(ops, name, globals()[name])
