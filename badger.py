@@ -98,17 +98,16 @@ def run_native(args, bc_len, true_barcodes):
         ranks[has] = packed
         whitelist = None
         if args.barcode_list:                                   # badger.py:82-88
-            w, wok = ops.pack16(tsvio.whitelist_records(args.barcode_list))
-            whitelist = ops.sorted_unique(w[wok])
+            whitelist = ops.pack16_sorted(tsvio.whitelist_records(args.barcode_list))     # packed, sorted, distinct: on the device
         tb = [rank(bc, bc_len) for bc in true_barcodes] if true_barcodes else None
-        centre, info = pipeline.assign_packed(ranks, has, threshold=args.threshold, n_cells=args.n_cells, interval=args.interval,
-                                              whitelist_sorted=whitelist, true_barcodes=tb, high_sens=args.high_sens,
-                                              centre_order="set")
+        (centre, has_centre), info = pipeline.assign_packed(ranks, has, threshold=args.threshold, n_cells=args.n_cells, interval=args.interval,
+                                                            whitelist_sorted=whitelist, true_barcodes=tb, high_sens=args.high_sens,
+                                                            centre_order="set", form="u32")
         logger.info("Graph construction done")
         print(1)                                                # barcode_graph.py:289 prints the round number
         print(2)
         logger.info("Clustering done")
-        tsv.write(args.output + "_output_file.tsv", centre)
+        tsv.write32(args.output + "_output_file.tsv", centre, has_centre)
         print(info["disconnected"])                             # badger.py:131-132
     return True
 

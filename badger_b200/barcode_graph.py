@@ -104,6 +104,64 @@ class _DistView:
         return ((k, self[k]) for k in self.keys())
 
 
+def rest_by_counts(ranks, counts, cutoff, need):
+    """bc_by_counts beyond the barcodes above the cutoff: the next `need` + 1 entries with count <= cutoff in count-descending
+    order, ties by first sighting (the short stretch the top-up loop of barcode_graph.py:273-276 may reach)."""
+    N = ranks.size
+    rest = np.nonzero(counts <= cutoff)[0]
+    m = min(rest.size, max(int(need) + 1, 1))
+    key = -counts[rest] * np.int64(N) + rest                                # unique: count-descending, then first-seen
+    pick = np.argpartition(key, m - 1)[:m] if m < rest.size else np.arange(rest.size)
+    return ranks[rest[pick[np.argsort(key[pick], kind="stable")]]]
+
+
+def walk_centres(N, n_cells, interval, top, hits, true_barcodes, have_list, rest_fn, bc_len=16):
+    """The walk of barcode_graph.py:259-277 over the head of `bc_by_counts`: top = the barcodes with count > cutoff in that
+    order, hits = their whitelist membership (None without a whitelist), rest_fn(need) = the entries that follow them, asked
+    for only when the top-up loop runs past the cutoff.  Same list, same order, same IndexError when N is too small."""
+    hi = n_cells + n_cells * interval * 0.01
+    lo = n_cells - n_cells * interval * 0.01
+    n_above = int(top.size)
+    rest_sorted = []
+
+    def by_counts_at(i, need):
+        if i < n_above:
+            return int(top[i])
+        if not rest_sorted:
+            rest_sorted.append(rest_fn(need))
+        j = i - n_above
+        if j >= rest_sorted[0].size:
+            raise IndexError("list index out of range")                     # :274 in the reference
+        return int(rest_sorted[0][j])
+
+    tbcs, n, i = [], 0, 0
+    if true_barcodes:
+        tbcs = [bc if isinstance(bc, (int, np.integer)) else rank(bc, bc_len) for bc in true_barcodes]   # packed callers pass ranks
+    elif have_list:
+        csum = np.cumsum(hits)
+        want = int(np.floor(hi)) + 1                                         # loop runs while n <= hi
+        if csum.size and csum[-1] >= want:
+            i = int(np.searchsorted(csum, want, side="left")) + 1
+            n = want
+        else:
+            i = n_above
+            n = int(csum[-1]) if csum.size else 0
+        tbcs = top[:i][hits[:i]].tolist()
+    else:
+        if n_above >= N and N <= int(np.floor(hi)) + 1:
+            raise IndexError("list index out of range")                     # :269 runs off the list
+        n = i = min(n_above, int(np.floor(hi)) + 1)
+        tbcs = top[:i].tolist()
+    missing = int(np.ceil(lo - n)) if n < lo else 0
+    while n < lo:
+        if i >= N:
+            raise IndexError("list index out of range")                     # :274 in the reference
+        tbcs.append(by_counts_at(i, missing))
+        i += 1
+        n += 1
+    return tbcs
+
+
 class BarcodeGraph:
 
     def __init__(self, threshold):
@@ -236,56 +294,14 @@ class BarcodeGraph:
         if first.size == 0:
             raise StatisticsError("mean requires at least one data point")
         cutoff = max((int(first.sum()) / first.size) / 5.0, 5)
-        hi = n_cells + n_cells * interval * 0.01
-        lo = n_cells - n_cells * interval * 0.01
         above = np.nonzero(self._cnt > cutoff)[0]                               # first-seen order
         above = above[np.argsort(-self._cnt[above], kind="stable")]             # count-descending, ties by first sighting
-        n_above = int(above.size)
         top = self._ranks[above]                                                # bc_by_counts[:n_above]
-        rest_sorted = []                                                        # bc_by_counts[n_above:], built on demand
-
-        def by_counts_at(i, need):
-            """bc_by_counts[i] with the guarantee that the next `need` positions are sorted as well."""
-            if i < n_above:
-                return int(top[i])
-            if not rest_sorted:
-                rest = np.nonzero(self._cnt <= cutoff)[0]
-                m = min(rest.size, max(int(need) + 1, 1))
-                key = -self._cnt[rest] * np.int64(N) + rest                    # unique: count-descending, then first-seen
-                pick = np.argpartition(key, m - 1)[:m] if m < rest.size else np.arange(rest.size)
-                rest_sorted.append(self._ranks[rest[pick[np.argsort(key[pick], kind="stable")]]])
-            j = i - n_above
-            if j >= rest_sorted[0].size:
-                raise IndexError("list index out of range")                     # :274 in the reference
-            return int(rest_sorted[0][j])
-
-        tbcs, n, i = [], 0, 0
-        if true_barcodes:
-            tbcs = [bc if isinstance(bc, int) else rank(bc, bc_len) for bc in true_barcodes]   # packed callers pass ranks
-        elif barcode_list:
-            hits = self._whitelist_hits(barcode_list, bc_len, top) if n_above else np.zeros(0, bool)
-            csum = np.cumsum(hits)
-            want = int(np.floor(hi)) + 1                                         # loop runs while n <= hi
-            if csum.size and csum[-1] >= want:
-                i = int(np.searchsorted(csum, want, side="left")) + 1
-                n = want
-            else:
-                i = n_above
-                n = int(csum[-1]) if csum.size else 0
-            tbcs = top[:i][hits[:i]].tolist()
-        else:
-            if n_above >= N and N <= int(np.floor(hi)) + 1:
-                raise IndexError("list index out of range")                     # :269 runs off the list
-            n = i = min(n_above, int(np.floor(hi)) + 1)
-            tbcs = top[:i].tolist()
-        missing = int(np.ceil(lo - n)) if n < lo else 0
-        while n < lo:
-            if i >= N:
-                raise IndexError("list index out of range")                     # :274 in the reference
-            tbcs.append(by_counts_at(i, missing))
-            i += 1
-            n += 1
-        return tbcs
+        hits = None
+        if not true_barcodes and barcode_list:
+            hits = self._whitelist_hits(barcode_list, bc_len, top) if top.size else np.zeros(0, bool)
+        return walk_centres(N, n_cells, interval, top, hits, true_barcodes, bool(barcode_list),
+                            lambda need: rest_by_counts(self._ranks, self._cnt, cutoff, need), bc_len)
 
     # ------------------------------------------------------------------ clustering (GPU rounds, dict views on the host)
     def cluster(self, true_barcodes, barcode_list, n_cells, bc_len, interval):

@@ -5,6 +5,7 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
@@ -20,6 +21,8 @@
 
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
+#include <cub/device/device_select.cuh>
+#include <thrust/iterator/counting_iterator.h>
 #include <thrust/iterator/transform_iterator.h>
 
 namespace {
@@ -85,7 +88,9 @@ struct DevCtx {
     unsigned long long host_stats[bdg::MAX_PASSES][2] = {};   // interval tests done / tiles listed per pass of the last launch
     unsigned long long generation = 0;                        // bumped by every host-buffer edge build on this device
     Buf dd[10];                                               // dedup: keys, idx, sorted keys/idx, heads, scan, run arrays, cub scratch
-    Buf cl[6];                                                // clustering: centres, centre index, level, claim min / max, index scratch
+    Buf cl[6];                                                // clustering: centres, centre index, level, claim min / max, flags
+    unsigned long long cl_token = 0;                          // read-map token the clustering result resident in cl[1] / cl[2] belongs to (0: none)
+    Buf ce[9];                                                // centre selection: positions above the cutoff, sort keys / values, results, scratch
     Buf as[8];                                                // masked dedup + per-read gather: all ranks, valid bytes, their scan, scratch, centre idx / value, result, counter
     unsigned long long map_token = 0, map_serial = 0;         // read map left on the device by bdg_dedup_reads (0: none)
     size_t map_rows = 0, map_reads = 0, map_distinct = 0;
@@ -96,7 +101,7 @@ struct DevCtx {
     // join form of the t = 2 edge construction (bdg_join.cuh): barcodes in the key order of every condition's row side / column
     // side, first column of every key, scratch keys (in / sorted) and radix-sort scratch, units per slab and their prefix sums
     // (one set per stream: the conditions of a block set run back to back on one stream)
-    Buf jn_rows[2], jn_cols[2], jn_tab[2], jn_key_in[2], jn_key_out[2], jn_cub[2], jn_counts[2], jn_offs[2], jn_lut;
+    Buf jn_rows[2], jn_cols[2], jn_tab[2], jn_tabc[2], jn_hist[2], jn_cub[2], jn_counts[2], jn_offs[2], jn_lut;
     int scheme_serial = 0;                                    // which scheme sits in this device's constant memory (0: none)
 };
 std::vector<DevCtx> g_ctx;
@@ -231,8 +236,8 @@ void launch_tiles_bip(int blocks, cudaStream_t st, const bdg::EdgeWork& w, const
 
 // Join form (t = 2), bdg_join.cuh.  The seed conditions are laid on a line by weight (a symmetric condition pairs each couple
 // once: weight 1; a shifted one pairs both value orders: weight 2) and the line is cut into nparts equal pieces: a part sorts and
-// joins only the conditions its piece touches, a condition on a cut is shared by unit range.  Per condition: keys -> radix sort
-// (rows once per block set, columns for the shifted conditions) -> first column of every key -> units per slab -> prefix sums ->
+// joins only the conditions its piece touches, a condition on a cut is shared by unit range.  Per condition: counting sort by the
+// key (rows once per block set, columns for the shifted conditions; its prefix sums are colstart) -> units per slab -> prefix sums ->
 // one persistent join launch.  The conditions of a block set follow one another and share the row order.  Consecutive block sets alternate between the caller's stream and an auxiliary one, so that one
 // condition's sorts and the tail of its join overlap the neighbour's join.
 int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, uint32_t* d_a, uint32_t* d_b, uint8_t* d_d, size_t cap,
@@ -265,13 +270,19 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
     CU_TRY(cudaMemsetAsync(d_plan, 0, PLAN_HDR * bdg::MAX_PASSES + 8 * bdg::SEED_MAX_CONDS, caller));
     for (int p = 0; p < bdg::MAX_PASSES; p++) ws->host_stats[p][0] = ws->host_stats[p][1] = 0;
     unsigned long long* d_cursors = (unsigned long long*)(d_plan + PLAN_HDR * bdg::MAX_PASSES);
-    size_t tmp_sort = 0, tmp_scan = 0;
-    CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_sort, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)N, 0, 24, caller));
-    CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_scan, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)(n_slabs + 1), caller));
-    const size_t tmp_bytes = std::max(tmp_sort, tmp_scan);
+    int max_bits = 0;
+    for (int c = 0; c < S.nconds; c++) max_bits = std::max(max_bits, (int)S.ka[c].key_bits);
+    const size_t max_keys = (size_t)1 << max_bits;
+    size_t tmp_a = 0, tmp_b = 0;
+    CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)(max_keys + 1), caller));
+    CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_b, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)(n_slabs + 1), caller));
+    const size_t tmp_bytes = std::max(tmp_a, tmp_b);
     for (int k = 0; k < 2; k++) {                           // one scratch set per stream
-        if (int e = ensure(ws->jn_key_in[k], N * 4)) return e;
-        if (int e = ensure(ws->jn_key_out[k], N * 4)) return e;
+        if (int e = ensure(ws->jn_hist[k], (max_keys + 1) * 4 * 2)) return e;       // bucket sizes | fill cursors
+        if (int e = ensure(ws->jn_tab[k], (max_keys + 1) * 4)) return e;
+        if (int e = ensure(ws->jn_tabc[k], (max_keys + 1) * 4)) return e;
+        if (int e = ensure(ws->jn_rows[k], N * 4)) return e;
+        if (int e = ensure(ws->jn_cols[k], N * 4)) return e;
         if (int e = ensure(ws->jn_cub[k], tmp_bytes)) return e;
         if (int e = ensure(ws->jn_counts[k], ((size_t)n_slabs + 1) * 4)) return e;
         if (int e = ensure(ws->jn_offs[k], ((size_t)n_slabs + 1) * 4)) return e;
@@ -297,28 +308,30 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
         if (new_set) { cur_set = set; k ^= 1; }
         cudaStream_t st = (fork && k == 1) ? ws->aux[1] : caller;
         if (fork && k == 1 && !aux_used) { CU_TRY(cudaStreamWaitEvent(st, ws->ev_start, 0)); aux_used = true; }
-        uint32_t* key_in = (uint32_t*)ws->jn_key_in[k].p;
-        uint32_t* key_out = (uint32_t*)ws->jn_key_out[k].p;
-        auto sort_side = [&](const bdg::SeedKey& key, Buf& dst) -> int {
-            if (int e = ensure(dst, N * 4)) return e;
-            bdg::join_keys_kernel<<<gb, 256, 0, st>>>(d_sorted, key_in, (uint32_t)N, key);
-            g_launches++;
+        // counting sort of the barcodes by one side's key: bucket sizes -> first position of every key (kept: colstart) -> scatter
+        auto bucket_side = [&](const bdg::SeedKey& key, Buf& dst, Buf& table) -> int {
+            const size_t nkeys = (size_t)1 << key.key_bits;
+            uint32_t* hist = (uint32_t*)ws->jn_hist[k].p;
+            uint32_t* fill = hist + (nkeys + 1);
+            CU_TRY(cudaMemsetAsync(hist, 0, (nkeys + 1) * 4 * 2, st));
+            bdg::join_hist_kernel<<<gb, 256, 0, st>>>(d_sorted, (uint32_t)N, key, hist);
             size_t bytes = ws->jn_cub[k].cap;
-            CU_TRY(cub::DeviceRadixSort::SortPairs(ws->jn_cub[k].p, bytes, (const uint32_t*)key_in, key_out, d_sorted, (uint32_t*)dst.p, (int)N, 0, (int)key.key_bits, st));
+            CU_TRY(cub::DeviceScan::ExclusiveSum(ws->jn_cub[k].p, bytes, (const uint32_t*)hist, (uint32_t*)table.p, (int)(nkeys + 1), st));
+            bdg::join_scatter_kernel<<<gb, 256, 0, st>>>(d_sorted, (uint32_t)N, key, (const uint32_t*)table.p, fill, (uint32_t*)dst.p);
+            g_launches += 2;
             return BDG_OK;
         };
-        if (new_set) { if (int e = sort_side(S.ka[c], ws->jn_rows[k])) return e; }      // the stream's row order: this block set
+        if (new_set) { if (int e = bucket_side(S.ka[c], ws->jn_rows[k], ws->jn_tab[k])) return e; }      // the stream's row order: this block set
         bdg::JoinArgs A{};
         A.rows = (const uint32_t*)ws->jn_rows[k].p;
-        if (S.cond[c].self) A.cols = A.rows;
-        else {
-            if (int e = sort_side(S.kb[c], ws->jn_cols[k])) return e;
+        if (S.cond[c].self) {
+            A.cols = A.rows;
+            A.colstart = (const uint32_t*)ws->jn_tab[k].p;
+        } else {
+            if (int e = bucket_side(S.kb[c], ws->jn_cols[k], ws->jn_tabc[k])) return e;
             A.cols = (const uint32_t*)ws->jn_cols[k].p;
+            A.colstart = (const uint32_t*)ws->jn_tabc[k].p;
         }
-        const uint32_t nkeys = 1u << S.kb[c].key_bits;
-        if (int e = ensure(ws->jn_tab[k], ((size_t)nkeys + 1) * 4)) return e;
-        bdg::join_colstart_kernel<<<gb, 256, 0, st>>>(A.cols, (uint32_t)N, S.kb[c], nkeys, (uint32_t*)ws->jn_tab[k].p);
-        A.colstart = (const uint32_t*)ws->jn_tab[k].p;
         A.offs = (const uint32_t*)ws->jn_offs[k].p;
         A.lut = (const uint8_t*)ws->jn_lut.p;
         A.cursor = d_cursors + c;
@@ -660,9 +673,10 @@ void bdg_shutdown(void)
         for (auto& b : c.cl) b.release();
         c.gather_a.release(); c.gather_b.release();
         for (auto& b : c.as) b.release();
+        for (auto& b : c.ce) b.release();
         for (auto& b : c.rot_sorted) b.release();
         for (int k = 0; k < 2; k++) {
-            c.jn_rows[k].release(); c.jn_cols[k].release(); c.jn_tab[k].release(); c.jn_key_in[k].release(); c.jn_key_out[k].release();
+            c.jn_rows[k].release(); c.jn_cols[k].release(); c.jn_tab[k].release(); c.jn_tabc[k].release(); c.jn_hist[k].release();
             c.jn_cub[k].release(); c.jn_counts[k].release(); c.jn_offs[k].release();
         }
         c.jn_lut.release();
@@ -886,8 +900,8 @@ static int dedup_core(DevCtx& c, uint32_t n, uint32_t* distinct, uint32_t* count
     uint32_t *d_distinct = d_sk, *d_counts = d_k, *d_pos = d_head;
     bdg::dedup_finish_kernel<<<blocks, 256, 0, st>>>(d_i, d_rk, d_rs, n_runs, n, d_distinct, d_counts, d_pos);
     g_launches += 2;
-    CU_TRY(cudaMemcpyAsync(distinct, d_distinct, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(counts, d_counts, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st));
+    if (distinct) CU_TRY(cudaMemcpyAsync(distinct, d_distinct, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st));
+    if (counts) CU_TRY(cudaMemcpyAsync(counts, d_counts, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st));
     if (sorted_pos) CU_TRY(cudaMemcpyAsync(sorted_pos, d_i, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st));   // order[pos] = run = ascending position
     if (sorted_distinct) CU_TRY(cudaMemcpyAsync(sorted_distinct, d_rk, (size_t)n_runs * 4, cudaMemcpyDeviceToHost, st));   // runs are numbered in key order
     if (keep_map || read_to_distinct) {
@@ -926,13 +940,14 @@ int bdg_dedup_reads(const uint32_t* ranks, const uint8_t* valid, size_t R_all, u
     if (!n_distinct || !n_valid || !token) return fail(BDG_ERR_ARG, "NULL result pointer");
     *n_distinct = 0; *n_valid = 0; *token = 0;
     if (R_all == 0) return BDG_OK;
-    if (!ranks || !distinct || !counts) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if (!ranks) return fail(BDG_ERR_ARG, "NULL pointer argument");
     if (R_all > 0x7FFFFFFFull) return fail(BDG_ERR_ARG, "more than 2^31 reads in one call");
     if (int rc = need_ctx()) return rc;
     DevCtx& c = g_ctx[0];
     CU_TRY(cudaSetDevice(c.dev));
     cudaStream_t st = c.stream;
     c.map_token = 0;
+    c.cl_token = 0;
     auto ensure = [&](Buf& b, size_t bytes) -> int {
         if (cudaError_t e = (cudaError_t)b.ensure(bytes))
             return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation of %zu bytes: %s", bytes, cudaGetErrorString(e));
@@ -974,6 +989,167 @@ int bdg_dedup_reads(const uint32_t* ranks, const uint8_t* valid, size_t R_all, u
     c.map_distinct = *n_distinct;
     c.map_token = ++c.map_serial;
     *token = c.map_token;
+    return BDG_OK;
+}
+
+// What bdg_dedup_reads left on the device, on demand (any pointer may be NULL): the arrays of its output list.
+int bdg_dedup_fetch(unsigned long long token, uint32_t* distinct, uint32_t* counts, uint32_t* sorted_pos, uint32_t* sorted_distinct)
+{
+    if (int rc = need_ctx()) return rc;
+    DevCtx& c = g_ctx[0];
+    if (token == 0 || token != c.map_token) return fail(BDG_ERR_ARG, "stale read-map token: a later dedup call has reused the workspaces");
+    CU_TRY(cudaSetDevice(c.dev));
+    const size_t n = c.map_distinct;
+    if (distinct) CU_TRY(cudaMemcpyAsync(distinct, c.dd[2].p, n * 4, cudaMemcpyDeviceToHost, c.stream));
+    if (counts) CU_TRY(cudaMemcpyAsync(counts, c.dd[0].p, n * 4, cudaMemcpyDeviceToHost, c.stream));
+    if (sorted_pos) CU_TRY(cudaMemcpyAsync(sorted_pos, c.dd[1].p, n * 4, cudaMemcpyDeviceToHost, c.stream));
+    if (sorted_distinct) CU_TRY(cudaMemcpyAsync(sorted_distinct, c.dd[6].p, n * 4, cudaMemcpyDeviceToHost, c.stream));
+    CU_TRY(cudaStreamSynchronize(c.stream));
+    return BDG_OK;
+}
+
+// ---- a-6 / centre selection, barcode_graph.py:252-267, over the distinct barcodes a dedup call left on the device ----
+// cutoff = max(mean(counts of the first n_cells barcodes in first-seen order) / 5, 5) (:255-256); the barcodes with
+// count > cutoff in count-descending order, ties in first-seen order (the head of `bc_by_counts`, :253), with their counts and
+// - when a whitelist is given - their membership (:264).  The short walk over that head stays with the caller.
+int bdg_centres_above(unsigned long long token, size_t n_cells, const uint32_t* sorted_wl, size_t W, uint32_t* top_ranks, uint32_t* top_counts,
+                      uint8_t* top_hits, size_t cap, size_t* n_above, double* cutoff)
+{
+    if (!n_above || !cutoff) return fail(BDG_ERR_ARG, "NULL result pointer");
+    *n_above = 0; *cutoff = 0.0;
+    if (int rc = need_ctx()) return rc;
+    DevCtx& c = g_ctx[0];
+    if (token == 0 || token != c.map_token) return fail(BDG_ERR_ARG, "stale read-map token: a later dedup call has reused the workspaces");
+    const size_t N = c.map_distinct;
+    const size_t first = std::min(n_cells, N);
+    if (first == 0) return fail(BDG_ERR_ARG, "mean requires at least one data point");
+    CU_TRY(cudaSetDevice(c.dev));
+    cudaStream_t st = c.stream;
+    auto ensure = [&](Buf& b, size_t bytes) -> int {
+        if (cudaError_t e = (cudaError_t)b.ensure(bytes))
+            return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation of %zu bytes: %s", bytes, cudaGetErrorString(e));
+        return BDG_OK;
+    };
+    const uint32_t* d_distinct = (const uint32_t*)c.dd[2].p;
+    const uint32_t* d_counts = (const uint32_t*)c.dd[0].p;
+    // ce[0] selected positions, [1] keys, [2] sorted keys, [3] sorted positions, [4] top ranks, [5] top counts, [6] hits, [7] scalars + cub scratch
+    if (int e = ensure(c.ce[7], 64)) return e;
+    unsigned long long* d_sum = (unsigned long long*)c.ce[7].p;
+    uint32_t* d_nsel = (uint32_t*)((char*)c.ce[7].p + 8);
+    CU_TRY(cudaMemsetAsync(d_sum, 0, 16, st));
+    bdg::sum_first_kernel<<<(int)std::min<size_t>((first + 255) / 256, (size_t)c.sms * 4), 256, 0, st>>>(d_counts, (uint32_t)first, d_sum);
+    g_launches++;
+    unsigned long long sum = 0;
+    CU_TRY(cudaMemcpyAsync(&sum, d_sum, 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    const double cut = std::max(((double)sum / (double)first) / 5.0, 5.0);
+    *cutoff = cut;
+    const uint32_t thr = (uint32_t)std::floor(cut);          // counts are integers: count > cutoff <=> count > floor(cutoff)
+    if (int e = ensure(c.ce[0], N * 4)) return e;
+    thrust::counting_iterator<uint32_t> all(0);
+    bdg::CountAbove pred{d_counts, thr};
+    size_t tmp = 0;
+    CU_TRY(cub::DeviceSelect::If(nullptr, tmp, all, (uint32_t*)c.ce[0].p, d_nsel, (int)N, pred, st));
+    if (int e = ensure(c.ce[8], tmp)) return e;
+    CU_TRY(cub::DeviceSelect::If(c.ce[8].p, tmp, all, (uint32_t*)c.ce[0].p, d_nsel, (int)N, pred, st));
+    uint32_t nsel = 0;
+    CU_TRY(cudaMemcpyAsync(&nsel, d_nsel, 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    *n_above = nsel;
+    if (nsel == 0) return BDG_OK;
+    if (nsel > cap) return fail(BDG_ERR_CAPACITY, "%u barcodes above the cutoff but room for %zu", nsel, cap);
+    if (!top_ranks || !top_counts) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    for (int k = 1; k <= 5; k++) if (int e = ensure(c.ce[k], (size_t)nsel * 4)) return e;
+    if (int e = ensure(c.ce[6], nsel)) return e;
+    const int nb = (int)std::min<size_t>(((size_t)nsel + 255) / 256, (size_t)c.sms * 4);
+    bdg::centres_keys_kernel<<<nb, 256, 0, st>>>((const uint32_t*)c.ce[0].p, d_counts, nsel, (uint32_t*)c.ce[1].p);
+    size_t tmp2 = 0;
+    CU_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp2, (const uint32_t*)c.ce[1].p, (uint32_t*)c.ce[2].p, (const uint32_t*)c.ce[0].p, (uint32_t*)c.ce[3].p, (int)nsel, 0, 32, st));
+    if (int e = ensure(c.ce[8], tmp2)) return e;
+    CU_TRY(cub::DeviceRadixSort::SortPairs(c.ce[8].p, tmp2, (const uint32_t*)c.ce[1].p, (uint32_t*)c.ce[2].p, (const uint32_t*)c.ce[0].p, (uint32_t*)c.ce[3].p, (int)nsel, 0, 32, st));
+    bdg::centres_gather_kernel<<<nb, 256, 0, st>>>((const uint32_t*)c.ce[3].p, d_distinct, d_counts, nsel, (uint32_t*)c.ce[4].p, (uint32_t*)c.ce[5].p);
+    g_launches += 2;
+    CU_TRY(cudaGetLastError());
+    if (top_hits) {
+        if (W > 0xFFFFFFFFull) return fail(BDG_ERR_ARG, "size exceeds 2^32");
+        if (W && !sorted_wl) return fail(BDG_ERR_ARG, "NULL pointer argument");
+        if (int e = ensure(c.io[0], std::max<size_t>(W, 1) * 4)) return e;
+        if (int e = ensure(c.io[3], 8)) return e;
+        unsigned long long* d_bad = (unsigned long long*)c.io[3].p;
+        CU_TRY(cudaMemcpyAsync(c.io[0].p, sorted_wl, W * 4, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemsetAsync(d_bad, 0xFF, 8, st));
+        if (W > 1) {
+            bdg::sorted_check_kernel<false><<<(int)std::min<size_t>((W + 255) / 256, (size_t)c.sms * 8), 256, 0, st>>>((const uint32_t*)c.io[0].p, (uint32_t)W, d_bad);
+            g_launches++;
+        }
+        if (int rc = bdg_dev_member_sorted((const uint32_t*)c.io[0].p, W, (const uint32_t*)c.ce[4].p, nsel, (uint8_t*)c.ce[6].p, st)) return rc;
+        unsigned long long first_bad = ~0ull;
+        CU_TRY(cudaMemcpyAsync(top_hits, c.ce[6].p, nsel, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(&first_bad, d_bad, 8, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(top_ranks, c.ce[4].p, (size_t)nsel * 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaMemcpyAsync(top_counts, c.ce[5].p, (size_t)nsel * 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        if (first_bad != ~0ull) return fail(BDG_ERR_ARG, "whitelist not sorted at index %llu", first_bad);
+        return BDG_OK;
+    }
+    CU_TRY(cudaMemcpyAsync(top_ranks, c.ce[4].p, (size_t)nsel * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(top_counts, c.ce[5].p, (size_t)nsel * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    return BDG_OK;
+}
+
+// bdg_assign_reads with a 5-byte result per row (centre barcode + "has a centre" byte).  centre_idx == NULL: the clustering a
+// bdg_cluster_resident call left on the device is used in place (nothing is uploaded).
+int bdg_assign_reads32(unsigned long long token, const int32_t* centre_idx, size_t N, uint32_t* centre_per_row, uint8_t* has_centre, size_t R_all,
+                       size_t* n_assigned)
+{
+    if (n_assigned) *n_assigned = 0;
+    if (R_all == 0) return BDG_OK;
+    if (!centre_per_row || !has_centre) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if (int rc = need_ctx()) return rc;
+    DevCtx& c = g_ctx[0];
+    if (token == 0 || token != c.map_token) return fail(BDG_ERR_ARG, "stale read-map token: a later dedup call has reused the workspaces");
+    if (N != c.map_distinct || R_all != c.map_rows) return fail(BDG_ERR_ARG, "sizes do not match the dedup call the token came from");
+    if (!centre_idx && N && c.cl_token != token) return fail(BDG_ERR_ARG, "no clustering result of this dedup call is resident on the device (bdg_cluster_resident)");
+    CU_TRY(cudaSetDevice(c.dev));
+    cudaStream_t st = c.stream;
+    auto ensure = [&](Buf& b, size_t bytes) -> int {
+        if (cudaError_t e = (cudaError_t)b.ensure(bytes))
+            return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation of %zu bytes: %s", bytes, cudaGetErrorString(e));
+        return BDG_OK;
+    };
+    // as[4] centre index per node (upload), as[5] centre value + has byte per distinct barcode, as[6] result per row, as[7] counter
+    if (int e = ensure(c.as[5], std::max<size_t>(N, 1) * 5)) return e;
+    if (int e = ensure(c.as[6], R_all * 5)) return e;
+    if (int e = ensure(c.as[7], 8)) return e;
+    const int32_t* d_ci = (const int32_t*)c.cl[1].p;
+    if (centre_idx) {
+        if (int e = ensure(c.as[4], std::max<size_t>(N, 1) * 4)) return e;
+        CU_TRY(cudaMemcpyAsync(c.as[4].p, centre_idx, N * 4, cudaMemcpyHostToDevice, st));
+        d_ci = (const int32_t*)c.as[4].p;
+    }
+    CU_TRY(cudaMemsetAsync(c.as[7].p, 0, 8, st));
+    uint32_t* d_cv = (uint32_t*)c.as[5].p;
+    uint8_t* d_ch = (uint8_t*)c.as[5].p + std::max<size_t>(N, 1) * 4;
+    uint32_t* d_out = (uint32_t*)c.as[6].p;
+    uint8_t* d_oh = (uint8_t*)c.as[6].p + R_all * 4;
+    if (N) {
+        const int nb = (int)std::min<size_t>((N + 255) / 256, (size_t)c.sms * 8);
+        bdg::centre_of_distinct32_kernel<<<nb, 256, 0, st>>>(d_ci, (const uint32_t*)c.dd[1].p /* first-seen -> node */,
+                                                             (const uint32_t*)c.dd[6].p /* node -> barcode */, (uint32_t)N, d_cv, d_ch);
+    }
+    const int rb = (int)std::min<size_t>((R_all + 255) / 256, (size_t)c.sms * 8);
+    bdg::assign_reads32_kernel<<<rb, 256, 0, st>>>(d_cv, d_ch, (const uint32_t*)c.dd[7].p, c.map_masked ? (const uint8_t*)c.as[1].p : nullptr,
+                                                   c.map_masked ? (const uint32_t*)c.as[2].p : nullptr, (uint32_t)R_all, d_out, d_oh,
+                                                   (unsigned long long*)c.as[7].p);
+    g_launches += 2;
+    CU_TRY(cudaGetLastError());
+    unsigned long long cnt = 0;
+    CU_TRY(cudaMemcpyAsync(centre_per_row, d_out, R_all * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(has_centre, d_oh, R_all, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(&cnt, c.as[7].p, 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (n_assigned) *n_assigned = (size_t)cnt;
     return BDG_OK;
 }
 
@@ -1038,6 +1214,54 @@ int bdg_pack16(const char* seqs, size_t R, uint32_t* out, uint8_t* valid)
     return BDG_OK;
 }
 
+
+// badger.py:82-88 for the array pipeline: the whitelist records packed (a-1), the invalid ones dropped, sorted and made
+// distinct on the device (cub radix sort + unique); out_sorted has room for R entries, *n receives the number kept.
+int bdg_pack16_sorted(const char* seqs, size_t R, uint32_t* out_sorted, size_t* n)
+{
+    if (!n) return fail(BDG_ERR_ARG, "NULL result pointer");
+    *n = 0;
+    if (R == 0) return BDG_OK;
+    if (!seqs || !out_sorted) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if (R > 0x7FFFFFFFull) return fail(BDG_ERR_ARG, "more than 2^31 records in one call");
+    if (int rc = need_ctx()) return rc;
+    DevCtx& c = g_ctx[0];
+    CU_TRY(cudaSetDevice(c.dev));
+    cudaStream_t st = c.stream;
+    auto ensure = [&](Buf& b, size_t bytes) -> int {
+        if (cudaError_t e = (cudaError_t)b.ensure(bytes))
+            return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation of %zu bytes: %s", bytes, cudaGetErrorString(e));
+        return BDG_OK;
+    };
+    // io[0] letters, io[1] ranks, io[2] validity; ce[0] kept ranks, ce[1] sorted, ce[2] distinct, ce[7] count, ce[8] cub scratch
+    if (int e = ensure(c.io[0], R * 16)) return e;
+    if (int e = ensure(c.io[1], R * 4)) return e;
+    if (int e = ensure(c.io[2], R)) return e;
+    for (int k = 0; k < 3; k++) if (int e = ensure(c.ce[k], R * 4)) return e;
+    if (int e = ensure(c.ce[7], 64)) return e;
+    uint32_t* d_n = (uint32_t*)c.ce[7].p;
+    CU_TRY(cudaMemcpyAsync(c.io[0].p, seqs, R * 16, cudaMemcpyHostToDevice, st));
+    if (int rc = bdg_dev_pack16((const char*)c.io[0].p, R, (uint32_t*)c.io[1].p, (uint8_t*)c.io[2].p, st)) return rc;
+    size_t t1 = 0, t2 = 0, t3 = 0;
+    CU_TRY(cub::DeviceSelect::Flagged(nullptr, t1, (const uint32_t*)c.io[1].p, (const uint8_t*)c.io[2].p, (uint32_t*)c.ce[0].p, d_n, (int)R, st));
+    CU_TRY(cub::DeviceRadixSort::SortKeys(nullptr, t2, (const uint32_t*)c.ce[0].p, (uint32_t*)c.ce[1].p, (int)R, 0, 32, st));
+    CU_TRY(cub::DeviceSelect::Unique(nullptr, t3, (const uint32_t*)c.ce[1].p, (uint32_t*)c.ce[2].p, d_n, (int)R, st));
+    if (int e = ensure(c.ce[8], std::max(t1, std::max(t2, t3)))) return e;
+    CU_TRY(cub::DeviceSelect::Flagged(c.ce[8].p, t1, (const uint32_t*)c.io[1].p, (const uint8_t*)c.io[2].p, (uint32_t*)c.ce[0].p, d_n, (int)R, st));
+    uint32_t kept = 0;
+    CU_TRY(cudaMemcpyAsync(&kept, d_n, 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (kept == 0) return BDG_OK;
+    CU_TRY(cub::DeviceRadixSort::SortKeys(c.ce[8].p, t2, (const uint32_t*)c.ce[0].p, (uint32_t*)c.ce[1].p, (int)kept, 0, 32, st));
+    CU_TRY(cub::DeviceSelect::Unique(c.ce[8].p, t3, (const uint32_t*)c.ce[1].p, (uint32_t*)c.ce[2].p, d_n, (int)kept, st));
+    uint32_t distinct = 0;
+    CU_TRY(cudaMemcpyAsync(&distinct, d_n, 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    CU_TRY(cudaMemcpyAsync(out_sorted, c.ce[2].p, (size_t)distinct * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    *n = distinct;
+    return BDG_OK;
+}
 
 // One device's share of a host-buffer edge build: upload, launch, read the count back (re-run once with the exact
 // size when the guess was too small).  Runs on its own host thread when several devices take part, because the
@@ -1242,8 +1466,9 @@ void bdg_edges_free(bdg_edges* e) { delete e; }
 
 // ---- f-3  cluster(): barcode_graph.py:279-301 -------------------------------------------------------------
 // d_ea / d_eb hold barcode VALUES on entry and node indices on return (converted in place).
+// centre_idx / level may be NULL: the result then only stays on the device (cl[1] / cl[2]) for bdg_assign_reads*.
 static int cluster_on_device(DevCtx& c, const uint32_t* d_sorted, size_t N, uint32_t* d_ea, uint32_t* d_eb, size_t E,
-                             const uint32_t* centres, size_t C, int rounds, int32_t* centre_idx, uint8_t* level)
+                             const uint32_t* centres, size_t C, int rounds, int32_t* centre_idx, uint8_t* level, size_t* n_has_edge = nullptr)
 {
     auto ensure = [&](Buf& b, size_t bytes) -> int {
         if (cudaError_t e = (cudaError_t)b.ensure(bytes))
@@ -1256,7 +1481,8 @@ static int cluster_on_device(DevCtx& c, const uint32_t* d_sorted, size_t N, uint
     if (int e = ensure(c.cl[2], N)) return e;
     if (int e = ensure(c.cl[3], N * 4)) return e;
     if (int e = ensure(c.cl[4], N * 4)) return e;
-    if (int e = ensure(c.cl[5], 4)) return e;
+    if (int e = ensure(c.cl[5], 16)) return e;
+    c.cl_token = 0;                                        // the resident result is about to be overwritten
     unsigned int* d_bad = (unsigned int*)c.cl[5].p;
     CU_TRY(cudaMemsetAsync(d_bad, 0, 4, c.stream));
     uint32_t* d_cen = (uint32_t*)c.cl[0].p;
@@ -1283,12 +1509,21 @@ static int cluster_on_device(DevCtx& c, const uint32_t* d_sorted, size_t N, uint
     }
     CU_TRY(cudaGetLastError());
     if (trace) { cudaStreamSynchronize(st); tr2 = now_ms(); }
-    CU_TRY(cudaMemcpyAsync(centre_idx, d_ci, N * 4, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaMemcpyAsync(level, d_lv, N, cudaMemcpyDeviceToHost, st));
+    if (centre_idx) CU_TRY(cudaMemcpyAsync(centre_idx, d_ci, N * 4, cudaMemcpyDeviceToHost, st));
+    if (level) CU_TRY(cudaMemcpyAsync(level, d_lv, N, cudaMemcpyDeviceToHost, st));
+    unsigned long long has_edge = 0;
+    if (n_has_edge) {
+        unsigned long long* d_cnt = (unsigned long long*)((char*)c.cl[5].p + 8);
+        CU_TRY(cudaMemsetAsync(d_cnt, 0, 8, st));
+        bdg::count_has_edge_kernel<<<nb, 256, 0, st>>>(d_lv, (uint32_t)N, d_cnt);
+        g_launches++;
+        CU_TRY(cudaMemcpyAsync(&has_edge, d_cnt, 8, cudaMemcpyDeviceToHost, st));
+    }
     unsigned int bad = 0;
     CU_TRY(cudaMemcpyAsync(&bad, d_bad, 4, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     if (bad) return fail(BDG_ERR_ARG, "an edge end point is not in the barcode array");
+    if (n_has_edge) *n_has_edge = (size_t)has_edge;
     if (trace)
         fprintf(stderr, "[bdg] cluster N=%zu E=%zu: (gather +) seed + index %.2f ms, %d rounds %.2f ms, read-back %.2f ms\n", N, E, tr1 - tr0, rounds,
                 tr2 - tr1, now_ms() - tr2);
@@ -1321,11 +1556,28 @@ int bdg_cluster_levels(const uint32_t* sorted_unique, size_t N, const uint32_t* 
     return cluster_on_device(c, (const uint32_t*)c.sorted.p, N, (uint32_t*)c.ea.p, (uint32_t*)c.eb.p, E, centres, C, rounds, centre_idx, level);
 }
 
+static int cluster_from_edges(bdg_edges* e, size_t N, const uint32_t* centres, size_t C, int rounds, int32_t* centre_idx, uint8_t* level, size_t* n_has_edge);
+
 int bdg_cluster_levels_from_edges(bdg_edges* e, size_t N, const uint32_t* centres, size_t C, int rounds, int32_t* centre_idx, uint8_t* level)
+{
+    if (N && (!centre_idx || !level)) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    return cluster_from_edges(e, N, centres, C, rounds, centre_idx, level, nullptr);
+}
+
+// The same with the result left on the device for bdg_assign_reads32(token, NULL, ...): no per-node array crosses PCIe.
+int bdg_cluster_resident(bdg_edges* e, size_t N, const uint32_t* centres, size_t C, int rounds, size_t* n_has_edge)
+{
+    if (n_has_edge) *n_has_edge = 0;
+    if (int rc = cluster_from_edges(e, N, centres, C, rounds, nullptr, nullptr, n_has_edge)) return rc;
+    if (e && !e->ctx.empty() && e->ctx[0] == 0 && N == g_ctx[0].map_distinct) g_ctx[0].cl_token = g_ctx[0].map_token;   // the result of THIS dedup's graph
+    return BDG_OK;
+}
+
+static int cluster_from_edges(bdg_edges* e, size_t N, const uint32_t* centres, size_t C, int rounds, int32_t* centre_idx, uint8_t* level, size_t* n_has_edge)
 {
     if (!e) return fail(BDG_ERR_ARG, "NULL edge handle");
     if (N == 0) return BDG_OK;
-    if (!centre_idx || !level || (C && !centres)) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if (C && !centres) return fail(BDG_ERR_ARG, "NULL pointer argument");
     if (e->ctx.empty()) return fail(BDG_ERR_ARG, "empty edge handle");
     if (N > 0x7FFFFFFFull || rounds < 0 || rounds > 253) return fail(BDG_ERR_ARG, "N must be < 2^31 and 0 <= rounds <= 253");
     for (size_t g = 0; g < e->ctx.size(); g++)
@@ -1354,11 +1606,11 @@ int bdg_cluster_levels_from_edges(bdg_edges* e, size_t N, const uint32_t* centre
             }
             off += k;
         }
-        return cluster_on_device(c, (const uint32_t*)c.sorted.p, N, (uint32_t*)c.gather_a.p, (uint32_t*)c.gather_b.p, total, centres, C, rounds, centre_idx, level);
+        return cluster_on_device(c, (const uint32_t*)c.sorted.p, N, (uint32_t*)c.gather_a.p, (uint32_t*)c.gather_b.p, total, centres, C, rounds, centre_idx, level, n_has_edge);
     }
     // the handle's edge VALUES are turned into node indices in place: the handle is consumed (stale afterwards)
     c.generation++;
-    return cluster_on_device(c, (const uint32_t*)c.sorted.p, N, (uint32_t*)c.ea.p, (uint32_t*)c.eb.p, e->count[0], centres, C, rounds, centre_idx, level);
+    return cluster_on_device(c, (const uint32_t*)c.sorted.p, N, (uint32_t*)c.ea.p, (uint32_t*)c.eb.p, e->count[0], centres, C, rounds, centre_idx, level, n_has_edge);
 }
 
 int bdg_member_sorted(const uint32_t* sorted_wl, size_t W, const uint32_t* q, size_t Q, uint8_t* hit)
@@ -1577,6 +1829,20 @@ int bdg_tsv_write_assignments(const bdg_tsv* t, const char* out_path, const uint
     std::string why;
     try {
         why = tsvio::tsv_write(t->t, out_path, centre_per_row, threads);
+    } catch (const std::bad_alloc&) {
+        return fail(BDG_ERR_OOM, "out of host memory while writing %s", out_path);
+    }
+    if (!why.empty()) return fail(BDG_ERR_IO, "%s", why.c_str());
+    return BDG_OK;
+}
+
+int bdg_tsv_write_assignments32(const bdg_tsv* t, const char* out_path, const uint32_t* centre_per_row, const uint8_t* has_centre, int threads)
+{
+    if (!t || !out_path) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if (t->t.rows && (!centre_per_row || !has_centre)) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    std::string why;
+    try {
+        why = tsvio::tsv_write(t->t, out_path, nullptr, threads, centre_per_row, has_centre);
     } catch (const std::bad_alloc&) {
         return fail(BDG_ERR_OOM, "out of host memory while writing %s", out_path);
     }

@@ -1,13 +1,12 @@
 // bdg_join.cuh -- edge construction at t = 2 by sort-merge joins on multi-block seeds (bdg_seed.cuh); sm_100a.
 // Reference semantics: index.py:77-93 (candidate filter S >= T) + barcode_graph.py:233-249 (3-way edit-distance verify, emit).
 //
-// Per condition c of the seed scheme the N barcodes are radix-sorted by the condition's join key (the barcode rides along as
-// the value; the sorted keys are scratch - the kernels read a key off the barcode again in a few shifts), once as rows
+// Per condition c of the seed scheme the N barcodes are bucketed by the condition's join key (the kernels read a key off a
+// barcode in a few shifts and masks, so only the barcodes are stored), once as rows
 // (fields of x) and - for the conditions with a shifted diagonal - once as columns (the matching fields of y).  Equal keys
 // are then adjacent on both sides: row i pairs with the column run colstart[key(i)] .. colstart[key(i) + 1].
-//   join_keys_kernel       barcode -> join key of one side of one condition
-//   (cub::DeviceRadixSort::SortPairs on the key bits)
-//   join_colstart_kernel   first column of every key value (lower bounds of all 2^key_bits keys in one streaming pass)
+//   join_hist_kernel / join_scatter_kernel  counting sort by the join key (one digit; cub's scan turns the bucket sizes into
+//                          colstart, the first column of every key value)
 //   join_band_kernel       per slab of 32 consecutive rows: number of work units (runs of <= JUNIT columns) it needs
 //   (cub::DeviceScan::ExclusiveSum: unit index -> slab)
 //   join_kernel<RS>        one persistent launch per condition: warps pull batches of units from an atomic cursor, stage the
@@ -50,18 +49,22 @@ struct JoinArgs {
     uint32_t one, mone;            // runtime 1 / -1: u * one + mone is u - 1 on the FMA pipe
 };
 
-__global__ void join_keys_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t n, SeedKey k)
+// ---- bucketing by join key: a counting sort in three launches (the key has <= 20 bits, so ONE digit: no radix passes) ----
+//   join_hist_kernel     bucket sizes (one global atomic per barcode; the 2^key_bits counters stay in L2)
+//   (cub::DeviceScan::ExclusiveSum over the counters: colstart, the first position of every key value)
+//   join_scatter_kernel  every barcode to the next free slot of its bucket
+// The order inside a bucket is whatever the atomics give: the join pairs whole buckets, so it does not matter.
+__global__ void join_hist_kernel(const uint32_t* __restrict__ in, uint32_t n, SeedKey k, uint32_t* __restrict__ hist)
 {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) out[i] = seed_key(__ldg(&in[i]), k);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&hist[seed_key(__ldg(&in[i]), k)], 1u);
 }
 
-// table[k] = first index j with key(cols[j]) >= k, k = 0 .. nkeys (table[nkeys] = n); cols sorted by key
-__global__ void join_colstart_kernel(const uint32_t* __restrict__ cols, uint32_t n, SeedKey key, uint32_t nkeys, uint32_t* __restrict__ table)
+__global__ void join_scatter_kernel(const uint32_t* __restrict__ in, uint32_t n, SeedKey k, const uint32_t* __restrict__ start, uint32_t* __restrict__ fill,
+                                    uint32_t* __restrict__ out)
 {
-    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j <= n; j += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t k_hi = j < n ? seed_key(__ldg(&cols[j]), key) : nkeys;               // keys k_lo .. k_hi start at j
-        const uint32_t k_lo = j > 0 ? seed_key(__ldg(&cols[j - 1]), key) + 1u : 0u;
-        for (uint32_t k = k_lo; k <= k_hi; k++) table[k] = (uint32_t)j;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t v = __ldg(&in[i]), key = seed_key(v, k);
+        out[__ldg(&start[key]) + atomicAdd(&fill[key], 1u)] = v;
     }
 }
 
@@ -92,35 +95,38 @@ struct JoinCtx {
     unsigned long long n_d2, n_score;
 };
 
-// exact stage on a batch of candidates of condition c.cond (one per lane).  A real call, not inlined: one copy of the exact
-// distance and of the score loop keeps the kernel's hot code inside the instruction cache (ncu: the fully inlined form
-// spent most of its issue slots waiting for instructions).
-__device__ __noinline__ void join_process(JoinCtx& c, const EdgeOut& out, uint2 e, bool active, int& q2n)
+// exact stage on a batch of candidates of one condition (one per lane): D by case analysis, hand-over table, survivors into the
+// scoring queue, full batches of that queue through the 6-mer score.  A real call, not inlined: one copy of the exact distance
+// and of the score loop keeps the kernel's hot code inside the instruction cache (ncu: the fully inlined form spent most of its
+// issue slots waiting for instructions).  Everything travels in registers: returns the queue fill | pairs with D <= 2 << 8 |
+// pairs handed to the score << 16.
+__device__ __noinline__ uint32_t join_process(uint2* q2, uint8_t* q2d, const uint8_t* lut, int want, int T, const EdgeOut out, uint2 e, bool active, int q2n)
 {
+    const int lane = threadIdx.x & 31;
     const uint32_t a = min(e.x, e.y), b = max(e.x, e.y);
     bool ok = active && a != b;
     int d = 3;
     if (ok) { d = dist_small(a, b); ok = d <= 2; }
-    c.n_d2 += __popc(__ballot_sync(FULL, ok));
-    if (ok) ok = __ldg(&c.lut[seed_flags(c_scheme, a, b)]) == (uint8_t)(2 * c.cond + (e.x > e.y ? 1 : 0));   // emitted by the first (condition, orientation) the pair meets
+    const uint32_t n_d2 = (uint32_t)__popc(__ballot_sync(FULL, ok));
+    if (ok) ok = __ldg(&lut[seed_flags(c_scheme, a, b)]) == (uint8_t)(want + (e.x > e.y ? 1 : 0));   // emitted by the first (condition, orientation) the pair meets
     const unsigned m = __ballot_sync(FULL, ok);
-    if (m == 0) return;
-    c.n_score += __popc(m);
+    if (m == 0) return (uint32_t)q2n | (n_d2 << 8);
     if (ok) {                                            // fewer than 32 entries wait on entry, so 32 more always fit
-        const int slot = q2n + __popc(m & ((1u << c.lane) - 1u));
-        c.q2[slot] = make_uint2(a, b);
-        c.q2d[slot] = (uint8_t)d;
+        const int slot = q2n + __popc(m & ((1u << lane) - 1u));
+        q2[slot] = make_uint2(a, b);
+        q2d[slot] = (uint8_t)d;
     }
     q2n += __popc(m);
     __syncwarp();
     while (q2n >= 32) {
         q2n -= 32;
-        const uint2 mv = c.q2[q2n + c.lane];
-        const uint8_t md = c.q2d[q2n + c.lane];
-        const bool good = qgram_score_compact(mv.x, mv.y) >= c.T;
+        const uint2 mv = q2[q2n + lane];
+        const uint8_t md = q2d[q2n + lane];
+        const bool good = qgram_score_compact(mv.x, mv.y) >= T;
         emit_warp(good, mv.x, mv.y, md, out);
         __syncwarp();
     }
+    return (uint32_t)q2n | (n_d2 << 8) | ((uint32_t)__popc(m) << 16);
 }
 
 __device__ __forceinline__ void join_drain(JoinCtx& c, const EdgeOut& out, int& qn, int& q2n, bool all)
@@ -130,7 +136,10 @@ __device__ __forceinline__ void join_drain(JoinCtx& c, const EdgeOut& out, int& 
         const int take = min(qn, 32);
         qn -= take;
         const uint2 e = c.lane < take ? c.q[qn + c.lane] : make_uint2(0u, 0u);
-        join_process(c, out, e, c.lane < take, q2n);
+        const uint32_t r = join_process(c.q2, c.q2d, c.lut, 2 * c.cond, c.T, out, e, c.lane < take, q2n);
+        q2n = (int)(r & 255u);
+        c.n_d2 += (r >> 8) & 255u;
+        c.n_score += r >> 16;
         __syncwarp();
     }
 }
@@ -173,7 +182,7 @@ __device__ __forceinline__ void join_push(uint32_t h, uint32_t x, const uint32_t
 }
 
 template <int RS>
-__global__ void __launch_bounds__(ENT, 5) join_kernel(const JoinArgs A, const EdgeOut out)
+__global__ void __launch_bounds__(ENT, 6) join_kernel(const JoinArgs A, const EdgeOut out)
 {
     constexpr int PH = 32 / RS;                          // column phases of a warp
     constexpr int STEP = 4 * PH;                         // columns per inner step

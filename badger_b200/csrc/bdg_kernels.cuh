@@ -343,6 +343,83 @@ __global__ void assign_reads_kernel(const uint64_t* __restrict__ centre_of_disti
     if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_assigned, mine);
 }
 
+// The same with a 5-byte result per row: centre barcode + "has a centre" byte.
+__global__ void centre_of_distinct32_kernel(const int32_t* __restrict__ centre_idx, const uint32_t* __restrict__ order,
+                                            const uint32_t* __restrict__ node_key, uint32_t n, uint32_t* __restrict__ out, uint8_t* __restrict__ has)
+{
+    for (uint32_t p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+        const int32_t c = __ldg(&centre_idx[__ldg(&order[p])]);
+        const bool ok = c >= 0 && (uint32_t)c < n;
+        out[p] = ok ? __ldg(&node_key[c]) : 0u;
+        has[p] = ok ? 1 : 0;
+    }
+}
+
+__global__ void assign_reads32_kernel(const uint32_t* __restrict__ centre_of_distinct, const uint8_t* __restrict__ has_of_distinct,
+                                      const uint32_t* __restrict__ read_to_distinct, const uint8_t* __restrict__ valid,
+                                      const uint32_t* __restrict__ excl, uint32_t n_rows, uint32_t* __restrict__ out, uint8_t* __restrict__ out_has,
+                                      unsigned long long* __restrict__ n_assigned)
+{
+    unsigned long long mine = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rows; i += gridDim.x * blockDim.x) {
+        uint32_t v = 0;
+        uint8_t h = 0;
+        if (!valid || __ldg(&valid[i])) {
+            const uint32_t p = __ldg(&read_to_distinct[valid ? __ldg(&excl[i]) : i]);
+            v = __ldg(&centre_of_distinct[p]);
+            h = __ldg(&has_of_distinct[p]);
+        }
+        out[i] = v;
+        out_has[i] = h;
+        mine += h;
+    }
+    for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(n_assigned, mine);
+}
+
+// ---- centre selection on the device (reference barcode_graph.py:252-258): sum of the first counts, the barcodes above the
+//      cutoff (cub select keeps their first-seen order), their count-descending stable order (cub radix sort of ~count) ----
+__global__ void sum_first_kernel(const uint32_t* __restrict__ counts, uint32_t n, unsigned long long* __restrict__ out)
+{
+    unsigned long long mine = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) mine += __ldg(&counts[i]);
+    for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, mine);
+}
+
+struct CountAbove {
+    const uint32_t* counts;
+    uint32_t thr;
+    __host__ __device__ __forceinline__ bool operator()(const uint32_t& p) const { return counts[p] > thr; }
+};
+
+__global__ void centres_keys_kernel(const uint32_t* __restrict__ pos, const uint32_t* __restrict__ counts, uint32_t n, uint32_t* __restrict__ keys)
+{
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) keys[j] = ~__ldg(&counts[__ldg(&pos[j])]);
+}
+
+__global__ void centres_gather_kernel(const uint32_t* __restrict__ pos, const uint32_t* __restrict__ distinct, const uint32_t* __restrict__ counts,
+                                      uint32_t n, uint32_t* __restrict__ top_ranks, uint32_t* __restrict__ top_counts)
+{
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t p = __ldg(&pos[j]);
+        top_ranks[j] = __ldg(&distinct[p]);
+        top_counts[j] = __ldg(&counts[p]);
+    }
+}
+
+// nodes that have an edge but are no centre (what `len(graph.edges.keys())`, badger.py:131, counts beside the centres)
+__global__ void count_has_edge_kernel(const uint8_t* __restrict__ level, uint32_t n, unsigned long long* __restrict__ out)
+{
+    unsigned long long mine = 0;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint8_t l = __ldg(&level[i]);
+        mine += (l != 255 && l != 0) ? 1 : 0;                 // 254 = untouched with an edge; 1, 2 = joined over an edge
+    }
+    for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, mine);
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Clustering rounds (row f-3, reference barcode_graph.py:279-301): level-synchronous and edge-parallel.
 //   round i: every edge (u,v), both directions: if u joined a centre at level i-1 and v is still free, u's

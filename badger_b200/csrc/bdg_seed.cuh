@@ -65,6 +65,7 @@ struct SeedScheme {
     SeedKey ka[SEED_MAX_CONDS], kb[SEED_MAX_CONDS];        // join key of the row side (fields of x) / column side (fields of y)
     int nflags;                                            // bits of seed_flags: 3 per block
     uint32_t hi_mask, lo_mask;                             // top bit of every block / the other bits of the blocks
+    uint32_t fmask[SEED_MAX_BLOCKS], fnet[SEED_MAX_BLOCKS]; // seed_flags: where block k's three flags sit in the zero-field word, and how far they move down
 };
 
 // x[fields of condition c] == y[the same fields moved by their diagonals]
@@ -105,7 +106,10 @@ BDG_HD uint32_t seed_flags(const SeedScheme& s, uint32_t a, uint32_t b)
     const uint32_t zb = ~(((xb & LM) + LM) | xb) & HI;
     const uint32_t z = (z0 >> 2) | (za >> 1) | zb;             // three flags below / at the top bit of every block (blocks have >= 4 bits)
     uint32_t f = 0;
-    for (int k = 0; k < s.nblocks; k++) f |= ((z >> (s.blo[k] + s.bn[k] - 3)) & 7u) << (3 * k);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k < SEED_MAX_BLOCKS; k++) f |= (z & s.fmask[k]) >> s.fnet[k];      // block k's flags move down to bit 3k (fmask 0: no such block)
     return f;
 }
 
@@ -124,6 +128,8 @@ inline bool seed_scheme_build(SeedScheme& s, const int* bases, int nblocks)
         if (bases[k] < 2) return false;                    // the flag extraction wants >= 4 bits per block
         s.hi_mask |= 1u << (s.blo[k] + s.bn[k] - 1);
         s.lo_mask |= low_mask(s.bn[k] - 1) << s.blo[k];
+        s.fmask[k] = 7u << (s.blo[k] + s.bn[k] - 3);
+        s.fnet[k] = (uint32_t)(s.blo[k] + s.bn[k] - 3 - 3 * k);
     }
     const int nf = nblocks - 2;
     {                                                      // block set by block set: its symmetric condition, then the shifted ones

@@ -271,8 +271,11 @@ constexpr uint64_t NO_CENTRE = 1ull << 32;
 
 // barcode_graph.py:395-410: header readID/barcode, one line per emitted row: id, then the centre (common.py:27-38 unrank)
 // or '*'.  centre[i] is per ROW (all rows, emitted or not); values >= 2^32 mean "unassigned".
-inline std::string tsv_write(const Tsv& t, const char* out_path, const uint64_t* centre, int threads)
+// Two forms of the per-row result: uint64 (>= 2^32: none) or uint32 + a "has a centre" byte (5 instead of 8 bytes per row).
+inline std::string tsv_write(const Tsv& t, const char* out_path, const uint64_t* centre64, int threads, const uint32_t* centre32 = nullptr,
+                             const uint8_t* has = nullptr)
 {
+    auto centre_of = [&](size_t i) -> uint64_t { return centre64 ? centre64[i] : (has[i] ? (uint64_t)centre32[i] : NO_CENTRE); };
     FILE* fo = fopen(out_path, "wb");
     if (!fo) return std::string("cannot create ") + out_path + ": " + strerror(errno);
     static const char HDR[] = "readID\tbarcode\n";
@@ -290,7 +293,7 @@ inline std::string tsv_write(const Tsv& t, const char* out_path, const uint64_t*
             size_t bytes = 0;
             auto [a, b] = span(k);
             for (size_t i = a; i < b; i++)
-                if (t.kind[i] & ROW_EMIT) bytes += (size_t)t.id_len[i] + 2 + (centre[i] < NO_CENTRE ? 16 : 1);
+                if (t.kind[i] & ROW_EMIT) bytes += (size_t)t.id_len[i] + 2 + (centre_of(i) < NO_CENTRE ? 16 : 1);
             part[k + 1] = bytes;
         };
         auto fill = [&](int k) {
@@ -301,7 +304,7 @@ inline std::string tsv_write(const Tsv& t, const char* out_path, const uint64_t*
                 memcpy(p, d + t.id_off[i], t.id_len[i]);
                 p += t.id_len[i];
                 *p++ = '\t';
-                const uint64_t c = centre[i];
+                const uint64_t c = centre_of(i);
                 if (c < NO_CENTRE) {
                     for (int j = 0; j < 16; j++) *p++ = "ACGT"[(c >> (2 * j)) & 3];
                 } else {

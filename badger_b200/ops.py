@@ -67,31 +67,73 @@ def dedup_first_seen(ranks: np.ndarray, want_map: bool = False, want_sorted_pos:
 
 
 class ReadMap:
-    """Result of dedup_reads: distinct barcodes in first-seen order, their counts and ascending positions on the host; the
-    read -> barcode map stays on the device under `token` until the next dedup call."""
+    """Result of dedup_reads.  The distinct barcodes (first-seen order), their counts, their ascending positions, the
+    ascending array and the read -> barcode map all stay on the device under `token` until the next dedup call; the four
+    arrays are downloaded when first asked for (`.distinct`, `.counts`, `.sorted_pos`, `.sorted_distinct`)."""
 
-    def __init__(self, distinct, counts, sorted_pos, n_valid, rows, token, sorted_distinct=None):
-        self.distinct, self.counts, self.sorted_pos = distinct, counts, sorted_pos
-        self.n_valid, self.rows, self.token = n_valid, rows, token
-        if sorted_distinct is None:                           # ascending order without a host sort
-            sorted_distinct = np.empty_like(distinct)
-            sorted_distinct[sorted_pos] = distinct
-        self.sorted_distinct = sorted_distinct
+    def __init__(self, n_distinct, n_valid, rows, token):
+        self.n_distinct, self.n_valid, self.rows, self.token = n_distinct, n_valid, rows, token
+        self._got = {}
+
+    def _fetch(self, name):
+        if name not in self._got:
+            n = self.n_distinct
+            arr = np.empty(n, np.uint32)
+            if n:
+                args = [ptr(arr) if k == name else None for k in ("distinct", "counts", "sorted_pos", "sorted_distinct")]
+                check(lib().bdg_dedup_fetch(self.token, *args))
+            self._got[name] = arr.astype(np.int64) if name == "counts" else arr
+        return self._got[name]
+
+    distinct = property(lambda self: self._fetch("distinct"))
+    counts = property(lambda self: self._fetch("counts"))
+    sorted_pos = property(lambda self: self._fetch("sorted_pos"))
+    sorted_distinct = property(lambda self: self._fetch("sorted_distinct"))
 
 
 def dedup_reads(ranks: np.ndarray, valid=None) -> ReadMap:
-    """barcode_graph.py:192-204 over the rows with valid[i] (None: all), compacted on the device; the per-read map is
-    kept there for assign_reads (include/badger_b200.h bdg_dedup_reads)."""
+    """barcode_graph.py:192-204 over the rows with valid[i] (None: all), compacted on the device; everything it produces is
+    kept there for edges_handle_resident / centres_above / assign_reads (include/badger_b200.h bdg_dedup_reads)."""
     r = np.ascontiguousarray(ranks, dtype=np.uint32)
     v = None if valid is None else np.ascontiguousarray(np.asarray(valid) != 0).view(np.uint8)
-    cap = r.size
-    distinct = np.empty(cap, np.uint32); counts = np.empty(cap, np.uint32); spos = np.empty(cap, np.uint32); sd = np.empty(cap, np.uint32)
     n, nv, tok = C.c_size_t(0), C.c_size_t(0), C.c_ulonglong(0)
     if r.size:
-        check(lib().bdg_dedup_reads(ptr(r), ptr(v) if v is not None else None, r.size, ptr(distinct), ptr(counts), ptr(spos), ptr(sd),
+        check(lib().bdg_dedup_reads(ptr(r), ptr(v) if v is not None else None, r.size, None, None, None, None,
                                     C.byref(n), C.byref(nv), C.byref(tok)))
-    k = int(n.value)
-    return ReadMap(distinct[:k].copy(), counts[:k].astype(np.int64), spos[:k].copy(), int(nv.value), int(r.size), int(tok.value), sd[:k].copy())
+    return ReadMap(int(n.value), int(nv.value), int(r.size), int(tok.value))
+
+
+def centres_above(rmap: ReadMap, n_cells: int, whitelist_sorted=None):
+    """barcode_graph.py:252-258 + 264 on the device: (cutoff, top ranks, their counts, whitelist hits or None) - the barcodes
+    with count > cutoff in the order of the reference's `bc_by_counts` (count descending, ties by first sighting)."""
+    wl = None if whitelist_sorted is None else np.ascontiguousarray(whitelist_sorted, dtype=np.uint32)
+    cap = 1 << 16
+    while True:
+        top = np.empty(cap, np.uint32); cnt = np.empty(cap, np.uint32)
+        hits = np.empty(cap, np.uint8) if wl is not None else None
+        n, cut = C.c_size_t(0), C.c_double(0.0)
+        rc = lib().bdg_centres_above(rmap.token, int(n_cells), ptr(wl) if wl is not None else None, 0 if wl is None else wl.size, ptr(top), ptr(cnt),
+                                     ptr(hits) if hits is not None else None, cap, C.byref(n), C.byref(cut))
+        if rc == _lib.BDG_ERR_CAPACITY:
+            cap = int(n.value)
+            continue
+        check(rc)
+        k = int(n.value)
+        return float(cut.value), top[:k], cnt[:k].astype(np.int64), (hits[:k].astype(bool) if hits is not None else None)
+
+
+def pack16_sorted(records) -> np.ndarray:
+    """badger.py:82-88 for the array pipeline: uint8[R, 16] records -> ascending distinct packed barcodes (records with letters
+    outside ACGT dropped), packed / sorted / made distinct on the device."""
+    arr = np.ascontiguousarray(records, dtype=np.uint8)
+    if arr.size % BC_LEN:
+        raise ValueError("pack16 needs records of exactly 16 characters")
+    R = arr.size // BC_LEN
+    out = np.empty(R, np.uint32)
+    n = C.c_size_t(0)
+    if R:
+        check(lib().bdg_pack16_sorted(ptr(arr), R, ptr(out), C.byref(n)))
+    return out[:int(n.value)].copy()
 
 
 def assign_reads(rmap: ReadMap, centre_idx: np.ndarray):
@@ -106,6 +148,19 @@ def assign_reads(rmap: ReadMap, centre_idx: np.ndarray):
         else:
             check(lib().bdg_assign_reads(rmap.token, ptr(ci), ci.size, ptr(out), out.size, C.byref(n)))
     return out, int(n.value)
+
+
+def assign_reads32(rmap: ReadMap, centre_idx=None):
+    """assign_reads with a 5-byte result per row: (centre uint32[R], has_centre bool-as-uint8[R], rows with a centre).
+    centre_idx None: the clustering EdgeHandle.cluster_resident left on the device is used in place."""
+    out = np.zeros(rmap.rows, np.uint32)
+    has = np.zeros(rmap.rows, np.uint8)
+    n = C.c_size_t(0)
+    if rmap.rows and rmap.token:
+        ci = None if centre_idx is None else np.ascontiguousarray(centre_idx, dtype=np.int32)
+        check(lib().bdg_assign_reads32(rmap.token, ptr(ci) if ci is not None else None, rmap.n_distinct if ci is None else ci.size, ptr(out), ptr(has),
+                                       out.size, C.byref(n)))
+    return out, has, int(n.value)
 
 
 class _PinnedPool:
@@ -188,6 +243,15 @@ class EdgeHandle:
             check(lib().bdg_cluster_levels_from_edges(self._h, self.n_nodes, ptr(cen), cen.size, int(rounds), ptr(ci), ptr(lv)))
         return _split_levels(ci, lv, want_has_edge)
 
+    def cluster_resident(self, centres: np.ndarray, rounds: int = 2) -> int:
+        """cluster_levels with the result left on the device for assign_reads32(rmap, None); CONSUMES the edges.  Returns the
+        number of non-centre nodes with at least one edge."""
+        cen = np.ascontiguousarray(centres, dtype=np.uint32)
+        n = C.c_size_t(0)
+        if self.n_nodes:
+            check(lib().bdg_cluster_resident(self._h, self.n_nodes, ptr(cen), cen.size, int(rounds), C.byref(n)))
+        return int(n.value)
+
     def free(self):
         if self._h is not None:
             lib().bdg_edges_free(self._h)
@@ -213,7 +277,7 @@ def edges_handle_resident(rmap: "ReadMap", t: int) -> EdgeHandle:
     """edges_handle over the ascending distinct barcodes the dedup_reads call left on the first device (no upload)."""
     h = C.c_void_p()
     check(lib().bdg_edges_build_resident(rmap.token, int(t), C.byref(h)))
-    return EdgeHandle(h, int(rmap.distinct.size))
+    return EdgeHandle(h, int(rmap.n_distinct))
 
 
 def edges_build(sorted_unique: np.ndarray, t: int):

@@ -53,6 +53,14 @@ class ExtractionTsv:
             raise ValueError("one centre per TSV row expected (%d rows, got %d)" % (self.rows, c.size))
         check(lib().bdg_tsv_write_assignments(self._h, str(out_path).encode(), ptr(c), int(threads)))
 
+    def write32(self, out_path: str, centre_per_row: np.ndarray, has_centre: np.ndarray, threads: int = 0) -> None:
+        """write() from the 5-byte form of the per-row result (ops.assign_reads32)."""
+        c = np.ascontiguousarray(centre_per_row, dtype=np.uint32)
+        h = np.ascontiguousarray(has_centre, dtype=np.uint8)
+        if c.size != self.rows or h.size != self.rows:
+            raise ValueError("one centre per TSV row expected (%d rows, got %d / %d)" % (self.rows, c.size, h.size))
+        check(lib().bdg_tsv_write_assignments32(self._h, str(out_path).encode(), ptr(c), ptr(h), int(threads)))
+
     def close(self):
         if self._h is not None:
             lib().bdg_tsv_close(self._h)

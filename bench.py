@@ -500,14 +500,14 @@ def whole_pipeline(t, wl, obs, valid, cfg):
     selection with whitelist membership, clustering rounds, per-read gather), host arrays in and out, wall clock."""
     from badger_b200 import pipeline
     wls = np.sort(wl)
-    pipeline.assign_packed(obs, valid, threshold=t, n_cells=cfg["n_cells"], whitelist_sorted=wls)      # warm
+    pipeline.assign_packed(obs, valid, threshold=t, n_cells=cfg["n_cells"], whitelist_sorted=wls, form="u32")      # warm
     reps, T = 3, {}
     t0 = time.perf_counter()
     for _ in range(reps):
-        out, info = pipeline.assign_packed(obs, valid, threshold=t, n_cells=cfg["n_cells"], whitelist_sorted=wls, timings=T)
+        out, info = pipeline.assign_packed(obs, valid, threshold=t, n_cells=cfg["n_cells"], whitelist_sorted=wls, timings=T, form="u32")
     dt = (time.perf_counter() - t0) / reps
     return {"reads_per_s": obs.size / dt, "ms": dt * 1e3, "stages_ms": {k: 1e3 * v / reps for k, v in T.items()}, **info,
-            "api": "badger_b200.pipeline.assign_packed (packed barcodes per read in, centre per read out)"}
+            "api": "badger_b200.pipeline.assign_packed(form='u32') (packed barcode + valid byte per read in, centre + flag byte per read out)"}
 
 
 def cli_file_to_file(t, wl, obs, valid, cfg):

@@ -63,6 +63,9 @@ void bdg_host_free(void* p);
 /* seqs: R records of exactly 16 bytes, no terminator.  valid[i] = 1 iff all 16 bytes are in "ACGT"
  * (the reference raises KeyError otherwise, common.py:24); out[i] is undefined when valid[i] == 0. */
 int bdg_pack16(const char* seqs, size_t R, uint32_t* out, uint8_t* valid);
+/* The whitelist file's records (badger.py:82-88) for the array pipeline: packed, records with other letters dropped, sorted,
+ * made distinct - all on the device.  out_sorted has room for R entries; *n receives the number kept. */
+int bdg_pack16_sorted(const char* seqs, size_t R, uint32_t* out_sorted, size_t* n);
 
 /* ---- a-2  index_bc_single_thread: barcode_graph.py:192-204 ------------------------------------------ */
 /* Dedup + count of R packed barcodes in read order (already length-filtered and valid).  distinct[] receives the
@@ -87,6 +90,22 @@ int bdg_dedup_reads(const uint32_t* ranks, const uint8_t* valid, size_t R_all, u
                     size_t* n_distinct, size_t* n_valid, unsigned long long* token);
 int bdg_assign_reads(unsigned long long token, const int32_t* centre_idx, size_t N, uint64_t* centre_per_row, size_t R_all,
                      size_t* n_assigned);
+/* The same with a 5-byte result per row (centre barcode + "has a centre" byte).  centre_idx == NULL: the clustering result a
+ * bdg_cluster_resident call left on the device is used in place - no per-node array crosses PCIe in either direction. */
+int bdg_assign_reads32(unsigned long long token, const int32_t* centre_idx, size_t N, uint32_t* centre_per_row, uint8_t* has_centre,
+                       size_t R_all, size_t* n_assigned);
+/* bdg_dedup_reads accepts NULL for distinct / counts / sorted_pos / sorted_distinct (nothing is downloaded then);
+ * bdg_dedup_fetch downloads any of them later, while the token is alive. */
+int bdg_dedup_fetch(unsigned long long token, uint32_t* distinct, uint32_t* counts, uint32_t* sorted_pos, uint32_t* sorted_distinct);
+
+/* ---- a-6 + centre selection: barcode_graph.py:252-267 over the distinct barcodes of a bdg_dedup_reads call ---------------- */
+/* *cutoff = max(mean(counts of the first n_cells barcodes in first-seen order) / 5, 5) (:255-256).  top_ranks / top_counts
+ * (room for cap entries) receive the barcodes with count > cutoff in count-descending order, ties in first-seen order: the head
+ * of the reference's `bc_by_counts` (:253).  top_hits (optional) receives `unrank(r) in barcode_list` (:264) for each of them,
+ * looked up in sorted_wl[W] on the device.  *n_above = their number; BDG_ERR_CAPACITY when it exceeds cap.  The walk over
+ * that head (:262-277) is a few thousand steps and stays with the caller. */
+int bdg_centres_above(unsigned long long token, size_t n_cells, const uint32_t* sorted_wl, size_t W, uint32_t* top_ranks,
+                      uint32_t* top_counts, uint8_t* top_hits, size_t cap, size_t* n_above, double* cutoff);
 
 /* ---- a-3 + a-4  QGramIndex.get_close + verify/emit: index.py:77-93, barcode_graph.py:224-249 ------ */
 /* Edge set {(a,b,D): a<b, S(a,b) >= T(t), D(a,b) <= t} over a STRICTLY INCREASING array of distinct
@@ -120,6 +139,9 @@ int bdg_cluster_levels(const uint32_t* sorted_unique, size_t N, const uint32_t* 
                        const uint32_t* centres, size_t C, int rounds, int32_t* centre_idx, uint8_t* level);
 int bdg_cluster_levels_from_edges(bdg_edges* e, size_t N, const uint32_t* centres, size_t C, int rounds, int32_t* centre_idx,
                                   uint8_t* level);
+/* The same with the result left on the first device for bdg_assign_reads32(token, NULL, ...).  *n_has_edge = nodes that are no
+ * centre and have at least one edge (what `len(graph.edges.keys())`, badger.py:131, counts beside the centres). */
+int bdg_cluster_resident(bdg_edges* e, size_t N, const uint32_t* centres, size_t C, int rounds, size_t* n_has_edge);
 
 /* ---- a-6  whitelist membership: `unrank(r) in barcode_list`, barcode_graph.py:262-267 -------------- */
 int bdg_member_sorted(const uint32_t* sorted_wl, size_t W, const uint32_t* q, size_t Q, uint8_t* hit);
@@ -214,6 +236,7 @@ int bdg_tsv_open(const char* path, int bc_len, int threads, bdg_tsv** out);
 size_t bdg_tsv_rows(const bdg_tsv* t);
 int bdg_tsv_barcodes(const bdg_tsv* t, char* seqs16, uint8_t* kind);
 int bdg_tsv_write_assignments(const bdg_tsv* t, const char* out_path, const uint64_t* centre_per_row, int threads);
+int bdg_tsv_write_assignments32(const bdg_tsv* t, const char* out_path, const uint32_t* centre_per_row, const uint8_t* has_centre, int threads);
 void bdg_tsv_close(bdg_tsv* t);
 
 /* Whitelist file, badger.py:82-88 (`set(file.read().split("\n"))`): the entries of exactly 16 characters, 16 bytes each

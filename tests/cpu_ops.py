@@ -76,30 +76,72 @@ def dedup_first_seen(ranks, want_map=False, want_sorted_pos=False):
     return out
 
 
+class ReadMap:
+    """Stand-in for ops.ReadMap: everything the device would keep, as host arrays."""
+
+    def __init__(self, distinct, counts, sorted_pos, n_valid, rows, token):
+        self.distinct, self.counts, self.sorted_pos = distinct, counts, sorted_pos
+        self.n_distinct, self.n_valid, self.rows, self.token = int(distinct.size), n_valid, rows, token
+        s = np.empty_like(distinct)
+        s[sorted_pos] = distinct
+        self.sorted_distinct = s
+        self.ci = None                                 # clustering left "on the device" by EdgeHandle.cluster_resident
+
+
 def dedup_reads(ranks, valid=None):
-    from badger_b200 import ops
     r = np.ascontiguousarray(ranks, dtype=np.uint32)
     v = np.ones(r.size, bool) if valid is None else np.asarray(valid, bool)
     if not v.any():
-        return ops.ReadMap(np.empty(0, np.uint32), np.empty(0, np.int64), np.empty(0, np.uint32), 0, int(r.size), 0)
+        return ReadMap(np.empty(0, np.uint32), np.empty(0, np.int64), np.empty(0, np.uint32), 0, int(r.size), 0)
     d, c, rmap, spos = dedup_first_seen(r[v], want_map=True, want_sorted_pos=True)
-    rm = ops.ReadMap(d, c, spos, int(v.sum()), int(r.size), 1)
+    rm = ReadMap(d, c, spos, int(v.sum()), int(r.size), 1)
     rm._cpu = (v, rmap)
     return rm
 
 
 def assign_reads(rm, centre_idx):
     none = np.uint64(1) << np.uint64(32)
-    out = np.full(rm.rows, none, np.uint64)
+    c32, has, n = assign_reads32(rm, centre_idx)
+    out = c32.astype(np.uint64)
+    out[has == 0] = none
+    return out, n
+
+
+def assign_reads32(rm, centre_idx=None):
+    out = np.zeros(rm.rows, np.uint32); has = np.zeros(rm.rows, np.uint8)
     if rm.token == 0:
-        return out, 0
+        return out, has, 0
+    if centre_idx is None:
+        centre_idx = _RESIDENT["ci"]
     v, rmap = rm._cpu
-    s = np.empty_like(rm.distinct)
-    s[rm.sorted_pos] = rm.distinct
+    s = rm.sorted_distinct
     ci = np.asarray(centre_idx, np.int32)[rm.sorted_pos]
-    cd = np.where(ci >= 0, s[np.maximum(ci, 0)].astype(np.uint64), none)
+    ok = ci >= 0
+    cd = np.where(ok, s[np.maximum(ci, 0)], 0).astype(np.uint32)
     out[v] = cd[rmap]
-    return out, int((out != none).sum())
+    has[v] = ok[rmap]
+    return out, has, int(has.sum())
+
+
+_RESIDENT = {"ci": None}
+
+
+def centres_above(rm, n_cells, whitelist_sorted=None):
+    """barcode_graph.py:252-258 restated on the host arrays (the GPU operator's contract)."""
+    first = rm.counts[:n_cells]
+    cutoff = max((int(first.sum()) / first.size) / 5.0, 5)
+    above = np.nonzero(rm.counts > cutoff)[0]
+    above = above[np.argsort(-rm.counts[above], kind="stable")]
+    top = rm.distinct[above]
+    hits = None
+    if whitelist_sorted is not None:
+        hits = member_sorted(np.ascontiguousarray(whitelist_sorted, dtype=np.uint32), top) if top.size else np.zeros(0, bool)
+    return float(cutoff), top, rm.counts[above], hits
+
+
+def pack16_sorted(records):
+    r, ok = pack16(records)
+    return np.unique(r[ok])
 
 
 def cluster_levels(sorted_unique, ea, eb, centres, rounds=2, want_has_edge=False):
@@ -143,6 +185,11 @@ class EdgeHandle:
     def cluster_levels(self, centres, rounds=2, want_has_edge=False):
         return cluster_levels(self.s, self.a, self.b, centres, rounds, want_has_edge)
 
+    def cluster_resident(self, centres, rounds=2):
+        ci, lv, has_edge = cluster_levels(self.s, self.a, self.b, centres, rounds, True)
+        _RESIDENT["ci"] = ci
+        return int(has_edge.sum())
+
     def free(self):
         pass
 
@@ -158,5 +205,6 @@ def edges_handle_resident(rm, t):
 def install(monkeypatch):
     from badger_b200 import ops
     for name in ("pack16", "edges_build", "edges_build_part", "member_sorted", "nearest_bounded", "kmer_score", "dedup_first_seen",
-                 "cluster_levels", "KmerIndex", "edges_handle", "edges_handle_resident", "dedup_reads", "assign_reads"):
+                 "cluster_levels", "KmerIndex", "edges_handle", "edges_handle_resident", "dedup_reads", "assign_reads", "assign_reads32", "centres_above",
+                 "pack16_sorted"):
         monkeypatch.setattr(ops, name, globals()[name])

@@ -478,8 +478,7 @@ def test_packed_pipeline_on_all_devices_matches_one_device():
     (bdg_cluster_levels_from_edges on a multi-device handle).  Needs >= 2 GPUs (gpurun --gpus 2)."""
     from badger_b200 import pipeline
     n_dev = badger_b200.init()
-    if n_dev < 2:
-        pytest.skip("one GPU visible")
+    many_devs = None if n_dev >= 2 else [0, 0]      # one GPU: two device contexts on it (own streams, workspaces, host threads, "peer" copies)
     rng = synth.rng_for(123)
     wl = synth.make_whitelist(50000, rng)
     cells = synth.pick_cells(wl, 1500, rng)
@@ -487,25 +486,75 @@ def test_packed_pipeline_on_all_devices_matches_one_device():
     wls = np.sort(wl)
     res = {}
     try:
-        for devs in ([0], None):
-            badger_b200.init(devs)
-            for t in (1, 2):
-                out, info = pipeline.assign_packed(obs, valid, threshold=t, n_cells=1500, whitelist_sorted=wls, high_sens=(t == 2))
+        for devs in ([0], many_devs):
+            assert badger_b200.init(devs) == (1 if devs == [0] else max(n_dev, 2))
+            for t, mode in ((1, -1), (2, -1), (2, 2)):                      # t = 2 also with the join form forced (the set is below its default size)
+                badger_b200._lib.check(badger_b200.lib().bdg_set_edge_mode(mode))
+                out, info = pipeline.assign_packed(obs, valid, threshold=t, n_cells=1500, whitelist_sorted=wls, high_sens=(t == 2 and mode == 2))
                 s = synth.sorted_unique(obs[valid])
                 h = ops.edges_handle(s, t)
                 e = ops.canonical(*h.copy())
                 ci, lv, has = h.cluster_levels(cells, 2, want_has_edge=True)
                 h.free()
-                res[(devs is None, t)] = (out, info, e, ci, lv, has)
+                res[(devs == [0], t, mode)] = (out, info, e, ci, lv, has)
     finally:
+        badger_b200._lib.check(badger_b200.lib().bdg_set_edge_mode(-1))
         badger_b200.init()
-    for t in (1, 2):
-        one, many = res[(False, t)], res[(True, t)]
+    for t, mode in ((1, -1), (2, -1), (2, 2)):
+        one, many = res[(True, t, mode)], res[(False, t, mode)]
         assert np.array_equal(one[0], many[0]) and one[1] == many[1]
         for x, y in zip(one[2], many[2]):
             assert np.array_equal(x, y)
         assert np.array_equal(one[3], many[3]) and np.array_equal(one[4], many[4]) and np.array_equal(one[5], many[5])
         assert one[1]["edges"] > 1000
+    for x, y in zip(res[(True, 2, -1)][2], res[(True, 2, 2)][2]):          # and the two t = 2 routes agree
+        assert np.array_equal(x, y)
+
+
+def test_resident_stages_vs_host_arrays():
+    """The stages that keep their per-barcode arrays on the device (centre head, clustering result, 5-byte per-read result,
+    whitelist packing) against the operators that return host arrays and numpy restatements of barcode_graph.py:252-258."""
+    from badger_b200 import pipeline
+    rng = synth.rng_for(321)
+    wl = synth.make_whitelist(40000, rng)
+    cells = synth.pick_cells(wl, 1200, rng)
+    obs, valid = synth.simulate_reads(cells, 250000, 0.05, rng)
+    wls = np.sort(wl)
+    # whitelist records -> sorted distinct packed barcodes on the device
+    recs = np.frombuffer(b"".join(synth.unrank_many(wl).tolist()) + b"ACGTNNNNACGTACGT" + synth.unrank_many(wl[:5]).tobytes(), np.uint8).reshape(-1, 16)
+    assert np.array_equal(ops.pack16_sorted(recs), wls)
+    assert ops.pack16_sorted(np.empty((0, 16), np.uint8)).size == 0
+    for n_cells in (1200, 50, 400000):
+        rm = ops.dedup_reads(obs, valid)
+        d, c = rm.distinct, rm.counts
+        first = c[:n_cells]
+        cutoff = max((int(first.sum()) / first.size) / 5.0, 5)
+        above = np.nonzero(c > cutoff)[0]
+        above = above[np.argsort(-c[above], kind="stable")]
+        for w in (None, wls):
+            cut, top, cnt, hits = ops.centres_above(rm, n_cells, w)
+            assert cut == cutoff and np.array_equal(top, d[above]) and np.array_equal(cnt, c[above])
+            assert (hits is None) == (w is None)
+            if w is not None:
+                assert np.array_equal(hits, np.isin(d[above], wls))
+    with pytest.raises(badger_b200.BadgerB200Error):
+        ops.centres_above(rm, 10, wls[::-1].copy())                          # whitelist not sorted
+    for t in (1, 2):
+        want, info = pipeline.assign_packed(obs, valid, threshold=t, n_cells=1200, whitelist_sorted=wls)
+        (c32, has), info2 = pipeline.assign_packed(obs, valid, threshold=t, n_cells=1200, whitelist_sorted=wls, form="u32")
+        assert info == info2 and np.array_equal(has.astype(bool), want != pipeline.NONE)
+        assert np.array_equal(c32[has != 0].astype(np.uint64), want[want != pipeline.NONE])
+        # the same through the host-array operators: edges copied out, clustering rounds from host arrays, 8-byte gather
+        rm = ops.dedup_reads(obs, valid)
+        s = rm.sorted_distinct
+        a, b, _ = ops.edges_build(s, t)
+        centres = np.asarray(list(dict.fromkeys(pipeline.select_centres(rm, 1200, 25, wls, None))), np.uint32)
+        ci, lv, has_edge = ops.cluster_levels(s, a, b, centres, 2, want_has_edge=True)
+        out, n = ops.assign_reads(rm, ci)
+        assert np.array_equal(out, want) and n == info["assigned_reads"]
+        assert info["disconnected"] == s.size - (int(has_edge.sum()) + centres.size) and info["edges"] == a.size
+        with pytest.raises(badger_b200.BadgerB200Error):
+            ops.assign_reads32(rm, None)                                     # no clustering result of this dedup is resident
 
 
 def test_member_vs_oracle():

@@ -88,7 +88,7 @@ def native_route(tsv, wlf, cfg, tmp, R, high_sens, other_output):
         T["pack16 of the reads (GPU)"] = time.perf_counter() - t0
         t0 = time.perf_counter()
         w, wok = ops.pack16(tsvio.whitelist_records(wlf))
-        whitelist = ops.sorted_unique(w[wok])
+        whitelist = ops.sorted_unique(w[wok])          # (badger.py itself packs and sorts the records on the device: ops.pack16_sorted)
         T["whitelist file -> sorted uint32 (native + GPU)"] = time.perf_counter() - t0
         t0 = time.perf_counter()
         centre, info = pipeline.assign_packed(ranks, has, threshold=cfg["threshold"], n_cells=cfg["n_cells"], interval=25,

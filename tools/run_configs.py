@@ -33,8 +33,9 @@ def main():
                 pipeline.assign_packed(obs[:200000], valid[:200000], threshold=cfg["threshold"], n_cells=100, whitelist_sorted=wls)   # warm
             T = {}
             t0 = time.perf_counter()
-            out, info = pipeline.assign_packed(obs, valid, threshold=cfg["threshold"], n_cells=cfg["n_cells"], whitelist_sorted=wls, timings=T)
+            out, info = pipeline.assign_packed(obs, valid, threshold=cfg["threshold"], n_cells=cfg["n_cells"], whitelist_sorted=wls, timings=T, form="u32")
             dt = time.perf_counter() - t0
+            out = out[0].astype(np.uint64) | (np.uint64(1) << np.uint64(32)) * (out[1] == 0)        # one array for the comparison below
             n = info["distinct"]
             same = None
             if first is None:
