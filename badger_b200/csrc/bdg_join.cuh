@@ -91,7 +91,7 @@ struct JoinCtx {
     uint2* q2;                     // (a, b) with D <= 2 that still need the 6-mer score
     uint8_t* q2d;
     const uint8_t* lut;
-    int lane, T, cond;
+    int lane, T, cond, shifted;    // shifted: 1 for a condition with a shifted diagonal (its two value orders are two hand-over indices)
     unsigned long long n_d2, n_score;
 };
 
@@ -100,7 +100,10 @@ struct JoinCtx {
 // and of the score loop keeps the kernel's hot code inside the instruction cache (ncu: the fully inlined form spent most of its
 // issue slots waiting for instructions).  Everything travels in registers: returns the queue fill | pairs with D <= 2 << 8 |
 // pairs handed to the score << 16.
-__device__ __noinline__ uint32_t join_process(uint2* q2, uint8_t* q2d, const uint8_t* lut, int want, int T, const EdgeOut out, uint2 e, bool active, int q2n)
+// want0 / want1: the hand-over index this pass owns for a candidate with row value < / > column value (the same for a symmetric
+// condition, whose buckets are in no particular order).
+__device__ __noinline__ uint32_t join_process(uint2* q2, uint8_t* q2d, const uint8_t* lut, int want0, int want1, int T, const EdgeOut out, uint2 e, bool active,
+                                              int q2n)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t a = min(e.x, e.y), b = max(e.x, e.y);
@@ -108,7 +111,7 @@ __device__ __noinline__ uint32_t join_process(uint2* q2, uint8_t* q2d, const uin
     int d = 3;
     if (ok) { d = dist_small(a, b); ok = d <= 2; }
     const uint32_t n_d2 = (uint32_t)__popc(__ballot_sync(FULL, ok));
-    if (ok) ok = __ldg(&lut[seed_flags(c_scheme, a, b)]) == (uint8_t)(want + (e.x > e.y ? 1 : 0));   // emitted by the first (condition, orientation) the pair meets
+    if (ok) ok = __ldg(&lut[seed_flags(c_scheme, a, b)]) == (uint8_t)(e.x > e.y ? want1 : want0);   // emitted by the first (condition, orientation) the pair meets
     const unsigned m = __ballot_sync(FULL, ok);
     if (m == 0) return (uint32_t)q2n | (n_d2 << 8);
     if (ok) {                                            // fewer than 32 entries wait on entry, so 32 more always fit
@@ -136,7 +139,7 @@ __device__ __forceinline__ void join_drain(JoinCtx& c, const EdgeOut& out, int& 
         const int take = min(qn, 32);
         qn -= take;
         const uint2 e = c.lane < take ? c.q[qn + c.lane] : make_uint2(0u, 0u);
-        const uint32_t r = join_process(c.q2, c.q2d, c.lut, 2 * c.cond, c.T, out, e, c.lane < take, q2n);
+        const uint32_t r = join_process(c.q2, c.q2d, c.lut, 2 * c.cond, 2 * c.cond + c.shifted, c.T, out, e, c.lane < take, q2n);
         q2n = (int)(r & 255u);
         c.n_d2 += (r >> 8) & 255u;
         c.n_score += r >> 16;
@@ -197,7 +200,7 @@ __global__ void __launch_bounds__(ENT, 6) join_kernel(const JoinArgs A, const Ed
     uint32_t* const sbM = s_b[wid][2];
     uint32_t* const sbK = s_b[wid][3];
     JoinCtx c;
-    c.q = s_q[wid]; c.q2 = s_q2[wid]; c.q2d = s_q2d[wid]; c.lut = A.lut; c.lane = lane; c.T = A.T; c.cond = A.cond; c.n_d2 = 0; c.n_score = 0;
+    c.q = s_q[wid]; c.q2 = s_q2[wid]; c.q2d = s_q2d[wid]; c.lut = A.lut; c.lane = lane; c.T = A.T; c.cond = A.cond; c.shifted = A.self ? 0 : 1; c.n_d2 = 0; c.n_score = 0;
     int qn = 0, q2n = 0;
     const uint32_t mone = A.mone;
     const unsigned long long t_start = global_ns();
