@@ -236,7 +236,7 @@ void launch_tiles_bip(int blocks, cudaStream_t st, const bdg::EdgeWork& w, const
 
 // Join form (t = 2), bdg_join.cuh.  The seed conditions are laid on a line by weight (a symmetric condition pairs each couple
 // once: weight 1; a shifted one pairs both value orders: weight 2) and the line is cut into nparts equal pieces: a part sorts and
-// joins only the conditions its piece touches, a condition on a cut is shared by unit range.  Per condition: counting sort by the
+// joins only the conditions its piece touches, a condition on a cut is shared by row range (cut at a bucket boundary).  Per condition: counting sort by the
 // key (rows once per block set, columns for the shifted conditions; its prefix sums are colstart) -> units per slab -> prefix sums ->
 // one persistent join launch.  The conditions of a block set follow one another and share the row order.  Consecutive block sets alternate between the caller's stream and an auxiliary one, so that one
 // condition's sorts and the tail of its join overlap the neighbour's join.
@@ -324,6 +324,8 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
         if (new_set) { if (int e = bucket_side(S.ka[c], ws->jn_rows[k], ws->jn_tab[k])) return e; }      // the stream's row order: this block set
         bdg::JoinArgs A{};
         A.rows = (const uint32_t*)ws->jn_rows[k].p;
+        A.rowstart = (const uint32_t*)ws->jn_tab[k].p;
+        A.nkeys = 1u << S.ka[c].key_bits;
         if (S.cond[c].self) {
             A.cols = A.rows;
             A.colstart = (const uint32_t*)ws->jn_tab[k].p;

@@ -44,7 +44,9 @@ struct JoinArgs {
     unsigned long long* stats;     // [0] units, [2] pairs tested, [3] candidates, [6] pairs with D <= 2, [7] pairs scored, [4]/[5] warp times
     uint32_t N, n_slabs;
     int cond, self;
-    uint32_t f0, f1, fden;         // this part works on the units [total * f0 / fden, total * f1 / fden) of the condition
+    const uint32_t* rowstart;      // (1 << key_bits) + 1 lower bounds into rows (== colstart for a symmetric condition)
+    uint32_t nkeys;
+    uint32_t f0, f1, fden;         // this part works on the rows [cut(f0), cut(f1)) of the condition: cuts at bucket boundaries near N * f / fden
     int T;
     uint32_t one, mone;            // runtime 1 / -1: u * one + mone is u - 1 on the FMA pipe
 };
@@ -68,19 +70,38 @@ __global__ void join_scatter_kernel(const uint32_t* __restrict__ in, uint32_t n,
     }
 }
 
+// Where a part's share of a condition starts / ends: the first row of the first bucket that begins at or behind N * f / fden.
+// Bucket boundaries depend on the bucket SIZES only, so every part finds the same cut whatever order its own counting sort
+// left inside the buckets, and a bucket is never split between parts.
+__device__ __forceinline__ uint32_t join_cut(const uint32_t* __restrict__ rowstart, uint32_t nkeys, uint32_t N, uint32_t f, uint32_t fden)
+{
+    if (f == 0) return 0u;
+    if (f >= fden) return N;
+    const uint32_t target = (uint32_t)((uint64_t)N * f / fden);
+    uint32_t lo = 0, hi = nkeys;                          // smallest key whose bucket starts at or behind the target (rowstart[nkeys] = N)
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&rowstart[mid]) < target) lo = mid + 1; else hi = mid;
+    }
+    return __ldg(&rowstart[lo]);
+}
+
 // units of every slab of 32 rows: its column run (first key's bucket .. last key's bucket; a symmetric condition pairs
 // each couple once - column index > row index - so its run starts behind the slab's first row) in pieces of JUNIT columns
 __global__ void join_band_kernel(const JoinArgs A, uint32_t* __restrict__ counts)
 {
     const SeedKey& ka = c_scheme.ka[A.cond];
+    const uint32_t r0 = join_cut(A.rowstart, A.nkeys, A.N, A.f0, A.fden), r1 = join_cut(A.rowstart, A.nkeys, A.N, A.f1, A.fden);
     for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s <= A.n_slabs; s += gridDim.x * blockDim.x) {
         uint32_t cnt = 0;
         if (s < A.n_slabs) {
-            const uint32_t i0 = s * JROWS, i1 = min(A.N, i0 + JROWS) - 1u;
-            uint32_t lo = __ldg(&A.colstart[seed_key(__ldg(&A.rows[i0]), ka)]);
-            const uint32_t hi = __ldg(&A.colstart[seed_key(__ldg(&A.rows[i1]), ka) + 1u]);
-            if (A.self) lo = max(lo, i0 + 1u);
-            cnt = hi > lo ? (hi - lo + JUNIT - 1) / JUNIT : 0u;
+            const uint32_t i0 = max(s * JROWS, r0), i1 = min(min(A.N, s * JROWS + JROWS), r1);      // the slab's rows of this part: [i0, i1)
+            if (i0 < i1) {
+                uint32_t lo = __ldg(&A.colstart[seed_key(__ldg(&A.rows[i0]), ka)]);
+                const uint32_t hi = __ldg(&A.colstart[seed_key(__ldg(&A.rows[i1 - 1u]), ka) + 1u]);
+                if (A.self) lo = max(lo, i0 + 1u);
+                cnt = hi > lo ? (hi - lo + JUNIT - 1) / JUNIT : 0u;
+            }
         }
         counts[s] = cnt;
     }
@@ -208,16 +229,16 @@ __global__ void __launch_bounds__(ENT, 6) join_kernel(const JoinArgs A, const Ed
     const SeedKey& ka = c_scheme.ka[A.cond];
     const SeedKey& kb = c_scheme.kb[A.cond];
     const bool self = A.self != 0;
-    const uint64_t total_units = __ldg(&A.offs[A.n_slabs]);
-    const uint32_t u_lo = (uint32_t)(total_units * A.f0 / A.fden), u_hi = (uint32_t)(total_units * A.f1 / A.fden);
-    const uint64_t n_batches = ((uint64_t)(u_hi - u_lo) + JBATCH - 1) / JBATCH;
+    const uint32_t total_units = __ldg(&A.offs[A.n_slabs]);
+    const uint32_t n_batches = (total_units + JBATCH - 1) / JBATCH;
+    const uint32_t r0 = join_cut(A.rowstart, A.nkeys, A.N, A.f0, A.fden), r1 = join_cut(A.rowstart, A.nkeys, A.N, A.f1, A.fden);   // this part's rows
 
     for (;;) {
         unsigned long long bi = 0;
         if (lane == 0) bi = atomicAdd(A.cursor, 1ull);
         bi = __shfl_sync(FULL, bi, 0);
         if (bi >= n_batches) break;
-        const uint32_t u0 = u_lo + (uint32_t)bi * JBATCH, u1 = (uint32_t)min((uint64_t)u_hi, (uint64_t)u0 + JBATCH);
+        const uint32_t u0 = (uint32_t)bi * JBATCH, u1 = min(total_units, u0 + JBATCH);
         // slab of the first unit: offs[lo] <= u0 < offs[hi] by a 32-ary search (offs is non-decreasing)
         uint32_t lo = 0, hi = A.n_slabs;
         while (hi - lo > 1) {
@@ -238,14 +259,15 @@ __global__ void __launch_bounds__(ENT, 6) join_kernel(const JoinArgs A, const Ed
             }
             const uint32_t chunk = u - __ldg(&A.offs[sl]);
             const uint32_t i0 = sl * JROWS, i = i0 + (uint32_t)lane;
-            const int last = (int)min(A.N - i0, (uint32_t)JROWS) - 1;            // last real row of the slab
-            const uint32_t x = i < A.N ? __ldg(&A.rows[i]) : 0u;
-            const uint32_t k = i < A.N ? seed_key(x, ka) : 0xFFFFFFFFu;         // a pad row matches no column
-            const uint32_t my_lo = i < A.N ? __ldg(&A.colstart[k]) : 0u;        // this row's bucket on the column side
-            const uint32_t my_hi = i < A.N ? __ldg(&A.colstart[k + 1u]) : 0u;
-            uint32_t run_lo = __shfl_sync(FULL, my_lo, 0);
+            const int first = (int)(max(i0, r0) - i0), last = (int)(min(min(A.N, i0 + (uint32_t)JROWS), r1) - i0) - 1;   // the slab's rows of this part
+            const bool mine = lane >= first && lane <= last;
+            const uint32_t x = mine ? __ldg(&A.rows[i]) : 0u;
+            const uint32_t k = mine ? seed_key(x, ka) : 0xFFFFFFFFu;            // a row of another part (or a pad row) matches no column
+            const uint32_t my_lo = mine ? __ldg(&A.colstart[k]) : 0u;           // this row's bucket on the column side
+            const uint32_t my_hi = mine ? __ldg(&A.colstart[k + 1u]) : 0u;
+            uint32_t run_lo = __shfl_sync(FULL, my_lo, first);
             const uint32_t run_hi = __shfl_sync(FULL, my_hi, last);
-            if (self) run_lo = max(run_lo, i0 + 1u);
+            if (self) run_lo = max(run_lo, i0 + (uint32_t)first + 1u);
             const uint32_t c0 = run_lo + chunk * (uint32_t)JUNIT, c1 = min(run_hi, c0 + (uint32_t)JUNIT);
             n_units++;
             for (uint32_t base = c0; base < c1; base += JCH) {
@@ -262,13 +284,13 @@ __global__ void __launch_bounds__(ENT, 6) join_kernel(const JoinArgs A, const Ed
                 }
                 __syncwarp();
 #pragma unroll 1
-                for (int q = 0; q * RS <= last; q++) {   // sub-slab q = rows q * RS .. + RS - 1 against their own column run
-                    uint32_t s_lo = __shfl_sync(FULL, my_lo, q * RS);
+                for (int q = first / RS; q * RS <= last; q++) {   // sub-slab q = rows q * RS .. + RS - 1 against their own column run
+                    uint32_t s_lo = __shfl_sync(FULL, my_lo, max(q * RS, first));
                     const uint32_t s_hi = __shfl_sync(FULL, my_hi, min(q * RS + RS - 1, last));
                     const uint32_t xq = __shfl_sync(FULL, x, q * RS + r);
                     const uint32_t kq = __shfl_sync(FULL, k, q * RS + r);
                     const uint32_t iq = i0 + (uint32_t)(q * RS + r);
-                    if (self) s_lo = max(s_lo, i0 + (uint32_t)(q * RS) + 1u);
+                    if (self) s_lo = max(s_lo, i0 + (uint32_t)max(q * RS, first) + 1u);
                     const uint32_t g_lo = max(s_lo, base), g_hi = min(s_hi, base + (uint32_t)ncols);
                     if (g_lo >= g_hi) continue;
                     const int gb = (int)(g_lo - base) & ~3, ge = (int)(g_hi - base);      // 16-byte aligned start
