@@ -103,6 +103,9 @@ struct DevCtx {
     // (one set per stream: the conditions of a block set run back to back on one stream)
     Buf jn_rows[2], jn_cols[2], jn_tab[2], jn_tabc[2], jn_hist[2], jn_cub[2], jn_counts[2], jn_offs[2], jn_lut;
     int scheme_serial = 0;                                    // which scheme sits in this device's constant memory (0: none)
+    cudaEvent_t ev_cond[bdg::SEED_MAX_CONDS] = {};            // bdg_edges_build_into: "condition c has appended its edges"
+    unsigned long long* snap_host = nullptr;                  // mapped page-locked: the edge count after every condition
+    unsigned long long* snap_dev = nullptr;
 };
 std::vector<DevCtx> g_ctx;
 
@@ -240,8 +243,18 @@ void launch_tiles_bip(int blocks, cudaStream_t st, const bdg::EdgeWork& w, const
 // key (rows once per block set, columns for the shifted conditions; its prefix sums are colstart) -> units per slab -> prefix sums ->
 // one persistent join launch.  The conditions of a block set follow one another and share the row order.  Consecutive block sets alternate between the caller's stream and an auxiliary one, so that one
 // condition's sorts and the tail of its join overlap the neighbour's join.
+// Host buffers the finished edges are copied into WHILE later conditions still run (bdg_edges_build_into): the conditions
+// then run on one stream, a snapshot of the edge count follows every join launch, and the ranges between two snapshots -
+// final, because their launches have ended - leave on the copy stream.
+struct JoinStream {
+    uint32_t* h_a;
+    uint32_t* h_b;
+    uint8_t* h_d;
+    size_t h_cap;
+};
+
 int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, uint32_t* d_a, uint32_t* d_b, uint8_t* d_d, size_t cap,
-                      unsigned long long* d_count, cudaStream_t caller, DevCtx* ws)
+                      unsigned long long* d_count, cudaStream_t caller, DevCtx* ws, const JoinStream* js = nullptr)
 {
     if (int rc = scheme_ready()) return rc;
     const bdg::SeedScheme& S = g_scheme;
@@ -291,9 +304,15 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
     if (int rc = grid_for(rs == 8 ? (const void*)bdg::join_kernel<8> : (const void*)bdg::join_kernel<32>, &grid, bdg::ENT)) return rc;
     const int gb = (int)std::min<size_t>((N + 255) / 256, (size_t)ws->sms * 8);
     const int bb = (int)std::min<size_t>(((size_t)n_slabs + 256) / 256, (size_t)ws->sms * 8);
-    const bool fork = !getenv("BDG_EDGE_SERIAL");
+    const bool fork = !js && !getenv("BDG_EDGE_SERIAL");
     if (fork) CU_TRY(cudaEventRecord(ws->ev_start, caller));
     bool aux_used = false;
+    int streamed[bdg::SEED_MAX_CONDS], n_streamed = 0;
+    if (js && !ws->snap_host) {
+        CU_TRY(cudaHostAlloc((void**)&ws->snap_host, sizeof(unsigned long long) * bdg::SEED_MAX_CONDS, cudaHostAllocMapped));
+        CU_TRY(cudaHostGetDevicePointer((void**)&ws->snap_dev, ws->snap_host, 0));
+        for (int c = 0; c < bdg::SEED_MAX_CONDS; c++) CU_TRY(cudaEventCreateWithFlags(&ws->ev_cond[c], cudaEventDisableTiming));
+    }
     bdg::EdgeOut o{d_a, d_b, d_d, d_count, (unsigned long long)cap};
     long long start = 0;
     int cur_set = -1, k = 1;                                 // k: scratch set / stream of the current block set
@@ -353,10 +372,31 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
         else bdg::join_kernel<32><<<grid, bdg::ENT, 0, st>>>(A, o);
         g_launches += 3;
         CU_TRY(cudaGetLastError());
+        if (js) {
+            bdg::join_snapshot_kernel<<<1, 1, 0, st>>>(d_count, ws->snap_dev + c);
+            g_launches++;
+            CU_TRY(cudaEventRecord(ws->ev_cond[c], st));
+            streamed[n_streamed++] = c;
+        }
     }
     if (aux_used) {
         CU_TRY(cudaEventRecord(ws->ev_done[1], ws->aux[1]));
         CU_TRY(cudaStreamWaitEvent(caller, ws->ev_done[1], 0));
+    }
+    if (js) {                                               // everything is enqueued: follow the conditions and copy what they have finished
+        cudaStream_t cp = ws->aux[2];
+        size_t done = 0;
+        for (int k = 0; k < n_streamed; k++) {
+            CU_TRY(cudaEventSynchronize(ws->ev_cond[streamed[k]]));
+            const size_t upto = (size_t)std::min<unsigned long long>(ws->snap_host[streamed[k]], js->h_cap);
+            if (upto > done) {
+                CU_TRY(cudaMemcpyAsync(js->h_a + done, d_a + done, (upto - done) * 4, cudaMemcpyDeviceToHost, cp));
+                CU_TRY(cudaMemcpyAsync(js->h_b + done, d_b + done, (upto - done) * 4, cudaMemcpyDeviceToHost, cp));
+                CU_TRY(cudaMemcpyAsync(js->h_d + done, d_d + done, upto - done, cudaMemcpyDeviceToHost, cp));
+                done = upto;
+            }
+        }
+        CU_TRY(cudaStreamSynchronize(cp));
     }
     return BDG_OK;
 }
@@ -364,7 +404,7 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
 // Launch the edge construction of one part on the current device / stream.  d_count is zeroed on the stream.
 // ws: the device's grow-only workspaces (plan, rotated keys, sort scratch); one in-flight call per device.
 int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts, uint32_t* d_a, uint32_t* d_b,
-                 uint8_t* d_d, size_t cap, unsigned long long* d_count, cudaStream_t st, DevCtx* ws)
+                 uint8_t* d_d, size_t cap, unsigned long long* d_count, cudaStream_t st, DevCtx* ws, const JoinStream* js = nullptr)
 {
     if (nparts < 1 || part < 0 || part >= nparts) return fail(BDG_ERR_ARG, "part %d of %d is not a valid part", part, nparts);
     if (N > 0xFFFFFFFFull) return fail(BDG_ERR_ARG, "N = %zu exceeds the 2^32 distinct 16-mers", N);
@@ -372,7 +412,7 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
     CU_TRY(cudaMemsetAsync(d_count, 0, sizeof(unsigned long long), st));
     if (t <= 0 || N < 2) return BDG_OK;   // D >= 1 for distinct barcodes: no edges (barcode_graph.py:245)
     const int mode = edge_mode_for(t, N);
-    if (mode == 2) return launch_edges_join(d_sorted, N, part, nparts, d_a, d_b, d_d, cap, d_count, st, ws);
+    if (mode == 2) return launch_edges_join(d_sorted, N, part, nparts, d_a, d_b, d_d, cap, d_count, st, ws, js);
     const bool sparse = mode == 1;
     const int passes = sparse ? bdg::n_passes(t) : 1;
     const void* kern = sparse ? (t == 1 ? (const void*)bdg::sparse_tile_kernel<1, 0, false> : (const void*)bdg::sparse_tile_kernel<2, 0, false>)
@@ -682,6 +722,7 @@ void bdg_shutdown(void)
             c.jn_cub[k].release(); c.jn_counts[k].release(); c.jn_offs[k].release();
         }
         c.jn_lut.release();
+        if (c.snap_host) { cudaFreeHost(c.snap_host); c.snap_host = nullptr; for (auto& e : c.ev_cond) if (e) cudaEventDestroy(e); }
     }
     g_ctx.clear();
 }
@@ -1411,6 +1452,70 @@ int bdg_edges_build_resident(unsigned long long token, int t, bdg_edges** out)
     if (rc) { delete res; return rc; }
     *out = res;
     return BDG_OK;
+}
+
+// One part's edges straight into caller buffers of `cap` entries each (page-locked ones copy at PCIe speed): with the join
+// form the finished edges of earlier seed conditions cross PCIe while later ones are still being joined.  *count receives the
+// number of edges found; when it exceeds cap only the first cap were stored and the call has to be repeated with more room.
+int bdg_edges_build_into(const uint32_t* sorted_unique, size_t N, int t, int part, int nparts, uint32_t* a, uint32_t* b, uint8_t* d, size_t cap,
+                         size_t* count)
+{
+    if (!count || (N && !sorted_unique) || (cap && (!a || !b || !d))) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    *count = 0;
+    if (nparts < 1 || part < 0 || part >= nparts) return fail(BDG_ERR_ARG, "part %d of %d is not a valid part", part, nparts);
+    if (int rc = need_ctx()) return rc;
+    DevCtx& c = g_ctx[0];
+    auto ensure = [&](Buf& bf, size_t bytes) -> int {
+        if (cudaError_t e = (cudaError_t)bf.ensure(bytes))
+            return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation of %zu bytes: %s", bytes, cudaGetErrorString(e));
+        return BDG_OK;
+    };
+    CU_TRY(cudaSetDevice(c.dev));
+    const size_t dcap = std::max<size_t>(cap, 1);
+    if (int e = ensure(c.sorted, std::max<size_t>(N, 1) * 4)) return e;
+    if (int e = ensure(c.count, 2 * sizeof(unsigned long long))) return e;
+    if (int e = ensure(c.ea, dcap * 4)) return e;
+    if (int e = ensure(c.eb, dcap * 4)) return e;
+    if (int e = ensure(c.ed, dcap)) return e;
+    c.generation++;                                         // older handles on this device lose their edges
+    CU_TRY(cudaMemcpyAsync(c.sorted.p, sorted_unique, N * 4, cudaMemcpyHostToDevice, c.stream));
+    unsigned long long* d_bad = (unsigned long long*)c.count.p + 1;
+    CU_TRY(cudaMemsetAsync(d_bad, 0xFF, 8, c.stream));
+    if (N > 1) {
+        bdg::sorted_check_kernel<true><<<(int)std::min<size_t>((N + 255) / 256, (size_t)c.sms * 8), 256, 0, c.stream>>>((const uint32_t*)c.sorted.p, (uint32_t)N, d_bad);
+        g_launches++;
+    }
+    const bool streaming = t > 0 && N >= 2 && edge_mode_for(t, N) == 2;
+    JoinStream js{a, b, d, cap};
+    for (int attempt = 0; attempt < 3; attempt++) {
+        if (int e = launch_edges((const uint32_t*)c.sorted.p, N, t, part, nparts, (uint32_t*)c.ea.p, (uint32_t*)c.eb.p, (uint8_t*)c.ed.p, cap,
+                                 (unsigned long long*)c.count.p, c.stream, &c, streaming ? &js : nullptr)) return e;
+        unsigned long long both[2] = {0, 0};
+        CU_TRY(cudaMemcpyAsync(both, c.count.p, sizeof(both), cudaMemcpyDeviceToHost, c.stream));
+        CU_TRY(cudaStreamSynchronize(c.stream));
+        if (both[1] != ~0ull) return fail(BDG_ERR_ARG, "input not strictly increasing at index %llu", both[1]);
+        if (both[0] >> 63) {                                // a sparse pass listed more tiles than its list holds: grow it and run again
+            unsigned long long hdr[(PLAN_HDR / 8) * bdg::MAX_PASSES];
+            CU_TRY(cudaMemcpy(hdr, c.plan.p, sizeof(hdr), cudaMemcpyDeviceToHost));
+            unsigned long long need = 0;
+            for (int p = 0; p < bdg::MAX_PASSES; p++) need = std::max(need, hdr[(PLAN_HDR / 8) * p + HDR_LIST / 8]);
+            for (int p = 0; p < bdg::MAX_PASSES; p++)
+                if (int e = ensure(c.tile_list[p], (size_t)need * sizeof(uint2))) return e;
+            continue;
+        }
+        *count = (size_t)both[0];
+        if (!streaming) {
+            const size_t k = std::min<size_t>(*count, cap);
+            if (k) {
+                CU_TRY(cudaMemcpyAsync(a, c.ea.p, k * 4, cudaMemcpyDeviceToHost, c.stream));
+                CU_TRY(cudaMemcpyAsync(b, c.eb.p, k * 4, cudaMemcpyDeviceToHost, c.stream));
+                CU_TRY(cudaMemcpyAsync(d, c.ed.p, k, cudaMemcpyDeviceToHost, c.stream));
+                CU_TRY(cudaStreamSynchronize(c.stream));
+            }
+        }
+        return BDG_OK;
+    }
+    return fail(BDG_ERR_CUDA, "edge construction did not settle after growing its tile lists");
 }
 
 int bdg_edges_build_part(const uint32_t* sorted_unique, size_t N, int t, int part, int nparts, bdg_edges** out)

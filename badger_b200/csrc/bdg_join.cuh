@@ -86,6 +86,12 @@ __device__ __forceinline__ uint32_t join_cut(const uint32_t* __restrict__ rowsta
     return __ldg(&rowstart[lo]);
 }
 
+// the edge count as it stands when the stream reaches this point (bdg_edges_build_into copies the finished edges out meanwhile)
+__global__ void join_snapshot_kernel(const unsigned long long* __restrict__ count, volatile unsigned long long* __restrict__ snap)
+{
+    *snap = *count;
+}
+
 // units of every slab of 32 rows: its column run (first key's bucket .. last key's bucket; a symmetric condition pairs
 // each couple once - column index > row index - so its run starts behind the slab's first row) in pieces of JUNIT columns
 __global__ void join_band_kernel(const JoinArgs A, uint32_t* __restrict__ counts)

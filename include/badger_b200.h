@@ -120,6 +120,12 @@ int bdg_edges_build_part(const uint32_t* sorted_unique, size_t N, int t, int par
 /* The same over the ascending distinct barcodes that the bdg_dedup_reads call named by `token` left on the first device: no
  * upload; with several devices the array fans out over NVLink peer copies. */
 int bdg_edges_build_resident(unsigned long long token, int t, bdg_edges** out);
+/* One part's edges straight into caller buffers of cap entries each (page-locked buffers - bdg_host_alloc - copy at PCIe
+ * speed).  With the join form the finished edges of earlier seed conditions cross PCIe while later conditions are still being
+ * joined, so the copy hides behind the kernels.  *count = edges found; if it exceeds cap only the first cap were stored: repeat
+ * the call with more room (the edge set is deterministic). */
+int bdg_edges_build_into(const uint32_t* sorted_unique, size_t N, int t, int part, int nparts, uint32_t* a, uint32_t* b, uint8_t* d,
+                         size_t cap, size_t* count);
 size_t bdg_edges_count(const bdg_edges* e);
 int bdg_edges_copy(const bdg_edges* e, uint32_t* a, uint32_t* b, uint8_t* d); /* caller-allocated, length = count */
 void bdg_edges_free(bdg_edges* e);
