@@ -401,7 +401,7 @@ def run_b200(args):
     clocks = sampler.stop()
     e2e = {"value": total_pairs * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(4 * n),
            "d2h_bytes_per_step": int(9 * ea.size + 8), "ms_per_step": 1000 * e2e_s / args.steps,
-           "api": "badger_b200.ops.edges_build_part -> bdg_edges_build_part (host buffers; every rank uploads the array and downloads its edges)"}
+           "api": "badger_b200.ops.edges_build_part -> bdg_edges_build_into (host buffers; every rank uploads the array, the edges cross PCIe while later seed conditions are still joined)"}
     del ea, eb, ed
 
     # ---- the other search strategy on the same input, for the record (one GPU only: it is several times slower)
