@@ -237,6 +237,8 @@ void launch_tiles_bip(int blocks, cudaStream_t st, const bdg::EdgeWork& w, const
         else FN<2, 2>(__VA_ARGS__);                                                   \
     } while (0)
 
+static double now_ms();
+
 // Join form (t = 2), bdg_join.cuh.  The seed conditions are laid on a line by weight (a symmetric condition pairs each couple
 // once: weight 1; a shifted one pairs both value orders: weight 2) and the line is cut into nparts equal pieces: a part sorts and
 // joins only the conditions its piece touches, a condition on a cut is shared by row range (cut at a bucket boundary).  Per condition: counting sort by the
@@ -316,6 +318,9 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
     bdg::EdgeOut o{d_a, d_b, d_d, d_count, (unsigned long long)cap};
     long long start = 0;
     int cur_set = -1, k = 1;                                 // k: scratch set / stream of the current block set
+    const bool trace = getenv("BDG_TRACE") != nullptr;
+    double t_prev = 0;
+    if (trace) { cudaStreamSynchronize(caller); t_prev = now_ms(); }
     for (int c = 0; c < S.nconds; c++) {
         const int w = S.cond[c].self ? 1 : 2;
         const long long c_lo = start * nparts, c_hi = (start + w) * nparts;
@@ -372,6 +377,12 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
         else bdg::join_kernel<32><<<grid, bdg::ENT, 0, st>>>(A, o);
         g_launches += 3;
         CU_TRY(cudaGetLastError());
+        if (trace) {                                        // development aid: per-condition wall time (serialises the streams)
+            CU_TRY(cudaStreamSynchronize(st));
+            const double now = now_ms();
+            fprintf(stderr, "[bdg] join cond %2d (%s, rows %u/%u..%u/%u): %.3f ms\n", c, S.cond[c].self ? "sym" : "shf", A.f0, A.fden, A.f1, A.fden, now - t_prev);
+            t_prev = now;
+        }
         if (js) {
             bdg::join_snapshot_kernel<<<1, 1, 0, st>>>(d_count, ws->snap_dev + c);
             g_launches++;

@@ -95,7 +95,11 @@ def dedup_reads(ranks: np.ndarray, valid=None) -> ReadMap:
     """barcode_graph.py:192-204 over the rows with valid[i] (None: all), compacted on the device; everything it produces is
     kept there for edges_handle_resident / centres_above / assign_reads (include/badger_b200.h bdg_dedup_reads)."""
     r = np.ascontiguousarray(ranks, dtype=np.uint32)
-    v = None if valid is None else np.ascontiguousarray(np.asarray(valid) != 0).view(np.uint8)
+    if valid is None:
+        v = None
+    else:
+        v = np.ascontiguousarray(valid)
+        v = v.view(np.uint8) if v.dtype == np.bool_ else (v != 0).view(np.uint8)     # a bool mask is used in place
     n, nv, tok = C.c_size_t(0), C.c_size_t(0), C.c_ulonglong(0)
     if r.size:
         check(lib().bdg_dedup_reads(ptr(r), ptr(v) if v is not None else None, r.size, None, None, None, None,
@@ -153,8 +157,12 @@ def assign_reads(rmap: ReadMap, centre_idx: np.ndarray):
 def assign_reads32(rmap: ReadMap, centre_idx=None):
     """assign_reads with a 5-byte result per row: (centre uint32[R], has_centre bool-as-uint8[R], rows with a centre).
     centre_idx None: the clustering EdgeHandle.cluster_resident left on the device is used in place."""
-    out = np.zeros(rmap.rows, np.uint32)
-    has = np.zeros(rmap.rows, np.uint8)
+    if rmap.rows and rmap.token:
+        out = _pinned.array(rmap.rows, np.uint32)            # page-locked: the per-row result comes back at PCIe speed
+        has = _pinned.array(rmap.rows, np.uint8)
+    else:
+        out = np.zeros(rmap.rows, np.uint32)
+        has = np.zeros(rmap.rows, np.uint8)
     n = C.c_size_t(0)
     if rmap.rows and rmap.token:
         ci = None if centre_idx is None else np.ascontiguousarray(centre_idx, dtype=np.int32)
