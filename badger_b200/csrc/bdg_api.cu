@@ -237,7 +237,12 @@ void launch_tiles_bip(int blocks, cudaStream_t st, const bdg::EdgeWork& w, const
         else FN<2, 2>(__VA_ARGS__);                                                   \
     } while (0)
 
-static double now_ms();
+double now_ms()
+{
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
 
 // Join form (t = 2), bdg_join.cuh.  The seed conditions are laid on a line by weight (a symmetric condition pairs each couple
 // once: weight 1; a shifted one pairs both value orders: weight 2) and the line is cut into nparts equal pieces: a part sorts and
@@ -1375,13 +1380,6 @@ static int edges_on_device(DevCtx& c, const uint32_t* sorted, size_t N, int t, i
     c.generation++;
     *n_out = (size_t)count;
     return BDG_OK;
-}
-
-static double now_ms()
-{
-    timespec ts;
-    clock_gettime(CLOCK_MONOTONIC, &ts);
-    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
 static int edges_on_devices(const uint32_t* sorted, size_t N, int t, const std::vector<int>& ctx_idx,
