@@ -186,7 +186,7 @@ int edge_mode_for(int t, size_t N)
 
 // ---- the seed scheme of the join form: built once on the host (bdg_seed.cuh), copied to every device that uses it ----
 bdg::SeedScheme g_scheme;
-std::vector<bdg::SeedSet> g_scheme_lut;
+std::vector<uint8_t> g_scheme_lut;
 int g_scheme_serial = 0;
 
 int scheme_ready()
@@ -203,7 +203,7 @@ int scheme_ready()
         }
     }
     if (!bdg::seed_scheme_build(g_scheme, bases, nb)) return fail(BDG_ERR_ARG, "BDG_JOIN_BLOCKS is not a usable block layout (3..6 blocks, 15 bases in all)");
-    g_scheme_lut.assign((size_t)1 << g_scheme.nflags, bdg::SeedSet{{0u, 0u, 0u, 0u}});
+    g_scheme_lut.assign((size_t)1 << g_scheme.nflags, 0);
     bdg::seed_lut_build(g_scheme, g_scheme_lut.data());
     g_scheme_serial = 1;
     return BDG_OK;
@@ -244,8 +244,8 @@ double now_ms()
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
-// Join form (t = 2), bdg_join.cuh.  The seed conditions are laid on a line by weight (cond_weight) and the line is cut into
-// nparts equal pieces: a part sorts and
+// Join form (t = 2), bdg_join.cuh.  The seed conditions are laid on a line by weight (a symmetric condition pairs each couple
+// once: weight 1; a shifted one pairs both value orders: weight 2) and the line is cut into nparts equal pieces: a part sorts and
 // joins only the conditions its piece touches, a condition on a cut is shared by row range (cut at a bucket boundary).  Per condition: counting sort by the
 // key (rows once per block set, columns for the shifted conditions; its prefix sums are colstart) -> units per slab -> prefix sums ->
 // one persistent join launch.  The conditions of a block set follow one another and share the row order.  Consecutive block sets alternate between the caller's stream and an auxiliary one, so that one
@@ -260,11 +260,6 @@ struct JoinStream {
     size_t h_cap;
 };
 
-// Relative cost of a condition for the deal to the parts.  A shifted condition pairs both value orders and buckets two sides,
-// a symmetric one pairs each couple once and buckets one side; the emitted edges are spread evenly by the owner hash.  Measured
-// per condition at C4 (BDG_TRACE): 0.69-0.79 ms symmetric, 0.80-1.18 ms shifted.
-int cond_weight(const bdg::SeedScheme& S, int c) { return S.cond[c].self ? 3 : 4; }
-
 int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, uint32_t* d_a, uint32_t* d_b, uint8_t* d_d, size_t cap,
                       unsigned long long* d_count, cudaStream_t caller, DevCtx* ws, const JoinStream* js = nullptr)
 {
@@ -276,9 +271,9 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
         return BDG_OK;
     };
     if (ws->scheme_serial != g_scheme_serial) {
-        if (int e = ensure(ws->jn_lut, g_scheme_lut.size() * sizeof(bdg::SeedSet))) return e;
+        if (int e = ensure(ws->jn_lut, g_scheme_lut.size())) return e;
         CU_TRY(cudaMemcpyToSymbolAsync(bdg::c_scheme, &g_scheme, sizeof(g_scheme), 0, cudaMemcpyHostToDevice, caller));
-        CU_TRY(cudaMemcpyAsync(ws->jn_lut.p, g_scheme_lut.data(), g_scheme_lut.size() * sizeof(bdg::SeedSet), cudaMemcpyHostToDevice, caller));
+        CU_TRY(cudaMemcpyAsync(ws->jn_lut.p, g_scheme_lut.data(), g_scheme_lut.size(), cudaMemcpyHostToDevice, caller));
         CU_TRY(cudaStreamSynchronize(caller));              // the host copies above are read asynchronously
         ws->scheme_serial = g_scheme_serial;
     }
@@ -288,7 +283,7 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
     const uint32_t n_slabs = (uint32_t)((N + bdg::JROWS - 1) / bdg::JROWS);
     // the part's piece of the weight line, in units of 1 / nparts
     int W = 0;
-    for (int c = 0; c < S.nconds; c++) W += cond_weight(S, c);
+    for (int c = 0; c < S.nconds; c++) W += S.cond[c].self ? 1 : 2;
     const long long piece_lo = (long long)part * W, piece_hi = (long long)(part + 1) * W;      // cond c covers [start_c * nparts, (start_c + w_c) * nparts)
     if (int e = ensure(ws->plan, PLAN_HDR * bdg::MAX_PASSES + 8 * bdg::SEED_MAX_CONDS)) return e;
     char* d_plan = (char*)ws->plan.p;
@@ -332,7 +327,7 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
     double t_prev = 0;
     if (trace) { cudaStreamSynchronize(caller); t_prev = now_ms(); }
     for (int c = 0; c < S.nconds; c++) {
-        const int w = cond_weight(S, c);
+        const int w = S.cond[c].self ? 1 : 2;
         const long long c_lo = start * nparts, c_hi = (start + w) * nparts;
         start += w;
         const long long lo = std::max(c_lo, piece_lo), hi = std::min(c_hi, piece_hi);
@@ -369,7 +364,7 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
             A.colstart = (const uint32_t*)ws->jn_tabc[k].p;
         }
         A.offs = (const uint32_t*)ws->jn_offs[k].p;
-        A.lut = (const bdg::SeedSet*)ws->jn_lut.p;
+        A.lut = (const uint8_t*)ws->jn_lut.p;
         A.cursor = d_cursors + c;
         A.stats = (unsigned long long*)(d_plan + HDR_STATS);
         A.N = (uint32_t)N;

@@ -39,7 +39,7 @@ struct JoinArgs {
     const uint32_t* cols;          // ... of the column-side key (== rows for a symmetric condition)
     const uint32_t* colstart;      // (1 << key_bits) + 1 lower bounds into cols
     const uint32_t* offs;          // exclusive prefix sums of the units per slab: n_slabs + 1 entries
-    const SeedSet* lut;            // meeting (condition, orientation) entries per value of seed_flags
+    const uint8_t* lut;            // hand-over table over seed_flags
     unsigned long long* cursor;    // batches handed out by this launch
     unsigned long long* stats;     // [0] units, [2] pairs tested, [3] candidates, [6] pairs with D <= 2, [7] pairs scored, [4]/[5] warp times
     uint32_t N, n_slabs;
@@ -117,7 +117,7 @@ struct JoinCtx {
     uint2* q;                      // candidates (x, y): row value, column value
     uint2* q2;                     // (a, b) with D <= 2 that still need the 6-mer score
     uint8_t* q2d;
-    const SeedSet* lut;
+    const uint8_t* lut;
     int lane, T, cond, shifted;    // shifted: 1 for a condition with a shifted diagonal (its two value orders are two hand-over indices)
     unsigned long long n_d2, n_score;
 };
@@ -127,9 +127,9 @@ struct JoinCtx {
 // and of the score loop keeps the kernel's hot code inside the instruction cache (ncu: the fully inlined form spent most of its
 // issue slots waiting for instructions).  Everything travels in registers: returns the queue fill | pairs with D <= 2 << 8 |
 // pairs handed to the score << 16.
-// want0 / want1: the entry this pass stands for with a candidate whose row value is < / > its column value (the same for a
-// symmetric condition, whose buckets are in no particular order).
-__device__ __noinline__ uint32_t join_process(uint2* q2, uint8_t* q2d, const SeedSet* lut, int want0, int want1, int T, const EdgeOut out, uint2 e, bool active,
+// want0 / want1: the hand-over index this pass owns for a candidate with row value < / > column value (the same for a symmetric
+// condition, whose buckets are in no particular order).
+__device__ __noinline__ uint32_t join_process(uint2* q2, uint8_t* q2d, const uint8_t* lut, int want0, int want1, int T, const EdgeOut out, uint2 e, bool active,
                                               int q2n)
 {
     const int lane = threadIdx.x & 31;
@@ -138,11 +138,7 @@ __device__ __noinline__ uint32_t join_process(uint2* q2, uint8_t* q2d, const See
     int d = 3;
     if (ok) { d = dist_small(a, b); ok = d <= 2; }
     const uint32_t n_d2 = (uint32_t)__popc(__ballot_sync(FULL, ok));
-    if (ok) {                                            // emitted by the pair's owner among the (condition, orientation) entries it meets
-        const uint4 set = __ldg(reinterpret_cast<const uint4*>(&lut[seed_flags(c_scheme, a, b)]));
-        const SeedSet m = {{set.x, set.y, set.z, set.w}};
-        ok = seed_pick(m, a, b) == (e.x > e.y ? want1 : want0);
-    }
+    if (ok) ok = __ldg(&lut[seed_flags(c_scheme, a, b)]) == (uint8_t)(e.x > e.y ? want1 : want0);   // emitted by the first (condition, orientation) the pair meets
     const unsigned m = __ballot_sync(FULL, ok);
     if (m == 0) return (uint32_t)q2n | (n_d2 << 8);
     if (ok) {                                            // fewer than 32 entries wait on entry, so 32 more always fit

@@ -15,8 +15,8 @@
 // equal-key buckets.  Conditions whose diagonals
 // are all 0 are symmetric ("self": one sort, each unordered couple once); the others pair (x, y) in both value orders.
 //   B = 4 (4,4,4,3 bases): 13 conditions on 14/16 key bits;  B = 5 (3 bases each): 25 conditions on 18 key bits.
-// A pair that meets several conditions is emitted by ONE of them, drawn by a hash of the pair from the set of meeting
-// (condition, orientation) entries; that set is looked up in a table over the pair's block-match flags (seed_flags).
+// A pair that meets several conditions is emitted by the FIRST (condition, orientation) in table order; that index is
+// looked up in a table over the pair's block-match flags (seed_flags / first_lut), built here on the host.
 //
 // Everything is __host__ __device__: tests/test_core_host.py compiles this header with g++ and checks, against the oracle's
 // distances, that the conditions are necessary for D <= 2, and that the emulated passes give the oracle's edge set.
@@ -175,68 +175,23 @@ inline bool seed_scheme_build(SeedScheme& s, const int* bases, int nblocks)
     return true;
 }
 
-// ---- which pass emits a pair that meets several conditions -----------------------------------------------------
-// Every (condition, orientation) a pair meets would find it; exactly one of them - the OWNER - emits it.  The owner is drawn
-// from the meeting ones by a hash of the pair, not "the first one": the edges (their 6-mer scores, their stores, their way
-// across PCIe) then spread evenly over the conditions, and so over the GPUs the conditions are dealt to.
-// Entry index e = 2 * condition + orientation (o = 0: (x, y) = (a, b); o = 1: (x, y) = (b, a); a < b).
-struct SeedSet { uint32_t w[4]; };          // bit e: entry e holds (SEED_MAX_CONDS * 2 <= 128)
-
-BDG_HD int nth_set_bit(uint32_t w, int k)   // position of the k-th (0-based) set bit; k < popc(w)
-{
-    for (int i = 0; i < k; i++) w &= w - 1;
-#if defined(__CUDA_ARCH__)
-    return __ffs(w) - 1;
-#else
-    return __builtin_ctz(w);
-#endif
-}
-
-BDG_HD int seed_pick(const SeedSet& m, uint32_t a, uint32_t b)   // SEED_NONE if the set is empty
-{
-    const int n0 = popc(m.w[0]), n1 = popc(m.w[1]), n2 = popc(m.w[2]), n3 = popc(m.w[3]);
-    const int n = n0 + n1 + n2 + n3;
-    if (n == 0) return SEED_NONE;
-    const uint32_t h = (a * 0x9E3779B1u) ^ (b * 0x85EBCA6Bu);
-    int k = (int)(((h >> 16) * (uint32_t)n) >> 16);                 // uniform in [0, n)
-    if (k < n0) return nth_set_bit(m.w[0], k);
-    k -= n0;
-    if (k < n1) return 32 + nth_set_bit(m.w[1], k);
-    k -= n1;
-    if (k < n2) return 64 + nth_set_bit(m.w[2], k);
-    return 96 + nth_set_bit(m.w[3], k - n2);
-}
-
-// by the definition (the kernels go through seed_flags and the table below)
-BDG_HD int seed_owner_slow(const SeedScheme& s, uint32_t a, uint32_t b)
-{
-    SeedSet m = {{0u, 0u, 0u, 0u}};
-    for (int c = 0; c < s.nconds; c++) {
-        if (seed_pred(s, c, a, b)) m.w[(2 * c) >> 5] |= 1u << ((2 * c) & 31);
-        if (!s.cond[c].self && seed_pred(s, c, b, a)) m.w[(2 * c + 1) >> 5] |= 1u << ((2 * c + 1) & 31);
-    }
-    return seed_pick(m, a, b);
-}
-
-BDG_HD int seed_owner(const SeedScheme& s, const SeedSet* lut, uint32_t a, uint32_t b) { return seed_pick(lut[seed_flags(s, a, b)], a, b); }
-
-// lut: 1 << s.nflags entries: the set of entries whose blocks all match, per value of seed_flags
-inline void seed_lut_build(const SeedScheme& s, SeedSet* lut)
+// lut: 1 << s.nflags entries
+inline void seed_lut_build(const SeedScheme& s, uint8_t* lut)
 {
     for (uint32_t f = 0; f < (1u << s.nflags); f++) {
-        SeedSet m = {{0u, 0u, 0u, 0u}};
-        for (int c = 0; c < s.nconds; c++) {
-            for (int o = 0; o < (s.cond[c].self ? 1 : 2); o++) {
+        uint8_t first = SEED_NONE;
+        for (int c = 0; c < s.nconds && first == SEED_NONE; c++) {
+            for (int o = 0; o < (s.cond[c].self ? 1 : 2) && first == SEED_NONE; o++) {
                 bool all = true;
                 for (int k = 0; k < s.cond[c].nf; k++) {
                     const int b = s.cond[c].blk[k];
                     const int bit = 3 * b + (s.cond[c].d[k] == 0 ? 0 : (o == 0 ? 1 : 2));
                     all = all && ((f >> bit) & 1u);
                 }
-                if (all) m.w[(2 * c + o) >> 5] |= 1u << ((2 * c + o) & 31);
+                if (all) first = (uint8_t)(2 * c + o);
             }
         }
-        lut[f] = m;
+        lut[f] = first;
     }
 }
 

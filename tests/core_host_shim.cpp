@@ -60,24 +60,23 @@ int shim_top_possible(int t, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t 
 
 // ---- multi-block seeds (bdg_seed.cuh): scheme tables, hand-over table, sort forms, and the join passes emulated on the host
 static bdg::SeedScheme g_scheme;
-static std::vector<bdg::SeedSet> g_lut;
+static std::vector<uint8_t> g_lut;
 int shim_scheme(const int* bases, int nblocks)          // returns the number of conditions, -1 if the layout is refused
 {
     if (!bdg::seed_scheme_build(g_scheme, bases, nblocks)) return -1;
-    g_lut.assign((size_t)1 << g_scheme.nflags, bdg::SeedSet{{0u, 0u, 0u, 0u}});
+    g_lut.assign((size_t)1 << g_scheme.nflags, 0);
     bdg::seed_lut_build(g_scheme, g_lut.data());
     return g_scheme.nconds;
 }
 int shim_scheme_nself(void) { return g_scheme.nself; }
 int shim_scheme_key_bits(int c) { return g_scheme.ka[c].key_bits; }
 int shim_scheme_row_sort(int c) { return g_scheme.cond[c].row_sort; }
-// first (condition, orientation) a pair meets by the definition; its owner by the definition and by the table over the flags
-void shim_scheme_first(const uint32_t* a, const uint32_t* b, size_t n, uint8_t* first, uint8_t* slow, uint8_t* fast)
+// first (condition, orientation) by the definition and by the table over the block-match flags
+void shim_scheme_first(const uint32_t* a, const uint32_t* b, size_t n, uint8_t* slow, uint8_t* fast)
 {
     for (size_t i = 0; i < n; i++) {
-        first[i] = (uint8_t)bdg::seed_first_slow(g_scheme, a[i], b[i]);
-        slow[i] = (uint8_t)bdg::seed_owner_slow(g_scheme, a[i], b[i]);
-        fast[i] = (uint8_t)bdg::seed_owner(g_scheme, g_lut.data(), a[i], b[i]);
+        slow[i] = (uint8_t)bdg::seed_first_slow(g_scheme, a[i], b[i]);
+        fast[i] = g_lut[bdg::seed_flags(g_scheme, a[i], b[i])];
         if (bdg::seed_flags(g_scheme, a[i], b[i]) != bdg::seed_flags_slow(g_scheme, a[i], b[i])) fast[i] = 254;   // must agree
     }
 }
@@ -123,7 +122,7 @@ size_t shim_join_emulate(const uint32_t* s, size_t n, uint32_t* oa, uint32_t* ob
                 const int d = bdg::dist_small(a, b);
                 if (d > 2) continue;
                 st[2]++;
-                if (bdg::seed_owner(S, g_lut.data(), a, b) != 2 * c + (S.cond[c].self || x < y ? 0 : 1)) continue;
+                if (g_lut[bdg::seed_flags(S, a, b)] != 2 * c + (x < y ? 0 : 1)) continue;
                 st[3]++;
                 if (bdg::qgram_score(a, b) < bdg::qgram_threshold(2)) continue;
                 st[4]++;
