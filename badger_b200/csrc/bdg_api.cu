@@ -101,7 +101,7 @@ struct DevCtx {
     // join form of the t = 2 edge construction (bdg_join.cuh): barcodes in the key order of every condition's row side / column
     // side, first column of every key, scratch keys (in / sorted) and radix-sort scratch, units per slab and their prefix sums
     // (one set per stream: the conditions of a block set run back to back on one stream)
-    Buf jn_rows[2], jn_cols[2], jn_tab[2], jn_tabc[2], jn_hist[2], jn_cub[2], jn_counts[2], jn_offs[2], jn_lut;
+    Buf jn_rows[2], jn_cols[2], jn_tab[2], jn_tabc[2], jn_hist[2], jn_cub[2], jn_counts[2], jn_offs[2], jn_lut, jn_weigh;
     int scheme_serial = 0;                                    // which scheme sits in this device's constant memory (0: none)
     cudaEvent_t ev_cond[bdg::SEED_MAX_CONDS] = {};            // bdg_edges_build_into: "condition c has appended its edges"
     unsigned long long* snap_host = nullptr;                  // mapped page-locked: the edge count after every condition
@@ -244,8 +244,8 @@ double now_ms()
     return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
-// Join form (t = 2), bdg_join.cuh.  The seed conditions are laid on a line by weight (a symmetric condition pairs each couple
-// once: weight 1; a shifted one pairs both value orders: weight 2) and the line is cut into nparts equal pieces: a part sorts and
+// Join form (t = 2), bdg_join.cuh.  The seed conditions are laid on a line by weight (their estimated work, see below) and the
+// line is cut into nparts equal pieces: a part sorts and
 // joins only the conditions its piece touches, a condition on a cut is shared by row range (cut at a bucket boundary).  Per condition: counting sort by the
 // key (rows once per block set, columns for the shifted conditions; its prefix sums are colstart) -> units per slab -> prefix sums ->
 // one persistent join launch.  The conditions of a block set follow one another and share the row order.  Consecutive block sets alternate between the caller's stream and an auxiliary one, so that one
@@ -281,9 +281,43 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
     int rs = (N >> S.ka[0].key_bits) < 48 ? 8 : 32;
     if (const char* e = getenv("BDG_JOIN_RS")) rs = atoi(e) == 8 ? 8 : 32;
     const uint32_t n_slabs = (uint32_t)((N + bdg::JROWS - 1) / bdg::JROWS);
-    // the part's piece of the weight line, in units of 1 / nparts
-    int W = 0;
-    for (int c = 0; c < S.nconds; c++) W += S.cond[c].self ? 1 : 2;
+    // Weights of the conditions for the deal to the parts: one part takes everything; several parts estimate every condition's
+    // pairs from bucket sizes over a sample (identical integer arithmetic on every part) and add the bucketing of its sides.
+    long long weight[bdg::SEED_MAX_CONDS];
+    for (int c = 0; c < S.nconds; c++) weight[c] = 1;
+    if (nparts > 1) {
+        uint32_t maxtab = tab;
+        for (int c = 0; c < S.nconds; c++) maxtab = std::max(maxtab, 1u << S.ka[c].key_bits);
+        const uint32_t stride = (uint32_t)std::max<size_t>(1, (N + (1u << 18) - 1) >> 18);
+        const size_t hist_bytes = (size_t)S.nconds * 2 * maxtab * 4;
+        if (int e = ensure(ws->jn_weigh, hist_bytes + 8 * bdg::SEED_MAX_CONDS)) return e;
+        uint32_t* d_hist = (uint32_t*)ws->jn_weigh.p;
+        unsigned long long* d_pairs = (unsigned long long*)((char*)ws->jn_weigh.p + hist_bytes);
+        CU_TRY(cudaMemsetAsync(ws->jn_weigh.p, 0, hist_bytes + 8 * bdg::SEED_MAX_CONDS, caller));
+        const uint32_t m = (uint32_t)((N + stride - 1) / stride);
+        bdg::join_weigh_hist_kernel<<<(int)std::min<uint32_t>((m + 255) / 256, (uint32_t)ws->sms * 8), 256, 0, caller>>>(d_sorted, (uint32_t)N, stride, S.nconds, maxtab, d_hist);
+        bdg::join_weigh_sum_kernel<<<ws->sms * 2, 256, 0, caller>>>(d_hist, S.nconds, maxtab, d_pairs);
+        g_launches += 2;
+        unsigned long long pairs[bdg::SEED_MAX_CONDS];
+        CU_TRY(cudaMemcpyAsync(pairs, d_pairs, 8 * S.nconds, cudaMemcpyDeviceToHost, caller));
+        CU_TRY(cudaStreamSynchronize(caller));
+        // cost in "tested pairs": the estimated pairs plus ~4 per barcode and bucketed side (measured at C4: 0.1 ms per side of
+        // 4.6e6 barcodes against 6.5e-9 ms per tested pair); scaled to <= 4096 so that the cut arithmetic stays small
+        unsigned long long cost[bdg::SEED_MAX_CONDS], top = 1;
+        for (int c = 0; c < S.nconds; c++) {
+            const unsigned long long sides = S.cond[c].self ? 1 : 2;
+            cost[c] = pairs[c] * stride * stride + 4ull * sides * N;
+            top = std::max(top, cost[c]);
+        }
+        for (int c = 0; c < S.nconds; c++) weight[c] = (long long)std::max<unsigned long long>(1, cost[c] * 4096 / top);
+        if (getenv("BDG_TRACE")) {
+            fprintf(stderr, "[bdg] join weights (part %d of %d):", part, nparts);
+            for (int c = 0; c < S.nconds; c++) fprintf(stderr, " %lld", weight[c]);
+            fprintf(stderr, "\n");
+        }
+    }
+    long long W = 0;
+    for (int c = 0; c < S.nconds; c++) W += weight[c];
     const long long piece_lo = (long long)part * W, piece_hi = (long long)(part + 1) * W;      // cond c covers [start_c * nparts, (start_c + w_c) * nparts)
     if (int e = ensure(ws->plan, PLAN_HDR * bdg::MAX_PASSES + 8 * bdg::SEED_MAX_CONDS)) return e;
     char* d_plan = (char*)ws->plan.p;
@@ -327,7 +361,7 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
     double t_prev = 0;
     if (trace) { cudaStreamSynchronize(caller); t_prev = now_ms(); }
     for (int c = 0; c < S.nconds; c++) {
-        const int w = S.cond[c].self ? 1 : 2;
+        const long long w = weight[c];
         const long long c_lo = start * nparts, c_hi = (start + w) * nparts;
         start += w;
         const long long lo = std::max(c_lo, piece_lo), hi = std::min(c_hi, piece_hi);
@@ -737,7 +771,7 @@ void bdg_shutdown(void)
             c.jn_rows[k].release(); c.jn_cols[k].release(); c.jn_tab[k].release(); c.jn_tabc[k].release(); c.jn_hist[k].release();
             c.jn_cub[k].release(); c.jn_counts[k].release(); c.jn_offs[k].release();
         }
-        c.jn_lut.release();
+        c.jn_lut.release(); c.jn_weigh.release();
         if (c.snap_host) { cudaFreeHost(c.snap_host); c.snap_host = nullptr; for (auto& e : c.ev_cond) if (e) cudaEventDestroy(e); }
     }
     g_ctx.clear();

@@ -86,6 +86,36 @@ __device__ __forceinline__ uint32_t join_cut(const uint32_t* __restrict__ rowsta
     return __ldg(&rowstart[lo]);
 }
 
+// ---- how much work is a condition?  (the deal of the conditions to several parts) -------------------------------------
+// Bucket sizes of every condition over a SAMPLE of the barcodes (every stride-th one): the number of (row, column) pairs a
+// condition has to test is sum_k rows_k * cols_k (a symmetric one: sum_k n_k (n_k - 1) / 2), and the sample's sum times
+// stride^2 estimates it.  Integer counts over the same sample on every part, so every part computes the same deal.
+__global__ void join_weigh_hist_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t stride, int nconds, uint32_t tab, uint32_t* __restrict__ hist)
+{
+    const uint32_t m = (n + stride - 1) / stride;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
+        const uint32_t x = __ldg(&in[(uint64_t)j * stride]);
+        for (int c = 0; c < nconds; c++) {
+            atomicAdd(&hist[(size_t)(2 * c) * tab + seed_key(x, c_scheme.ka[c])], 1u);
+            if (!c_scheme.cond[c].self) atomicAdd(&hist[(size_t)(2 * c + 1) * tab + seed_key(x, c_scheme.kb[c])], 1u);
+        }
+    }
+}
+
+__global__ void join_weigh_sum_kernel(const uint32_t* __restrict__ hist, int nconds, uint32_t tab, unsigned long long* __restrict__ out)
+{
+    for (int c = 0; c < nconds; c++) {
+        const bool self = c_scheme.cond[c].self != 0;
+        unsigned long long mine = 0;
+        for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < tab; k += gridDim.x * blockDim.x) {
+            const unsigned long long r = __ldg(&hist[(size_t)(2 * c) * tab + k]);
+            mine += self ? r * (r - (r ? 1 : 0)) / 2 : r * __ldg(&hist[(size_t)(2 * c + 1) * tab + k]);
+        }
+        for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(FULL, mine, o);
+        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&out[c], mine);
+    }
+}
+
 // the edge count as it stands when the stream reaches this point (bdg_edges_build_into copies the finished edges out meanwhile)
 __global__ void join_snapshot_kernel(const unsigned long long* __restrict__ count, volatile unsigned long long* __restrict__ snap)
 {
