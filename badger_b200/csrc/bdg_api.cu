@@ -286,9 +286,9 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
     long long weight[bdg::SEED_MAX_CONDS];
     for (int c = 0; c < S.nconds; c++) weight[c] = 1;
     if (nparts > 1) {
-        uint32_t maxtab = tab;
+        uint32_t maxtab = 1;
         for (int c = 0; c < S.nconds; c++) maxtab = std::max(maxtab, 1u << S.ka[c].key_bits);
-        const uint32_t stride = (uint32_t)std::max<size_t>(1, (N + (1u << 18) - 1) >> 18);
+        const uint32_t stride = (uint32_t)std::max<size_t>(1, (N + (1u << 17) - 1) >> 17);
         const size_t hist_bytes = (size_t)S.nconds * 2 * maxtab * 4;
         if (int e = ensure(ws->jn_weigh, hist_bytes + 8 * bdg::SEED_MAX_CONDS)) return e;
         uint32_t* d_hist = (uint32_t*)ws->jn_weigh.p;
@@ -302,11 +302,14 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
         CU_TRY(cudaMemcpyAsync(pairs, d_pairs, 8 * S.nconds, cudaMemcpyDeviceToHost, caller));
         CU_TRY(cudaStreamSynchronize(caller));
         // cost in "tested pairs": the estimated pairs plus ~4 per barcode and bucketed side (measured at C4: 0.1 ms per side of
-        // 4.6e6 barcodes against 6.5e-9 ms per tested pair); scaled to <= 4096 so that the cut arithmetic stays small
+        // 4.6e6 barcodes against 6.5e-9 ms per tested pair); scaled to <= 4096 so that the cut arithmetic stays small.  A pair of
+        // a symmetric condition counts twice: on barcode data (clusters around the cell barcodes) the pairs that are really
+        // close - the ones that cost an exact distance, a hand-over check and a score - sit on diagonal 0 (measured per
+        // condition at C4, BDG_TRACE: 0.7-1.7 ms symmetric against 0.8-1.4 ms shifted at half / all the pairs of a bucket).
         unsigned long long cost[bdg::SEED_MAX_CONDS], top = 1;
         for (int c = 0; c < S.nconds; c++) {
             const unsigned long long sides = S.cond[c].self ? 1 : 2;
-            cost[c] = pairs[c] * stride * stride + 4ull * sides * N;
+            cost[c] = pairs[c] * stride * stride * (S.cond[c].self ? 2 : 1) + 4ull * sides * N;
             top = std::max(top, cost[c]);
         }
         for (int c = 0; c < S.nconds; c++) weight[c] = (long long)std::max<unsigned long long>(1, cost[c] * 4096 / top);

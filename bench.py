@@ -381,6 +381,12 @@ def run_b200(args):
     stats = step.stats()
     ms_total = max_over_ranks(ms)
     step_ms = ms / args.steps             # this rank's average step (all launches of the step, CUDA events)
+    ms_ranks = [step_ms]
+    if world > 1:
+        tt = torch.zeros(world, dtype=torch.float64, device=dev)
+        tt[rank] = step_ms
+        dist.all_reduce(tt)
+        ms_ranks = [float(x) for x in tt.tolist()]
     value = total_pairs * args.steps / (ms_total * 1e-3)
     edges_total = sum_over_ranks(n_edges_part)
 
@@ -459,7 +465,7 @@ def run_b200(args):
                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "u32", "data": "synthetic",
                "config": config_dict(args.config, cfg, n),
-               "details": {"edges": edges_total, "edges_rank0": n_edges_part, "edge_mode": mode, "l2": "flushed between timed iterations (256 MB write)",
+               "details": {"edges": edges_total, "edges_rank0": n_edges_part, "ms_per_step_by_rank": ms_ranks, "edge_mode": mode, "l2": "flushed between timed iterations (256 MB write)",
                            "partition": "array replicated; work units of the sorted orders dealt round-robin to ranks; no data-path collective"},
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
                "reads_per_s": cfg["reads"] * args.steps / (ms_total * 1e-3)}
