@@ -344,8 +344,12 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
         if (int e = ensure(ws->jn_counts[k], ((size_t)n_slabs + 1) * 4)) return e;
         if (int e = ensure(ws->jn_offs[k], ((size_t)n_slabs + 1) * 4)) return e;
     }
+    int occ = 6;                                            // resident CTAs per SM the kernel is compiled for (registers per thread follow)
+    if (const char* e = getenv("BDG_JOIN_OCC")) occ = atoi(e) == 4 ? 4 : (atoi(e) == 5 ? 5 : 6);
+    const void* kern = rs == 8 ? (occ == 4 ? (const void*)bdg::join_kernel<8, 4> : occ == 5 ? (const void*)bdg::join_kernel<8, 5> : (const void*)bdg::join_kernel<8, 6>)
+                               : (occ == 4 ? (const void*)bdg::join_kernel<32, 4> : occ == 5 ? (const void*)bdg::join_kernel<32, 5> : (const void*)bdg::join_kernel<32, 6>);
     int grid = 0;
-    if (int rc = grid_for(rs == 8 ? (const void*)bdg::join_kernel<8> : (const void*)bdg::join_kernel<32>, &grid, bdg::ENT)) return rc;
+    if (int rc = grid_for(kern, &grid, bdg::ENT)) return rc;
     const int gb = (int)std::min<size_t>((N + 255) / 256, (size_t)ws->sms * 8);
     const int bb = (int)std::min<size_t>(((size_t)n_slabs + 256) / 256, (size_t)ws->sms * 8);
     const bool fork = !js && !getenv("BDG_EDGE_SERIAL");
@@ -415,8 +419,15 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
         bdg::join_band_kernel<<<bb, 256, 0, st>>>(A, (uint32_t*)ws->jn_counts[k].p);
         size_t bytes = ws->jn_cub[k].cap;
         CU_TRY(cub::DeviceScan::ExclusiveSum(ws->jn_cub[k].p, bytes, (const uint32_t*)ws->jn_counts[k].p, (uint32_t*)ws->jn_offs[k].p, (int)(n_slabs + 1), st));
-        if (rs == 8) bdg::join_kernel<8><<<grid, bdg::ENT, 0, st>>>(A, o);
-        else bdg::join_kernel<32><<<grid, bdg::ENT, 0, st>>>(A, o);
+        if (rs == 8) {
+            if (occ == 4) bdg::join_kernel<8, 4><<<grid, bdg::ENT, 0, st>>>(A, o);
+            else if (occ == 5) bdg::join_kernel<8, 5><<<grid, bdg::ENT, 0, st>>>(A, o);
+            else bdg::join_kernel<8, 6><<<grid, bdg::ENT, 0, st>>>(A, o);
+        } else {
+            if (occ == 4) bdg::join_kernel<32, 4><<<grid, bdg::ENT, 0, st>>>(A, o);
+            else if (occ == 5) bdg::join_kernel<32, 5><<<grid, bdg::ENT, 0, st>>>(A, o);
+            else bdg::join_kernel<32, 6><<<grid, bdg::ENT, 0, st>>>(A, o);
+        }
         g_launches += 3;
         CU_TRY(cudaGetLastError());
         if (trace) {                                        // development aid: per-condition wall time (serialises the streams)

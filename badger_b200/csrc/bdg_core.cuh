@@ -405,6 +405,23 @@ BDG_HD int qgram_score(uint32_t a, uint32_t b, uint64_t* mult = nullptr)
     return s;
 }
 
+// Two halves of the score for the join kernel: the three middle diagonals, where nearly all of a close pair's shared 6-mers
+// sit (their count alone usually reaches the threshold), and the other eighteen as a compact loop.  near + far == qgram_score.
+BDG_HD int qgram_score_near(uint32_t a, uint32_t b)
+{
+    return popc(run6(~mism(a, b) & EVEN)) + popc(run6(~mism(a, b >> 2) & (EVEN >> 2))) + popc(run6(~mism(a, b << 2) & (EVEN << 2)));
+}
+BDG_HD int qgram_score_far(uint32_t a, uint32_t b)
+{
+    int s = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int k = 2; k <= 10; k++)
+        s += popc(run6(~mism(a, b >> (2 * k)) & (EVEN >> (2 * k)))) + popc(run6(~mism(a, b << (2 * k)) & (EVEN << (2 * k))));
+    return s;
+}
+
 // The same score as a compact loop (one diagonal pair per trip, nothing unrolled): the join kernel keeps its whole hot path
 // inside the instruction cache, and 21 unrolled diagonals are a third of it.
 BDG_HD int qgram_score_compact(uint32_t a, uint32_t b)

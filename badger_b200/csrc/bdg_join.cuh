@@ -28,8 +28,8 @@ constexpr int JCH = 128;           // columns staged at a time
 constexpr int JPAD = 32;           // slack behind the staged columns (steps may start up to one step early)
 constexpr int JUNIT = 2048;        // columns per work unit
 constexpr int JBATCH = 4;          // units per cursor fetch
-constexpr int JQCAP = 160;         // candidate queue entries per warp
-constexpr int JQ2CAP = 64;         // entries of the scoring queue
+constexpr int JQCAP = 120;         // candidate queue entries per warp (with the other arrays: 6 CTAs of 8 warps per SM)
+constexpr int JQ2CAP = 64;         // entries of each of the two scoring queues
 constexpr int JROWS = 32;          // rows per slab
 
 __constant__ SeedScheme c_scheme;
@@ -155,14 +155,17 @@ struct JoinCtx {
 // exact stage on a batch of candidates of one condition (one per lane): D by case analysis, hand-over table, survivors into the
 // scoring queue, full batches of that queue through the 6-mer score.  A real call, not inlined: one copy of the exact distance
 // and of the score loop keeps the kernel's hot code inside the instruction cache (ncu: the fully inlined form spent most of its
-// issue slots waiting for instructions).  Everything travels in registers: returns the queue fill | pairs with D <= 2 << 8 |
-// pairs handed to the score << 16.
+// issue slots waiting for instructions).  Everything travels in registers: returns the two queue fills (8 bits each) | pairs
+// with D <= 2 << 16 | pairs handed to the score << 24.
 // want0 / want1: the hand-over index this pass owns for a candidate with row value < / > column value (the same for a symmetric
 // condition, whose buckets are in no particular order).
 __device__ __noinline__ uint32_t join_process(uint2* q2, uint8_t* q2d, const uint8_t* lut, int want0, int want1, int T, const EdgeOut out, uint2 e, bool active,
                                               int q2n)
 {
+    // q2 holds two queues: entries [0, 64) pairs that still need their score, entries [64, 128) pairs whose three middle
+    // diagonals did not reach the threshold and need the other eighteen; q2n = fill of the first | fill of the second << 8
     const int lane = threadIdx.x & 31;
+    int n1 = q2n & 255, n2 = q2n >> 8;
     const uint32_t a = min(e.x, e.y), b = max(e.x, e.y);
     bool ok = active && a != b;
     int d = 3;
@@ -170,23 +173,37 @@ __device__ __noinline__ uint32_t join_process(uint2* q2, uint8_t* q2d, const uin
     const uint32_t n_d2 = (uint32_t)__popc(__ballot_sync(FULL, ok));
     if (ok) ok = __ldg(&lut[seed_flags(c_scheme, a, b)]) == (uint8_t)(e.x > e.y ? want1 : want0);   // emitted by the first (condition, orientation) the pair meets
     const unsigned m = __ballot_sync(FULL, ok);
-    if (m == 0) return (uint32_t)q2n | (n_d2 << 8);
+    if (m == 0) return (uint32_t)q2n | (n_d2 << 16);
     if (ok) {                                            // fewer than 32 entries wait on entry, so 32 more always fit
-        const int slot = q2n + __popc(m & ((1u << lane) - 1u));
+        const int slot = n1 + __popc(m & ((1u << lane) - 1u));
         q2[slot] = make_uint2(a, b);
         q2d[slot] = (uint8_t)d;
     }
-    q2n += __popc(m);
+    n1 += __popc(m);
     __syncwarp();
-    while (q2n >= 32) {
-        q2n -= 32;
-        const uint2 mv = q2[q2n + lane];
-        const uint8_t md = q2d[q2n + lane];
-        const bool good = qgram_score_compact(mv.x, mv.y) >= T;
-        emit_warp(good, mv.x, mv.y, md, out);
+    while (n1 >= 32) {                                   // full batches: score of the middle diagonals; what they decide is emitted
+        n1 -= 32;
+        const uint2 mv = q2[n1 + lane];
+        const uint8_t md = q2d[n1 + lane];
+        const int near = qgram_score_near(mv.x, mv.y);
+        emit_warp(near >= T, mv.x, mv.y, md, out);
+        const unsigned rest = __ballot_sync(FULL, near < T);
+        if (near < T) {
+            const int slot = JQ2CAP + n2 + __popc(rest & ((1u << lane) - 1u));
+            q2[slot] = mv;
+            q2d[slot] = (uint8_t)(md | (near << 2));     // distance (1 or 2) and the part of the score that is known
+        }
+        n2 += __popc(rest);
         __syncwarp();
+        if (n2 >= 32) {                                  // a full batch of the undecided: the other eighteen diagonals
+            n2 -= 32;
+            const uint2 fv = q2[JQ2CAP + n2 + lane];
+            const uint8_t fd = q2d[JQ2CAP + n2 + lane];
+            emit_warp((int)(fd >> 2) + qgram_score_far(fv.x, fv.y) >= T, fv.x, fv.y, fd & 3, out);
+            __syncwarp();
+        }
     }
-    return (uint32_t)q2n | (n_d2 << 8) | ((uint32_t)__popc(m) << 16);
+    return (uint32_t)n1 | ((uint32_t)n2 << 8) | (n_d2 << 16) | ((uint32_t)__popc(m) << 24);
 }
 
 __device__ __forceinline__ void join_drain(JoinCtx& c, const EdgeOut& out, int& qn, int& q2n, bool all)
@@ -197,9 +214,9 @@ __device__ __forceinline__ void join_drain(JoinCtx& c, const EdgeOut& out, int& 
         qn -= take;
         const uint2 e = c.lane < take ? c.q[qn + c.lane] : make_uint2(0u, 0u);
         const uint32_t r = join_process(c.q2, c.q2d, c.lut, 2 * c.cond, 2 * c.cond + c.shifted, c.T, out, e, c.lane < take, q2n);
-        q2n = (int)(r & 255u);
-        c.n_d2 += (r >> 8) & 255u;
-        c.n_score += r >> 16;
+        q2n = (int)(r & 0xFFFFu);
+        c.n_d2 += (r >> 16) & 255u;
+        c.n_score += r >> 24;
         __syncwarp();
     }
 }
@@ -241,15 +258,15 @@ __device__ __forceinline__ void join_push(uint32_t h, uint32_t x, const uint32_t
     }
 }
 
-template <int RS>
-__global__ void __launch_bounds__(ENT, 6) join_kernel(const JoinArgs A, const EdgeOut out)
+template <int RS, int OCC>
+__global__ void __launch_bounds__(ENT, OCC) join_kernel(const JoinArgs A, const EdgeOut out)
 {
     constexpr int PH = 32 / RS;                          // column phases of a warp
     constexpr int STEP = 4 * PH;                         // columns per inner step
     __shared__ __align__(16) uint32_t s_b[EW][4][JCH + JPAD];   // y, y >> 2, y << 2, key of the staged columns
     __shared__ uint2 s_q[EW][JQCAP];
-    __shared__ uint2 s_q2[EW][JQ2CAP];
-    __shared__ uint8_t s_q2d[EW][JQ2CAP];
+    __shared__ uint2 s_q2[EW][2 * JQ2CAP];              // pairs that need their score | pairs that need the far diagonals
+    __shared__ uint8_t s_q2d[EW][2 * JQ2CAP];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int r = lane & (RS - 1), ph = lane / RS;
     uint32_t* const sb0 = s_b[wid][0];
@@ -363,14 +380,23 @@ __global__ void __launch_bounds__(ENT, 6) join_kernel(const JoinArgs A, const Ed
         }
     }
     join_drain(c, out, qn, q2n, true);
-    if (q2n > 0) {                                       // fewer than 32 by construction
+    {                                                    // what is left in the two scoring queues: fewer than 32 each
+        const int n1 = q2n & 255, n2 = q2n >> 8;
         bool ok = false;
         uint32_t a = 0, b = 0;
         int d = 0;
-        if (lane < q2n) {
+        if (lane < n1) {
             const uint2 e = c.q2[lane];
             a = e.x; b = e.y; d = c.q2d[lane];
             ok = qgram_score_compact(a, b) >= A.T;
+        }
+        emit_warp(ok, a, b, d, out);
+        ok = false;
+        if (lane < n2) {
+            const uint2 e = c.q2[JQ2CAP + lane];
+            const uint8_t fd = c.q2d[JQ2CAP + lane];
+            a = e.x; b = e.y; d = fd & 3;
+            ok = (int)(fd >> 2) + qgram_score_far(a, b) >= A.T;
         }
         emit_warp(ok, a, b, d, out);
     }

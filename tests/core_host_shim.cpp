@@ -82,7 +82,8 @@ void shim_scheme_first(const uint32_t* a, const uint32_t* b, size_t n, uint8_t* 
 }
 void shim_qgram_compact(const uint32_t* a, const uint32_t* b, size_t n, uint8_t* full, uint8_t* compact)
 {
-    for (size_t i = 0; i < n; i++) { full[i] = (uint8_t)bdg::qgram_score(a[i], b[i]); compact[i] = (uint8_t)bdg::qgram_score_compact(a[i], b[i]); }
+    for (size_t i = 0; i < n; i++) { full[i] = (uint8_t)bdg::qgram_score(a[i], b[i]); compact[i] = (uint8_t)bdg::qgram_score_compact(a[i], b[i]);
+                                     if (bdg::qgram_score_near(a[i], b[i]) + bdg::qgram_score_far(a[i], b[i]) != (int)full[i]) compact[i] = 255; }
 }
 void shim_scheme_keys(int c, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* ka, uint32_t* kb, uint8_t* pred)
 {
