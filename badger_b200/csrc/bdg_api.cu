@@ -350,6 +350,7 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
                                : (occ == 4 ? (const void*)bdg::join_kernel<32, 4> : occ == 5 ? (const void*)bdg::join_kernel<32, 5> : (const void*)bdg::join_kernel<32, 6>);
     int grid = 0;
     if (int rc = grid_for(kern, &grid, bdg::ENT)) return rc;
+    if (const char* e = getenv("BDG_JOIN_CTAS")) grid = std::min(grid, ws->sms * std::max(1, atoi(e)));   // CTAs per SM of a join launch
     const int gb = (int)std::min<size_t>((N + 255) / 256, (size_t)ws->sms * 8);
     const int bb = (int)std::min<size_t>(((size_t)n_slabs + 256) / 256, (size_t)ws->sms * 8);
     const bool fork = !js && !getenv("BDG_EDGE_SERIAL");
@@ -484,6 +485,7 @@ int launch_edges(const uint32_t* d_sorted, size_t N, int t, int part, int nparts
                                                                                      : (const void*)bdg::edges_kernel<3>);
     int grid = 0;
     if (int rc = grid_for(kern, &grid, bdg::ENT)) return rc;
+    if (const char* e = getenv("BDG_JOIN_CTAS")) grid = std::min(grid, ws->sms * std::max(1, atoi(e)));   // CTAs per SM of a join launch
     Plan plan;
     build_plan(N, part, nparts, grid * bdg::EW, plan, bdg::SB_MAX);
     const uint32_t n_items = plan.item_start.empty() ? 0 : plan.item_start.back();
