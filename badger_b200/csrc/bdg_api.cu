@@ -95,7 +95,8 @@ struct DevCtx {
     unsigned long long map_token = 0, map_serial = 0;         // read map left on the device by bdg_dedup_reads (0: none)
     size_t map_rows = 0, map_reads = 0, map_distinct = 0;
     bool map_masked = false;
-    Buf gather_a, gather_b;                                   // edge ends of ALL devices of a multi-device handle, gathered here for cluster()
+    Buf gather_a, gather_b;                                   // node indices of the edge ends: this device's own, and (first device) those of ALL devices, gathered for cluster()
+    Buf top16;                                                // first node of every high half of the barcode (the node of an edge end is searched in that run)
     Buf io[4];                                                // host-buffer calls of pack16 / membership: inputs, outputs, check flag
     Buf nn[9];                                                // sparse nearest: rotated keys + payload (in/out) of queries and targets, scratch
     // join form of the t = 2 edge construction (bdg_join.cuh): barcodes in the key order of every condition's row side / column
@@ -779,7 +780,7 @@ void bdg_shutdown(void)
         for (auto& b : c.nn) b.release();
         for (auto& b : c.io) b.release();
         for (auto& b : c.cl) b.release();
-        c.gather_a.release(); c.gather_b.release();
+        c.gather_a.release(); c.gather_b.release(); c.top16.release();
         for (auto& b : c.as) b.release();
         for (auto& b : c.ce) b.release();
         for (auto& b : c.rot_sorted) b.release();
@@ -1633,8 +1634,25 @@ void bdg_edges_free(bdg_edges* e) { delete e; }
 // ---- f-3  cluster(): barcode_graph.py:279-301 -------------------------------------------------------------
 // d_ea / d_eb hold barcode VALUES on entry and node indices on return (converted in place).
 // centre_idx / level may be NULL: the result then only stays on the device (cl[1] / cl[2]) for bdg_assign_reads*.
+// values -> node indices of the E edges (ea, eb) on device c (its own copy of the sorted array), written to (oa, ob); on c.stream
+static int index_edges(DevCtx& c, size_t N, const uint32_t* d_ea, const uint32_t* d_eb, size_t E, uint32_t* d_oa, uint32_t* d_ob)
+{
+    if (cudaError_t e = (cudaError_t)c.top16.ensure(65537 * 4))
+        return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation: %s", cudaGetErrorString(e));
+    const int nb = (int)std::min<size_t>((N + 256) / 256, (size_t)c.sms * 8);
+    bdg::top_start_kernel<<<nb, 256, 0, c.stream>>>((const uint32_t*)c.sorted.p, (uint32_t)N, (uint32_t*)c.top16.p);
+    if (E) {
+        const int eb = (int)std::min<size_t>((E + 255) / 256, (size_t)c.sms * 16);
+        bdg::cluster_index_kernel<<<eb, 256, 0, c.stream>>>((const uint32_t*)c.sorted.p, (const uint32_t*)c.top16.p, d_ea, d_eb, E, d_oa, d_ob);
+    }
+    g_launches += 2;
+    CU_TRY(cudaGetLastError());
+    return BDG_OK;
+}
+
 static int cluster_on_device(DevCtx& c, const uint32_t* d_sorted, size_t N, uint32_t* d_ea, uint32_t* d_eb, size_t E,
-                             const uint32_t* centres, size_t C, int rounds, int32_t* centre_idx, uint8_t* level, size_t* n_has_edge = nullptr)
+                             const uint32_t* centres, size_t C, int rounds, int32_t* centre_idx, uint8_t* level, size_t* n_has_edge = nullptr,
+                             bool indexed = false)
 {
     auto ensure = [&](Buf& b, size_t bytes) -> int {
         if (cudaError_t e = (cudaError_t)b.ensure(bytes))
@@ -1664,7 +1682,9 @@ static int cluster_on_device(DevCtx& c, const uint32_t* d_sorted, size_t N, uint
     if (C) bdg::cluster_seed_kernel<<<(int)std::min<size_t>((C + 255) / 256, (size_t)c.sms * 8), 256, 0, st>>>(d_sorted, (uint32_t)N, d_cen, (uint32_t)C, d_ci, d_lv);
     g_launches += 2;
     if (E) {
-        bdg::cluster_index_kernel<<<eb, 256, 0, st>>>(d_sorted, (uint32_t)N, d_ea, d_eb, E, d_lv, d_bad);
+        if (!indexed)                                       // (d_sorted is c.sorted on every path that reaches here)
+            if (int e = index_edges(c, N, d_ea, d_eb, E, d_ea, d_eb)) return e;
+        bdg::cluster_mark_kernel<<<eb, 256, 0, st>>>(d_ea, d_eb, E, d_lv, d_bad);
         g_launches++;
         if (trace) { cudaStreamSynchronize(st); tr1 = now_ms(); }
         for (int r = 1; r <= rounds; r++) {
@@ -1762,17 +1782,33 @@ static int cluster_from_edges(bdg_edges* e, size_t N, const uint32_t* centres, s
             return fail(err == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "gather buffer of %zu edges: %s", total, cudaGetErrorString(err));
         if (cudaError_t err = (cudaError_t)c.gather_b.ensure(std::max<size_t>(total, 1) * 4))
             return fail(err == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "gather buffer of %zu edges: %s", total, cudaGetErrorString(err));
+        // every device turns its own edges into node indices (its copy of the array, its SMs), then the indices travel
         size_t off = 0;
         for (size_t g = 0; g < e->ctx.size(); g++) {
-            const DevCtx& src = g_ctx[e->ctx[g]];
+            DevCtx& src = g_ctx[e->ctx[g]];
             const size_t k = e->count[g];
-            if (k) {
-                CU_TRY(cudaMemcpyPeerAsync((uint32_t*)c.gather_a.p + off, c.dev, src.ea.p, src.dev, k * 4, c.stream));
-                CU_TRY(cudaMemcpyPeerAsync((uint32_t*)c.gather_b.p + off, c.dev, src.eb.p, src.dev, k * 4, c.stream));
+            if (k == 0) continue;
+            if (&src == &c) {
+                CU_TRY(cudaSetDevice(c.dev));
+                if (int rc = index_edges(c, N, (const uint32_t*)c.ea.p, (const uint32_t*)c.eb.p, k, (uint32_t*)c.gather_a.p + off, (uint32_t*)c.gather_b.p + off)) return rc;
+            } else {
+                CU_TRY(cudaSetDevice(src.dev));
+                if (cudaError_t err = (cudaError_t)src.gather_a.ensure(k * 4)) return fail(BDG_ERR_OOM, "index buffer: %s", cudaGetErrorString(err));
+                if (cudaError_t err = (cudaError_t)src.gather_b.ensure(k * 4)) return fail(BDG_ERR_OOM, "index buffer: %s", cudaGetErrorString(err));
+                if (int rc = index_edges(src, N, (const uint32_t*)src.ea.p, (const uint32_t*)src.eb.p, k, (uint32_t*)src.gather_a.p, (uint32_t*)src.gather_b.p)) return rc;
+                CU_TRY(cudaMemcpyPeerAsync((uint32_t*)c.gather_a.p + off, c.dev, src.gather_a.p, src.dev, k * 4, src.stream));
+                CU_TRY(cudaMemcpyPeerAsync((uint32_t*)c.gather_b.p + off, c.dev, src.gather_b.p, src.dev, k * 4, src.stream));
             }
             off += k;
         }
-        return cluster_on_device(c, (const uint32_t*)c.sorted.p, N, (uint32_t*)c.gather_a.p, (uint32_t*)c.gather_b.p, total, centres, C, rounds, centre_idx, level, n_has_edge);
+        for (size_t g = 0; g < e->ctx.size(); g++) {             // the rounds start when every part has arrived
+            DevCtx& src = g_ctx[e->ctx[g]];
+            if (&src == &c || e->count[g] == 0) continue;
+            CU_TRY(cudaSetDevice(src.dev));
+            CU_TRY(cudaStreamSynchronize(src.stream));
+        }
+        CU_TRY(cudaSetDevice(c.dev));
+        return cluster_on_device(c, (const uint32_t*)c.sorted.p, N, (uint32_t*)c.gather_a.p, (uint32_t*)c.gather_b.p, total, centres, C, rounds, centre_idx, level, n_has_edge, true);
     }
     // the handle's edge VALUES are turned into node indices in place: the handle is consumed (stale afterwards)
     c.generation++;

@@ -457,23 +457,54 @@ __global__ void cluster_seed_kernel(const uint32_t* __restrict__ sorted, uint32_
     }
 }
 
-// barcode values of the edge list -> node indices, in place
-// and mark both ends "has an edge" (level 254; centres keep their 0, later rounds overwrite the mark of whoever they reach)
+// top[h] = first node whose barcode has the high half h (h = 0 .. 65536): the node of a barcode is then found in a run of
+// N / 65536 entries instead of all N (10 probes instead of 26 at N = 5e7)
+__global__ void top_start_kernel(const uint32_t* __restrict__ sorted, uint32_t n, uint32_t* __restrict__ top)
+{
+    for (uint64_t j = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; j <= n; j += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t k_hi = j < n ? (__ldg(&sorted[j]) >> 16) : 65536u;
+        const uint32_t k_lo = j > 0 ? (__ldg(&sorted[j - 1]) >> 16) + 1u : 0u;
+        for (uint32_t k = k_lo; k <= k_hi; k++) top[k] = (uint32_t)j;
+    }
+}
+
 constexpr uint8_t LEVEL_NONE = 255, LEVEL_HAS_EDGE = 254;
-// An end point that is not a node (a value absent from `sorted`) raises *bad and the edge is dropped (both ends 0xFFFFFFFF).
+// An end point that is not a node (a value absent from `sorted`) becomes NO_NODE at both ends of its edge; cluster_mark_kernel
+// raises the error flag for it and the claim kernel skips it.
 constexpr uint32_t NO_NODE = 0xFFFFFFFFu;
-__global__ void cluster_index_kernel(const uint32_t* __restrict__ sorted, uint32_t n, uint32_t* __restrict__ ea, uint32_t* __restrict__ eb, uint64_t n_edges,
-                                     uint8_t* __restrict__ level, unsigned int* __restrict__ bad)
+
+__device__ __forceinline__ uint32_t node_of(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ top, uint32_t v)
+{
+    uint32_t lo = __ldg(&top[v >> 16]), hi = __ldg(&top[(v >> 16) + 1u]);
+    const uint32_t end = hi;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&sorted[mid]) < v) lo = mid + 1; else hi = mid;
+    }
+    return (lo < end && __ldg(&sorted[lo]) == v) ? lo : NO_NODE;
+}
+
+// barcode values of an edge list -> node indices (in place when out == in).  Runs on the device that holds the edges.
+__global__ void cluster_index_kernel(const uint32_t* __restrict__ sorted, const uint32_t* __restrict__ top, const uint32_t* ea, const uint32_t* eb,
+                                     uint64_t n_edges, uint32_t* oa, uint32_t* ob)
 {
     for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (uint64_t)gridDim.x * blockDim.x) {
-        const uint32_t va = ea[e], vb = eb[e];
-        uint32_t ia = lower_bound_u32(sorted, n, va), ib = lower_bound_u32(sorted, n, vb);
-        if (ia >= n || ib >= n || __ldg(&sorted[ia]) != va || __ldg(&sorted[ib]) != vb) { *bad = 1u; ia = ib = NO_NODE; }
-        ea[e] = ia;
-        eb[e] = ib;
-        if (ia == NO_NODE) continue;
-        if (level[ia] == LEVEL_NONE) level[ia] = LEVEL_HAS_EDGE;               // every writer stores the same value
-        if (level[ib] == LEVEL_NONE) level[ib] = LEVEL_HAS_EDGE;
+        uint32_t ia = node_of(sorted, top, ea[e]), ib = node_of(sorted, top, eb[e]);
+        if (ia == NO_NODE || ib == NO_NODE) ia = ib = NO_NODE;
+        oa[e] = ia;
+        ob[e] = ib;
+    }
+}
+
+// mark both ends of every edge "has an edge" (level 254; centres keep their 0, later rounds overwrite the mark of whoever they reach)
+__global__ void cluster_mark_kernel(const uint32_t* __restrict__ ia, const uint32_t* __restrict__ ib, uint64_t n_edges, uint8_t* __restrict__ level,
+                                    unsigned int* __restrict__ bad)
+{
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n_edges; e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t u = __ldg(&ia[e]), v = __ldg(&ib[e]);
+        if (u == NO_NODE) { *bad = 1u; continue; }
+        if (level[u] == LEVEL_NONE) level[u] = LEVEL_HAS_EDGE;                 // every writer stores the same value
+        if (level[v] == LEVEL_NONE) level[v] = LEVEL_HAS_EDGE;
     }
 }
 

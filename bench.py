@@ -55,7 +55,11 @@ A_QUICK = {1: 14.5, 2: 16.5}       # 58 / 66 SASS instructions per 4 pairs
 A_LIGHT = {1: 1.25, 2: 6.0}
 A_EXACT = 110                      # loads, un-rotation, pass predicates, dist_small
 A_SCORE = 220                      # qgram_score, only for pairs with D <= t
-A_JOIN = {"unit": 160, "pair": 22.0, "cand": 85, "d2": 50, "score": 220}
+A_JOIN = {"unit": 160, "pair": 22.0, "cand": 85, "d2": 50, "score": 150}
+# Share of those instructions that issue on the ALU pipe (LOP3, SHF, ISETP, SEL, VOTE ...; the rest are IMAD on the FMA pipe):
+# sm__inst_executed_pipe_alu / (pipe_alu + pipe_fma) of the join kernel in the committed ncu capture (profiles/).  The kernel is
+# bound by that pipe (ncu: math-pipe throttle and not-selected are its top stalls), so its roofline is the ALU pipe's issue rate.
+ALU_SHARE = {"join": 0.845, "sparse": 0.81, "dense": 0.6}
 A_PAIR_SURVEY = {1: 15, 2: 25}   # SURVEY.md §8(d) nominal per-pair figure of a plain all-pairs kernel, reported alongside
 NCU_TRAFFIC = None               # bytes per step of the dominant kernel from the committed ncu capture (profiles/), with its label
 
@@ -442,13 +446,18 @@ def run_b200(args):
                 hbm = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
             except Exception:
                 hbm = 6451.8
-            roof = {"bound": "int_issue", "kernel": passes, "achieved": achieved, "peak": peak, "unit": "Tinst/s", "frac": achieved / peak if peak else None,
+            alu_peak = probe["lop3"]
+            alu_achieved = achieved * ALU_SHARE[mode]
+            roof = {"bound": "int_alu_pipe", "kernel": passes, "achieved": alu_achieved, "peak": alu_peak, "unit": "Tinst/s",
+                    "frac": alu_achieved / alu_peak if alu_peak else None,
+                    "issue_model": {"achieved": achieved, "peak": peak, "frac": achieved / peak if peak else None,
+                                    "note": "all algorithmic instructions against the LOP3+IMAD 1:1 dual-pipe issue rate (the figure round 1 reported)"},
                     "traffic": NCU_TRAFFIC["bytes"] if NCU_TRAFFIC and NCU_TRAFFIC["workload"] == (args.config, args.reads, t, mode, world) else None,
                     "traffic_note": (NCU_TRAFFIC["label"] if NCU_TRAFFIC else "no ncu capture of this build yet") +
                                     "; the algorithmic bytes are hbm.algorithmic_bytes_per_step",
-                    "how": "achieved = algorithmic integer instructions of rank 0's step (unit counts from the kernels' own counters x per-unit "
-                           "costs counted from the SASS, DESIGN.md: %s) / %.3f ms (CUDA events, this run); peak = measured issue rate of an "
-                           "independent LOP3+IMAD 1:1 stream on this GPU (bdg_dev_pipe_probe, this run)" % (
+                    "how": "achieved = ALU-pipe share (%.3f, ncu) of the algorithmic integer instructions of rank 0's step (unit counts from the "
+                           "kernels' own counters x per-unit costs counted from the SASS, DESIGN.md: %s) / %.3f ms (CUDA events, this run); peak = "
+                           "measured issue rate of an independent LOP3 stream on this GPU (bdg_dev_pipe_probe, this run)" % (ALU_SHARE[mode],
                                json.dumps(A_JOIN if mode == "join" else {"tile": A_TILE, "pair": A_QUICK.get(t) if mode == "sparse" else A_LIGHT.get(t),
                                                                          "cand": A_EXACT, "score": A_SCORE}), step_ms),
                     "work": stats,
