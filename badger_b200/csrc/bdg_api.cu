@@ -1208,6 +1208,56 @@ int bdg_centres_above(unsigned long long token, size_t n_cells, const uint32_t* 
     return BDG_OK;
 }
 
+// The stretch of `bc_by_counts` right behind the head bdg_centres_above returns (barcode_graph.py:273-276 runs into it when too few
+// centres were found): the first `need` barcodes with count <= floor(cutoff) in count-descending order, ties in first-seen
+// order.  One stable stream compaction per count value, from floor(cutoff) downwards, until enough are found.
+int bdg_centres_rest(unsigned long long token, double cutoff, size_t need, uint32_t* out_ranks, size_t* n_out)
+{
+    if (!n_out) return fail(BDG_ERR_ARG, "NULL result pointer");
+    *n_out = 0;
+    if (need == 0) return BDG_OK;
+    if (!out_ranks) return fail(BDG_ERR_ARG, "NULL pointer argument");
+    if (int rc = need_ctx()) return rc;
+    DevCtx& c = g_ctx[0];
+    if (token == 0 || token != c.map_token) return fail(BDG_ERR_ARG, "stale read-map token: a later dedup call has reused the workspaces");
+    const size_t N = c.map_distinct;
+    CU_TRY(cudaSetDevice(c.dev));
+    cudaStream_t st = c.stream;
+    auto ensure = [&](Buf& b, size_t bytes) -> int {
+        if (cudaError_t e = (cudaError_t)b.ensure(bytes))
+            return fail(e == cudaErrorMemoryAllocation ? BDG_ERR_OOM : BDG_ERR_CUDA, "device allocation of %zu bytes: %s", bytes, cudaGetErrorString(e));
+        return BDG_OK;
+    };
+    const uint32_t* d_distinct = (const uint32_t*)c.dd[2].p;
+    const uint32_t* d_counts = (const uint32_t*)c.dd[0].p;
+    if (int e = ensure(c.ce[0], N * 4)) return e;
+    if (int e = ensure(c.ce[4], std::min(need, N) * 4)) return e;
+    if (int e = ensure(c.ce[5], std::min(need, N) * 4)) return e;
+    if (int e = ensure(c.ce[7], 64)) return e;
+    uint32_t* d_nsel = (uint32_t*)((char*)c.ce[7].p + 8);
+    thrust::counting_iterator<uint32_t> all(0);
+    size_t tmp = 0;
+    CU_TRY(cub::DeviceSelect::If(nullptr, tmp, all, (uint32_t*)c.ce[0].p, d_nsel, (int)N, bdg::CountIs{d_counts, 0u}, st));
+    if (int e = ensure(c.ce[8], tmp)) return e;
+    size_t got = 0;
+    for (long long v = (long long)std::floor(cutoff); v >= 1 && got < need; v--) {
+        CU_TRY(cub::DeviceSelect::If(c.ce[8].p, tmp, all, (uint32_t*)c.ce[0].p, d_nsel, (int)N, bdg::CountIs{d_counts, (uint32_t)v}, st));
+        uint32_t nsel = 0;
+        CU_TRY(cudaMemcpyAsync(&nsel, d_nsel, 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        const size_t take = std::min<size_t>(nsel, need - got);
+        if (take == 0) continue;
+        const int nb = (int)std::min<size_t>((take + 255) / 256, (size_t)c.sms * 4);
+        bdg::centres_gather_kernel<<<nb, 256, 0, st>>>((const uint32_t*)c.ce[0].p, d_distinct, d_counts, (uint32_t)take, (uint32_t*)c.ce[4].p, (uint32_t*)c.ce[5].p);
+        g_launches++;
+        CU_TRY(cudaMemcpyAsync(out_ranks + got, c.ce[4].p, take * 4, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        got += take;
+    }
+    *n_out = got;
+    return BDG_OK;
+}
+
 // bdg_assign_reads with a 5-byte result per row (centre barcode + "has a centre" byte).  centre_idx == NULL: the clustering a
 // bdg_cluster_resident call left on the device is used in place (nothing is uploaded).
 int bdg_assign_reads32(unsigned long long token, const int32_t* centre_idx, size_t N, uint32_t* centre_per_row, uint8_t* has_centre, size_t R_all,

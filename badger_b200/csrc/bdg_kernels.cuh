@@ -393,6 +393,12 @@ struct CountAbove {
     __host__ __device__ __forceinline__ bool operator()(const uint32_t& p) const { return counts[p] > thr; }
 };
 
+struct CountIs {
+    const uint32_t* counts;
+    uint32_t v;
+    __host__ __device__ __forceinline__ bool operator()(const uint32_t& p) const { return counts[p] == v; }
+};
+
 __global__ void centres_keys_kernel(const uint32_t* __restrict__ pos, const uint32_t* __restrict__ counts, uint32_t n, uint32_t* __restrict__ keys)
 {
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) keys[j] = ~__ldg(&counts[__ldg(&pos[j])]);

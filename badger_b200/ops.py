@@ -126,6 +126,17 @@ def centres_above(rmap: ReadMap, n_cells: int, whitelist_sorted=None):
         return float(cut.value), top[:k], cnt[:k].astype(np.int64), (hits[:k].astype(bool) if hits is not None else None)
 
 
+def centres_rest(rmap: ReadMap, cutoff: float, need: int) -> np.ndarray:
+    """The `need` barcodes that follow the head of centres_above in `bc_by_counts` (count <= cutoff, count-descending, ties by
+    first sighting): what the top-up loop of barcode_graph.py:273-276 walks into."""
+    need = int(min(max(need, 0), rmap.n_distinct))
+    out = np.empty(need, np.uint32)
+    n = C.c_size_t(0)
+    if need:
+        check(lib().bdg_centres_rest(rmap.token, float(cutoff), need, ptr(out), C.byref(n)))
+    return out[:int(n.value)].copy()
+
+
 def pack16_sorted(records) -> np.ndarray:
     """badger.py:82-88 for the array pipeline: uint8[R, 16] records -> ascending distinct packed barcodes (records with letters
     outside ACGT dropped), packed / sorted / made distinct on the device."""
@@ -158,8 +169,8 @@ def assign_reads32(rmap: ReadMap, centre_idx=None):
     """assign_reads with a 5-byte result per row: (centre uint32[R], has_centre bool-as-uint8[R], rows with a centre).
     centre_idx None: the clustering EdgeHandle.cluster_resident left on the device is used in place."""
     if rmap.rows and rmap.token:
-        out = _pinned.array(rmap.rows, np.uint32)            # page-locked: the per-row result comes back at PCIe speed
-        has = _pinned.array(rmap.rows, np.uint8)
+        out = _pinned.array(rmap.rows, np.uint32, eager=False)   # page-locked from the second call on: the per-row result
+        has = _pinned.array(rmap.rows, np.uint8, eager=False)    # then comes back at PCIe speed
     else:
         out = np.zeros(rmap.rows, np.uint32)
         has = np.zeros(rmap.rows, np.uint8)
@@ -181,6 +192,7 @@ class _PinnedPool:
     def __init__(self):
         self.free = []           # (capacity, address)
         self.held = 0
+        self.wanted = set()      # size classes a lazy caller asked for once already
 
     def take(self, nbytes):
         best = None
@@ -204,11 +216,19 @@ class _PinnedPool:
         else:
             lib().bdg_host_free(addr)
 
-    def array(self, n, dtype):
+    def array(self, n, dtype, eager=True):
+        """eager=False: page-locked memory is only taken from the pool, or allocated when a block of this size class was wanted
+        before (cudaHostAlloc costs ~0.4 ms per MB: it pays for a loop over batches, not for a single call)."""
         dtype = np.dtype(dtype)
         nbytes = int(n) * dtype.itemsize
         if nbytes < self.MIN_BYTES:
             return np.empty(n, dtype)
+        if not eager:
+            size_class = nbytes.bit_length()
+            fits = any(cap >= nbytes and cap <= 4 * nbytes for cap, _ in self.free)
+            if not fits and size_class not in self.wanted:
+                self.wanted.add(size_class)
+                return np.empty(n, dtype)
         cap, addr = self.take(nbytes)
         buf = (C.c_char * nbytes).from_address(addr)
         arr = np.frombuffer(buf, dtype=dtype, count=n)        # writable: the ctypes buffer is; views keep `arr` alive through .base

@@ -35,9 +35,10 @@ class _Token:
 
 def select_centres(rm, n_cells, interval, whitelist_sorted, true_barcodes):
     """barcode_graph.py:252-277 with the counting, the count-ordered head of the barcode list and its whitelist membership on
-    the device (ops.centres_above); the per-barcode arrays are downloaded only if the top-up loop has to go below the cutoff."""
+    the device (ops.centres_above, and ops.centres_rest if the top-up loop has to go below the cutoff): no per-barcode array is
+    downloaded."""
     from statistics import StatisticsError
-    from .barcode_graph import rest_by_counts, walk_centres
+    from .barcode_graph import walk_centres
     if rm.n_distinct == 0 or n_cells <= 0:
         raise StatisticsError("mean requires at least one data point")
     tb = None if true_barcodes is None else [int(x) for x in true_barcodes]
@@ -46,7 +47,7 @@ def select_centres(rm, n_cells, interval, whitelist_sorted, true_barcodes):
     if hits is None and have_list and not tb:
         hits = np.zeros(0, bool)
     return walk_centres(rm.n_distinct, n_cells, interval, top, hits, tb, have_list,
-                        lambda need: rest_by_counts(rm.distinct, rm.counts, cutoff, need))
+                        lambda need: ops.centres_rest(rm, cutoff, int(need) + 1))
 
 
 def assign_packed(ranks, valid=None, *, threshold, n_cells, interval=25, whitelist_sorted=None, true_barcodes=None,

@@ -106,6 +106,9 @@ int bdg_dedup_fetch(unsigned long long token, uint32_t* distinct, uint32_t* coun
  * that head (:262-277) is a few thousand steps and stays with the caller. */
 int bdg_centres_above(unsigned long long token, size_t n_cells, const uint32_t* sorted_wl, size_t W, uint32_t* top_ranks,
                       uint32_t* top_counts, uint8_t* top_hits, size_t cap, size_t* n_above, double* cutoff);
+/* The stretch of `bc_by_counts` right behind that head, for the top-up loop of barcode_graph.py:273-276: the first `need`
+ * barcodes with count <= floor(cutoff), count-descending, ties in first-seen order (out_ranks has room for `need`). */
+int bdg_centres_rest(unsigned long long token, double cutoff, size_t need, uint32_t* out_ranks, size_t* n_out);
 
 /* ---- a-3 + a-4  QGramIndex.get_close + verify/emit: index.py:77-93, barcode_graph.py:224-249 ------ */
 /* Edge set {(a,b,D): a<b, S(a,b) >= T(t), D(a,b) <= t} over a STRICTLY INCREASING array of distinct

@@ -139,6 +139,11 @@ def centres_above(rm, n_cells, whitelist_sorted=None):
     return float(cutoff), top, rm.counts[above], hits
 
 
+def centres_rest(rm, cutoff, need):
+    from badger_b200.barcode_graph import rest_by_counts
+    return rest_by_counts(rm.distinct, rm.counts, cutoff, need - 1)[:need]
+
+
 def pack16_sorted(records):
     r, ok = pack16(records)
     return np.unique(r[ok])
@@ -205,6 +210,6 @@ def edges_handle_resident(rm, t):
 def install(monkeypatch):
     from badger_b200 import ops
     for name in ("pack16", "edges_build", "edges_build_part", "member_sorted", "nearest_bounded", "kmer_score", "dedup_first_seen",
-                 "cluster_levels", "KmerIndex", "edges_handle", "edges_handle_resident", "dedup_reads", "assign_reads", "assign_reads32", "centres_above",
+                 "cluster_levels", "KmerIndex", "edges_handle", "edges_handle_resident", "dedup_reads", "assign_reads", "assign_reads32", "centres_above", "centres_rest",
                  "pack16_sorted"):
         monkeypatch.setattr(ops, name, globals()[name])

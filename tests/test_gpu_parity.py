@@ -537,6 +537,17 @@ def test_resident_stages_vs_host_arrays():
             assert (hits is None) == (w is None)
             if w is not None:
                 assert np.array_equal(hits, np.isin(d[above], wls))
+            from badger_b200.barcode_graph import rest_by_counts
+            for need in (1, 7, 3000, 10 ** 9):                                # the stretch behind the head, count level by count level
+                want = rest_by_counts(d, c, cutoff, min(need, d.size) - 1)[:need]
+                assert np.array_equal(ops.centres_rest(rm, cut, need), want)
+    # too few whitelisted barcodes above the cutoff: the walk tops the list up from below it (barcode_graph.py:273-276)
+    few = np.sort(cells[:300])
+    got = pipeline.select_centres(rm, 1200, 25, few, None)
+    g = badger_b200.BarcodeGraph.from_arrays(2, rm.distinct, rm.counts, with_dict=False)
+    tok = object()
+    g._wl_cache = (tok, few)
+    assert got == g.get_cluster_centers(None, 16, tok, 1200, 25) and len(got) >= 900
     with pytest.raises(badger_b200.BadgerB200Error):
         ops.centres_above(rm, 10, wls[::-1].copy())                          # whitelist not sorted
     for t in (1, 2):
