@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <ctime>
+#include <mutex>
 #include <new>
 #include <string>
 #include <thread>
@@ -190,8 +191,11 @@ bdg::SeedScheme g_scheme;
 std::vector<uint8_t> g_scheme_lut;
 int g_scheme_serial = 0;
 
+std::mutex g_scheme_mutex;        // the devices of one build call arrive on their own host threads
+
 int scheme_ready()
 {
+    std::lock_guard<std::mutex> lock(g_scheme_mutex);
     if (g_scheme_serial) return BDG_OK;
     int bases[bdg::SEED_MAX_BLOCKS] = {3, 3, 3, 3, 3};
     int nb = 5;
