@@ -324,6 +324,22 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
             fprintf(stderr, "\n");
         }
     }
+    // Order of the conditions along the line: block set by block set (a set shares its row order), the sets taken alternately
+    // from the front and from the back of the table.  A pair that meets several conditions is emitted by the first one in TABLE
+    // order, so the early sets own most of the edges; alternating spreads the edges (their scores, stores and PCIe bytes) over
+    // the parts.
+    int order[bdg::SEED_MAX_CONDS], n_order = 0;
+    {
+        int set_first[bdg::SEED_MAX_CONDS], set_last[bdg::SEED_MAX_CONDS], n_sets = 0;
+        for (int c = 0; c < S.nconds; c++) {
+            if (S.cond[c].row_sort == c) { set_first[n_sets] = c; set_last[n_sets] = c; n_sets++; }
+            else set_last[n_sets - 1] = c;
+        }
+        for (int i = 0, lo = 0, hi = n_sets - 1; lo <= hi; i++) {
+            const int k = (i & 1) ? hi-- : lo++;
+            for (int c = set_first[k]; c <= set_last[k]; c++) order[n_order++] = c;
+        }
+    }
     long long W = 0;
     for (int c = 0; c < S.nconds; c++) W += weight[c];
     const long long piece_lo = (long long)part * W, piece_hi = (long long)(part + 1) * W;      // cond c covers [start_c * nparts, (start_c + w_c) * nparts)
@@ -373,7 +389,8 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
     const bool trace = getenv("BDG_TRACE") != nullptr;
     double t_prev = 0;
     if (trace) { cudaStreamSynchronize(caller); t_prev = now_ms(); }
-    for (int c = 0; c < S.nconds; c++) {
+    for (int oi = 0; oi < n_order; oi++) {
+        const int c = order[oi];
         const long long w = weight[c];
         const long long c_lo = start * nparts, c_hi = (start + w) * nparts;
         start += w;

@@ -31,10 +31,14 @@ def main():
             if k not in warmed:
                 warmed.add(k)
                 pipeline.assign_packed(obs[:200000], valid[:200000], threshold=cfg["threshold"], n_cells=100, whitelist_sorted=wls)   # warm
-            T = {}
-            t0 = time.perf_counter()
-            out, info = pipeline.assign_packed(obs, valid, threshold=cfg["threshold"], n_cells=cfg["n_cells"], whitelist_sorted=wls, timings=T, form="u32")
-            dt = time.perf_counter() - t0
+            first_s = None
+            for rep in range(2):                      # the first full-size call grows every workspace (cudaMalloc, page-locked pools); the second is the steady state
+                T = {}
+                t0 = time.perf_counter()
+                out, info = pipeline.assign_packed(obs, valid, threshold=cfg["threshold"], n_cells=cfg["n_cells"], whitelist_sorted=wls, timings=T, form="u32")
+                dt = time.perf_counter() - t0
+                if rep == 0:
+                    first_s = dt
             out = out[0].astype(np.uint64) | (np.uint64(1) << np.uint64(32)) * (out[1] == 0)        # one array for the comparison below
             n = info["distinct"]
             same = None
@@ -44,7 +48,7 @@ def main():
                 same = bool(np.array_equal(first[0], out) and first[1] == info)
             print(json.dumps({"config": name, "n_gpus": k, "threshold": cfg["threshold"], **info, "seconds": round(dt, 4), "reads_per_s": obs.size / dt,
                               "pairs_decided_per_s_edges_stage": n * (n - 1) / 2 / max(T.get("edges", 1e-9), 1e-9),
-                              "stages_s": {k2: round(v, 4) for k2, v in T.items()}, "synthesis_s": round(gen_s, 1), "synthesis_workers": workers,
+                              "stages_s": {k2: round(v, 4) for k2, v in T.items()}, "first_call_seconds": round(first_s, 4), "synthesis_s": round(gen_s, 1), "synthesis_workers": workers,
                               "identical_to_first_device_set": same}), flush=True)
             del out
 
