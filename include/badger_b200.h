@@ -38,11 +38,14 @@ enum {
     BDG_ERR_IO = -7        /* a file could not be opened, mapped or written */
 };
 
-/* Rows of the sorted distinct-barcode array are dealt to parts (GPUs / ranks) in tiles of this many
- * rows, boustrophedon order: tile I belongs to part  m<P ? m : 2P-1-m,  m = I mod 2P.  The parts' edge lists
- * are disjoint and their union is the full edge set.  (Dense mode: a part emits every edge whose SMALLER
- * barcode lies in one of its tiles; sparse mode deals the rows of every pass's own sort order the same way.)
- * Replaces the 10 000-barcode chunks dealt to worker processes in barcode_graph.py:26,164-189. */
+/* How the edge construction is dealt to parts (GPUs / ranks); the parts' edge lists are disjoint and their union is the full edge
+ * set, so they are simply concatenated (no exchange step).  Replaces the 10 000-barcode chunks dealt to worker processes in
+ * barcode_graph.py:26,164-189.
+ *   join form (t = 2): the seed conditions are laid on a line by estimated work and the line is cut into nparts equal pieces; a
+ *     part buckets and joins only the conditions its piece touches, a condition on a cut is shared by row range, cut at a bucket
+ *     boundary (the same on every part, because it depends on the bucket sizes only);
+ *   sparse / dense forms: rows of the (rotated) sort order in tiles of BDG_ROW_TILE rows, boustrophedon: tile I belongs to part
+ *     m<P ? m : 2P-1-m,  m = I mod 2P (dense: a part emits every edge whose SMALLER barcode lies in one of its tiles). */
 #define BDG_ROW_TILE 2048
 
 /* ---- life cycle ------------------------------------------------------------------------------- */
