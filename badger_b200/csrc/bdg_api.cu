@@ -290,7 +290,7 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
     // pairs from bucket sizes over a sample (identical integer arithmetic on every part) and add the bucketing of its sides.
     long long weight[bdg::SEED_MAX_CONDS];
     for (int c = 0; c < S.nconds; c++) weight[c] = 1;
-    if (nparts > 1) {
+    if (nparts > 1 || getenv("BDG_TRACE")) {                 // (traced runs print the estimate beside the measured time of every condition)
         uint32_t maxtab = 1;
         for (int c = 0; c < S.nconds; c++) maxtab = std::max(maxtab, 1u << S.ka[c].key_bits);
         const uint32_t stride = (uint32_t)std::max<size_t>(1, (N + (1u << 17) - 1) >> 17);
@@ -456,7 +456,8 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
         if (trace) {                                        // development aid: per-condition wall time (serialises the streams)
             CU_TRY(cudaStreamSynchronize(st));
             const double now = now_ms();
-            fprintf(stderr, "[bdg] join cond %2d (%s, rows %u/%u..%u/%u): %.3f ms\n", c, S.cond[c].self ? "sym" : "shf", A.f0, A.fden, A.f1, A.fden, now - t_prev);
+            fprintf(stderr, "[bdg] join cond %2d (%s, rows %u/%u..%u/%u, weight %lld): %.3f ms\n", c, S.cond[c].self ? "sym" : "shf", A.f0, A.fden, A.f1, A.fden,
+                    weight[c], now - t_prev);
             t_prev = now;
         }
         if (js) {
