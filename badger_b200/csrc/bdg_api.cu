@@ -306,21 +306,22 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
         unsigned long long pairs[bdg::SEED_MAX_CONDS];
         CU_TRY(cudaMemcpyAsync(pairs, d_pairs, 8 * S.nconds, cudaMemcpyDeviceToHost, caller));
         CU_TRY(cudaStreamSynchronize(caller));
-        // cost in "tested pairs": the estimated pairs plus ~4 per barcode and bucketed side (measured at C4: 0.1 ms per side of
-        // 4.6e6 barcodes against 6.5e-9 ms per tested pair); scaled to <= 4096 so that the cut arithmetic stays small.  A pair of
-        // a symmetric condition counts twice: on barcode data (clusters around the cell barcodes) the pairs that are really
-        // close - the ones that cost an exact distance, a hand-over check and a score - sit on diagonal 0 (measured per
-        // condition at C4, BDG_TRACE: 0.7-1.7 ms symmetric against 0.8-1.4 ms shifted at half / all the pairs of a bucket).
+        // Cost model fitted to the per-condition times of a traced C4 run (BDG_TRACE; 25 conditions, rms error 8 %):
+        //   time ~ pairs x (1.45 for a symmetric condition, 1 for a shifted one) + 2.4 x N.
+        // A symmetric condition's pairs are counted once (n (n - 1) / 2) and hold most of the really close pairs of barcode data -
+        // the ones that cost an exact distance, a hand-over check and a score sit on diagonal 0; the N term is the bucketing and
+        // the per-slab bookkeeping.  Scaled to <= 4096 so that the cut arithmetic stays small.
         unsigned long long cost[bdg::SEED_MAX_CONDS], top = 1;
         for (int c = 0; c < S.nconds; c++) {
-            const unsigned long long sides = S.cond[c].self ? 1 : 2;
-            cost[c] = pairs[c] * stride * stride * (S.cond[c].self ? 2 : 1) + 4ull * sides * N;
+            cost[c] = pairs[c] * stride * stride * (S.cond[c].self ? 29 : 20) + 48ull * N;
             top = std::max(top, cost[c]);
         }
         for (int c = 0; c < S.nconds; c++) weight[c] = (long long)std::max<unsigned long long>(1, cost[c] * 4096 / top);
         if (getenv("BDG_TRACE")) {
             fprintf(stderr, "[bdg] join weights (part %d of %d):", part, nparts);
             for (int c = 0; c < S.nconds; c++) fprintf(stderr, " %lld", weight[c]);
+            fprintf(stderr, "\n[bdg] join estimated pairs:");
+            for (int c = 0; c < S.nconds; c++) fprintf(stderr, " %llu", pairs[c] * stride * stride);
             fprintf(stderr, "\n");
         }
     }
