@@ -61,7 +61,11 @@ A_JOIN = {"unit": 160, "pair": 22.0, "cand": 85, "d2": 50, "score": 150}
 # bound by that pipe (ncu: math-pipe throttle and not-selected are its top stalls), so its roofline is the ALU pipe's issue rate.
 ALU_SHARE = {"join": 0.845, "sparse": 0.81, "dense": 0.6}
 A_PAIR_SURVEY = {1: 15, 2: 25}   # SURVEY.md §8(d) nominal per-pair figure of a plain all-pairs kernel, reported alongside
-NCU_TRAFFIC = None               # bytes per step of the dominant kernel from the committed ncu capture (profiles/), with its label
+# DRAM bytes per step of the dominant kernel from the committed ncu capture of the same command (profiles/r2_join_c4_ncu_full.txt:
+# dram__bytes_read.sum + dram__bytes_write.sum of a join launch, mean of launches 1-3 = 38.2 MB + 0.7 MB, times the 25 launches
+# of a step).  Not measured in the timed run - ncu cannot run inside it - hence the label.
+NCU_TRAFFIC = {"bytes": int(25 * (38.21e6 + 0.69e6)), "workload": ("C4", None, 2, "join", 1),
+               "label": "25 join launches x (dram read + write of one launch), ncu --set full capture profiles/r2_join_c4_ncu_full.txt of this build"}
 
 
 def parse():
