@@ -73,6 +73,7 @@ def lib():
     L.bdg_kmer_index_query.argtypes = [_vp, _vp, _sz, _i, _sz, _vp, _vp, _vp, _vp, C.POINTER(_sz)]
     L.bdg_kmer_index_free.argtypes = [_vp]
     L.bdg_kmer_index_free.restype = None
+    L.bdg_kmer_index_info.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_double)]
     L.bdg_dev_edges_build.argtypes = [_vp, _sz, _i, _i, _i, _vp, _vp, _vp, _sz, _vp, _vp]
     L.bdg_set_edge_mode.argtypes = [_i]
     L.bdg_dev_edges_stats.argtypes = [C.POINTER(C.c_ulonglong), _vp]

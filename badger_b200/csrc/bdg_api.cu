@@ -725,6 +725,10 @@ struct bdg_kmer_index {
     size_t W = 0;
     Buf wl;
     Buf outb[6];
+    Buf kstart, post, scratch;        // posting lists: first posting of every 6-mer (4097 words), string ids grouped by 6-mer
+    bool posted = false;
+    cudaEvent_t ev[2] = {nullptr, nullptr};   // around the last query's kernel
+    bool timed = false;
 };
 
 extern "C" {
@@ -1966,7 +1970,7 @@ int bdg_nearest_bounded(const uint32_t* q, size_t Q, const uint32_t* targets, si
 }
 
 // ---- a-5  KmerIndexer / QGramIndex: the known strings stay on the device between queries ------------------
-int bdg_kmer_index_create(const uint32_t* wl, size_t W, bdg_kmer_index** out)
+static int kmer_index_create(const uint32_t* wl, size_t W, bool postings, bdg_kmer_index** out)
 {
     if (!out || (W && !wl)) return fail(BDG_ERR_ARG, "NULL pointer argument");
     *out = nullptr;
@@ -1984,7 +1988,57 @@ int bdg_kmer_index_create(const uint32_t* wl, size_t W, bdg_kmer_index** out)
     cudaError_t e = cudaMemcpyAsync(ix->wl.p, wl, W * 4, cudaMemcpyHostToDevice, g_ctx[0].stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(g_ctx[0].stream);
     if (e != cudaSuccess) { bdg_kmer_index_free(ix); return fail(BDG_ERR_CUDA, "upload of the index failed: %s", cudaGetErrorString(e)); }
+    // posting lists of the strings' 6-mers (kmer_indexer.py:29-32): worth it once a bucket is a small share of the strings
+    size_t min_w = 4096;
+    if (const char* v = getenv("BDG_KMER_POST_MIN_W")) min_w = (size_t)std::max(0ll, atoll(v));
+    if (postings && W >= min_w && W > 0) {
+        cudaStream_t st = g_ctx[0].stream;
+        const int sms = g_ctx[0].sms;
+        size_t tmp = 0;
+        bool ok = ix->kstart.ensure(4097 * 4) == BDG_OK && ix->scratch.ensure(2 * 4097 * 4) == BDG_OK;
+        ok = ok && cub::DeviceScan::ExclusiveSum(nullptr, tmp, (const uint32_t*)nullptr, (uint32_t*)nullptr, 4097, st) == cudaSuccess;
+        Buf cubtmp;
+        ok = ok && cubtmp.ensure(tmp) == BDG_OK;
+        if (ok) {
+            uint32_t* hist = (uint32_t*)ix->scratch.p;
+            uint32_t* fill = hist + 4097;
+            const int nb = (int)std::min<size_t>((W + 255) / 256, (size_t)sms * 8);
+            ok = cudaMemsetAsync(hist, 0, 2 * 4097 * 4, st) == cudaSuccess;
+            bdg::kidx_hist_kernel<<<nb, 256, 0, st>>>((const uint32_t*)ix->wl.p, (uint32_t)W, hist);
+            ok = ok && cub::DeviceScan::ExclusiveSum(cubtmp.p, tmp, (const uint32_t*)hist, (uint32_t*)ix->kstart.p, 4097, st) == cudaSuccess;
+            uint32_t n_post = 0;
+            ok = ok && cudaMemcpyAsync(&n_post, (uint32_t*)ix->kstart.p + 4096, 4, cudaMemcpyDeviceToHost, st) == cudaSuccess;
+            ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
+            ok = ok && ix->post.ensure(std::max<size_t>(n_post, 1) * 4) == BDG_OK;
+            if (ok) {
+                bdg::kidx_scatter_kernel<<<nb, 256, 0, st>>>((const uint32_t*)ix->wl.p, (uint32_t)W, (const uint32_t*)ix->kstart.p, fill, (uint32_t*)ix->post.p);
+                g_launches += 2;
+                ok = cudaStreamSynchronize(st) == cudaSuccess && cudaGetLastError() == cudaSuccess;
+            }
+        }
+        cubtmp.release();
+        if (!ok) { bdg_kmer_index_free(ix); return fail(BDG_ERR_CUDA, "building the 6-mer posting lists failed: %s", cudaGetErrorString(cudaGetLastError())); }
+        ix->posted = true;
+    }
+    if (cudaEventCreate(&ix->ev[0]) != cudaSuccess || cudaEventCreate(&ix->ev[1]) != cudaSuccess) {
+        bdg_kmer_index_free(ix);
+        return fail(BDG_ERR_CUDA, "event creation failed");
+    }
     *out = ix;
+    return BDG_OK;
+}
+
+int bdg_kmer_index_create(const uint32_t* wl, size_t W, bdg_kmer_index** out) { return kmer_index_create(wl, W, true, out); }
+
+int bdg_kmer_index_info(const bdg_kmer_index* ix, int* posted, double* kernel_ms)
+{
+    if (!ix) return fail(BDG_ERR_ARG, "NULL index handle");
+    if (posted) *posted = ix->posted ? 1 : 0;
+    if (kernel_ms) {
+        float ms = 0.f;
+        if (ix->timed) CU_TRY(cudaEventElapsedTime(&ms, ix->ev[0], ix->ev[1]));
+        *kernel_ms = ms;
+    }
     return BDG_OK;
 }
 
@@ -1992,8 +2046,9 @@ void bdg_kmer_index_free(bdg_kmer_index* ix)
 {
     if (!ix) return;
     cudaSetDevice(ix->dev);
-    ix->wl.release();
+    ix->wl.release(); ix->kstart.release(); ix->post.release(); ix->scratch.release();
     for (auto& b : ix->outb) b.release();
+    for (auto& e : ix->ev) if (e) cudaEventDestroy(e);
     delete ix;
 }
 
@@ -2021,13 +2076,23 @@ int bdg_kmer_index_query(bdg_kmer_index* ix, const uint32_t* q, size_t Q, int mi
     unsigned long long *d_mult = (unsigned long long*)ix->outb[4].p, *d_total = (unsigned long long*)ix->outb[5].p;
     CU_TRY(cudaMemsetAsync(d_total, 0, 8, c->stream));
     CU_TRY(cudaMemcpyAsync(d_q, q, Q * 4, cudaMemcpyHostToDevice, c->stream));
-    const uint32_t gy_total = (uint32_t)((Q + bdg::KS_QB - 1) / bdg::KS_QB);
-    const uint32_t gx = (uint32_t)((W + bdg::NT - 1) / bdg::NT);
-    if (gy_total > 65535u) return fail(BDG_ERR_ARG, "Q too large for one call (> 65535*256 queries)");
-    bdg::kmer_score_kernel<<<dim3(gx, gy_total), bdg::NT, 0, c->stream>>>(d_q, (uint32_t)Q, (const uint32_t*)ix->wl.p, (uint32_t)W, min_kmers,
-                                                                       (unsigned long long)cap, d_hq, d_hw, d_cnt, d_mult, d_total);
+    CU_TRY(cudaEventRecord(ix->ev[0], c->stream));
+    if (ix->posted) {                                       // walk the buckets of the queries' own 6-mers
+        const unsigned blocks = (unsigned)std::min<unsigned long long>((unsigned long long)Q * 11, (unsigned long long)c->sms * 64);
+        bdg::kmer_post_kernel<<<blocks, bdg::NT, 0, c->stream>>>(d_q, (uint32_t)Q, (const uint32_t*)ix->wl.p, (const uint32_t*)ix->kstart.p,
+                                                               (const uint32_t*)ix->post.p, std::max(min_kmers, 1), (unsigned long long)cap, d_hq, d_hw,
+                                                               d_cnt, d_mult, d_total);
+    } else {
+        const uint32_t gy_total = (uint32_t)((Q + bdg::KS_QB - 1) / bdg::KS_QB);
+        const uint32_t gx = (uint32_t)((W + bdg::NT - 1) / bdg::NT);
+        if (gy_total > 65535u) return fail(BDG_ERR_ARG, "Q too large for one call (> 65535*256 queries)");
+        bdg::kmer_score_kernel<<<dim3(gx, gy_total), bdg::NT, 0, c->stream>>>(d_q, (uint32_t)Q, (const uint32_t*)ix->wl.p, (uint32_t)W, min_kmers,
+                                                                           (unsigned long long)cap, d_hq, d_hw, d_cnt, d_mult, d_total);
+    }
     g_launches++;
     CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(ix->ev[1], c->stream));
+    ix->timed = true;
     unsigned long long tot = 0;
     CU_TRY(cudaMemcpyAsync(&tot, d_total, 8, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(cudaStreamSynchronize(c->stream));
@@ -2052,7 +2117,7 @@ int bdg_kmer_score(const uint32_t* q, size_t Q, const uint32_t* wl, size_t W, in
     if (Q == 0 || W == 0) return BDG_OK;
     if (!q || !wl || (cap && (!hit_q || !hit_w || !cnt || !mult))) return fail(BDG_ERR_ARG, "NULL pointer argument");
     bdg_kmer_index* ix = nullptr;
-    if (int rc = bdg_kmer_index_create(wl, W, &ix)) return rc;
+    if (int rc = kmer_index_create(wl, W, Q >= 64, &ix)) return rc;       // a one-off call with few queries: the scan costs less than the lists
     const int rc = bdg_kmer_index_query(ix, q, Q, min_kmers, cap, hit_q, hit_w, cnt, mult, total);
     bdg_kmer_index_free(ix);
     return rc;

@@ -405,6 +405,42 @@ BDG_HD int qgram_score(uint32_t a, uint32_t b, uint64_t* mult = nullptr)
     return s;
 }
 
+// Does the 6-mer at position p of w occur at an earlier position of w?  (Posting lists hold a string once per distinct 6-mer,
+// and a query walks a bucket once per distinct 6-mer of its own.)
+BDG_HD bool kmer_seen_before(uint32_t w, int p)
+{
+    const uint32_t k = (w >> (2 * p)) & 0xFFFu;
+    bool seen = false;
+    for (int e = 0; e < p; e++) seen = seen || ((w >> (2 * e)) & 0xFFFu) == k;
+    return seen;
+}
+
+// The score together with the set of query positions p whose 6-mer occurs anywhere in b (bit 2p of *marks): the posting-list form
+// of kmer_indexer.py:49-61 emits a (query, entry) pair from the bucket of the FIRST such position only.
+BDG_HD int qgram_score_marks(uint32_t a, uint32_t b, uint32_t* marks)
+{
+    int s = 0;
+    uint32_t any = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int k = 0; k <= 10; k++) {
+        {
+            const uint32_t r = run6(~mism(a, b >> (2 * k)) & (EVEN >> (2 * k)));
+            s += popc(r);
+            any |= r;
+        }
+        if (k == 0) continue;
+        {
+            const uint32_t r = run6(~mism(a, b << (2 * k)) & (EVEN << (2 * k)));
+            s += popc(r);
+            any |= r;
+        }
+    }
+    *marks = any;
+    return s;
+}
+
 // Two halves of the score for the join kernel: the three middle diagonals, where nearly all of a close pair's shared 6-mers
 // sit (their count alone usually reaches the threshold), and the other eighteen as a compact loop.  near + far == qgram_score.
 BDG_HD int qgram_score_near(uint32_t a, uint32_t b)

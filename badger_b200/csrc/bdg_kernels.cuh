@@ -86,7 +86,87 @@ __global__ void nearest_finish_kernel(const uint32_t* __restrict__ keys, uint32_
 }
 
 // ---------------------------------------------------------------------------------------------------
-// kmer_score_kernel (a-5): thread per whitelist entry, queries broadcast from shared memory; exact S with
+// Posting-list form of the same operator (the reference's own data structure, kmer_indexer.py:29-32 / index.py:29-41, on the
+// device): the known strings' 6-mers as 4096 buckets of string ids (a 6-mer that occurs twice in a string is listed once).
+// A query walks the buckets of its own 6-mers: work = sum of <= 11 bucket sizes (~3 % of W for random strings) instead of W.
+//   kidx_hist_kernel / kidx_scatter_kernel   counting sort of the (6-mer, id) postings (one digit of 12 bits)
+//   kmer_post_kernel                          one CTA per (query, query position p): skipped when the 6-mer at p already occurred
+//                                             at an earlier position of the query; else every id of the bucket gets the exact
+//                                             score, and is emitted from THIS bucket iff p is the first query position whose
+//                                             6-mer occurs in the entry (so every hit is emitted exactly once).
+// ---------------------------------------------------------------------------------------------------
+__global__ void kidx_hist_kernel(const uint32_t* __restrict__ wl, uint32_t W, uint32_t* __restrict__ hist)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < W; i += gridDim.x * blockDim.x) {
+        const uint32_t w = __ldg(&wl[i]);
+        for (int p = 0; p <= 10; p++)
+            if (!kmer_seen_before(w, p)) atomicAdd(&hist[(w >> (2 * p)) & 0xFFFu], 1u);
+    }
+}
+
+__global__ void kidx_scatter_kernel(const uint32_t* __restrict__ wl, uint32_t W, const uint32_t* __restrict__ start, uint32_t* __restrict__ fill,
+                                    uint32_t* __restrict__ post)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < W; i += gridDim.x * blockDim.x) {
+        const uint32_t w = __ldg(&wl[i]);
+        for (int p = 0; p <= 10; p++) {
+            if (kmer_seen_before(w, p)) continue;
+            const uint32_t k = (w >> (2 * p)) & 0xFFFu;
+            post[__ldg(&start[k]) + atomicAdd(&fill[k], 1u)] = i;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(NT) kmer_post_kernel(const uint32_t* __restrict__ q, uint32_t Q, const uint32_t* __restrict__ wl,
+                                                       const uint32_t* __restrict__ start, const uint32_t* __restrict__ post, int min_kmers,
+                                                       unsigned long long cap, uint32_t* __restrict__ hit_q, uint32_t* __restrict__ hit_w,
+                                                       uint8_t* __restrict__ cnt, unsigned long long* __restrict__ mult,
+                                                       unsigned long long* __restrict__ total)
+{
+    const int lane = threadIdx.x & 31;
+    for (uint64_t item = blockIdx.x; item < (uint64_t)Q * 11; item += gridDim.x) {
+        const uint32_t qi = (uint32_t)(item / 11);
+        const int p = (int)(item % 11);
+        const uint32_t a = __ldg(&q[qi]);
+        if (kmer_seen_before(a, p)) continue;                         // that bucket was walked for the earlier position
+        const uint32_t k = (a >> (2 * p)) & 0xFFFu;
+        const uint32_t lo = __ldg(&start[k]), hi = __ldg(&start[k + 1]);
+        for (uint32_t base = lo; base < hi; base += NT) {             // whole warps stay in the loop together
+            const uint32_t j = base + threadIdx.x;
+            bool ok = false;
+            uint32_t wi = 0, b = 0;
+            int s = 0;
+            if (j < hi) {
+                wi = __ldg(&post[j]);
+                b = __ldg(&wl[wi]);
+                uint32_t marks = 0;
+                s = qgram_score_marks(a, b, &marks);
+                ok = s >= min_kmers && (marks & ((1u << (2 * p)) - 1u)) == 0;      // no earlier query position has a 6-mer of this entry
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, ok);
+            if (m == 0) continue;
+            unsigned long long at = 0;
+            const int leader = __ffs(m) - 1;
+            if (lane == leader) at = atomicAdd(total, (unsigned long long)__popc(m));
+            at = __shfl_sync(0xffffffffu, at, leader);
+            if (ok) {
+                const unsigned long long pos = at + __popc(m & ((1u << lane) - 1u));
+                if (pos < cap) {
+                    uint64_t mu;
+                    qgram_score(a, b, &mu);
+                    hit_q[pos] = qi;
+                    hit_w[pos] = wi;
+                    cnt[pos] = (uint8_t)s;
+                    mult[pos] = mu;
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kmer_score_kernel (a-5), brute-force form (kept for small string sets): thread per whitelist entry, queries broadcast from
+// shared memory; exact S with
 // per-position multiplicities; hits appended through a warp-aggregated cursor.
 // ---------------------------------------------------------------------------------------------------
 constexpr int KS_QB = 256;

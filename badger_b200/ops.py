@@ -406,9 +406,11 @@ def _kmer_query(call, q, n_known, min_kmers, cap):
             continue
         check(rc)
         n = int(total.value)
-        m = mult[:n]
-        nib = np.stack([(m >> np.uint64(4 * p)) & np.uint64(15) for p in range(11)], 1).astype(np.uint8) if n else np.zeros((0, 11), np.uint8)
-        return hq[:n].copy(), hw[:n].copy(), cnt[:n].copy(), nib
+        by = mult[:n].view(np.uint8).reshape(n, 8)          # little-endian: nibble p of the word = nibble p & 1 of byte p >> 1
+        nib = np.empty((n, 16), np.uint8)
+        np.bitwise_and(by, 15, out=nib[:, 0::2])
+        np.right_shift(by, 4, out=nib[:, 1::2])
+        return hq[:n].copy(), hw[:n].copy(), cnt[:n].copy(), nib[:, :11]
 
 
 def kmer_score(q: np.ndarray, wl: np.ndarray, min_kmers: int = 1, cap: int | None = None):
@@ -431,6 +433,12 @@ class KmerIndex:
     def query(self, q: np.ndarray, min_kmers: int = 1, cap: int | None = None):
         L = lib()
         return _kmer_query(lambda *a: L.bdg_kmer_index_query(self._h, *a), q, self.size, min_kmers, cap)
+
+    def info(self) -> dict:
+        """{"postings": queries walk 6-mer posting lists (else they scan every string), "kernel_ms": the last query's kernel}."""
+        posted, ms = C.c_int(0), C.c_double(0.0)
+        check(lib().bdg_kmer_index_info(self._h, C.byref(posted), C.byref(ms)))
+        return {"postings": bool(posted.value), "kernel_ms": float(ms.value)}
 
     def free(self):
         if self._h is not None and self._h.value:

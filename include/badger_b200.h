@@ -181,6 +181,9 @@ int bdg_kmer_index_create(const uint32_t* wl, size_t W, bdg_kmer_index** out);
 int bdg_kmer_index_query(bdg_kmer_index* ix, const uint32_t* q, size_t Q, int min_kmers, size_t cap, uint32_t* hit_q,
                          uint32_t* hit_w, uint8_t* cnt, uint64_t* mult, size_t* total);
 void bdg_kmer_index_free(bdg_kmer_index* ix);
+/* *posted: 1 when the index holds 6-mer posting lists (from 4096 strings on; BDG_KMER_POST_MIN_W) and queries walk the buckets
+ * of their own 6-mers, 0 when every query scans every string.  *kernel_ms: device time of the last query's kernel.  Either may be NULL. */
+int bdg_kmer_index_info(const bdg_kmer_index* ix, int* posted, double* kernel_ms);
 
 /* ---- device-resident variants (bench.py "value" path; torch owns the memory and the stream) -------- */
 /* Edge construction over rows of part/nparts.  d_count (one uint64, device) is zeroed by the call and receives

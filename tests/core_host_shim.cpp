@@ -85,6 +85,33 @@ void shim_qgram_compact(const uint32_t* a, const uint32_t* b, size_t n, uint8_t*
     for (size_t i = 0; i < n; i++) { full[i] = (uint8_t)bdg::qgram_score(a[i], b[i]); compact[i] = (uint8_t)bdg::qgram_score_compact(a[i], b[i]);
                                      if (bdg::qgram_score_near(a[i], b[i]) + bdg::qgram_score_far(a[i], b[i]) != (int)full[i]) compact[i] = 255; }
 }
+// The posting-list form of a-5 (kmer_post_kernel) on the host: buckets of string ids per 6-mer, a query walks the buckets of its
+// distinct 6-mers and a hit is emitted from the bucket of the first query position whose 6-mer occurs in the entry.
+size_t shim_kmer_post_emulate(const uint32_t* q, size_t Q, const uint32_t* wl, size_t W, int min_kmers, uint32_t* hq, uint32_t* hw, uint8_t* cnt,
+                              size_t cap, unsigned long long* evaluated)
+{
+    std::vector<std::vector<uint32_t>> bucket(4096);
+    for (size_t i = 0; i < W; i++)
+        for (int p = 0; p <= 10; p++)
+            if (!bdg::kmer_seen_before(wl[i], p)) bucket[(wl[i] >> (2 * p)) & 0xFFFu].push_back((uint32_t)i);
+    size_t n = 0;
+    *evaluated = 0;
+    for (size_t x = 0; x < Q; x++)
+        for (int p = 0; p <= 10; p++) {
+            if (bdg::kmer_seen_before(q[x], p)) continue;
+            for (uint32_t wi : bucket[(q[x] >> (2 * p)) & 0xFFFu]) {
+                uint32_t marks = 0;
+                const int s = bdg::qgram_score_marks(q[x], wl[wi], &marks);
+                (*evaluated)++;
+                if (s != bdg::qgram_score(q[x], wl[wi])) return (size_t)-1;
+                if (s >= min_kmers && (marks & ((1u << (2 * p)) - 1u)) == 0) {
+                    if (n < cap) { hq[n] = (uint32_t)x; hw[n] = wi; cnt[n] = (uint8_t)s; }
+                    n++;
+                }
+            }
+        }
+    return n;
+}
 void shim_scheme_keys(int c, const uint32_t* a, const uint32_t* b, size_t n, uint32_t* ka, uint32_t* kb, uint8_t* pred)
 {
     for (size_t i = 0; i < n; i++) {

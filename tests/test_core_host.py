@@ -42,6 +42,8 @@ def shim(tmp_path_factory):
     L.shim_join_emulate.argtypes = [u32p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     L.shim_join_emulate.restype = C.c_size_t
     L.shim_qgram_compact.argtypes = [u32p, u32p, C.c_size_t, u8p, u8p]
+    L.shim_kmer_post_emulate.argtypes = [u32p, C.c_size_t, u32p, C.c_size_t, C.c_int, u32p, u32p, u8p, C.c_size_t, u64p]
+    L.shim_kmer_post_emulate.restype = C.c_size_t
     return L
 
 
@@ -507,3 +509,24 @@ def test_compact_score_equals_the_unrolled_one(shim):
     full = np.zeros(a.size, np.uint8); compact = np.zeros(a.size, np.uint8)
     shim.shim_qgram_compact(a, b, a.size, full, compact)
     assert np.array_equal(full, compact) and full.max() > 50
+
+
+@pytest.mark.parametrize("min_kmers", [1, 3, 5])
+def test_posting_list_form_emits_every_hit_once(shim, min_kmers):
+    """a-5 through the 6-mer posting lists (kmer_post_kernel's rule, on the host): the hits, each exactly once, are the oracle's
+    (q, w) pairs with S >= min_kmers, found with a few per cent of the Q x W evaluations."""
+    rng = np.random.default_rng(41)
+    wl = rng.integers(0, 1 << 32, 20000, dtype=np.uint64).astype(np.uint32)
+    wl[:20] = np.asarray([0, 0x55555555, 0xAAAAAAAA, 0xFFFFFFFF, 0x11111111, 0x44444444, 0x1B1B1B1B, 0xE4E4E4E4, 0x00000001, 0x40000000] * 2,
+                         np.uint32)
+    near = wl[rng.integers(0, wl.size, 60)] ^ (np.uint32(3) << (2 * rng.integers(0, 16, 60)).astype(np.uint32))
+    q = np.concatenate([wl[:30], near, rng.integers(0, 1 << 32, 60, dtype=np.uint64).astype(np.uint32)])
+    cap = 1 << 20
+    hq = np.zeros(cap, np.uint32); hw = np.zeros(cap, np.uint32); cnt = np.zeros(cap, np.uint8); ev = np.zeros(1, np.uint64)
+    n = shim.shim_kmer_post_emulate(q, q.size, wl, wl.size, min_kmers, hq, hw, cnt, cap, ev)
+    assert 0 < n <= cap
+    wc, _ = orc.kmer_score(q, wl, want_mult=False)
+    wq, ww = np.nonzero(wc >= min_kmers)
+    o = np.lexsort((hw[:n], hq[:n]))
+    assert np.array_equal(hq[:n][o], wq) and np.array_equal(hw[:n][o], ww) and np.array_equal(cnt[:n][o], wc[wq, ww])
+    assert int(ev[0]) < 0.05 * q.size * wl.size

@@ -616,7 +616,14 @@ def test_nearest_large_sparse_path(max_d, monkeypatch):
     assert (am >= 0).sum() > 1000
 
 
-def test_kmer_score_vs_oracle():
+@pytest.fixture(params=["postings", "scan"])
+def kmer_form(request, monkeypatch):
+    """Both forms of a-5: the 6-mer posting lists (default from 4096 strings on) and the scan of every string."""
+    monkeypatch.setenv("BDG_KMER_POST_MIN_W", "0" if request.param == "postings" else str(1 << 40))
+    return request.param
+
+
+def test_kmer_score_vs_oracle(kmer_form):
     rng = np.random.default_rng(10)
     wl = rng.integers(0, 1 << 32, 3000, dtype=np.uint64).astype(np.uint32)
     wl[:20] = np.asarray([0, 0x55555555, 0xAAAAAAAA, 0xFFFFFFFF, 0x11111111] * 4, np.uint32)   # low complexity
@@ -632,7 +639,27 @@ def test_kmer_score_vs_oracle():
     assert hw.size >= 5
 
 
-def test_resident_kmer_index_many_queries():
+def test_kmer_postings_large_string_set():
+    """The posting lists at a whitelist-like size: 300 k strings, queries one substitution / one shift away from entries, and the
+    low-complexity words whose 6-mers repeat inside the word (listed once per string, walked once per query)."""
+    rng = np.random.default_rng(13)
+    wl = np.unique(rng.integers(0, 1 << 32, 300000, dtype=np.uint64).astype(np.uint32))
+    wl[:6] = np.asarray([0, 0x55555555, 0xAAAAAAAA, 0xFFFFFFFF, 0x11111111, 0x1B1B1B1B], np.uint32)
+    src = wl[rng.integers(0, wl.size, 40)]
+    q = np.concatenate([wl[:8], src ^ (np.uint32(2) << (2 * rng.integers(0, 16, 40)).astype(np.uint32)), src[:20] << np.uint32(2),
+                        src[20:] >> np.uint32(2)])
+    ix = ops.KmerIndex(wl)
+    for mk in (1, 4):
+        hq, hw, cnt, mult = ix.query(q, min_kmers=mk)
+        wc, wm = orc.kmer_score(q, wl)
+        wq, ww = np.nonzero(wc >= mk)
+        o = np.lexsort((hw, hq))
+        assert np.array_equal(hq[o], wq) and np.array_equal(hw[o], ww)
+        assert np.array_equal(cnt[o], wc[wq, ww]) and np.array_equal(mult[o], wm[wq, ww])
+    ix.free()
+
+
+def test_resident_kmer_index_many_queries(kmer_form):
     """KmerIndexer / QGramIndex keep their strings on the device (ops.KmerIndex): repeated queries, growth after append."""
     rng = np.random.default_rng(12)
     wl = rng.integers(0, 1 << 32, 5000, dtype=np.uint64).astype(np.uint32)
