@@ -103,7 +103,7 @@ struct DevCtx {
     // join form of the t = 2 edge construction (bdg_join.cuh): barcodes in the key order of every condition's row side / column
     // side, first column of every key, scratch keys (in / sorted) and radix-sort scratch, units per slab and their prefix sums
     // (one set per stream: the conditions of a block set run back to back on one stream)
-    Buf jn_rows[2], jn_cols[2], jn_tab[2], jn_tabc[2], jn_hist[2], jn_cub[2], jn_counts[2], jn_offs[2], jn_lut, jn_weigh;
+    Buf jn_rows[2], jn_cols[2], jn_tab[2], jn_tabc[2], jn_hist[2], jn_cub[2], jn_counts[2], jn_offs[2], jn_rank[2], jn_lut, jn_weigh;
     int scheme_serial = 0;                                    // which scheme sits in this device's constant memory (0: none)
     cudaEvent_t ev_cond[bdg::SEED_MAX_CONDS] = {};            // bdg_edges_build_into: "condition c has appended its edges"
     unsigned long long* snap_host = nullptr;                  // mapped page-locked: the edge count after every condition
@@ -290,18 +290,24 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
     // pairs from bucket sizes over a sample (identical integer arithmetic on every part) and add the bucketing of its sides.
     long long weight[bdg::SEED_MAX_CONDS];
     for (int c = 0; c < S.nconds; c++) weight[c] = 1;
+    const double t_weigh = getenv("BDG_TRACE") ? (cudaStreamSynchronize(caller), now_ms()) : 0.0;
     if (nparts > 1 || getenv("BDG_TRACE")) {                 // (traced runs print the estimate beside the measured time of every condition)
-        uint32_t maxtab = 1;
+        uint32_t maxtab = 4;
         for (int c = 0; c < S.nconds; c++) maxtab = std::max(maxtab, 1u << S.ka[c].key_bits);
+        bdg::WeighSlots slots{};
+        for (int c = 0; c < S.nconds; c++) {
+            slots.row[c] = S.cond[c].row_sort == c ? (uint8_t)slots.n++ : slots.row[S.cond[c].row_sort];
+            slots.col[c] = S.cond[c].self ? slots.row[c] : (uint8_t)slots.n++;
+        }
         const uint32_t stride = (uint32_t)std::max<size_t>(1, (N + (1u << 17) - 1) >> 17);
-        const size_t hist_bytes = (size_t)S.nconds * 2 * maxtab * 4;
+        const size_t hist_bytes = (size_t)slots.n * maxtab * 4;
         if (int e = ensure(ws->jn_weigh, hist_bytes + 8 * bdg::SEED_MAX_CONDS)) return e;
         uint32_t* d_hist = (uint32_t*)ws->jn_weigh.p;
         unsigned long long* d_pairs = (unsigned long long*)((char*)ws->jn_weigh.p + hist_bytes);
         CU_TRY(cudaMemsetAsync(ws->jn_weigh.p, 0, hist_bytes + 8 * bdg::SEED_MAX_CONDS, caller));
         const uint32_t m = (uint32_t)((N + stride - 1) / stride);
-        bdg::join_weigh_hist_kernel<<<(int)std::min<uint32_t>((m + 255) / 256, (uint32_t)ws->sms * 8), 256, 0, caller>>>(d_sorted, (uint32_t)N, stride, S.nconds, maxtab, d_hist);
-        bdg::join_weigh_sum_kernel<<<ws->sms * 2, 256, 0, caller>>>(d_hist, S.nconds, maxtab, d_pairs);
+        bdg::join_weigh_hist_kernel<<<(int)std::min<uint32_t>((m + 255) / 256, (uint32_t)ws->sms * 8), 256, 0, caller>>>(d_sorted, (uint32_t)N, stride, S.nconds, maxtab, slots, d_hist);
+        bdg::join_weigh_sum_kernel<<<dim3((maxtab / 4 + 1023) / 1024, S.nconds), 256, 0, caller>>>(d_hist, maxtab, slots, d_pairs);
         g_launches += 2;
         unsigned long long pairs[bdg::SEED_MAX_CONDS];
         CU_TRY(cudaMemcpyAsync(pairs, d_pairs, 8 * S.nconds, cudaMemcpyDeviceToHost, caller));
@@ -318,6 +324,7 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
         }
         for (int c = 0; c < S.nconds; c++) weight[c] = (long long)std::max<unsigned long long>(1, cost[c] * 4096 / top);
         if (getenv("BDG_TRACE")) {
+            fprintf(stderr, "[bdg] join work estimate: %.3f ms\n", now_ms() - t_weigh);
             fprintf(stderr, "[bdg] join weights (part %d of %d):", part, nparts);
             for (int c = 0; c < S.nconds; c++) fprintf(stderr, " %lld", weight[c]);
             fprintf(stderr, "\n[bdg] join estimated pairs:");
@@ -356,12 +363,15 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
     CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_a, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)(max_keys + 1), caller));
     CU_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_b, (const uint32_t*)nullptr, (uint32_t*)nullptr, (int)(n_slabs + 1), caller));
     const size_t tmp_bytes = std::max(tmp_a, tmp_b);
+    bool ranked = true;                                     // counting sort with one atomic per barcode (its place in the bucket is kept)
+    if (const char* e = getenv("BDG_JOIN_RANK")) ranked = atoi(e) != 0;
     for (int k = 0; k < 2; k++) {                           // one scratch set per stream
         if (int e = ensure(ws->jn_hist[k], (max_keys + 1) * 4 * 2)) return e;       // bucket sizes | fill cursors
         if (int e = ensure(ws->jn_tab[k], (max_keys + 1) * 4)) return e;
         if (int e = ensure(ws->jn_tabc[k], (max_keys + 1) * 4)) return e;
         if (int e = ensure(ws->jn_rows[k], N * 4)) return e;
         if (int e = ensure(ws->jn_cols[k], N * 4)) return e;
+        if (ranked) { if (int e = ensure(ws->jn_rank[k], N * 4)) return e; }
         if (int e = ensure(ws->jn_cub[k], tmp_bytes)) return e;
         if (int e = ensure(ws->jn_counts[k], ((size_t)n_slabs + 1) * 4)) return e;
         if (int e = ensure(ws->jn_offs[k], ((size_t)n_slabs + 1) * 4)) return e;
@@ -407,11 +417,19 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
             const size_t nkeys = (size_t)1 << key.key_bits;
             uint32_t* hist = (uint32_t*)ws->jn_hist[k].p;
             uint32_t* fill = hist + (nkeys + 1);
-            CU_TRY(cudaMemsetAsync(hist, 0, (nkeys + 1) * 4 * 2, st));
-            bdg::join_hist_kernel<<<gb, 256, 0, st>>>(d_sorted, (uint32_t)N, key, hist);
             size_t bytes = ws->jn_cub[k].cap;
-            CU_TRY(cub::DeviceScan::ExclusiveSum(ws->jn_cub[k].p, bytes, (const uint32_t*)hist, (uint32_t*)table.p, (int)(nkeys + 1), st));
-            bdg::join_scatter_kernel<<<gb, 256, 0, st>>>(d_sorted, (uint32_t)N, key, (const uint32_t*)table.p, fill, (uint32_t*)dst.p);
+            if (ranked) {
+                uint32_t* rank = (uint32_t*)ws->jn_rank[k].p;
+                CU_TRY(cudaMemsetAsync(hist, 0, (nkeys + 1) * 4, st));
+                bdg::join_hist_rank_kernel<<<gb, 256, 0, st>>>(d_sorted, (uint32_t)N, key, hist, rank);
+                CU_TRY(cub::DeviceScan::ExclusiveSum(ws->jn_cub[k].p, bytes, (const uint32_t*)hist, (uint32_t*)table.p, (int)(nkeys + 1), st));
+                bdg::join_scatter_rank_kernel<<<gb, 256, 0, st>>>(d_sorted, (uint32_t)N, key, (const uint32_t*)table.p, rank, (uint32_t*)dst.p);
+            } else {
+                CU_TRY(cudaMemsetAsync(hist, 0, (nkeys + 1) * 4 * 2, st));
+                bdg::join_hist_kernel<<<gb, 256, 0, st>>>(d_sorted, (uint32_t)N, key, hist);
+                CU_TRY(cub::DeviceScan::ExclusiveSum(ws->jn_cub[k].p, bytes, (const uint32_t*)hist, (uint32_t*)table.p, (int)(nkeys + 1), st));
+                bdg::join_scatter_kernel<<<gb, 256, 0, st>>>(d_sorted, (uint32_t)N, key, (const uint32_t*)table.p, fill, (uint32_t*)dst.p);
+            }
             g_launches += 2;
             return BDG_OK;
         };
@@ -472,6 +490,7 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
         CU_TRY(cudaEventRecord(ws->ev_done[1], ws->aux[1]));
         CU_TRY(cudaStreamWaitEvent(caller, ws->ev_done[1], 0));
     }
+    if (trace) { cudaStreamSynchronize(caller); fprintf(stderr, "[bdg] join part %d of %d: %.3f ms from entry to the last condition\n", part, nparts, now_ms() - t_weigh); }
     if (js) {                                               // everything is enqueued: follow the conditions and copy what they have finished
         cudaStream_t cp = ws->aux[2];
         size_t done = 0;
@@ -815,7 +834,7 @@ void bdg_shutdown(void)
             c.jn_rows[k].release(); c.jn_cols[k].release(); c.jn_tab[k].release(); c.jn_tabc[k].release(); c.jn_hist[k].release();
             c.jn_cub[k].release(); c.jn_counts[k].release(); c.jn_offs[k].release();
         }
-        c.jn_lut.release(); c.jn_weigh.release();
+        c.jn_lut.release(); c.jn_weigh.release(); for (auto& b : c.jn_rank) b.release();
         if (c.snap_host) { cudaFreeHost(c.snap_host); c.snap_host = nullptr; for (auto& e : c.ev_cond) if (e) cudaEventDestroy(e); }
     }
     g_ctx.clear();

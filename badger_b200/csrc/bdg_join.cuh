@@ -70,6 +70,22 @@ __global__ void join_scatter_kernel(const uint32_t* __restrict__ in, uint32_t n,
     }
 }
 
+// The same sort with ONE atomic per barcode: the counting pass keeps what its atomic returned (the barcode's place inside its
+// bucket), the scatter is then a plain gather of start[key] + place.
+__global__ void join_hist_rank_kernel(const uint32_t* __restrict__ in, uint32_t n, SeedKey k, uint32_t* __restrict__ hist, uint32_t* __restrict__ rank)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) rank[i] = atomicAdd(&hist[seed_key(__ldg(&in[i]), k)], 1u);
+}
+
+__global__ void join_scatter_rank_kernel(const uint32_t* __restrict__ in, uint32_t n, SeedKey k, const uint32_t* __restrict__ start,
+                                         const uint32_t* __restrict__ rank, uint32_t* __restrict__ out)
+{
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t v = __ldg(&in[i]);
+        out[__ldg(&start[seed_key(v, k)]) + __ldg(&rank[i])] = v;
+    }
+}
+
 // Where a part's share of a condition starts / ends: the first row of the first bucket that begins at or behind N * f / fden.
 // Bucket boundaries depend on the bucket SIZES only, so every part finds the same cut whatever order its own counting sort
 // left inside the buckets, and a bucket is never split between parts.
@@ -90,30 +106,41 @@ __device__ __forceinline__ uint32_t join_cut(const uint32_t* __restrict__ rowsta
 // Bucket sizes of every condition over a SAMPLE of the barcodes (every stride-th one): the number of (row, column) pairs a
 // condition has to test is sum_k rows_k * cols_k (a symmetric one: sum_k n_k (n_k - 1) / 2), and the sample's sum times
 // stride^2 estimates it.  Integer counts over the same sample on every part, so every part computes the same deal.
-__global__ void join_weigh_hist_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t stride, int nconds, uint32_t tab, uint32_t* __restrict__ hist)
+struct WeighSlots { uint8_t row[SEED_MAX_CONDS], col[SEED_MAX_CONDS]; int n; };   // table of a condition's row / column key (a block set shares its row table)
+
+__global__ void join_weigh_hist_kernel(const uint32_t* __restrict__ in, uint32_t n, uint32_t stride, int nconds, uint32_t tab, const WeighSlots ws,
+                                       uint32_t* __restrict__ hist)
 {
     const uint32_t m = (n + stride - 1) / stride;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < m; j += gridDim.x * blockDim.x) {
         const uint32_t x = __ldg(&in[(uint64_t)j * stride]);
         for (int c = 0; c < nconds; c++) {
-            atomicAdd(&hist[(size_t)(2 * c) * tab + seed_key(x, c_scheme.ka[c])], 1u);
-            if (!c_scheme.cond[c].self) atomicAdd(&hist[(size_t)(2 * c + 1) * tab + seed_key(x, c_scheme.kb[c])], 1u);
+            if (c_scheme.cond[c].row_sort == c) atomicAdd(&hist[(size_t)ws.row[c] * tab + seed_key(x, c_scheme.ka[c])], 1u);
+            if (!c_scheme.cond[c].self) atomicAdd(&hist[(size_t)ws.col[c] * tab + seed_key(x, c_scheme.kb[c])], 1u);
         }
     }
 }
 
-__global__ void join_weigh_sum_kernel(const uint32_t* __restrict__ hist, int nconds, uint32_t tab, unsigned long long* __restrict__ out)
+// grid (x, nconds): condition blockIdx.y, four counters per thread and step
+__global__ void join_weigh_sum_kernel(const uint32_t* __restrict__ hist, uint32_t tab, const WeighSlots ws, unsigned long long* __restrict__ out)
 {
-    for (int c = 0; c < nconds; c++) {
-        const bool self = c_scheme.cond[c].self != 0;
-        unsigned long long mine = 0;
-        for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < tab; k += gridDim.x * blockDim.x) {
-            const unsigned long long r = __ldg(&hist[(size_t)(2 * c) * tab + k]);
-            mine += self ? r * (r - (r ? 1 : 0)) / 2 : r * __ldg(&hist[(size_t)(2 * c + 1) * tab + k]);
+    const int c = blockIdx.y;
+    const bool self = c_scheme.cond[c].self != 0;
+    const uint4* __restrict__ hr = reinterpret_cast<const uint4*>(hist + (size_t)ws.row[c] * tab);
+    const uint4* __restrict__ hc = reinterpret_cast<const uint4*>(hist + (size_t)ws.col[c] * tab);
+    unsigned long long mine = 0;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < tab / 4; k += gridDim.x * blockDim.x) {
+        const uint4 r = __ldg(&hr[k]);
+        if (self) {
+            mine += (unsigned long long)r.x * (r.x - (r.x ? 1 : 0)) / 2 + (unsigned long long)r.y * (r.y - (r.y ? 1 : 0)) / 2 +
+                    (unsigned long long)r.z * (r.z - (r.z ? 1 : 0)) / 2 + (unsigned long long)r.w * (r.w - (r.w ? 1 : 0)) / 2;
+        } else if (r.x | r.y | r.z | r.w) {
+            const uint4 q = __ldg(&hc[k]);
+            mine += (unsigned long long)r.x * q.x + (unsigned long long)r.y * q.y + (unsigned long long)r.z * q.z + (unsigned long long)r.w * q.w;
         }
-        for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(FULL, mine, o);
-        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&out[c], mine);
     }
+    for (int o = 16; o; o >>= 1) mine += __shfl_down_sync(FULL, mine, o);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&out[c], mine);
 }
 
 // the edge count as it stands when the stream reaches this point (bdg_edges_build_into copies the finished edges out meanwhile)
