@@ -2010,7 +2010,7 @@ static int kmer_index_create(const uint32_t* wl, size_t W, bool postings, bdg_km
     // posting lists of the strings' 6-mers (kmer_indexer.py:29-32): worth it once a bucket is a small share of the strings
     size_t min_w = 4096;
     if (const char* v = getenv("BDG_KMER_POST_MIN_W")) min_w = (size_t)std::max(0ll, atoll(v));
-    if (postings && W >= min_w && W > 0) {
+    if (postings && W >= min_w && W > 0 && W <= 0xFFFFFFFFull / 11) {          // (the postings are counted in 32 bits)
         cudaStream_t st = g_ctx[0].stream;
         const int sms = g_ctx[0].sms;
         size_t tmp = 0;

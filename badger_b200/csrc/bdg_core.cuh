@@ -270,7 +270,9 @@ BDG_HD bool pass_possible(int t, int p, uint32_t alo, uint32_t ahi, uint32_t blo
 //   ed(a,b[:15]):   1 deletion from a + <=1 substitution   -> diagonal 0 before it, -1 after it
 // X0 / XP / XM are the mismatch marks on diagonals 0 / +1 / -1 with out-of-range columns marked.
 // ---------------------------------------------------------------------------------------------
-BDG_HD int dist_small(uint32_t a, uint32_t b, bool plain_only = false)
+// prefiltered: the caller's candidates already passed quick_marks' test (the join kernel), so the quick reject is left out -
+// it only ever saves work, the case analysis behind it is exact on its own.
+BDG_HD int dist_small(uint32_t a, uint32_t b, bool plain_only = false, bool prefiltered = false)
 {
     const uint32_t X0 = mism(a, b);
     const int h = popc(X0);
@@ -280,7 +282,7 @@ BDG_HD int dist_small(uint32_t a, uint32_t b, bool plain_only = false)
     // quick reject: with <= 2 operations every column 0..14 of a is either matched on diagonal 0, +1 or -1 or
     // consumed by an operation, so more than two columns that mismatch on all three diagonals prove D >= 3
     // (column 15 is left out: the truncated variants drop it for free).  Rejects ~90 % of the candidates.
-    if (popc(X0 & XP & XM & 0x15555555u) > 2) return 3;
+    if (!prefiltered && popc(X0 & XP & XM & 0x15555555u) > 2) return 3;
     const uint32_t low1 = X0 & (0u - X0);              // first mismatch on the main diagonal (position L)
     const uint32_t ge1 = 0u - low1;                    // columns >= L (all bits from low1 upwards)
     const uint32_t gt1 = ge1 << 2;                     // columns >  L (marker bits; ge1 has both bits of a column set)

@@ -196,7 +196,7 @@ __device__ __noinline__ uint32_t join_process(uint2* q2, uint8_t* q2d, const uin
     const uint32_t a = min(e.x, e.y), b = max(e.x, e.y);
     bool ok = active && a != b;
     int d = 3;
-    if (ok) { d = dist_small(a, b); ok = d <= 2; }
+    if (ok) { d = dist_small(a, b, false, true); ok = d <= 2; }
     const uint32_t n_d2 = (uint32_t)__popc(__ballot_sync(FULL, ok));
     if (ok) ok = __ldg(&lut[seed_flags(c_scheme, a, b)]) == (uint8_t)(e.x > e.y ? want1 : want0);   // emitted by the first (condition, orientation) the pair meets
     const unsigned m = __ballot_sync(FULL, ok);

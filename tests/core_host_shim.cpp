@@ -13,6 +13,7 @@ void shim_pairs(const uint32_t* a, const uint32_t* b, size_t n, uint8_t* pre1, u
         pre1[i] = bdg::prefilter_t1(a[i], b[i]);
         pre2[i] = bdg::prefilter_t2(a[i], b[i]);
         dsmall[i] = (uint8_t)bdg::dist_small(a[i], b[i], false);
+        if (bdg::dist_small(a[i], b[i], false, true) != (int)dsmall[i]) dsmall[i] = 200;    // without its quick reject: the same value
         dplain[i] = (uint8_t)bdg::dist_small(a[i], b[i], true);
         bdg::Dist3 r = bdg::myers3(a[i], b[i]);
         dfull[i] = (uint8_t)r.full; da15[i] = (uint8_t)r.a15; db15[i] = (uint8_t)r.b15;
@@ -147,7 +148,7 @@ size_t shim_join_emulate(const uint32_t* s, size_t n, uint32_t* oa, uint32_t* ob
                 if (x == y || !bdg::quick_pass(x, y, 2)) continue;
                 st[1]++;
                 const uint32_t a = x < y ? x : y, b = x < y ? y : x;
-                const int d = bdg::dist_small(a, b);
+                const int d = bdg::dist_small(a, b, false, true);
                 if (d > 2) continue;
                 st[2]++;
                 if (g_lut[bdg::seed_flags(S, a, b)] != 2 * c + (x < y ? 0 : 1)) continue;
