@@ -55,17 +55,30 @@ class QGramIndex:
 
     def get_close(self, barcode, number):
         """index.py:77-93: numbers j > number with S(barcode, entry_j) >= threshold (order unspecified)."""
-        if self.q != 6 or len(barcode) != 16:
+        return self.get_close_many([barcode], [number])[0]
+
+    def get_close_many(self, barcodes, numbers):
+        """get_close for a batch of queries - the loop of barcode_graph.py:233-236 as ONE kernel launch over the resident index.
+        Returns one list per query."""
+        if len(barcodes) != len(numbers):
+            raise ValueError("one number per barcode expected")
+        if self.q != 6 or any(len(b) != 16 for b in barcodes):
             raise NotImplementedError("the B200 path indexes 16-bp barcodes by 6-mers only")
-        if not self._packed:
-            return []
+        if not self._packed or not len(barcodes):
+            return [[] for _ in barcodes]
         if self._arr is None:                          # (re)build the device-resident index after add_to_index
             self._arr = ops.KmerIndex(np.asarray(self._packed, dtype=np.uint32))
-        q = np.asarray([rank(barcode, 16)], dtype=np.uint32)
-        _, hw, _, _ = self._arr.query(q, min_kmers=self.threshold)
-        out = {}
-        for w in np.sort(hw).tolist():
-            j = self._numbers[w]
-            if j > number:
-                out[j] = True          # duplicates of a number collapse like dict keys do in the reference
-        return list(out)
+        q = np.asarray([rank(b, 16) for b in barcodes], dtype=np.uint32)
+        hq, hw, _, _ = self._arr.query(q, min_kmers=self.threshold)
+        o = np.lexsort((hw, hq))
+        hq, hw = hq[o], hw[o]
+        first = np.searchsorted(hq, np.arange(len(barcodes) + 1))
+        res = []
+        for i, number in enumerate(numbers):
+            out = {}
+            for w in hw[first[i]:first[i + 1]].tolist():
+                j = self._numbers[w]
+                if j > number:
+                    out[j] = True      # duplicates of a number collapse like dict keys do in the reference
+            res.append(list(out))
+        return res

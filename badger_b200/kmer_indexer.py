@@ -2,8 +2,8 @@
 
 ``get_occurrences`` counts, for a query, the shared k-mer position pairs with every known string and
 returns the best ones in the reference's dict order.  The counting (kmer_indexer.py:52-55) is the Q x W
-scoring kernel ``bdg_kmer_score``; the selection logic (kmer_indexer.py:57-75) is host code that follows the
-reference line by line.  The GPU path covers what the barcode hot path needs - 16-bp strings, k = 6
+scoring kernel ``bdg_kmer_score``; the selection rules (kmer_indexer.py:57-75: minimum count, hits_delta below
+the best, stable order by count, max_hits, one entry per string) are array operations on the host.  The GPU path covers what the barcode hot path needs - 16-bp strings, k = 6
 (SURVEY.md §8 a-5); other shapes (the R1-adapter search of the extraction step, which is out of scope)
 raise NotImplementedError rather than fall back to a CPU implementation.
 """
@@ -23,16 +23,12 @@ class KmerIndexer:
         self.seq_list = list(known_strings)
         self.k = kmer_size
         self._packed = None
+        self._words = None
 
     def _get_kmers(self, seq):
-        """kmer_indexer.py:20-27."""
-        if len(seq) < self.k:
-            return
-        kmer = seq[:self.k]
-        yield kmer
-        for i in range(self.k, len(seq)):
-            kmer = kmer[1:] + seq[i]
-            yield kmer
+        """The k-mers of seq from left to right (kmer_indexer.py:20-27)."""
+        for i in range(len(seq) - self.k + 1):
+            yield seq[i:i + self.k]
 
     def append(self, barcode):
         self.seq_list.append(barcode)
@@ -52,30 +48,30 @@ class KmerIndexer:
             return {}
         self._require_gpu_shape(sequence)
         if self._packed is None:                      # (re)build the device-resident index after a change of the string list
-            self._packed = ops.KmerIndex(ops.pack16(self.seq_list)[0])
+            self._words = ops.pack16(self.seq_list)[0]
+            self._packed = ops.KmerIndex(self._words)
         q = ops.pack16([sequence])[0]
         _, hw, cnt, mult = self._packed.query(q, min_kmers=1)
         if hw.size == 0:
             return {}
-        first_pos = np.argmax(mult > 0, axis=1)
-        order = np.lexsort((hw, first_pos))            # dict insertion order of the reference: first touch
-        result = []
-        for o in order.tolist():
-            i, count = int(hw[o]), int(cnt[o])
-            if count < min_kmers:
-                continue
-            if ignore_equal and self.seq_list[i] == sequence:
-                continue
-            positions = [p for p in range(11) for _ in range(int(mult[o, p]))]
-            result.append((self.seq_list[i], count, positions))
-        if not result:
+        # the reference's dict order is first touch: by the first query position with a match, then by place in the string list
+        order = np.lexsort((hw, np.argmax(mult > 0, axis=1)))
+        hw, cnt, mult = hw[order], cnt[order].astype(np.int64), mult[order]
+        keep = cnt >= min_kmers
+        if ignore_equal:
+            keep &= self._words[hw] != q[0]            # valid 16-mers: equal words are equal strings
+        if not keep.any():
             return {}
-        top_hits = max(result, key=lambda x: x[1])[1]
-        result = filter(lambda x: x[1] >= top_hits - hits_delta, result)
-        result = sorted(result, reverse=True, key=lambda x: x[1])
-        if max_hits == 0:
-            return {x[0]: x for x in result}
-        return {x[0]: x for x in list(result)[:max_hits]}
+        keep &= cnt >= cnt[keep].max() - hits_delta
+        sel = np.flatnonzero(keep)
+        sel = sel[np.argsort(-cnt[sel], kind="stable")]
+        if max_hits:
+            sel = sel[:max_hits]
+        out = {}
+        for o in sel.tolist():                         # a string listed twice keeps its first place and its last value, as in the reference
+            s = self.seq_list[int(hw[o])]
+            out[s] = (s, int(cnt[o]), np.repeat(np.arange(11), mult[o]).tolist())
+        return out
 
 
 class ArrayKmerIndexer(KmerIndexer):

@@ -186,6 +186,8 @@ def test_qgram_index_interface(monkeypatch, capsys):
     ix.add_to_index("ATTACAGATTCCATGC", 1818173756)
     assert ix.get_close("ATTACAGATTCCATGC", 1818173756) == [2977727730]
     assert ix.get_close("GATTACAGATTCCATG", 2977727730) == []
+    assert ix.get_close_many(["ATTACAGATTCCATGC", "GATTACAGATTCCATG"], [1818173756, 2977727730]) == [[2977727730], []]
+    assert ix.get_close_many([], []) == []
     assert ix.rank("ACGTAC") == orc.rank("ACGTAC" + "A" * 10) & 0xFFF
 
 
