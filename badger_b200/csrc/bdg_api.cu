@@ -396,7 +396,8 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
     }
     bdg::EdgeOut o{d_a, d_b, d_d, d_count, (unsigned long long)cap};
     long long start = 0;
-    int cur_set = -1, k = 1;                                 // k: scratch set / stream of the current block set
+    int cur_set = -1, k = 1;                                 // k: scratch set / stream of the current condition
+    int row_set[2] = {-1, -1};                               // block set whose row order the scratch set holds
     const bool trace = getenv("BDG_TRACE") != nullptr;
     double t_prev = 0;
     if (trace) { cudaStreamSynchronize(caller); t_prev = now_ms(); }
@@ -407,9 +408,14 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
         start += w;
         const long long lo = std::max(c_lo, piece_lo), hi = std::min(c_hi, piece_hi);
         if (lo >= hi) continue;
+        // The whole job alternates its two streams block set by block set (a set sorts its rows once).  A part of several has few
+        // conditions, often of one set: it alternates condition by condition, so that the bucketing of one condition runs beside
+        // the join of the other, and sorts the rows again when the stream's row order is of another set.
         const int set = S.cond[c].row_sort;
-        const bool new_set = set != cur_set;
-        if (new_set) { cur_set = set; k ^= 1; }
+        if (nparts > 1 || set != cur_set) k ^= 1;
+        cur_set = set;
+        const bool new_set = row_set[k] != set;
+        row_set[k] = set;
         cudaStream_t st = (fork && k == 1) ? ws->aux[1] : caller;
         if (fork && k == 1 && !aux_used) { CU_TRY(cudaStreamWaitEvent(st, ws->ev_start, 0)); aux_used = true; }
         // counting sort of the barcodes by one side's key: bucket sizes -> first position of every key (kept: colstart) -> scatter
