@@ -106,6 +106,7 @@ struct DevCtx {
     Buf jn_rows[2], jn_cols[2], jn_tab[2], jn_tabc[2], jn_hist[2], jn_cub[2], jn_counts[2], jn_offs[2], jn_rank[2], jn_lut, jn_weigh;
     int scheme_serial = 0;                                    // which scheme sits in this device's constant memory (0: none)
     cudaEvent_t ev_cond[bdg::SEED_MAX_CONDS] = {};            // bdg_edges_build_into: "condition c has appended its edges"
+    cudaEvent_t ev_pre[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};   // streaming form: scratch set k is bucketed / its join has finished
     unsigned long long* snap_host = nullptr;                  // mapped page-locked: the edge count after every condition
     unsigned long long* snap_dev = nullptr;
 };
@@ -385,14 +386,21 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
     if (const char* e = getenv("BDG_JOIN_CTAS")) grid = std::min(grid, ws->sms * std::max(1, atoi(e)));   // CTAs per SM of a join launch
     const int gb = (int)std::min<size_t>((N + 255) / 256, (size_t)ws->sms * 8);
     const int bb = (int)std::min<size_t>(((size_t)n_slabs + 256) / 256, (size_t)ws->sms * 8);
+    // Two ways to keep the bucketing of one condition out of the way of the joins.  The resident form forks: its two streams
+    // carry whole conditions (bucketing + join) and overlap each other.  The streaming form (js) must be able to say "edges
+    // [0, n) are complete" after every condition, so its joins stay on ONE stream in order, and only the bucketing of the next
+    // condition runs ahead on a second stream, into the other scratch set.
     const bool fork = !js && !getenv("BDG_EDGE_SERIAL");
-    if (fork) CU_TRY(cudaEventRecord(ws->ev_start, caller));
+    const bool ahead = js && !getenv("BDG_EDGE_SERIAL");
+    if (fork || ahead) CU_TRY(cudaEventRecord(ws->ev_start, caller));
+    bool set_joined[2] = {false, false};                     // ahead: a join on scratch set k is in flight / done (ev_join[k] recorded)
     bool aux_used = false;
     int streamed[bdg::SEED_MAX_CONDS], n_streamed = 0;
     if (js && !ws->snap_host) {
         CU_TRY(cudaHostAlloc((void**)&ws->snap_host, sizeof(unsigned long long) * bdg::SEED_MAX_CONDS, cudaHostAllocMapped));
         CU_TRY(cudaHostGetDevicePointer((void**)&ws->snap_dev, ws->snap_host, 0));
         for (int c = 0; c < bdg::SEED_MAX_CONDS; c++) CU_TRY(cudaEventCreateWithFlags(&ws->ev_cond[c], cudaEventDisableTiming));
+        for (int q = 0; q < 2; q++) { CU_TRY(cudaEventCreateWithFlags(&ws->ev_pre[q], cudaEventDisableTiming)); CU_TRY(cudaEventCreateWithFlags(&ws->ev_join[q], cudaEventDisableTiming)); }
     }
     bdg::EdgeOut o{d_a, d_b, d_d, d_count, (unsigned long long)cap};
     long long start = 0;
@@ -412,12 +420,17 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
         // conditions, often of one set: it alternates condition by condition, so that the bucketing of one condition runs beside
         // the join of the other, and sorts the rows again when the stream's row order is of another set.
         const int set = S.cond[c].row_sort;
-        if (nparts > 1 || set != cur_set) k ^= 1;
+        if (nparts > 1 || ahead || set != cur_set) k ^= 1;
         cur_set = set;
         const bool new_set = row_set[k] != set;
         row_set[k] = set;
-        cudaStream_t st = (fork && k == 1) ? ws->aux[1] : caller;
+        cudaStream_t st = (fork && k == 1) ? ws->aux[1] : caller;           // the join's stream
+        cudaStream_t sp = ahead ? ws->aux[1] : st;                           // the bucketing's stream
         if (fork && k == 1 && !aux_used) { CU_TRY(cudaStreamWaitEvent(st, ws->ev_start, 0)); aux_used = true; }
+        if (ahead) {
+            if (!aux_used) { CU_TRY(cudaStreamWaitEvent(sp, ws->ev_start, 0)); aux_used = true; }
+            if (set_joined[k]) CU_TRY(cudaStreamWaitEvent(sp, ws->ev_join[k], 0));      // the last join that read this scratch set
+        }
         // counting sort of the barcodes by one side's key: bucket sizes -> first position of every key (kept: colstart) -> scatter
         auto bucket_side = [&](const bdg::SeedKey& key, Buf& dst, Buf& table) -> int {
             const size_t nkeys = (size_t)1 << key.key_bits;
@@ -426,15 +439,15 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
             size_t bytes = ws->jn_cub[k].cap;
             if (ranked) {
                 uint32_t* rank = (uint32_t*)ws->jn_rank[k].p;
-                CU_TRY(cudaMemsetAsync(hist, 0, (nkeys + 1) * 4, st));
-                bdg::join_hist_rank_kernel<<<gb, 256, 0, st>>>(d_sorted, (uint32_t)N, key, hist, rank);
-                CU_TRY(cub::DeviceScan::ExclusiveSum(ws->jn_cub[k].p, bytes, (const uint32_t*)hist, (uint32_t*)table.p, (int)(nkeys + 1), st));
-                bdg::join_scatter_rank_kernel<<<gb, 256, 0, st>>>(d_sorted, (uint32_t)N, key, (const uint32_t*)table.p, rank, (uint32_t*)dst.p);
+                CU_TRY(cudaMemsetAsync(hist, 0, (nkeys + 1) * 4, sp));
+                bdg::join_hist_rank_kernel<<<gb, 256, 0, sp>>>(d_sorted, (uint32_t)N, key, hist, rank);
+                CU_TRY(cub::DeviceScan::ExclusiveSum(ws->jn_cub[k].p, bytes, (const uint32_t*)hist, (uint32_t*)table.p, (int)(nkeys + 1), sp));
+                bdg::join_scatter_rank_kernel<<<gb, 256, 0, sp>>>(d_sorted, (uint32_t)N, key, (const uint32_t*)table.p, rank, (uint32_t*)dst.p);
             } else {
-                CU_TRY(cudaMemsetAsync(hist, 0, (nkeys + 1) * 4 * 2, st));
-                bdg::join_hist_kernel<<<gb, 256, 0, st>>>(d_sorted, (uint32_t)N, key, hist);
-                CU_TRY(cub::DeviceScan::ExclusiveSum(ws->jn_cub[k].p, bytes, (const uint32_t*)hist, (uint32_t*)table.p, (int)(nkeys + 1), st));
-                bdg::join_scatter_kernel<<<gb, 256, 0, st>>>(d_sorted, (uint32_t)N, key, (const uint32_t*)table.p, fill, (uint32_t*)dst.p);
+                CU_TRY(cudaMemsetAsync(hist, 0, (nkeys + 1) * 4 * 2, sp));
+                bdg::join_hist_kernel<<<gb, 256, 0, sp>>>(d_sorted, (uint32_t)N, key, hist);
+                CU_TRY(cub::DeviceScan::ExclusiveSum(ws->jn_cub[k].p, bytes, (const uint32_t*)hist, (uint32_t*)table.p, (int)(nkeys + 1), sp));
+                bdg::join_scatter_kernel<<<gb, 256, 0, sp>>>(d_sorted, (uint32_t)N, key, (const uint32_t*)table.p, fill, (uint32_t*)dst.p);
             }
             g_launches += 2;
             return BDG_OK;
@@ -464,9 +477,13 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
         A.T = bdg::qgram_threshold(2);
         A.one = 1u;
         A.mone = 0xFFFFFFFFu;
-        bdg::join_band_kernel<<<bb, 256, 0, st>>>(A, (uint32_t*)ws->jn_counts[k].p);
+        bdg::join_band_kernel<<<bb, 256, 0, sp>>>(A, (uint32_t*)ws->jn_counts[k].p);
         size_t bytes = ws->jn_cub[k].cap;
-        CU_TRY(cub::DeviceScan::ExclusiveSum(ws->jn_cub[k].p, bytes, (const uint32_t*)ws->jn_counts[k].p, (uint32_t*)ws->jn_offs[k].p, (int)(n_slabs + 1), st));
+        CU_TRY(cub::DeviceScan::ExclusiveSum(ws->jn_cub[k].p, bytes, (const uint32_t*)ws->jn_counts[k].p, (uint32_t*)ws->jn_offs[k].p, (int)(n_slabs + 1), sp));
+        if (ahead) {
+            CU_TRY(cudaEventRecord(ws->ev_pre[k], sp));
+            CU_TRY(cudaStreamWaitEvent(st, ws->ev_pre[k], 0));
+        }
         if (rs == 8) {
             if (occ == 4) bdg::join_kernel<8, 4><<<grid, bdg::ENT, 0, st>>>(A, o);
             else if (occ == 5) bdg::join_kernel<8, 5><<<grid, bdg::ENT, 0, st>>>(A, o);
@@ -478,6 +495,7 @@ int launch_edges_join(const uint32_t* d_sorted, size_t N, int part, int nparts, 
         }
         g_launches += 3;
         CU_TRY(cudaGetLastError());
+        if (ahead) { CU_TRY(cudaEventRecord(ws->ev_join[k], st)); set_joined[k] = true; }
         if (trace) {                                        // development aid: per-condition wall time (serialises the streams)
             CU_TRY(cudaStreamSynchronize(st));
             const double now = now_ms();
@@ -841,7 +859,8 @@ void bdg_shutdown(void)
             c.jn_cub[k].release(); c.jn_counts[k].release(); c.jn_offs[k].release();
         }
         c.jn_lut.release(); c.jn_weigh.release(); for (auto& b : c.jn_rank) b.release();
-        if (c.snap_host) { cudaFreeHost(c.snap_host); c.snap_host = nullptr; for (auto& e : c.ev_cond) if (e) cudaEventDestroy(e); }
+        if (c.snap_host) { cudaFreeHost(c.snap_host); c.snap_host = nullptr; for (auto& e : c.ev_cond) if (e) cudaEventDestroy(e);
+                           for (int q = 0; q < 2; q++) { if (c.ev_pre[q]) cudaEventDestroy(c.ev_pre[q]); if (c.ev_join[q]) cudaEventDestroy(c.ev_join[q]); } }
     }
     g_ctx.clear();
 }

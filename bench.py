@@ -410,7 +410,18 @@ def run_b200(args):
     for _ in range(args.steps):
         ea, eb, ed = ops.edges_build_part(s_host, t, rank, world)
     torch.cuda.synchronize()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_mine = time.perf_counter() - t0
+    e2e_s = max_over_ranks(e2e_mine)
+
+    def by_rank(x):                                        # every rank's own figure, for the record
+        if world == 1:
+            return [float(x)]
+        tt = torch.zeros(world, dtype=torch.float64, device=dev)
+        tt[rank] = float(x)
+        dist.all_reduce(tt)
+        return [float(v) for v in tt.tolist()]
+    e2e_ms_ranks = by_rank(1000 * e2e_mine / args.steps)
+    edges_ranks = [int(v) for v in by_rank(n_edges_part)]
     barrier()
     clocks = sampler.stop()
     e2e = {"value": total_pairs * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(4 * n),
@@ -478,7 +489,8 @@ def run_b200(args):
                "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                "dtype": "u32", "data": "synthetic",
                "config": config_dict(args.config, cfg, n),
-               "details": {"edges": edges_total, "edges_rank0": n_edges_part, "ms_per_step_by_rank": ms_ranks, "edge_mode": mode, "l2": "flushed between timed iterations (256 MB write)",
+               "details": {"edges": edges_total, "edges_rank0": n_edges_part, "edges_by_rank": edges_ranks, "ms_per_step_by_rank": ms_ranks,
+                           "e2e_ms_per_step_by_rank": e2e_ms_ranks, "edge_mode": mode, "l2": "flushed between timed iterations (256 MB write)",
                            "partition": "array replicated; work units of the sorted orders dealt round-robin to ranks; no data-path collective"},
                "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
                "reads_per_s": cfg["reads"] * args.steps / (ms_total * 1e-3)}

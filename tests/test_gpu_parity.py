@@ -356,8 +356,9 @@ def test_stale_edge_handle_is_refused():
     L.bdg_edges_free(h1); L.bdg_edges_free(h2)
 
 
-@pytest.mark.parametrize("nparts", [2, 3, 8])
+@pytest.mark.parametrize("nparts", [1, 2, 3, 8])
 def test_parts_union_equals_full(nparts, mode):
+    """ops.edges_build_part is the streaming form (bdg_edges_build_into): nparts = 1 checks it against the resident form."""
     s = clustered_set(77, 200, 20000, 0.06)
     fa, fb, fd = ops.edges_build(s, 2)
     rows = []
