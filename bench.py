@@ -62,9 +62,9 @@ A_JOIN = {"unit": 160, "pair": 22.0, "cand": 85, "d2": 50, "score": 150}
 ALU_SHARE = {"join": 0.845, "sparse": 0.81, "dense": 0.6}
 A_PAIR_SURVEY = {1: 15, 2: 25}   # SURVEY.md §8(d) nominal per-pair figure of a plain all-pairs kernel, reported alongside
 # DRAM bytes per step of the dominant kernel from the committed ncu capture of the same command (profiles/r2_join_c4_ncu_full.txt:
-# dram__bytes_read.sum + dram__bytes_write.sum of a join launch, mean of launches 1-3 = 38.2 MB + 0.7 MB, times the 25 launches
+# dram__bytes_read.sum + dram__bytes_write.sum of a join launch, mean of launches 1-3 = 38.21 MB + 0.14 MB, times the 25 launches
 # of a step).  Not measured in the timed run - ncu cannot run inside it - hence the label.
-NCU_TRAFFIC = {"bytes": int(25 * (38.21e6 + 0.69e6)), "workload": ("C4", None, 2, "join", 1),
+NCU_TRAFFIC = {"bytes": int(25 * (38.21e6 + 0.14e6)), "workload": ("C4", None, 2, "join", 1),
                "label": "25 join launches x (dram read + write of one launch), ncu --set full capture profiles/r2_join_c4_ncu_full.txt of this build"}
 
 
@@ -453,7 +453,7 @@ def run_b200(args):
         roof = None
         if alg is not None:
             achieved = alg / (step_ms * 1e-3) / 1e12
-            passes = {"join": "join_kernel (one persistent launch over all seed conditions) behind 25 radix sorts by seed key",
+            passes = {"join": "join_kernel (one persistent launch per seed condition, 25 per step) behind counting sorts by seed key",
                       "sparse": "sparse_scan_kernel + sparse_tile_kernel<%d,p>, %d passes per step" % (t, 2 if t == 1 else 3),
                       "dense": "edges_kernel<%d>" % t}[mode]
             hbm_bytes = int(9 * n_edges_part + 4 * n * ({"join": 2 * 25 + 25, "sparse": 2 if t == 1 else 3, "dense": 1}[mode]))

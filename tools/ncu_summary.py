@@ -2,8 +2,9 @@
 """Summarise ncu output into the small text files kept under profiles/.
 
   ncu_summary.py rep  <file.ncu-rep> [kernel-regex]   key metrics of every profiled launch (--set full capture)
-  ncu_summary.py list <launches.csv>                  per-kernel launch count, total and share of device time
-                                                      (--metrics gpu__time_duration.sum capture)
+  ncu_summary.py list <launches.csv> [first count]    per-kernel launch count, total and share of device time
+                                                      (--metrics gpu__time_duration.sum capture); first / count keep
+                                                      that window of the launches, e.g. the timed steps of bench.py
 Reads only files; runs `ncu -i` locally (no GPU needed).
 """
 import csv
@@ -59,13 +60,14 @@ def rep(path, pattern=None):
                 print("  %-92s %s %s" % (k, d[k], units[hdr.index(k)]))
 
 
-def launches(path):
+def launches(path, first=0, count=None):
     lines = [ln for ln in open(path) if ln.startswith('"')]
-    rows = list(csv.DictReader(io.StringIO("".join(lines))))
+    rows = [r for r in csv.DictReader(io.StringIO("".join(lines))) if r.get("Metric Name") == "gpu__time_duration.sum"]
+    if first or count is not None:
+        print("launches %d .. %d of %d" % (first, first + (count if count is not None else len(rows) - first) - 1, len(rows)))
+        rows = rows[first:first + count] if count is not None else rows[first:]
     agg = OrderedDict()
     for r in rows:
-        if r.get("Metric Name") != "gpu__time_duration.sum":
-            continue
         name = re.sub(r"\(.*", "", r["Kernel Name"]).replace("void ", "")
         ns = float(r["Metric Value"].replace(",", ""))
         a = agg.setdefault(name, [0, 0.0, r["Grid Size"], r["Block Size"]])
@@ -84,4 +86,4 @@ if __name__ == "__main__":
     if sys.argv[1] == "rep":
         rep(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
     else:
-        launches(sys.argv[2])
+        launches(sys.argv[2], int(sys.argv[3]) if len(sys.argv) > 3 else 0, int(sys.argv[4]) if len(sys.argv) > 4 else None)
