@@ -5,8 +5,10 @@
 // barcode in a few shifts and masks, so only the barcodes are stored), once as rows
 // (fields of x) and - for the conditions with a shifted diagonal - once as columns (the matching fields of y).  Equal keys
 // are then adjacent on both sides: row i pairs with the column run colstart[key(i)] .. colstart[key(i) + 1].
-//   join_hist_kernel / join_scatter_kernel  counting sort by the join key (one digit; cub's scan turns the bucket sizes into
-//                          colstart, the first column of every key value)
+//   join_hist_rank_kernel / join_scatter_rank_kernel  counting sort by the join key (one digit; cub's scan turns the bucket
+//                          sizes into colstart, the first column of every key value) with one atomic per barcode: the counting
+//                          pass keeps the place its atomic returned.  (join_hist_kernel / join_scatter_kernel: the two-atomic
+//                          form, BDG_JOIN_RANK=0.)
 //   join_band_kernel       per slab of 32 consecutive rows: number of work units (runs of <= JUNIT columns) it needs
 //   (cub::DeviceScan::ExclusiveSum: unit index -> slab)
 //   join_kernel<RS>        one persistent launch per condition: warps pull batches of units from an atomic cursor, stage the
@@ -16,8 +18,8 @@
 //                          the 6-mer score in a second queue), edges are appended with one atomic per warp.
 // A unit's 32 rows are worked through as 32/RS sub-slabs of RS rows x 32/RS column phases, each against its own column run:
 // RS = 32 when the key buckets are long, RS = 8 when they are short (fewer rows span fewer foreign buckets).
-// The conditions are dealt to the parts (GPUs / ranks) by weight, a condition on a part boundary is split by unit range,
-// so a part sorts only the conditions it works on.  No block-level barrier anywhere.
+// The conditions are dealt to the parts (GPUs / ranks) by estimated work (join_weigh_*), a condition on a part boundary is split
+// by row range at a bucket boundary (join_cut), so a part sorts only the conditions it works on.  No block-level barrier anywhere.
 #pragma once
 #include "bdg_edges.cuh"
 #include "bdg_seed.cuh"
