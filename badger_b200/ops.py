@@ -392,20 +392,24 @@ def nearest_bounded(q: np.ndarray, targets_in_order: np.ndarray, max_d: int = 2)
     return am, dist
 
 
-def _kmer_query(call, q, n_known, min_kmers, cap):
+def _kmer_query(call, q, n_known, min_kmers, cap, hint=None):
+    """hint: a one-element list that carries the room the last call needed to the next one (a resident index is queried many
+    times with similar batches; a first guess that is too small costs one repeated launch with the exact size)."""
     q = np.ascontiguousarray(q, dtype=np.uint32)
     if cap is None:
-        cap = max(1024, 4 * n_known)
+        cap = hint[0] if hint and hint[0] else max(1 << 16, min(4 * n_known, 2048 * max(int(q.size), 1)))
     while True:
         hq = np.empty(cap, np.uint32); hw = np.empty(cap, np.uint32)
         cnt = np.empty(cap, np.uint8); mult = np.empty(cap, np.uint64)
         total = C.c_size_t(0)
         rc = call(ptr(q), q.size, int(min_kmers), cap, ptr(hq), ptr(hw), ptr(cnt), ptr(mult), C.byref(total))
         if rc == _lib.BDG_ERR_CAPACITY:
-            cap = int(total.value)
+            cap = int(total.value) + int(total.value) // 8
             continue
         check(rc)
         n = int(total.value)
+        if hint is not None:
+            hint[0] = max(1 << 16, n + n // 8)
         by = mult[:n].view(np.uint8).reshape(n, 8)          # little-endian: nibble p of the word = nibble p & 1 of byte p >> 1
         nib = np.empty((n, 16), np.uint8)
         np.bitwise_and(by, 15, out=nib[:, 0::2])
@@ -429,10 +433,11 @@ class KmerIndex:
         self.size = int(known.size)
         self._h = C.c_void_p()
         check(lib().bdg_kmer_index_create(ptr(known), known.size, C.byref(self._h)))
+        self._room = [0]
 
     def query(self, q: np.ndarray, min_kmers: int = 1, cap: int | None = None):
         L = lib()
-        return _kmer_query(lambda *a: L.bdg_kmer_index_query(self._h, *a), q, self.size, min_kmers, cap)
+        return _kmer_query(lambda *a: L.bdg_kmer_index_query(self._h, *a), q, self.size, min_kmers, cap, self._room)
 
     def info(self) -> dict:
         """{"postings": queries walk 6-mer posting lists (else they scan every string), "kernel_ms": the last query's kernel}."""
